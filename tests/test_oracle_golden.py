@@ -1,0 +1,137 @@
+"""The oracle (oracle/afb_oracle.py) against vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  CPU only.  Same ATen kernels on both sides => bit-exact expected;
+a 1e-6 tolerance is allowed on float values because the fixture was written with 1 thread."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import afb_oracle as O
+
+T = lambda a: torch.from_numpy(np.asarray(a)).clone()
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def test_scatter_mean_hand_example():
+    # 3 slots, 5 sources: slot0 <- {s0, s3}, slot2 <- {s1, s2, s4}, slot1 untouched (count clamps to 1 -> stays 0)
+    src = torch.tensor([[1., 2., 4., 5., 9.], [10., 20., 40., 50., 90.]])
+    idx = torch.tensor([0, 2, 2, 0, 2]).unsqueeze(0).expand(2, -1)
+    out = torch.zeros(2, 3)
+    O.scatter_mean_2_0_8(src, idx, 1, out)
+    exp = torch.tensor([[3., 0., 5.], [30., 0., 50.]])
+    assert torch.equal(out, exp)
+
+
+def test_scatter_mean_vs_naive_loop():
+    g = torch.Generator().manual_seed(0)
+    src = torch.randn(7, 50, generator=g)
+    idx1 = torch.randint(0, 11, (50,), generator=g)
+    out = torch.zeros(7, 11)
+    O.scatter_mean_2_0_8(src, idx1.unsqueeze(0).expand(7, -1), 1, out)
+    ref = torch.zeros(7, 11)
+    cnt = torch.zeros(11)
+    for j in range(50):                      # sequential, ascending source order
+        ref[:, idx1[j]] += src[:, j]
+        cnt[idx1[j]] += 1
+    ref /= cnt.clamp(min=1)
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize('name', ['real_dims', 'one_slot'])
+def test_read_golden(golden_dir, name):
+    g = load(golden_dir, f'read_{name}.npz')
+    obj_n = int(g['obj_n'])
+    keys = [T(g[f'key{c}']) for c in range(obj_n)]
+    vals = [T(g[f'val{c}']) for c in range(obj_n)]
+    info = [T(g[f'info_before{c}']) for c in range(obj_n)]
+    rr = O.matcher_forward(keys, vals, info, T(g['q_in']), T(g['q_out']), 1e-3, update_bank=True)
+    assert rr.out.shape == g['out'].shape
+    np.testing.assert_allclose(rr.out.numpy(), g['out'], rtol=0, atol=1e-6)
+    for c in range(obj_n):
+        np.testing.assert_allclose(info[c].numpy(), g[f'info_after{c}'], rtol=0, atol=1e-6)
+        # usage counts are integers and must reproduce the info delta exactly
+        delta = g[f'info_after{c}'][:, 1] - g[f'info_before{c}'][:, 1]
+        np.testing.assert_allclose(np.log(rr.cnt[c].numpy() + 1), delta, atol=2e-6)
+
+
+@pytest.mark.parametrize('name', ['small_evict', 'small_evict2', 'small_allmerge', 'small_allappend', 'real_dims'])
+def test_update_golden(golden_dir, name):
+    g = load(golden_dir, f'update_{name}.npz')
+    obj_n = int(g['obj_n'])
+    fb = O.OracleFeatureBank(obj_n, int(g['budget']), 'cpu', update_rate=0.1, thres_close=float(g['thres_close']))
+    assert fb.class_budget == float(g['class_budget'])
+    fb.init_bank([T(g[f'key_init{c}']) for c in range(obj_n)], [T(g[f'val_init{c}']) for c in range(obj_n)])
+    evictions = 0
+    for t in range(1, int(g['frames']) + 1):
+        rr = O.matcher_forward(fb.keys, fb.values, fb.info, T(g[f'f{t}_q_in']), T(g[f'f{t}_q_out']), 1e-3, True)
+        np.testing.assert_allclose(rr.out.numpy(), g[f'f{t}_out'], rtol=0, atol=1e-6)
+        for c in range(obj_n):
+            np.testing.assert_allclose(fb.info[c].numpy(), g[f'f{t}_info_read{c}'], rtol=0, atol=1e-6)
+        fb.update([T(g[f'f{t}_pk{c}']) for c in range(obj_n)], [T(g[f'f{t}_pv{c}']) for c in range(obj_n)], t)
+        for c in range(obj_n):
+            assert fb.keys[c].shape == g[f'f{t}_key{c}'].shape, (t, c)
+            np.testing.assert_allclose(fb.keys[c].numpy(), g[f'f{t}_key{c}'], rtol=0, atol=1e-6)
+            np.testing.assert_allclose(fb.values[c].numpy(), g[f'f{t}_val{c}'], rtol=0, atol=1e-6)
+            np.testing.assert_allclose(fb.info[c].numpy(), g[f'f{t}_info{c}'], rtol=0, atol=1e-6)
+            d = fb.last_decisions[c]
+            assert d.n_after == fb.keys[c].shape[1]
+            assert len(d.merge_q) + len(d.append_q) == g[f'f{t}_pk{c}'].shape[1]
+            evictions += d.remove is not None
+        np.testing.assert_array_equal(fb.peak_n, g[f'f{t}_peak_n'])
+        np.testing.assert_array_equal(fb.replace_n, g[f'f{t}_replace_n'])
+    if 'evict' in name:
+        assert evictions > 0
+
+
+def test_append_api_and_budget(golden_dir):
+    g = load(golden_dir, 'misc.npz')
+    fb = O.OracleFeatureBank(2, 1000, 'cpu')
+    fb.append([T(g[f'k0_{c}']) for c in range(2)], [T(g[f'v0_{c}']) for c in range(2)], frame_idx=2)
+    fb.append([T(g[f'k1_{c}']) for c in range(2)], [T(g[f'v1_{c}']) for c in range(2)], frame_idx=7)
+    for c in range(2):
+        np.testing.assert_array_equal(fb.keys[c].numpy(), g[f'key{c}'])
+        np.testing.assert_array_equal(fb.values[c].numpy(), g[f'val{c}'])
+        np.testing.assert_array_equal(fb.info[c].numpy(), g[f'info{c}'])
+    np.testing.assert_array_equal(fb.peak_n, g['peak_n'])
+    assert fb.class_budget == float(g['class_budget_obj2']) == 400.0
+    assert O.OracleFeatureBank(3, 1000).class_budget == float(g['class_budget_obj3']) == 333
+
+
+def test_uncertainty_and_pad(golden_dir):
+    g = load(golden_dir, 'misc.npz')
+    np.testing.assert_array_equal(O.calc_uncertainty(T(g['unc_in'])).numpy(), g['unc_out'])
+    (y,), pad = O.pad_divide_by([T(g['pad_in'])], 16, (30, 53))
+    np.testing.assert_array_equal(y.numpy(), g['pad_out'])
+    assert tuple(pad) == tuple(int(v) for v in g['pad_array']) == (5, 6, 1, 1)
+    # 480x854 -> 480x864 with lw=5, uw=5? (SURVEY: 853 -> lw=5,uw=6); both conventions from the same formula
+    (_,), pad = O.pad_divide_by([torch.zeros(1, 1, 480, 853)], 16, (480, 853))
+    assert pad == (5, 6, 0, 0)
+
+
+def test_urr_golden(golden_dir):
+    g = load(golden_dir, 'urr_h32w48.npz')
+    fs = tuple(int(v) for v in g['feature_shape'])
+    p_up, unc, conf, local_match = O.urr_pre(T(g['p']), T(g['r1']), fs)
+    np.testing.assert_allclose(local_match.numpy(), g['local_match'], rtol=0, atol=1e-6)
+    out = O.urr_post(p_up, unc, conf, T(g['q_local']))
+    np.testing.assert_allclose(out.numpy(), g['out'], rtol=0, atol=1e-6)
+
+
+def test_remove_threshold_semantics():
+    """Appendix A item 9: T = int(min)+1 recomputed from survivors; strict '>'; T jumps over integers."""
+    fb = O.OracleFeatureBank(1, 4, 'cpu')      # class_budget 4 (obj_n != 2 -> no 0.8 factor)
+    n = 6
+    fb.init_bank([torch.zeros(2, n)], [torch.zeros(3, n)])
+    fb.keys[0][0] = torch.arange(n, dtype=torch.float)
+    fb.info[0][:, 0] = 0
+    fb.info[0][:, 1] = torch.tensor([0.5, 5.0, 5.5, 3.0, 7.25, 1.0]) * 2      # frame_idx 2 -> LFU = col1/2
+    dec = fb._remove(0, 2, 2)                  # need kept <= 2
+    # LFU = [.5, 5, 5.5, 3, 7.25, 1]; T=1 keeps {5,5.5,3,7.25} (4 > 2) ; T=int(3)+1=4 keeps {5,5.5,7.25}; T=int(5)+1=6 keeps {7.25}
+    assert dec.thresholds == [1, 4, 6]
+    assert dec.keep_mask.tolist() == [False, False, False, False, True, False]
+    assert fb.keys[0][0].tolist() == [4.0]
+    assert dec.balance == 1
