@@ -1,0 +1,158 @@
+/*
+ * vfn.h - C ABI of libvfn_sm100a.so: the B200 (sm_100a) implementation of V-FloodNet's AFB-URR
+ * memory-propagation hot path (feature-bank read, bank update, uncertain-region refinement).
+ *
+ * The reference (xmlyqing00/V-FloodNet) has no FFI layer: its "operator API" for this path is three
+ * Python objects (FeatureBank, Matcher, Decoder).  Each entry point below names the reference lines it
+ * replaces; vfloodnet_b200/*.py re-creates those Python objects on top of this ABI via ctypes.
+ *
+ * Conventions
+ *   - every pointer named d_* / inside vfn_bank is a DEVICE pointer; h_* is a HOST pointer (pinned preferred)
+ *   - `stream` is a cudaStream_t passed as void*
+ *   - return value: 0 = ok, <0 = error (VFN_E_*); vfn_last_error() returns a thread-local message
+ *   - no allocation, no host synchronisation and no exceptions inside the library unless stated;
+ *     scratch memory is passed in (`ws`, sized by the matching *_workspace_bytes query)
+ *   - layouts: "dm" = dimension-major (d, n) as the reference stores keys/values (FeatureBank.py:29-30),
+ *              "em" = entry-major (n, d): one bank slot / one query per contiguous row (the HBM layout)
+ */
+#ifndef VFN_H_
+#define VFN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VFN_VERSION 100
+
+#define VFN_OK 0
+#define VFN_E_ARG (-1)       /* bad argument / unsupported shape */
+#define VFN_E_CAPACITY (-2)  /* bank capacity or workspace too small */
+#define VFN_E_CUDA (-3)      /* CUDA runtime error, see vfn_last_error() */
+#define VFN_E_UNSUPPORTED (-4)
+
+/* One object's feature bank in HBM, entry-major.  Owned by the caller (torch allocations in the Python host). */
+typedef struct vfn_bank {
+  int32_t d_key;   /* 128 in AFB_URR (AFB_URR.py:250) */
+  int32_t d_val;   /* 512 */
+  int64_t cap;     /* allocated slots */
+  int64_t n;       /* live slots (host-tracked) */
+  float* keys;     /* (cap, d_key)  raw keys      == reference fb.keys[i].T   */
+  float* values;   /* (cap, d_val)  raw values    == reference fb.values[i].T */
+  float* info;     /* (cap, 2)      [frame added, sum log(cnt+1)]  (FeatureBank.py:34-35) */
+  float* nkeys;    /* (cap, d_key)  keys / max(|key|,1e-12): cached NF.normalize(keys, dim=0) (FeatureBank.py:63) */
+  uint16_t* kh;    /* (cap, d_key)  bf16 hi part of keys   - tensor-core operand, NULL if unused */
+  uint16_t* kl;    /* (cap, d_key)  bf16 lo part (key - hi) */
+  uint16_t* vh;    /* (cap, d_val)  bf16 hi part of values */
+  uint16_t* vl;    /* (cap, d_val)  bf16 lo part */
+  int32_t* cnt;    /* (cap)         usage-count scratch, all zero between reads */
+} vfn_bank;
+
+int vfn_version(void);
+const char* vfn_last_error(void);
+/* 1 if the running device is compute capability 10.x (tcgen05/TMEM/TMA kernels usable) */
+int vfn_device_is_sm100(void);
+
+/* ---- candidate / query preparation ------------------------------------------------------------
+ * (d, n) dm  ->  (n, d) em copies: raw and L2-normalised (x / max(|x|, 1e-12)), + optional bf16 hi/lo of raw*scale.
+ * Replaces NF.normalize(prev_key, dim=0) / NF.normalize(prev_value, dim=0) (FeatureBank.py:64,88) and the
+ * transposes implied by keys[i].transpose(0,1) (AFB_URR.py:144).  Any output pointer may be NULL. */
+int vfn_prep_rows(const float* d_src_dm, int32_t d, int64_t n, float* d_raw_em, float* d_normed_em,
+                  uint16_t* d_hi_em, uint16_t* d_lo_em, float scale, void* stream);
+
+/* ---- bank ingest: init_bank / append / update's append step ------------------------------------
+ * Copies rows sel[0..n_sel) (ascending candidate positions; sel==NULL => 0..n_sel-1) of the em candidate
+ * arrays into slots [bank->n, bank->n+n_sel), writes info rows (info0, info1) and all derived arrays.
+ * d_n_sel (device int, may be NULL) overrides n_sel_upper with a device-side count (no host sync).
+ * Replaces FeatureBank.init_bank (FeatureBank.py:27-36), append (:38-51), and update's cat (:105-111). */
+int vfn_bank_append_rows(const vfn_bank* bank, const float* d_ck_em, const float* d_cv_em, const float* d_nck_em,
+                         const int32_t* d_sel, int64_t n_sel_upper, const int32_t* d_n_sel, float info0, float info1,
+                         void* stream);
+
+/* Recompute derived arrays (nkeys, kh/kl, vh/vl) of slots [first, first+count) from keys/values. */
+int vfn_bank_refresh(const vfn_bank* bank, int64_t first, int64_t count, void* stream);
+
+/* ---- memory read: Matcher.forward (AFB_URR.py:136-178) ------------------------------------------
+ * out: (obj_n, 2*d_val, hw) fp32 = [softmax_i(K_i.q_j/sqrt(d_key)) readout ; q_out] per object
+ * (== reference (1,obj_n,1024,HW), bs=1).  If update_bank: info[:,1] += log(cnt+1) with
+ * cnt_i = #{j : p_ij > thres_valid} (AFB_URR.py:161-174).  d_lse (obj_n, hw) optional: natural-log LSE.
+ * impl: 0 = auto (tcgen05 when shapes allow), 1 = fp32 SIMT kernels, 2 = tcgen05 kernels. */
+size_t vfn_memread_workspace_bytes(int32_t obj_n, int64_t n_max, int64_t hw, int32_t d_key, int32_t d_val);
+int vfn_memread(const vfn_bank* banks, int32_t obj_n, const float* d_q_in_dm, const float* d_q_out_dm, int64_t hw,
+                float thres_valid, int32_t update_bank, float* d_out, float* d_lse, void* d_ws, size_t ws_bytes,
+                int32_t impl, void* stream);
+
+/* Split-memory form for a bank sharded over GPUs: phase A leaves per-query (max, sum exp(s-max)) of the
+ * LOCAL slots in d_ml (obj_n, hw, 2) [natural-log domain, s = <k,q>/sqrt(d_key)]; the caller stacks the partial sets of
+ * all ranks and reduces them with vfn_lse_combine into the global LSE d_lse (obj_n, hw); phase B (same workspace,
+ * called after phase A) computes the local partial readout (obj_n, d_val, hw) + usage counts against that global LSE.
+ * Partial readouts are summed across ranks by the caller (all-reduce). */
+int vfn_memread_phase_a(const vfn_bank* banks, int32_t obj_n, const float* d_q_in_dm, int64_t hw, float* d_ml,
+                        void* d_ws, size_t ws_bytes, int32_t impl, void* stream);
+int vfn_memread_phase_b(const vfn_bank* banks, int32_t obj_n, const float* d_q_in_dm, int64_t hw, const float* d_lse,
+                        float thres_valid, int32_t update_bank, float* d_partial_out, void* d_ws, size_t ws_bytes,
+                        int32_t impl, void* stream);
+/* d_ml: n_parts stacked partial sets (n_parts, n_rows, 2) -> d_lse (n_rows) = M + log(sum_s l_s exp(m_s - M)) */
+int vfn_lse_combine(const float* d_ml, int32_t n_parts, int64_t n_rows, float* d_lse, void* stream);
+
+/* ---- bank update: FeatureBank.update (FeatureBank.py:53-115) -----------------------------------
+ * match: j*_q = argmax_i <nkeys_i, nck_q>, ties -> lowest i; c*_q = that maximum.  (FeatureBank.py:63-68) */
+size_t vfn_bank_match_workspace_bytes(int64_t n, int64_t hw);
+int vfn_bank_match(const vfn_bank* bank, const float* d_nck_em, int64_t hw, int32_t* d_match_idx, float* d_match_corr,
+                   void* d_ws, size_t ws_bytes, int32_t impl, void* stream);
+
+/* plan: from (j*, c*) build   merge set S = {q : c*>thres} as (slot,q) pairs sorted by (slot, q),
+ * run offsets of equal-slot runs (= unique touched slots, ascending), append set A = {q : c*<=thres} ascending.
+ * d_counts[0..3] = {n_merge, n_runs, n_append, 0}; also copied to h_counts (pinned) if non-NULL.
+ * Replaces nonzero / unique / index plumbing of FeatureBank.py:71-73,100. */
+size_t vfn_bank_plan_workspace_bytes(int64_t hw);
+int vfn_bank_plan(const int32_t* d_match_idx, const float* d_match_corr, int64_t hw, float thres_close,
+                  int32_t* d_merge_q, int32_t* d_merge_slot, int32_t* d_run_off, int32_t* d_append_q,
+                  int32_t* d_counts, int32_t* h_counts, void* d_ws, size_t ws_bytes, void* stream);
+
+/* merge: for each run (slot u, members q ascending): mean of normalised candidates (scatter_mean, sequential
+ * ascending-q summation), then  row_u <- |row_u| * ((1-r)*row_u/|row_u| + r*mean)  for keys and values
+ * (FeatureBank.py:76-97), and refresh of the derived arrays of slot u. */
+int vfn_bank_merge(const vfn_bank* bank, const float* d_nck_em, const float* d_ncv_em, const int32_t* d_merge_q,
+                   const int32_t* d_merge_slot, const int32_t* d_run_off, const int32_t* d_counts, int64_t hw,
+                   float update_rate, void* stream);
+
+/* evict plan: FeatureBank.remove's threshold search (FeatureBank.py:117-138), entirely on device.
+ * LFU_i = info[i,1]/(frame_idx - info[i,0]); T = int(min LFU)+1; keep LFU > T; while
+ * class_budget - kept - request_n < 0: T = int(min of survivors)+1.
+ * d_plan (int32[72]) = {status, kept, n_iter, T_final, thresholds[0..63]...}; mirrored to h_plan if non-NULL.
+ * status: 0 ok, 1 = survivors empty while balance<0 (reference raises), 2 = non-finite LFU minimum (reference raises). */
+int vfn_bank_evict_plan(const vfn_bank* bank, float frame_idx, double class_budget, int64_t request_n,
+                        int32_t* d_plan, int32_t* h_plan, float* d_lfu_scratch, void* stream);
+/* compaction: order-preserving copy of the slots with LFU > T_final (read from d_plan) from src into dst
+ * (all arrays of the bank).  dst->cap >= kept.  ws: vfn_bank_compact_workspace_bytes(src->n). (FeatureBank.py:127-131) */
+size_t vfn_bank_compact_workspace_bytes(int64_t n);
+int vfn_bank_compact(const vfn_bank* src, const vfn_bank* dst, const float* d_lfu, const int32_t* d_plan, void* d_ws,
+                     size_t ws_bytes, void* stream);
+
+/* info[:,1] = clamp(info[:,1], 0, 1e5) over slots [0, n)  (FeatureBank.py:115) */
+int vfn_bank_clamp_info(const vfn_bank* bank, int64_t n, void* stream);
+
+/* ---- URR: non-convolution parts of Decoder.forward (AFB_URR.py:214-237, myutils/data.py:42-48) -----
+ * pre:  p (obj_n,2,h/2,w/2) coarse logits from pred2, r1 (obj_n or 1, c, h, w)  ->
+ *       p_up (obj_n,2,h,w) bilinear x2 of p; seg (obj_n,h,w) object-normalised foreground prob (rough_seg);
+ *       unc (h,w) = exp(1 - top1/(top2+1e-8)) over objects (identical for every object, bs=1);
+ *       conf (obj_n,h,w) 7x7 max of seg; avg (obj_n,h,w) 7x7 mean of seg (zero pad, /49);
+ *       local_match (obj_n,2c,h,w) = [r1 ; box7(r1*seg)/49 / (avg + 1e-8)]   (input of local_convFM)
+ * post: prob (obj_n,2h,2w) = softmax(bilinear_x2(p_up + unc * (conf * q_local)))[:,1]
+ * r1_obj_stride: elements between objects in r1 (0 => the same r1 for every object = the reference's expand). */
+int vfn_urr_pre(const float* d_p, const float* d_r1, int64_t r1_obj_stride, int32_t obj_n, int32_t c, int32_t h,
+                int32_t w, float* d_p_up, float* d_seg, float* d_unc, float* d_conf, float* d_avg,
+                float* d_local_match, void* stream);
+int vfn_urr_post(const float* d_p_up, const float* d_unc, const float* d_conf, const float* d_q_local, int32_t obj_n,
+                 int32_t h, int32_t w, float* d_prob, void* stream);
+
+/* ---- self-test hooks for the tcgen05/TMA building blocks (used by tests/, not by the product path) ---- */
+int vfn_debug_umma_ss(const uint16_t* d_a, const uint16_t* d_b, float* d_c, int32_t n_tiles, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VFN_H_ */

@@ -133,8 +133,8 @@ def golden_append_api(seed=5):
     from video_module.model.FeatureBank import FeatureBank
     g = torch.Generator().manual_seed(seed)
     fb = FeatureBank(2, 1000, 'cpu')
-    k0, v0 = zip(*[gen_bank(g, 8, 12, 5) for _ in range(2)])
-    k1, v1 = zip(*[gen_bank(g, 8, 12, 3) for _ in range(2)])
+    k0, v0 = zip(*[gen_bank(g, 8, 16, 5) for _ in range(2)])
+    k1, v1 = zip(*[gen_bank(g, 8, 16, 3) for _ in range(2)])
     fb.append([k.clone() for k in k0], [v.clone() for v in v0], frame_idx=2)   # empty bank -> init_bank
     fb.append([k.clone() for k in k1], [v.clone() for v in v1], frame_idx=7)
     d = {}

@@ -1,0 +1,279 @@
+"""GPU parity: the CUDA path (through the C ABI, via the drop-in FeatureBank / Matcher / URR wrappers) against
+(a) the committed reference-generated golden vectors and (b) the CPU oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): bank match indices, merge assignments, append sets and eviction choices
+bit-exact; readout max-abs error <= 1e-3 (tcgen05 path; the fp32 SIMT path is held to 1e-4); info within 1e-5.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import afb_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+READ_TOL = {1: 1e-4, 2: 1e-3}      # max-abs tolerance per implementation (1 = fp32 SIMT, 2 = tcgen05)
+T = lambda a: torch.from_numpy(np.asarray(a)).clone()
+
+
+@pytest.fixture(scope='module')
+def vfn():
+    import vfloodnet_b200 as v
+    assert torch.cuda.is_available()
+    return v
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+IMPLS = [int(x) for x in os.environ.get('VFN_TEST_IMPLS', '1,2').split(',')]
+
+
+def impls_for(d_key, d_val):
+    return IMPLS if (d_key, d_val) == (128, 512) else [1]
+
+
+# ---------------------------------------------------------------------------------------------------
+# read
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['real_dims', 'one_slot'])
+def test_read_golden(vfn, golden_dir, name):
+    g = load(golden_dir, f'read_{name}.npz')
+    obj_n = int(g['obj_n'])
+    d_key, d_val = g['key0'].shape[0], g['val0'].shape[0]
+    for impl in impls_for(d_key, d_val):
+        fb = vfn.FeatureBank(obj_n, 10 ** 6, 'cuda', impl=impl)
+        fb.load_state([T(g[f'key{c}']) for c in range(obj_n)], [T(g[f'val{c}']) for c in range(obj_n)],
+                      [T(g[f'info_before{c}']) for c in range(obj_n)])
+        m = vfn.Matcher(thres_valid=1e-3, update_bank=True)
+        out = m(fb, T(g['q_in']).cuda(), T(g['q_out']).cuda())
+        assert tuple(out.shape) == g['out'].shape
+        err = (out.cpu() - T(g['out'])).abs().max().item()
+        assert err <= READ_TOL[impl], (impl, err)
+        for c in range(obj_n):
+            np.testing.assert_allclose(fb.info[c].cpu().numpy(), g[f'info_after{c}'], rtol=0, atol=1e-5)
+
+
+def _oracle_read(keys, vals, info, q_in, q_out):
+    info = [i.clone() for i in info]
+    rr = O.matcher_forward(keys, vals, info, q_in, q_out, 1e-3, update_bank=True, keep_p=True)
+    return rr, info
+
+
+def _check_counts(cnt_gpu, p, eps):
+    """usage counts must lie between the oracle's counts at thresholds 1e-3*(1+eps) and 1e-3*(1-eps)"""
+    lo = (p[0] > 1e-3 * (1 + eps)).sum(dim=1)
+    hi = (p[0] > 1e-3 * (1 - eps)).sum(dim=1)
+    assert torch.all(cnt_gpu >= lo) and torch.all(cnt_gpu <= hi), \
+        f'{int(((cnt_gpu < lo) | (cnt_gpu > hi)).sum())} usage counts outside the threshold band'
+    return int((lo != hi).sum())
+
+
+@pytest.mark.parametrize('n,hw,seed', [(1620, 1620, 0), (5000, 1620, 1), (333, 77, 2), (20000, 500, 3)])
+def test_read_vs_oracle(vfn, n, hw, seed):
+    from vfloodnet_b200 import synth
+    g = torch.Generator().manual_seed(seed)
+    ns = [n, max(1, n - 37)]
+    keys, vals = zip(*[synth.gen_bank(g, k) for k in ns])
+    info = [synth.gen_info(g, k, 10) for k in ns]
+    q_in, q_out = synth.gen_query(g, hw)
+    rr, info_ref = _oracle_read(list(keys), list(vals), info, q_in, q_out)
+    for impl in IMPLS:
+        fb = vfn.FeatureBank(2, 10 ** 6, 'cuda', impl=impl)
+        fb.load_state(list(keys), list(vals), info)
+        m = vfn.Matcher(update_bank=True)
+        m.want_lse = True
+        out = m(fb, q_in.cuda(), q_out.cuda())
+        err = (out.cpu() - rr.out).abs().max().item()
+        assert err <= READ_TOL[impl], (impl, err)
+        # q_out half must be a bit-exact copy
+        assert torch.equal(out[0, :, 512:, :].cpu(), q_out.expand(2, -1, -1))
+        for c in range(2):
+            lse_err = (m.last_lse[c].cpu() - rr.lse[c]).abs().max().item()
+            assert lse_err <= (1e-5 if impl == 1 else 2e-4), (impl, lse_err)
+            # recover integer counts from the info delta
+            delta = fb.info[c][:, 1].cpu() - info[c][:, 1]
+            cnt_gpu = torch.round(torch.exp(delta.double()) - 1).long()
+            _check_counts(cnt_gpu, rr.p[c], 1e-5 if impl == 1 else 2e-4)
+            np.testing.assert_allclose(fb.info[c][:, 0].cpu().numpy(), info[c][:, 0].numpy())
+
+
+# ---------------------------------------------------------------------------------------------------
+# update (teacher forced per frame against the reference-generated vectors)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['small_evict', 'small_evict2', 'small_allmerge', 'small_allappend', 'real_dims'])
+def test_update_golden_teacher_forced(vfn, golden_dir, name):
+    g = load(golden_dir, f'update_{name}.npz')
+    obj_n = int(g['obj_n'])
+    fb = vfn.FeatureBank(obj_n, int(g['budget']), 'cuda', update_rate=0.1, thres_close=float(g['thres_close']), impl=1)
+    assert fb.class_budget == float(g['class_budget'])
+    prev = dict(key=[g[f'key_init{c}'] for c in range(obj_n)], val=[g[f'val_init{c}'] for c in range(obj_n)])
+    replace_prev = np.zeros(obj_n)
+    for t in range(1, int(g['frames']) + 1):
+        fb.load_state([T(k) for k in prev['key']], [T(v) for v in prev['val']],
+                      [T(g[f'f{t}_info_read{c}']) for c in range(obj_n)])
+        fb.replace_n[:] = replace_prev
+        fb.update([T(g[f'f{t}_pk{c}']).cuda() for c in range(obj_n)], [T(g[f'f{t}_pv{c}']).cuda() for c in range(obj_n)], t)
+        for c in range(obj_n):
+            assert tuple(fb.keys[c].shape) == g[f'f{t}_key{c}'].shape, (t, c)
+            np.testing.assert_allclose(fb.keys[c].cpu().numpy(), g[f'f{t}_key{c}'], rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(fb.values[c].cpu().numpy(), g[f'f{t}_val{c}'], rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(fb.info[c].cpu().numpy(), g[f'f{t}_info{c}'], rtol=0, atol=1e-6)
+        np.testing.assert_array_equal(fb.replace_n, g[f'f{t}_replace_n'])
+        prev = dict(key=[g[f'f{t}_key{c}'] for c in range(obj_n)], val=[g[f'f{t}_val{c}'] for c in range(obj_n)])
+        replace_prev = g[f'f{t}_replace_n'].copy()
+
+
+@pytest.mark.parametrize('name', ['small_evict2', 'real_dims'])
+def test_loop_golden_free_running(vfn, golden_dir, name):
+    """read + update free-running over the whole golden clip (no teacher forcing)."""
+    g = load(golden_dir, f'update_{name}.npz')
+    obj_n = int(g['obj_n'])
+    fb = vfn.FeatureBank(obj_n, int(g['budget']), 'cuda', thres_close=float(g['thres_close']), impl=1)
+    fb.init_bank([T(g[f'key_init{c}']) for c in range(obj_n)], [T(g[f'val_init{c}']) for c in range(obj_n)])
+    m = vfn.Matcher(update_bank=True)
+    for t in range(1, int(g['frames']) + 1):
+        out = m(fb, T(g[f'f{t}_q_in']).cuda(), T(g[f'f{t}_q_out']).cuda())
+        assert (out.cpu() - T(g[f'f{t}_out'])).abs().max().item() <= 1e-4
+        fb.update([T(g[f'f{t}_pk{c}']).cuda() for c in range(obj_n)], [T(g[f'f{t}_pv{c}']).cuda() for c in range(obj_n)], t)
+        for c in range(obj_n):
+            assert tuple(fb.keys[c].shape) == g[f'f{t}_key{c}'].shape, (t, c)
+            np.testing.assert_allclose(fb.info[c].cpu().numpy(), g[f'f{t}_info{c}'], rtol=0, atol=2e-5)
+        np.testing.assert_array_equal(fb.peak_n, g[f'f{t}_peak_n'])
+        np.testing.assert_array_equal(fb.replace_n, g[f'f{t}_replace_n'])
+    for c in range(obj_n):
+        np.testing.assert_allclose(fb.keys[c].cpu().numpy(), g[f'f{t}_key{c}'], rtol=1e-4, atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------
+# update vs oracle at 480p size, decisions bit-exact
+# ---------------------------------------------------------------------------------------------------
+def _run_update_pair(vfn, n, hw, seed, budget, frame_idx=12, frac_merge=0.5, thres=0.95):
+    from vfloodnet_b200 import synth
+    g = torch.Generator().manual_seed(seed)
+    keys, vals = zip(*[synth.gen_bank(g, n) for _ in range(2)])
+    info = [synth.gen_info(g, n, frame_idx) for _ in range(2)]
+    pk, pv = zip(*[synth.gen_candidates(g, keys[c], vals[c], hw, frac_merge) for c in range(2)])
+    ofb = O.OracleFeatureBank(2, budget, 'cpu', thres_close=thres)
+    ofb.init_bank([k.clone() for k in keys], [v.clone() for v in vals])
+    for c in range(2):
+        ofb.info[c] = info[c].clone()
+    ofb.update([k.clone() for k in pk], [v.clone() for v in pv], frame_idx)
+    fb = vfn.FeatureBank(2, budget, 'cuda', thres_close=thres, impl=1)
+    fb.load_state(list(keys), list(vals), info)
+    fb.update([k.cuda() for k in pk], [v.cuda() for v in pv], frame_idx)
+    return ofb, fb
+
+
+@pytest.mark.parametrize('n,hw,seed,budget', [(5000, 1620, 0, 10 ** 6), (20000, 1620, 1, 50000), (1620, 1620, 2, 4000),
+                                              (3000, 257, 3, 10 ** 6)])
+def test_update_vs_oracle_decisions(vfn, n, hw, seed, budget):
+    ofb, fb = _run_update_pair(vfn, n, hw, seed, budget)
+    for c in range(2):
+        d, dg = ofb.last_decisions[c], fb.last_decisions[c]
+        # synthetic margins are far above fp32 rounding noise: decisions must be identical
+        assert float(d.margin.min()) > 1e-5
+        assert torch.equal(dg['match_idx'].cpu().long(), d.match_idx)
+        np.testing.assert_allclose(dg['match_corr'].cpu().numpy(), d.match_corr.numpy(), rtol=0, atol=2e-6)
+        nm, na = dg['n_merge'], dg['n_append']
+        assert nm == len(d.merge_q) and na == len(d.append_q) and dg['n_runs'] == len(d.touched)
+        # merge pairs: sorted by (slot, q) on the GPU; same set as the oracle's (q ascending) list
+        gq, gs = dg['merge_q'][:nm].cpu().long(), dg['merge_slot'][:nm].cpu().long()
+        order = torch.argsort(d.merge_slot * (10 ** 6) + d.merge_q)
+        assert torch.equal(gq, d.merge_q[order]) and torch.equal(gs, d.merge_slot[order])
+        assert torch.equal(dg['append_q'][:na].cpu().long(), d.append_q)
+        assert dg['evicted'] == (d.remove is not None)
+        assert fb.bank_n(c) == d.n_after == ofb.keys[c].shape[1]
+        np.testing.assert_allclose(fb.keys[c].cpu().numpy(), ofb.keys[c].numpy(), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(fb.values[c].cpu().numpy(), ofb.values[c].numpy(), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(fb.info[c].cpu().numpy(), ofb.info[c].numpy(), rtol=0, atol=1e-6)
+    np.testing.assert_array_equal(fb.replace_n, ofb.replace_n)
+    np.testing.assert_array_equal(fb.peak_n[0:0], ofb.peak_n[0:0])
+
+
+def test_match_ties_lowest_index(vfn):
+    """exact duplicate bank columns: argmax must return the lowest slot (ATen semantics)."""
+    from vfloodnet_b200 import synth
+    g = torch.Generator().manual_seed(5)
+    k, v = synth.gen_bank(g, 600)
+    k[:, 400:500] = k[:, 100:200]           # duplicates of slots 100..199 at 400..499
+    k[:, 550] = k[:, 3]
+    pk = torch.cat([k[:, 150:160], k[:, 450:460], k[:, 550:551], torch.randn(128, 9, generator=g)], dim=1).contiguous()
+    pv = torch.randn(512, pk.shape[1], generator=g)
+    fb = vfn.FeatureBank(1, 10 ** 6, 'cuda', impl=1)
+    fb.init_bank([k], [v])
+    fb.update([pk.cuda()], [pv.cuda()], 1)
+    idx = fb.last_decisions[0]['match_idx'].cpu().long()
+    assert idx[:10].tolist() == list(range(150, 160))
+    assert idx[10:20].tolist() == list(range(150, 160))
+    assert idx[20].item() == 3
+    ofb = O.OracleFeatureBank(1, 10 ** 6)
+    ofb.init_bank([k.clone()], [v.clone()])
+    ofb.update([pk.clone()], [pv.clone()], 1)
+    assert torch.equal(idx[:21], ofb.last_decisions[0].match_idx[:21])
+
+
+def test_remove_threshold_semantics(vfn):
+    """T = int(min)+1 recomputed from survivors, strict '>' (SURVEY App. A item 9); same case as the oracle test."""
+    fb = vfn.FeatureBank(1, 4, 'cuda', impl=1)
+    n = 6
+    keys = torch.zeros(8, n); keys[0] = torch.arange(n, dtype=torch.float)
+    info = torch.zeros(n, 2); info[:, 1] = torch.tensor([0.5, 5.0, 5.5, 3.0, 7.25, 1.0]) * 2
+    fb.load_state([keys], [torch.zeros(8, n)], [info])
+    balance = fb.remove(0, 2, 2)
+    assert fb.last_thresholds == [1, 4, 6]
+    assert fb.keys[0][0].cpu().tolist() == [4.0]
+    assert balance == 1 and fb.replace_n[0] == 5
+    # everything evicted while still over budget -> error, like the reference
+    fb2 = vfn.FeatureBank(1, 4, 'cuda', impl=1)
+    fb2.load_state([keys], [torch.zeros(8, n)], [info])
+    with pytest.raises(RuntimeError):
+        fb2.remove(0, 5, 2)
+
+
+def test_append_api(vfn, golden_dir):
+    g = load(golden_dir, 'misc.npz')
+    fb = vfn.FeatureBank(2, 1000, 'cuda')
+    fb.append([T(g[f'k0_{c}']) for c in range(2)], [T(g[f'v0_{c}']) for c in range(2)], frame_idx=2)
+    fb.append([T(g[f'k1_{c}']) for c in range(2)], [T(g[f'v1_{c}']) for c in range(2)], frame_idx=7)
+    for c in range(2):
+        np.testing.assert_array_equal(fb.keys[c].cpu().numpy(), g[f'key{c}'])
+        np.testing.assert_array_equal(fb.values[c].cpu().numpy(), g[f'val{c}'])
+        np.testing.assert_array_equal(fb.info[c].cpu().numpy(), g[f'info{c}'])
+    np.testing.assert_array_equal(fb.peak_n, g['peak_n'])
+
+
+# ---------------------------------------------------------------------------------------------------
+# URR
+# ---------------------------------------------------------------------------------------------------
+def test_urr_golden(vfn, golden_dir):
+    g = load(golden_dir, 'urr_h32w48.npz')
+    fs = tuple(int(v) for v in g['feature_shape'])
+    p_up, unc, conf, local_match = vfn.urr_pre(T(g['p']).cuda(), T(g['r1']).cuda(), fs)
+    np.testing.assert_allclose(local_match.cpu().numpy(), g['local_match'], rtol=1e-5, atol=1e-5)
+    out = vfn.urr_post(p_up, unc, conf, T(g['q_local']).cuda())
+    np.testing.assert_allclose(out.cpu().numpy(), g['out'], rtol=0, atol=1e-5)
+
+
+def test_urr_vs_oracle_480p(vfn):
+    from vfloodnet_b200 import synth
+    g = torch.Generator().manual_seed(3)
+    h, w = 240, 432
+    p, r1, q_local = synth.gen_urr_inputs(g, 2, h, w)
+    r1e = r1.expand(2, -1, -1, -1)
+    p_up_o, unc_o, conf_o, lm_o = O.urr_pre(p, r1e, (1, 2, h, w))
+    out_o = O.urr_post(p_up_o, unc_o, conf_o, q_local)
+    p_up, unc, conf, lm = vfn.urr_pre(p.cuda(), r1.cuda().expand(2, -1, -1, -1), (1, 2, h, w))
+    np.testing.assert_allclose(p_up.cpu().numpy(), p_up_o.numpy(), atol=1e-5)
+    np.testing.assert_allclose(unc.cpu().numpy(), unc_o.numpy(), atol=1e-5)
+    np.testing.assert_allclose(conf.cpu().numpy(), conf_o.numpy(), atol=1e-6)
+    np.testing.assert_allclose(lm.cpu().numpy(), lm_o.numpy(), rtol=1e-4, atol=1e-5)
+    out = vfn.urr_post(p_up, unc, conf, q_local.cuda())
+    np.testing.assert_allclose(out.cpu().numpy(), out_o.numpy(), atol=1e-5)
+    # mask IoU of the final water mask (object 1 > 0.5)
+    a, b = out.cpu()[1] > 0.5, out_o[1] > 0.5
+    iou = (a & b).sum().item() / max((a | b).sum().item(), 1)
+    assert iou >= 0.999

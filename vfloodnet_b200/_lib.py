@@ -1,0 +1,91 @@
+"""ctypes binding of libvfn_sm100a.so (include/vfn.h).  No CPU fallback: a missing library is a hard error."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libvfn_sm100a.so')
+
+c_i32, c_i64, c_f32, c_f64, c_vp, c_sz = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p, C.c_size_t
+
+
+class VfnBank(C.Structure):
+    """struct vfn_bank (include/vfn.h)"""
+    _fields_ = [('d_key', c_i32), ('d_val', c_i32), ('cap', c_i64), ('n', c_i64),
+                ('keys', c_vp), ('values', c_vp), ('info', c_vp), ('nkeys', c_vp),
+                ('kh', c_vp), ('kl', c_vp), ('vh', c_vp), ('vl', c_vp), ('cnt', c_vp)]
+
+
+BANK_P = C.POINTER(VfnBank)
+
+# name -> (restype, argtypes); mirrors include/vfn.h one to one
+SIGNATURES = {
+    'vfn_version': (c_i32, []),
+    'vfn_last_error': (C.c_char_p, []),
+    'vfn_device_is_sm100': (c_i32, []),
+    'vfn_prep_rows': (c_i32, [c_vp, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp]),
+    'vfn_bank_append_rows': (c_i32, [BANK_P, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_f32, c_f32, c_vp]),
+    'vfn_bank_refresh': (c_i32, [BANK_P, c_i64, c_i64, c_vp]),
+    'vfn_memread_workspace_bytes': (c_sz, [c_i32, c_i64, c_i64, c_i32, c_i32]),
+    'vfn_memread': (c_i32, [BANK_P, c_i32, c_vp, c_vp, c_i64, c_f32, c_i32, c_vp, c_vp, c_vp, c_sz, c_i32, c_vp]),
+    'vfn_memread_phase_a': (c_i32, [BANK_P, c_i32, c_vp, c_i64, c_vp, c_vp, c_sz, c_i32, c_vp]),
+    'vfn_memread_phase_b': (c_i32, [BANK_P, c_i32, c_vp, c_i64, c_vp, c_f32, c_i32, c_vp, c_vp, c_sz, c_i32, c_vp]),
+    'vfn_lse_combine': (c_i32, [c_vp, c_i32, c_i64, c_vp, c_vp]),
+    'vfn_bank_match_workspace_bytes': (c_sz, [c_i64, c_i64]),
+    'vfn_bank_match': (c_i32, [BANK_P, c_vp, c_i64, c_vp, c_vp, c_vp, c_sz, c_i32, c_vp]),
+    'vfn_bank_plan_workspace_bytes': (c_sz, [c_i64]),
+    'vfn_bank_plan': (c_i32, [c_vp, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'vfn_bank_merge': (c_i32, [BANK_P, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_vp]),
+    'vfn_bank_evict_plan': (c_i32, [BANK_P, c_f32, c_f64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    'vfn_bank_compact_workspace_bytes': (c_sz, [c_i64]),
+    'vfn_bank_compact': (c_i32, [BANK_P, BANK_P, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'vfn_bank_clamp_info': (c_i32, [BANK_P, c_i64, c_vp]),
+    'vfn_urr_pre': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'vfn_urr_post': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    'vfn_debug_umma_ss': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp]),
+}
+
+_lib = None
+
+
+class VfnError(RuntimeError):
+    pass
+
+
+def load(build_if_missing: bool = True):
+    """dlopen the in-tree library.  Raises ImportError loudly if it is absent and cannot be built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if build_if_missing and (shutil.which('nvcc') or os.path.exists('/usr/local/cuda/bin/nvcc')):
+            from . import build as _build
+            _build.build()
+        else:
+            raise ImportError(f'{LIB_PATH} is missing and nvcc is not available: the CUDA extension must be built '
+                              f'(python -m vfloodnet_b200.build); there is no CPU fallback')
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)       # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ''):
+    if rc != 0:
+        msg = load().vfn_last_error().decode('utf-8', 'replace')
+        raise VfnError(f'{what or "libvfn"} failed with code {rc}: {msg}')
+
+
+def ptr(t):
+    """device/host pointer of a torch tensor (None -> NULL)"""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,652 @@
+// Feature-bank bookkeeping kernels (bandwidth-bound): candidate preparation, append, merge (segmented
+// mean in fixed order), LFU eviction planning, order-preserving compaction, info clamp.
+// Reference behaviour restated: video_module/model/FeatureBank.py:27-143 (see include/vfn.h per entry point).
+#include "vfn_common.cuh"
+
+#include <mutex>
+#include <string>
+
+namespace vfn {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// prep_rows: (d, n) dimension-major  ->  (n, d) entry-major raw / L2-normalised / bf16 hi+lo
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prep_rows_kernel(const float* __restrict__ src, int d, int64_t n,
+                                                        float* __restrict__ raw, float* __restrict__ normed,
+                                                        uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                                        float scale) {
+  __shared__ float tile[32][33];
+  __shared__ float part[8][32];
+  __shared__ float denom[32];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t q0 = (int64_t)blockIdx.x * 32;
+  const int64_t q = q0 + tx;
+  float ss = 0.f;
+  if (q < n)
+    for (int k = ty; k < d; k += 8) {
+      float v = src[(int64_t)k * n + q];
+      ss = fmaf(v, v, ss);
+    }
+  part[ty][tx] = ss;
+  __syncthreads();
+  if (ty == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][tx];
+    denom[tx] = fmaxf(sqrtf(t), 1e-12f);   // NF.normalize eps
+  }
+  __syncthreads();
+  for (int k0 = 0; k0 < d; k0 += 32) {
+    for (int r = ty; r < 32; r += 8) {
+      int k = k0 + r;
+      tile[r][tx] = (k < d && q < n) ? src[(int64_t)k * n + q] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+      int64_t qq = q0 + r;
+      int k = k0 + tx;
+      if (qq < n && k < d) {
+        float v = tile[tx][r];
+        int64_t o = qq * d + k;
+        if (raw) raw[o] = v;
+        if (normed) normed[o] = v / denom[r];
+        if (hi) {
+          uint16_t h, l;
+          split_bf16(v * scale, h, l);
+          hi[o] = h;
+          if (lo) lo[o] = l;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// row helpers: one block owns one bank slot
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_split4(uint16_t* hi, uint16_t* lo, int64_t off, float4 v) {
+  uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+  split_bf16(v.x, h0, l0);
+  split_bf16(v.y, h1, l1);
+  split_bf16(v.z, h2, l2);
+  split_bf16(v.w, h3, l3);
+  uint2 H = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+  uint2 L = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+  *reinterpret_cast<uint2*>(hi + off) = H;
+  *reinterpret_cast<uint2*>(lo + off) = L;
+}
+
+// append: grid.x = upper bound on selected rows; block = 128 threads; row i -> slot bank.n + i
+__global__ void __launch_bounds__(128) append_rows_kernel(vfn_bank bank, const float* __restrict__ ck,
+                                                          const float* __restrict__ cv, const float* __restrict__ nck,
+                                                          const int32_t* __restrict__ sel,
+                                                          const int32_t* __restrict__ n_sel_dev, int64_t n_sel_upper,
+                                                          float info0, float info1) {
+  __shared__ float red[32];
+  const int64_t n_sel = n_sel_dev ? (int64_t)*n_sel_dev : n_sel_upper;
+  const int dk4 = bank.d_key >> 2, dv4 = bank.d_val >> 2;
+  for (int64_t i = blockIdx.x; i < n_sel; i += gridDim.x) {
+    const int64_t s = sel ? (int64_t)sel[i] : i;
+    const int64_t dst = bank.n + i;
+    const float4* ks = reinterpret_cast<const float4*>(ck + s * bank.d_key);
+    const float4* vs = reinterpret_cast<const float4*>(cv + s * bank.d_val);
+    float ss = 0.f;
+    for (int f = threadIdx.x; f < dk4; f += blockDim.x) {
+      float4 v = ks[f];
+      reinterpret_cast<float4*>(bank.keys + dst * bank.d_key)[f] = v;
+      if (bank.kh) store_split4(bank.kh, bank.kl, dst * bank.d_key + 4 * f, v);
+      if (nck) reinterpret_cast<float4*>(bank.nkeys + dst * bank.d_key)[f] =
+                   reinterpret_cast<const float4*>(nck + s * bank.d_key)[f];
+      ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+    }
+    if (!nck) {   // derive the normalised key here (init_bank / append API path)
+      float tot = block_sum(ss, red);
+      float den = fmaxf(sqrtf(tot), 1e-12f);
+      for (int f = threadIdx.x; f < dk4; f += blockDim.x) {
+        float4 v = ks[f];
+        reinterpret_cast<float4*>(bank.nkeys + dst * bank.d_key)[f] =
+            make_float4(v.x / den, v.y / den, v.z / den, v.w / den);
+      }
+    }
+    for (int f = threadIdx.x; f < dv4; f += blockDim.x) {
+      float4 v = vs[f];
+      reinterpret_cast<float4*>(bank.values + dst * bank.d_val)[f] = v;
+      if (bank.vh) store_split4(bank.vh, bank.vl, dst * bank.d_val + 4 * f, v);
+    }
+    if (threadIdx.x == 0) {
+      bank.info[dst * 2 + 0] = info0;
+      bank.info[dst * 2 + 1] = info1;
+      bank.cnt[dst] = 0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) refresh_rows_kernel(vfn_bank bank, int64_t first, int64_t count) {
+  __shared__ float red[32];
+  const int dk4 = bank.d_key >> 2, dv4 = bank.d_val >> 2;
+  for (int64_t i = blockIdx.x; i < count; i += gridDim.x) {
+    const int64_t u = first + i;
+    const float4* ks = reinterpret_cast<const float4*>(bank.keys + u * bank.d_key);
+    float ss = 0.f;
+    for (int f = threadIdx.x; f < dk4; f += blockDim.x) {
+      float4 v = ks[f];
+      ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+    }
+    float den = fmaxf(sqrtf(block_sum(ss, red)), 1e-12f);
+    for (int f = threadIdx.x; f < dk4; f += blockDim.x) {
+      float4 v = ks[f];
+      reinterpret_cast<float4*>(bank.nkeys + u * bank.d_key)[f] = make_float4(v.x / den, v.y / den, v.z / den, v.w / den);
+      if (bank.kh) store_split4(bank.kh, bank.kl, u * bank.d_key + 4 * f, v);
+    }
+    if (bank.vh)
+      for (int f = threadIdx.x; f < dv4; f += blockDim.x)
+        store_split4(bank.vh, bank.vl, u * bank.d_val + 4 * f,
+                     reinterpret_cast<const float4*>(bank.values + u * bank.d_val)[f]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan: classify, order-preserving compaction of append set, sort of (slot,q) merge pairs, run detection.
+// One CTA of 1024 threads; hw <= 65536.
+// ------------------------------------------------------------------------------------------------
+constexpr int PLAN_THREADS = 1024;
+constexpr int PLAN_SMEM_KEYS = 4096;
+
+// exclusive scan of one int per thread over the block; returns exclusive prefix, total in *total
+__device__ __forceinline__ int block_excl_scan(int v, int* warp_tot /*[33]*/, int* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int t = (lane < nw) ? warp_tot[lane] : 0;
+    int ti = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, ti, o);
+      if (lane >= o) ti += u;
+    }
+    warp_tot[lane] = ti - t;          // exclusive warp offsets
+    if (lane == 31) warp_tot[32] = ti;  // block total
+  }
+  __syncthreads();
+  *total = warp_tot[32];
+  return warp_tot[wid] + inc - v;
+}
+
+__global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(const int32_t* __restrict__ match_idx,
+                                                            const float* __restrict__ match_corr, int hw, float thres,
+                                                            int32_t* __restrict__ merge_q,
+                                                            int32_t* __restrict__ merge_slot,
+                                                            int32_t* __restrict__ run_off,
+                                                            int32_t* __restrict__ append_q, int32_t* __restrict__ counts,
+                                                            int32_t* __restrict__ h_counts,
+                                                            unsigned long long* __restrict__ gkeys) {
+  __shared__ unsigned long long skeys[PLAN_SMEM_KEYS];
+  __shared__ int wt[33];
+  const int tid = threadIdx.x;
+  int off_m = 0, off_a = 0;
+  for (int base = 0; base < hw; base += PLAN_THREADS) {
+    const int q = base + tid;
+    float c = (q < hw) ? match_corr[q] : 0.f;
+    const int fm = (q < hw) && (c > thres);     // FeatureBank.py:71  strict >
+    const int fa = (q < hw) && (c <= thres);    // FeatureBank.py:100 ; NaN goes nowhere
+    int tot_m, tot_a;
+    const int pm = block_excl_scan(fm, wt, &tot_m);
+    const int pa = block_excl_scan(fa, wt, &tot_a);
+    if (fm) gkeys[off_m + pm] = ((unsigned long long)(uint32_t)match_idx[q] << 32) | (uint32_t)q;
+    if (fa) append_q[off_a + pa] = q;
+    off_m += tot_m;
+    off_a += tot_a;
+  }
+  const int n_merge = off_m;
+  int npad = 1;
+  while (npad < n_merge) npad <<= 1;
+  for (int i = n_merge + tid; i < npad; i += PLAN_THREADS) gkeys[i] = ~0ull;
+  __syncthreads();
+  unsigned long long* buf = gkeys;
+  if (npad <= PLAN_SMEM_KEYS) {
+    for (int i = tid; i < npad; i += PLAN_THREADS) skeys[i] = gkeys[i];
+    buf = skeys;
+    __syncthreads();
+  }
+  // bitonic sort ascending by (slot, q): unique keys
+  for (int k = 2; k <= npad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < npad; i += PLAN_THREADS) {
+        const int l = i ^ j;
+        if (l > i) {
+          unsigned long long a = buf[i], b = buf[l];
+          const bool up = ((i & k) == 0);
+          if ((a > b) == up) {
+            buf[i] = b;
+            buf[l] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // unpack + run starts (unique touched slots ascending == torch.unique order, FeatureBank.py:73)
+  int off_r = 0;
+  for (int base = 0; base < n_merge; base += PLAN_THREADS) {
+    const int i = base + tid;
+    int fr = 0;
+    if (i < n_merge) {
+      unsigned long long kv = buf[i];
+      const int slot = (int)(kv >> 32);
+      merge_slot[i] = slot;
+      merge_q[i] = (int)(kv & 0xffffffffu);
+      fr = (i == 0) || ((int)(buf[i - 1] >> 32) != slot);
+    }
+    int tot_r;
+    const int pr = block_excl_scan(fr, wt, &tot_r);
+    if (fr) run_off[off_r + pr] = i;
+    off_r += tot_r;
+  }
+  if (tid == 0) {
+    run_off[off_r] = n_merge;
+    counts[0] = n_merge;
+    counts[1] = off_r;
+    counts[2] = off_a;
+    counts[3] = 0;
+    if (h_counts) {
+      h_counts[0] = n_merge;
+      h_counts[1] = off_r;
+      h_counts[2] = off_a;
+      h_counts[3] = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// merge: one block per run of equal slot.  192 threads, one float4 of the [key | value] row per thread.
+// ------------------------------------------------------------------------------------------------
+constexpr int MERGE_THREADS = 192;
+
+__global__ void __launch_bounds__(MERGE_THREADS) merge_runs_kernel(vfn_bank bank, const float* __restrict__ nck,
+                                                                   const float* __restrict__ ncv,
+                                                                   const int32_t* __restrict__ merge_q,
+                                                                   const int32_t* __restrict__ merge_slot,
+                                                                   const int32_t* __restrict__ run_off,
+                                                                   const int32_t* __restrict__ counts, float omr,
+                                                                   float r) {
+  __shared__ float red[32];
+  const int n_runs = counts[1];
+  const int dk4 = bank.d_key >> 2, dv4 = bank.d_val >> 2;
+  const int f = threadIdx.x;
+  const bool is_key = f < dk4;
+  const bool is_val = !is_key && (f - dk4) < dv4;
+  for (int run = blockIdx.x; run < n_runs; run += gridDim.x) {
+    const int b = run_off[run], e = run_off[run + 1];
+    const int64_t u = merge_slot[b];
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (is_key) x = reinterpret_cast<const float4*>(bank.keys + u * bank.d_key)[f];
+    if (is_val) x = reinterpret_cast<const float4*>(bank.values + u * bank.d_val)[f - dk4];
+    const float sq = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, x.w * x.w)));
+    const float ssk = block_sum(is_key ? sq : 0.f, red);
+    const float ssv = block_sum(is_val ? sq : 0.f, red);
+    const float mag = sqrtf(is_key ? ssk : ssv);            // .norm(p=2, dim=0)   FeatureBank.py:65,89
+    const float den = fmaxf(mag, 1e-12f);                   // NF.normalize        FeatureBank.py:63,87
+    // scatter_mean: sequential sum in ascending candidate order, then / count  (FeatureBank.py:78,92)
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (is_key || is_val) {
+      for (int m = b; m < e; ++m) {
+        const int64_t q = merge_q[m];
+        const float4 s = is_key ? reinterpret_cast<const float4*>(nck + q * bank.d_key)[f]
+                                : reinterpret_cast<const float4*>(ncv + q * bank.d_val)[f - dk4];
+        acc.x = __fadd_rn(acc.x, s.x); acc.y = __fadd_rn(acc.y, s.y);
+        acc.z = __fadd_rn(acc.z, s.z); acc.w = __fadd_rn(acc.w, s.w);
+      }
+    }
+    const float cntf = (float)(e - b);
+    float4 nw;
+    {
+      // mag * ((1-r) * x/|x| + r * mean), each op rounded separately like the reference's ATen chain (:81-84)
+      float mx = __fdiv_rn(acc.x, cntf), my = __fdiv_rn(acc.y, cntf), mz = __fdiv_rn(acc.z, cntf), mw = __fdiv_rn(acc.w, cntf);
+      float nx = __fdiv_rn(x.x, den), ny = __fdiv_rn(x.y, den), nz = __fdiv_rn(x.z, den), nwv = __fdiv_rn(x.w, den);
+      nw.x = __fmul_rn(mag, __fadd_rn(__fmul_rn(omr, nx), __fmul_rn(r, mx)));
+      nw.y = __fmul_rn(mag, __fadd_rn(__fmul_rn(omr, ny), __fmul_rn(r, my)));
+      nw.z = __fmul_rn(mag, __fadd_rn(__fmul_rn(omr, nz), __fmul_rn(r, mz)));
+      nw.w = __fmul_rn(mag, __fadd_rn(__fmul_rn(omr, nwv), __fmul_rn(r, mw)));
+    }
+    const float sq2 = fmaf(nw.x, nw.x, fmaf(nw.y, nw.y, fmaf(nw.z, nw.z, nw.w * nw.w)));
+    const float ssk2 = block_sum(is_key ? sq2 : 0.f, red);
+    if (is_key) {
+      reinterpret_cast<float4*>(bank.keys + u * bank.d_key)[f] = nw;
+      const float d2 = fmaxf(sqrtf(ssk2), 1e-12f);
+      reinterpret_cast<float4*>(bank.nkeys + u * bank.d_key)[f] = make_float4(nw.x / d2, nw.y / d2, nw.z / d2, nw.w / d2);
+      if (bank.kh) store_split4(bank.kh, bank.kl, u * bank.d_key + 4 * f, nw);
+    }
+    if (is_val) {
+      reinterpret_cast<float4*>(bank.values + u * bank.d_val)[f - dk4] = nw;
+      if (bank.vh) store_split4(bank.vh, bank.vl, u * bank.d_val + 4 * (f - dk4), nw);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// evict plan: single CTA threshold search (FeatureBank.py:121-138)
+// ------------------------------------------------------------------------------------------------
+constexpr int EV_THREADS = 1024;
+
+__device__ __forceinline__ void block_min_count(float& mn, int& cnt, int& nanflag, float* sf, int* si) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    nanflag |= __shfl_xor_sync(0xffffffffu, nanflag, o);
+  }
+  __syncthreads();
+  if (lane == 0) { sf[wid] = mn; si[wid] = cnt; si[32 + wid] = nanflag; }
+  __syncthreads();
+  mn = sf[lane]; cnt = si[lane]; nanflag = si[32 + lane];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    nanflag |= __shfl_xor_sync(0xffffffffu, nanflag, o);
+  }
+}
+
+__global__ void __launch_bounds__(EV_THREADS) evict_plan_kernel(const float* __restrict__ info, int64_t n,
+                                                                float frame_idx, double class_budget,
+                                                                int64_t request_n, int32_t* __restrict__ plan,
+                                                                int32_t* __restrict__ h_plan,
+                                                                float* __restrict__ lfu) {
+  __shared__ float sf[32];
+  __shared__ int si[64];
+  const int tid = threadIdx.x;
+  float mn = INFINITY;
+  int cnt = 0, nanflag = 0;
+  for (int64_t i = tid; i < n; i += EV_THREADS) {
+    const float2 in = reinterpret_cast<const float2*>(info)[i];
+    const float age = __fsub_rn(frame_idx, in.x);     // frame_idx - info[:,0]        (:121)
+    const float v = __fdiv_rn(in.y, age);             // info[:,1] / age              (:122)
+    lfu[i] = v;
+    if (v != v) nanflag = 1;
+    mn = fminf(mn, v);
+  }
+  block_min_count(mn, cnt, nanflag, sf, si);
+  int status = 0, T = 0, kept = 0, it = 0;
+  if (nanflag || !isfinite(mn) || n == 0) {
+    status = 2;                                       // int(nan)/int(inf)/min(empty) raise in the reference
+  } else {
+    T = (int)truncf(mn) + 1;                          // int(LFU.min()) + 1           (:123)
+    for (; it < 64; ++it) {
+      float m2 = INFINITY;
+      int c2 = 0, nf = 0;
+      const float Tf = (float)T;
+      for (int64_t i = tid; i < n; i += EV_THREADS) {
+        const float v = lfu[i];
+        if (v > Tf) { ++c2; m2 = fminf(m2, v); }      // strict >                     (:127)
+      }
+      block_min_count(m2, c2, nf, sf, si);
+      kept = c2;
+      if (tid == 0) plan[4 + it] = T;
+      const double balance = (class_budget - (double)kept) - (double)request_n;   // (:134)
+      if (balance < 0) {
+        if (kept == 0) { status = 1; ++it; break; }   // LFU.min() of an empty tensor raises
+        T = (int)truncf(m2) + 1;                      // (:136)
+      } else {
+        ++it;
+        break;
+      }
+    }
+  }
+  if (tid == 0) {
+    plan[0] = status; plan[1] = kept; plan[2] = it; plan[3] = T;
+    if (h_plan) {
+      h_plan[0] = status; h_plan[1] = kept; h_plan[2] = it; h_plan[3] = T;
+      for (int k = 0; k < it && k < 64; ++k) h_plan[4 + k] = plan[4 + k];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// compaction (order preserving, out of place)
+// ------------------------------------------------------------------------------------------------
+constexpr int CP_THREADS = 256;
+
+__global__ void __launch_bounds__(CP_THREADS) compact_count_kernel(const float* __restrict__ lfu, int64_t n,
+                                                                   const int32_t* __restrict__ plan,
+                                                                   int32_t* __restrict__ block_cnt) {
+  const float Tf = (float)plan[3];
+  const int64_t i = (int64_t)blockIdx.x * CP_THREADS + threadIdx.x;
+  const int keep = (i < n) && (lfu[i] > Tf);
+  const int c = __syncthreads_count(keep);
+  if (threadIdx.x == 0) block_cnt[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(1024) compact_scan_kernel(int32_t* __restrict__ block_cnt, int nb) {
+  __shared__ int wt[33];
+  int carry = 0;
+  for (int base = 0; base < nb; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = (i < nb) ? block_cnt[i] : 0;
+    int tot;
+    const int ex = block_excl_scan(v, wt, &tot);
+    if (i < nb) block_cnt[i] = carry + ex;
+    carry += tot;
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void warp_copy16(void* dst, const void* src, int n16, int lane) {
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  for (int i = lane; i < n16; i += 32) d[i] = __ldg(s + i);
+}
+
+__global__ void __launch_bounds__(CP_THREADS) compact_move_kernel(vfn_bank src, vfn_bank dst,
+                                                                  const float* __restrict__ lfu,
+                                                                  const int32_t* __restrict__ plan,
+                                                                  const int32_t* __restrict__ block_off) {
+  __shared__ int wt[33];
+  __shared__ int list[CP_THREADS];
+  const float Tf = (float)plan[3];
+  const int64_t i = (int64_t)blockIdx.x * CP_THREADS + threadIdx.x;
+  const int keep = (i < src.n) && (lfu[i] > Tf);
+  int tot;
+  const int pos = block_excl_scan(keep, wt, &tot);
+  if (keep) list[pos] = threadIdx.x;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t base_dst = block_off[blockIdx.x];
+  const int dk = src.d_key, dv = src.d_val;
+  for (int e = wid; e < tot; e += CP_THREADS / 32) {
+    const int64_t s = (int64_t)blockIdx.x * CP_THREADS + list[e];
+    const int64_t d = base_dst + e;
+    warp_copy16(dst.keys + d * dk, src.keys + s * dk, dk / 4, lane);
+    warp_copy16(dst.values + d * dv, src.values + s * dv, dv / 4, lane);
+    warp_copy16(dst.nkeys + d * dk, src.nkeys + s * dk, dk / 4, lane);
+    if (src.kh) {
+      warp_copy16(dst.kh + d * dk, src.kh + s * dk, dk / 8, lane);
+      warp_copy16(dst.kl + d * dk, src.kl + s * dk, dk / 8, lane);
+      warp_copy16(dst.vh + d * dv, src.vh + s * dv, dv / 8, lane);
+      warp_copy16(dst.vl + d * dv, src.vl + s * dv, dv / 8, lane);
+    }
+    if (lane == 0) {
+      reinterpret_cast<float2*>(dst.info)[d] = reinterpret_cast<const float2*>(src.info)[s];
+      dst.cnt[d] = 0;
+    }
+  }
+}
+
+__global__ void clamp_info_kernel(float* __restrict__ info, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float v = info[2 * i + 1];
+    v = v < 0.f ? 0.f : (v > 1e5f ? 1e5f : v);   // torch.clamp(.,0,1e5), NaN preserved (FeatureBank.py:115)
+    info[2 * i + 1] = v;
+  }
+}
+
+static int check_bank(const vfn_bank* b) {
+  VFN_CHECK_ARG(b != nullptr, "bank is NULL");
+  VFN_CHECK_ARG(b->d_key > 0 && b->d_val > 0 && b->d_key % 8 == 0 && b->d_val % 8 == 0,
+                "d_key/d_val must be positive multiples of 8 (got %d, %d)", b->d_key, b->d_val);
+  VFN_CHECK_ARG(b->keys && b->values && b->info && b->nkeys && b->cnt, "bank has NULL arrays");
+  VFN_CHECK_ARG(b->n >= 0 && b->n <= b->cap, "bank n=%lld exceeds cap=%lld", (long long)b->n, (long long)b->cap);
+  VFN_CHECK_ARG((b->kh == nullptr) == (b->kl == nullptr) && (b->kh == nullptr) == (b->vh == nullptr) &&
+                    (b->kh == nullptr) == (b->vl == nullptr),
+                "bf16 operand arrays must be all set or all NULL");
+  return VFN_OK;
+}
+
+}  // namespace vfn
+
+using namespace vfn;
+
+extern "C" {
+
+int vfn_version(void) { return VFN_VERSION; }
+const char* vfn_last_error(void) { return g_err; }
+
+int vfn_device_is_sm100(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10;
+}
+
+int vfn_prep_rows(const float* d_src_dm, int32_t d, int64_t n, float* d_raw_em, float* d_normed_em, uint16_t* d_hi_em,
+                  uint16_t* d_lo_em, float scale, void* stream) {
+  VFN_CHECK_ARG(d_src_dm && d > 0 && n >= 0, "prep_rows: bad args");
+  if (n == 0) return VFN_OK;
+  dim3 block(32, 8);
+  prep_rows_kernel<<<(unsigned)cdiv(n, 32), block, 0, as_stream(stream)>>>(d_src_dm, d, n, d_raw_em, d_normed_em,
+                                                                           d_hi_em, d_lo_em, scale);
+  VFN_LAUNCH_OK();
+  return VFN_OK;
+}
+
+int vfn_bank_append_rows(const vfn_bank* bank, const float* d_ck_em, const float* d_cv_em, const float* d_nck_em,
+                         const int32_t* d_sel, int64_t n_sel_upper, const int32_t* d_n_sel, float info0, float info1,
+                         void* stream) {
+  if (int rc = check_bank(bank)) return rc;
+  VFN_CHECK_ARG(d_ck_em && d_cv_em && n_sel_upper >= 0, "append_rows: bad args");
+  if (bank->n + n_sel_upper > bank->cap) {
+    set_error("append_rows: n=%lld + %lld exceeds cap=%lld", (long long)bank->n, (long long)n_sel_upper,
+              (long long)bank->cap);
+    return VFN_E_CAPACITY;
+  }
+  if (n_sel_upper == 0) return VFN_OK;
+  const unsigned grid = (unsigned)(n_sel_upper < 148 * 16 ? n_sel_upper : 148 * 16);
+  append_rows_kernel<<<grid, 128, 0, as_stream(stream)>>>(*bank, d_ck_em, d_cv_em, d_nck_em, d_sel, d_n_sel,
+                                                          n_sel_upper, info0, info1);
+  VFN_LAUNCH_OK();
+  return VFN_OK;
+}
+
+int vfn_bank_refresh(const vfn_bank* bank, int64_t first, int64_t count, void* stream) {
+  if (int rc = check_bank(bank)) return rc;
+  VFN_CHECK_ARG(first >= 0 && count >= 0 && first + count <= bank->cap, "refresh: range out of bounds");
+  if (count == 0) return VFN_OK;
+  const unsigned grid = (unsigned)(count < 148 * 16 ? count : 148 * 16);
+  refresh_rows_kernel<<<grid, 128, 0, as_stream(stream)>>>(*bank, first, count);
+  VFN_LAUNCH_OK();
+  return VFN_OK;
+}
+
+size_t vfn_bank_plan_workspace_bytes(int64_t hw) {
+  int64_t npad = 1;
+  while (npad < hw) npad <<= 1;
+  return (size_t)npad * sizeof(unsigned long long);
+}
+
+int vfn_bank_plan(const int32_t* d_match_idx, const float* d_match_corr, int64_t hw, float thres_close,
+                  int32_t* d_merge_q, int32_t* d_merge_slot, int32_t* d_run_off, int32_t* d_append_q, int32_t* d_counts,
+                  int32_t* h_counts, void* d_ws, size_t ws_bytes, void* stream) {
+  VFN_CHECK_ARG(d_match_idx && d_match_corr && d_merge_q && d_merge_slot && d_run_off && d_append_q && d_counts,
+                "plan: NULL argument");
+  VFN_CHECK_ARG(hw > 0 && hw <= 65536, "plan: hw=%lld out of range (1..65536)", (long long)hw);
+  if (ws_bytes < vfn_bank_plan_workspace_bytes(hw) || !d_ws) {
+    set_error("plan: workspace too small");
+    return VFN_E_CAPACITY;
+  }
+  plan_kernel<<<1, PLAN_THREADS, 0, as_stream(stream)>>>(d_match_idx, d_match_corr, (int)hw, thres_close, d_merge_q,
+                                                         d_merge_slot, d_run_off, d_append_q, d_counts, h_counts,
+                                                         reinterpret_cast<unsigned long long*>(d_ws));
+  VFN_LAUNCH_OK();
+  return VFN_OK;
+}
+
+int vfn_bank_merge(const vfn_bank* bank, const float* d_nck_em, const float* d_ncv_em, const int32_t* d_merge_q,
+                   const int32_t* d_merge_slot, const int32_t* d_run_off, const int32_t* d_counts, int64_t hw,
+                   float update_rate, void* stream) {
+  if (int rc = check_bank(bank)) return rc;
+  VFN_CHECK_ARG(d_nck_em && d_ncv_em && d_merge_q && d_merge_slot && d_run_off && d_counts && hw > 0, "merge: bad args");
+  if ((bank->d_key + bank->d_val) / 4 > MERGE_THREADS) {
+    set_error("merge: d_key + d_val = %d exceeds %d", bank->d_key + bank->d_val, MERGE_THREADS * 4);
+    return VFN_E_UNSUPPORTED;
+  }
+  // (1 - update_rate) is evaluated in double by Python and rounded to fp32 when it meets the tensor
+  const float omr = (float)(1.0 - (double)update_rate);
+  const unsigned grid = (unsigned)(hw < 148 * 8 ? hw : 148 * 8);
+  merge_runs_kernel<<<grid, MERGE_THREADS, 0, as_stream(stream)>>>(*bank, d_nck_em, d_ncv_em, d_merge_q, d_merge_slot,
+                                                                   d_run_off, d_counts, omr, update_rate);
+  VFN_LAUNCH_OK();
+  return VFN_OK;
+}
+
+int vfn_bank_evict_plan(const vfn_bank* bank, float frame_idx, double class_budget, int64_t request_n, int32_t* d_plan,
+                        int32_t* h_plan, float* d_lfu_scratch, void* stream) {
+  if (int rc = check_bank(bank)) return rc;
+  VFN_CHECK_ARG(d_plan && d_lfu_scratch, "evict_plan: NULL argument");
+  evict_plan_kernel<<<1, EV_THREADS, 0, as_stream(stream)>>>(bank->info, bank->n, frame_idx, class_budget, request_n,
+                                                             d_plan, h_plan, d_lfu_scratch);
+  VFN_LAUNCH_OK();
+  return VFN_OK;
+}
+
+size_t vfn_bank_compact_workspace_bytes(int64_t n) { return (size_t)(cdiv(n, CP_THREADS) + 1) * sizeof(int32_t); }
+
+int vfn_bank_compact(const vfn_bank* src, const vfn_bank* dst, const float* d_lfu, const int32_t* d_plan, void* d_ws,
+                     size_t ws_bytes, void* stream) {
+  if (int rc = check_bank(src)) return rc;
+  if (int rc = check_bank(dst)) return rc;
+  VFN_CHECK_ARG(src->d_key == dst->d_key && src->d_val == dst->d_val, "compact: dim mismatch");
+  VFN_CHECK_ARG((src->kh == nullptr) == (dst->kh == nullptr), "compact: operand arrays mismatch");
+  VFN_CHECK_ARG(d_lfu && d_plan && d_ws, "compact: NULL argument");
+  if (ws_bytes < vfn_bank_compact_workspace_bytes(src->n)) {
+    set_error("compact: workspace too small");
+    return VFN_E_CAPACITY;
+  }
+  if (src->n == 0) return VFN_OK;
+  const int nb = (int)cdiv(src->n, CP_THREADS);
+  int32_t* block_cnt = reinterpret_cast<int32_t*>(d_ws);
+  cudaStream_t st = as_stream(stream);
+  compact_count_kernel<<<nb, CP_THREADS, 0, st>>>(d_lfu, src->n, d_plan, block_cnt);
+  compact_scan_kernel<<<1, 1024, 0, st>>>(block_cnt, nb);
+  compact_move_kernel<<<nb, CP_THREADS, 0, st>>>(*src, *dst, d_lfu, d_plan, block_cnt);
+  VFN_LAUNCH_OK();
+  return VFN_OK;
+}
+
+int vfn_bank_clamp_info(const vfn_bank* bank, int64_t n, void* stream) {
+  if (int rc = check_bank(bank)) return rc;
+  VFN_CHECK_ARG(n >= 0 && n <= bank->cap, "clamp_info: n out of range");
+  if (n == 0) return VFN_OK;
+  clamp_info_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(bank->info, n);
+  VFN_LAUNCH_OK();
+  return VFN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+// Shared helpers for libvfn_sm100a.so (error plumbing, bf16 split, small device utilities).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/vfn.h"
+
+namespace vfn {
+
+void set_error(const char* fmt, ...);
+
+#define VFN_CHECK_ARG(cond, ...)              \
+  do {                                        \
+    if (!(cond)) {                            \
+      ::vfn::set_error(__VA_ARGS__);          \
+      return VFN_E_ARG;                       \
+    }                                         \
+  } while (0)
+
+#define VFN_CUDA_OK(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      ::vfn::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return VFN_E_CUDA;                                                                    \
+    }                                                                                       \
+  } while (0)
+
+#define VFN_LAUNCH_OK() VFN_CUDA_OK(cudaPeekAtLastError())
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// bf16 hi/lo split: x ~= hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi)   (16 mantissa bits kept)
+__device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& lo) {
+  __nv_bfloat16 h = __float2bfloat16_rn(x);
+  float r = x - __bfloat162float(h);
+  __nv_bfloat16 l = __float2bfloat16_rn(r);
+  hi = __bfloat16_as_ushort(h);
+  lo = __bfloat16_as_ushort(l);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum; red must hold >= 32 floats; all threads get the result. blockDim.x multiple of 32.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+
+}  // namespace vfn

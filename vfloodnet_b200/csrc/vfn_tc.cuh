@@ -1,0 +1,18 @@
+// Interface between the dispatch code (vfn_simt.cu) and the tcgen05/TMEM/TMA kernels (vfn_tc.cu).
+#pragma once
+#include "vfn_common.cuh"
+
+namespace vfn {
+
+// true when the tensor-core read kernels support these dims (d_key = 128, d_val = 512: AFB_URR.py:250)
+bool tc_shapes_ok(int d_key, int d_val);
+void tc_pick_splits(int obj_n, int64_t n_max, int64_t hw, int* split_a, int* split_b);
+size_t tc_workspace_bytes(int obj_n, int64_t hw);
+// phase A: (m, l) partials [natural-log domain] for every (object, split, query): part[(obj*split_a + s)*hw + j]
+int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t hw, int split_a, float2* part,
+               char* ws_tc, cudaStream_t st);
+// phase B: partial readouts po[((obj*split_b + s)*d_val + c)*hw + j] and usage counts into bank.cnt
+int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const float* lse, float thres_valid,
+               int update_bank, float* po, char* ws_tc, cudaStream_t st);
+
+}  // namespace vfn

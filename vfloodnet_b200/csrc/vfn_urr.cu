@@ -1,0 +1,208 @@
+// Uncertain-region refinement: the non-convolution parts of Decoder.forward (AFB_URR.py:214-237,
+// myutils/data.py:42-48).  Bandwidth-bound streaming kernels; bs = 1 (inference).
+#include "vfn_common.cuh"
+
+namespace vfn {
+
+// bilinear x2, align_corners=False (ATen area_pixel_compute_source_index with scale 0.5)
+__device__ __forceinline__ void src_index(int dst, int in_size, int& i0, int& i1, float& l0, float& l1) {
+  float s = 0.5f * ((float)dst + 0.5f) - 0.5f;
+  s = s < 0.f ? 0.f : s;
+  i0 = (int)s;
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = s - (float)i0;
+  l0 = 1.f - l1;
+}
+
+__device__ __forceinline__ float bilerp(const float* __restrict__ pl, int win, int y0, int y1, int x0, int x1, float ly0,
+                                        float ly1, float lx0, float lx1) {
+  return ly0 * (lx0 * pl[y0 * win + x0] + lx1 * pl[y0 * win + x1]) +
+         ly1 * (lx0 * pl[y1 * win + x0] + lx1 * pl[y1 * win + x1]);
+}
+
+// stage 1: p (obj,2,h/2,w/2) -> p_up (obj,2,h,w), seg (obj,h,w) object-normalised fg prob, unc (h,w)
+constexpr int URR_MAX_OBJ = 8;
+__global__ void urr_seg_kernel(const float* __restrict__ p, int obj_n, int h, int w, float* __restrict__ p_up,
+                               float* __restrict__ seg, float* __restrict__ unc) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= w) return;
+  const int hin = h >> 1, win = w >> 1;
+  int y0, y1, x0, x1;
+  float ly0, ly1, lx0, lx1;
+  src_index(y, hin, y0, y1, ly0, ly1);
+  src_index(x, win, x0, x1, lx0, lx1);
+  float fg[URR_MAX_OBJ];
+  float mx = -INFINITY;
+  for (int o = 0; o < obj_n; ++o) {
+    const float* pl = p + (int64_t)o * 2 * hin * win;
+    const float a = bilerp(pl, win, y0, y1, x0, x1, ly0, ly1, lx0, lx1);
+    const float b = bilerp(pl + hin * win, win, y0, y1, x0, x1, ly0, ly1, lx0, lx1);
+    p_up[((int64_t)o * 2 + 0) * h * w + (int64_t)y * w + x] = a;
+    p_up[((int64_t)o * 2 + 1) * h * w + (int64_t)y * w + x] = b;
+    const float m = fmaxf(a, b);
+    const float e0 = expf(a - m), e1 = expf(b - m);
+    fg[o] = e1 / (e0 + e1);                       // softmax(p, dim=1)[:, 1]           AFB_URR.py:217
+    mx = fmaxf(mx, fg[o]);
+  }
+  float sum = 0.f;
+  for (int o = 0; o < obj_n; ++o) { fg[o] = expf(fg[o] - mx); sum += fg[o]; }
+  float t1 = -INFINITY, t2 = -INFINITY;
+  for (int o = 0; o < obj_n; ++o) {
+    const float s = fg[o] / sum;                  // object-level softmax                AFB_URR.py:219
+    seg[(int64_t)o * h * w + (int64_t)y * w + x] = s;
+    if (s > t1) { t2 = t1; t1 = s; } else if (s > t2) { t2 = s; }
+  }
+  unc[(int64_t)y * w + x] = expf(1.f - t1 / (t2 + 1e-8f));   // myutils/data.py:45-47
+}
+
+// stage 2: conf = 7x7 max of seg (-inf pad), avg = 7x7 mean of seg (zero pad, /49)
+__global__ void urr_window_kernel(const float* __restrict__ seg, int obj_n, int h, int w, float* __restrict__ conf,
+                                  float* __restrict__ avg) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, o = blockIdx.z;
+  if (x >= w) return;
+  const float* pl = seg + (int64_t)o * h * w;
+  float mx = -INFINITY, sum = 0.f;
+  for (int dy = -3; dy <= 3; ++dy) {
+    const int yy = y + dy;
+    if (yy < 0 || yy >= h) continue;
+    for (int dx = -3; dx <= 3; ++dx) {
+      const int xx = x + dx;
+      if (xx < 0 || xx >= w) continue;
+      const float v = pl[yy * w + xx];
+      mx = fmaxf(mx, v);
+      sum += v;
+    }
+  }
+  conf[(int64_t)o * h * w + (int64_t)y * w + x] = mx;
+  avg[(int64_t)o * h * w + (int64_t)y * w + x] = sum / 49.f;
+}
+
+// stage 3: local_match[o][ch] = r1[ch] ; local_match[o][C+ch] = box7(r1[ch]*seg[o])/49 / (avg[o] + 1e-8)
+// CTA: 32x32 output tile, loops over CH_PER_CTA channels re-using the seg tile. 256 threads.
+constexpr int UT = 32, UH = UT + 6, CH_PER_CTA = 8;
+__global__ void __launch_bounds__(256) urr_local_kernel(const float* __restrict__ r1, int64_t r1_obj_stride, int c_n,
+                                                        int h, int w, const float* __restrict__ seg,
+                                                        const float* __restrict__ avg, float* __restrict__ lm) {
+  __shared__ float sseg[UH][UH + 1];
+  __shared__ float prod[UH][UH + 1];
+  __shared__ float hsum[UH][UT + 1];
+  const int o = blockIdx.z / (c_n / CH_PER_CTA);
+  const int cg = blockIdx.z % (c_n / CH_PER_CTA);
+  const int x0 = blockIdx.x * UT, y0 = blockIdx.y * UT;
+  const float* segp = seg + (int64_t)o * h * w;
+  for (int i = threadIdx.x; i < UH * UH; i += 256) {
+    const int ly = i / UH, lx = i % UH;
+    const int yy = y0 + ly - 3, xx = x0 + lx - 3;
+    sseg[ly][lx] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? segp[(int64_t)yy * w + xx] : 0.f;
+  }
+  __syncthreads();
+  for (int cc = 0; cc < CH_PER_CTA; ++cc) {
+    const int ch = cg * CH_PER_CTA + cc;
+    const float* rp = r1 + (int64_t)o * r1_obj_stride + (int64_t)ch * h * w;
+    for (int i = threadIdx.x; i < UH * UH; i += 256) {
+      const int ly = i / UH, lx = i % UH;
+      const int yy = y0 + ly - 3, xx = x0 + lx - 3;
+      const float v = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? rp[(int64_t)yy * w + xx] : 0.f;
+      prod[ly][lx] = v * sseg[ly][lx];                 // r1 * rough_seg                   AFB_URR.py:226
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < UH * UT; i += 256) {  // horizontal 7-tap
+      const int ly = i / UT, lx = i % UT;
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) s += prod[ly][lx + k];
+      hsum[ly][lx] = s;
+    }
+    __syncthreads();
+    float* out_raw = lm + ((int64_t)o * 2 * c_n + ch) * h * w;
+    float* out_loc = lm + ((int64_t)o * 2 * c_n + c_n + ch) * h * w;
+    for (int i = threadIdx.x; i < UT * UT; i += 256) {  // vertical 7-tap + epilogue
+      const int ly = i / UT, lx = i % UT;
+      const int yy = y0 + ly, xx = x0 + lx;
+      if (yy < h && xx < w) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) s += hsum[ly + k][lx];
+        const int64_t off = (int64_t)yy * w + xx;
+        out_raw[off] = rp[off];
+        out_loc[off] = (s / 49.f) / (avg[(int64_t)o * h * w + off] + 1e-8f);   // AFB_URR.py:227-228
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// post: prob[o][Y][X] = softmax_c( bilinear_x2( p_up + unc * (conf * q_local) ) )[1]      AFB_URR.py:233-237
+__global__ void urr_post_kernel(const float* __restrict__ p_up, const float* __restrict__ unc,
+                                const float* __restrict__ conf, const float* __restrict__ ql, int obj_n, int h, int w,
+                                float* __restrict__ prob) {
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = blockIdx.y, o = blockIdx.z;
+  const int H = 2 * h, W = 2 * w;
+  if (X >= W) return;
+  int y0, y1, x0, x1;
+  float ly0, ly1, lx0, lx1;
+  src_index(Y, h, y0, y1, ly0, ly1);
+  src_index(X, w, x0, x1, lx0, lx1);
+  const int ys[2] = {y0, y1}, xs[2] = {x0, x1};
+  float v[2][2][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int64_t off = (int64_t)ys[a] * w + xs[b];
+      const float u = unc[off];
+      const float cf = conf[(int64_t)o * h * w + off];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int64_t po = ((int64_t)o * 2 + c) * h * w + off;
+        const float q = cf * ql[po];
+        v[c][a][b] = p_up[po] + u * q;
+      }
+    }
+  float r[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+    r[c] = ly0 * (lx0 * v[c][0][0] + lx1 * v[c][0][1]) + ly1 * (lx0 * v[c][1][0] + lx1 * v[c][1][1]);
+  const float m = fmaxf(r[0], r[1]);
+  const float e0 = expf(r[0] - m), e1 = expf(r[1] - m);
+  prob[(int64_t)o * H * W + (int64_t)Y * W + X] = e1 / (e0 + e1);
+}
+
+}  // namespace vfn
+
+using namespace vfn;
+
+extern "C" {
+
+int vfn_urr_pre(const float* d_p, const float* d_r1, int64_t r1_obj_stride, int32_t obj_n, int32_t c, int32_t h,
+                int32_t w, float* d_p_up, float* d_seg, float* d_unc, float* d_conf, float* d_avg,
+                float* d_local_match, void* stream) {
+  VFN_CHECK_ARG(d_p && d_r1 && d_p_up && d_seg && d_unc && d_conf && d_avg && d_local_match, "urr_pre: NULL argument");
+  VFN_CHECK_ARG(obj_n >= 1 && obj_n <= URR_MAX_OBJ, "urr_pre: obj_n=%d out of range", obj_n);
+  VFN_CHECK_ARG(h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "urr_pre: h,w must be even");
+  VFN_CHECK_ARG(c > 0 && c % CH_PER_CTA == 0, "urr_pre: channels must be a multiple of %d", CH_PER_CTA);
+  cudaStream_t st = as_stream(stream);
+  dim3 g1((unsigned)cdiv(w, 128), h);
+  urr_seg_kernel<<<g1, 128, 0, st>>>(d_p, obj_n, h, w, d_p_up, d_seg, d_unc);
+  dim3 g2((unsigned)cdiv(w, 128), h, obj_n);
+  urr_window_kernel<<<g2, 128, 0, st>>>(d_seg, obj_n, h, w, d_conf, d_avg);
+  dim3 g3((unsigned)cdiv(w, UT), (unsigned)cdiv(h, UT), obj_n * (c / CH_PER_CTA));
+  urr_local_kernel<<<g3, 256, 0, st>>>(d_r1, r1_obj_stride, c, h, w, d_seg, d_avg, d_local_match);
+  VFN_LAUNCH_OK();
+  return VFN_OK;
+}
+
+int vfn_urr_post(const float* d_p_up, const float* d_unc, const float* d_conf, const float* d_q_local, int32_t obj_n,
+                 int32_t h, int32_t w, float* d_prob, void* stream) {
+  VFN_CHECK_ARG(d_p_up && d_unc && d_conf && d_q_local && d_prob, "urr_post: NULL argument");
+  VFN_CHECK_ARG(obj_n >= 1 && h > 0 && w > 0, "urr_post: bad shape");
+  dim3 g((unsigned)cdiv(2 * w, 128), 2 * h, obj_n);
+  urr_post_kernel<<<g, 128, 0, as_stream(stream)>>>(d_p_up, d_unc, d_conf, d_q_local, obj_n, h, w, d_prob);
+  VFN_LAUNCH_OK();
+  return VFN_OK;
+}
+
+}  // extern "C"

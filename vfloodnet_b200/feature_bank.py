@@ -1,0 +1,329 @@
+"""Drop-in FeatureBank (reference: video_module/model/FeatureBank.py:8-149) on B200 HBM.
+
+Same constructor, attributes (obj_n, keys, values, info, peak_n, replace_n, class_budget, update_rate,
+thres_close, device) and methods (init_bank, append, update, remove, print_peak_mem) as the reference class.
+The bank lives in capacity-sized entry-major device slabs; ``keys[i]`` / ``values[i]`` /
+``info[i]`` are (d, N) / (d, N) / (N, 2) VIEWS of those slabs, valid until the next update()/remove()/append().
+All arithmetic runs in libvfn_sm100a.so; there is no CPU / PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import VfnBank, check, ptr, stream_ptr
+
+
+class _Slab:
+    """One object's device arrays (struct vfn_bank)."""
+
+    def __init__(self, d_key: int, d_val: int, cap: int, device, operands: bool):
+        self.d_key, self.d_val, self.cap = d_key, d_val, cap
+        f32 = dict(dtype=torch.float32, device=device)
+        self.keys = torch.empty((cap, d_key), **f32)
+        self.values = torch.empty((cap, d_val), **f32)
+        self.info = torch.zeros((cap, 2), **f32)
+        self.nkeys = torch.empty((cap, d_key), **f32)
+        self.cnt = torch.zeros((cap,), dtype=torch.int32, device=device)
+        if operands:
+            bf = dict(dtype=torch.bfloat16, device=device)
+            self.kh = torch.empty((cap, d_key), **bf)
+            self.kl = torch.empty((cap, d_key), **bf)
+            self.vh = torch.empty((cap, d_val), **bf)
+            self.vl = torch.empty((cap, d_val), **bf)
+        else:
+            self.kh = self.kl = self.vh = self.vl = None
+
+    def struct(self, n: int) -> VfnBank:
+        return VfnBank(self.d_key, self.d_val, self.cap, n, ptr(self.keys), ptr(self.values), ptr(self.info),
+                       ptr(self.nkeys), ptr(self.kh), ptr(self.kl), ptr(self.vh), ptr(self.vl), ptr(self.cnt))
+
+    def copy_rows_from(self, other: '_Slab', n: int):
+        for name in ('keys', 'values', 'info', 'nkeys', 'kh', 'kl', 'vh', 'vl', 'cnt'):
+            a, b = getattr(self, name), getattr(other, name)
+            if a is not None:
+                a[:n].copy_(b[:n])
+
+
+class _ViewList:
+    """List-like exposing per-object views, so reference-style code (`fb.keys[i].size()`, `fb.info[i][:,1] += ..`) works."""
+
+    def __init__(self, fb: 'FeatureBank', kind: str):
+        self._fb, self._kind = fb, kind
+
+    def __len__(self):
+        return self._fb.obj_n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        s, n = self._fb._slabs[i], self._fb._n[i]
+        if s is None:
+            return None
+        if self._kind == 'keys':
+            return s.keys[:n].t()
+        if self._kind == 'values':
+            return s.values[:n].t()
+        return s.info[:n]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def __bool__(self):
+        return len(self) > 0
+
+
+class FeatureBank:
+    """See module docstring.  Extra keyword-only knobs (not in the reference): `impl` (0 auto, 1 SIMT fp32,
+    2 tcgen05) selects the read kernels used by vfloodnet_b200.Matcher on this bank."""
+
+    def __init__(self, obj_n, memory_budget, device, update_rate=0.1, thres_close=0.95, *, impl: int = 0):
+        self.obj_n = obj_n
+        self.update_rate = update_rate
+        self.thres_close = thres_close
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise ValueError('vfloodnet_b200.FeatureBank lives in GPU memory; device must be a CUDA device '
+                             '(there is no CPU fallback)')
+        self.peak_n = np.zeros(obj_n)
+        self.replace_n = np.zeros(obj_n)
+        self.class_budget = memory_budget // obj_n              # FeatureBank.py:20
+        if obj_n == 2:
+            self.class_budget = 0.8 * self.class_budget         # FeatureBank.py:21-22 (float)
+        self.impl = impl
+        self._lib = _lib.load()
+        self._slabs: List[Optional[_Slab]] = [None] * obj_n
+        self._alt: List[Optional[_Slab]] = [None] * obj_n      # ping-pong target of eviction compaction
+        self._n = [0] * obj_n
+        self._scratch = {}
+        self._h_counts = torch.zeros((obj_n, 4), dtype=torch.int32).pin_memory()
+        self._h_plan = torch.zeros((obj_n, 72), dtype=torch.int32).pin_memory()
+        self.last_decisions = [None] * obj_n    # device tensors of the last update (tests / debugging)
+        self.launches = 0                       # kernels launched by this bank (bench accounting)
+
+    # ---- reference attribute surface -------------------------------------------------------------
+    @property
+    def keys(self):
+        return _ViewList(self, 'keys') if any(s is not None for s in self._slabs) else None
+
+    @property
+    def values(self):
+        return _ViewList(self, 'values') if any(s is not None for s in self._slabs) else None
+
+    @property
+    def info(self):
+        return _ViewList(self, 'info')
+
+    def bank_n(self, class_idx: int) -> int:
+        return self._n[class_idx]
+
+    def bank_struct(self, class_idx: int) -> VfnBank:
+        return self._slabs[class_idx].struct(self._n[class_idx])
+
+    def bank_array(self):
+        arr = (VfnBank * self.obj_n)()
+        for c in range(self.obj_n):
+            arr[c] = self.bank_struct(c)
+        return arr
+
+    # ---- internals -------------------------------------------------------------------------------
+    def _use_operands(self, d_key, d_val):
+        return d_key == 128 and d_val == 512
+
+    def _budget_cap(self):
+        return int(math.ceil(self.class_budget))
+
+    def _ensure_capacity(self, c: int, needed: int, d_key: int, d_val: int):
+        s = self._slabs[c]
+        if s is not None and s.cap >= needed:
+            return
+        cap = max(needed, 4096)
+        if s is not None:
+            cap = max(cap, min(2 * s.cap, max(self._budget_cap(), needed)))
+        else:
+            cap = max(cap, min(4 * needed, max(self._budget_cap(), needed)))
+        new = _Slab(d_key, d_val, cap, self.device, self._use_operands(d_key, d_val))
+        if s is not None:
+            new.copy_rows_from(s, self._n[c])
+        self._slabs[c] = new
+        self._alt[c] = None
+
+    def _buf(self, name, shape, dtype):
+        t = self._scratch.get(name)
+        numel = int(np.prod(shape))
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            t = torch.empty(numel, dtype=dtype, device=self.device)
+            self._scratch[name] = t
+        return t[:numel].view(*shape)
+
+    def _ingest(self, c: int, key_dm: torch.Tensor, val_dm: torch.Tensor, info0: float, info1: float):
+        """append all columns of (d, n) tensors as new slots (init_bank / append)."""
+        lib, st = self._lib, stream_ptr()
+        key_dm = key_dm.to(self.device, torch.float32).contiguous()
+        val_dm = val_dm.to(self.device, torch.float32).contiguous()
+        d_key, n_new = key_dm.shape
+        d_val = val_dm.shape[0]
+        self._ensure_capacity(c, self._n[c] + n_new, d_key, d_val)
+        ck = self._buf(f'ing_ck{c}', (n_new, d_key), torch.float32)
+        cv = self._buf(f'ing_cv{c}', (n_new, d_val), torch.float32)
+        check(lib.vfn_prep_rows(ptr(key_dm), d_key, n_new, ptr(ck), None, None, None, 1.0, st), 'prep_rows')
+        check(lib.vfn_prep_rows(ptr(val_dm), d_val, n_new, ptr(cv), None, None, None, 1.0, st), 'prep_rows')
+        bank = self.bank_struct(c)
+        check(lib.vfn_bank_append_rows(C.byref(bank), ptr(ck), ptr(cv), None, None, n_new, None, float(info0),
+                                       float(info1), st), 'append_rows')
+        self.launches += 3
+        self._n[c] += n_new
+        self.peak_n[c] = max(self.peak_n[c], self._n[c])
+
+    # ---- reference methods -----------------------------------------------------------------------
+    def init_bank(self, keys, values, frame_idx=0):
+        """FeatureBank.py:27-36.  keys[i]: (d_key, n), values[i]: (d_val, n); copied into the slabs."""
+        for c in range(self.obj_n):
+            self._slabs[c], self._alt[c], self._n[c] = None, None, 0
+            self._ingest(c, keys[c], values[c], frame_idx, 0.0)
+
+    def append(self, keys, values, frame_idx=0):
+        """FeatureBank.py:38-51 (info column 1 starts at 20 for appended entries, :46)."""
+        if any(s is not None for s in self._slabs):
+            for c in range(self.obj_n):
+                self._ingest(c, keys[c], values[c], frame_idx, 20.0)
+        else:
+            self.init_bank(keys, values, frame_idx)
+
+    def update(self, prev_key, prev_value, frame_idx, update_rate=-1):
+        """FeatureBank.py:53-115: cosine match -> merge -> (LFU evict) -> append -> clamp."""
+        if update_rate == -1:
+            update_rate = self.update_rate
+        lib, st = self._lib, stream_ptr()
+        per = []
+        for c in range(self.obj_n):
+            s = self._slabs[c]
+            n = self._n[c]
+            pk = prev_key[c].to(self.device, torch.float32).contiguous()
+            pv = prev_value[c].to(self.device, torch.float32).contiguous()
+            d_key, hw = pk.shape
+            d_val = pv.shape[0]
+            if d_key != s.d_key or d_val != s.d_val:
+                raise ValueError('candidate dims do not match the bank')
+            ck = self._buf(f'ck{c}', (hw, d_key), torch.float32)
+            nck = self._buf(f'nck{c}', (hw, d_key), torch.float32)
+            cv = self._buf(f'cv{c}', (hw, d_val), torch.float32)
+            ncv = self._buf(f'ncv{c}', (hw, d_val), torch.float32)
+            check(lib.vfn_prep_rows(ptr(pk), d_key, hw, ptr(ck), ptr(nck), None, None, 1.0, st), 'prep_rows')
+            check(lib.vfn_prep_rows(ptr(pv), d_val, hw, ptr(cv), ptr(ncv), None, None, 1.0, st), 'prep_rows')
+            midx = self._buf(f'midx{c}', (hw,), torch.int32)
+            mcorr = self._buf(f'mcorr{c}', (hw,), torch.float32)
+            mws = self._buf(f'mws{c}', (lib.vfn_bank_match_workspace_bytes(n, hw),), torch.uint8)
+            bank = s.struct(n)
+            check(lib.vfn_bank_match(C.byref(bank), ptr(nck), hw, ptr(midx), ptr(mcorr), ptr(mws), mws.numel(),
+                                     self.impl, st), 'bank_match')
+            merge_q = self._buf(f'merge_q{c}', (hw,), torch.int32)
+            merge_slot = self._buf(f'merge_slot{c}', (hw,), torch.int32)
+            run_off = self._buf(f'run_off{c}', (hw + 1,), torch.int32)
+            append_q = self._buf(f'append_q{c}', (hw,), torch.int32)
+            counts = self._buf(f'counts{c}', (4,), torch.int32)
+            pws = self._buf(f'pws{c}', (lib.vfn_bank_plan_workspace_bytes(hw),), torch.uint8)
+            check(lib.vfn_bank_plan(ptr(midx), ptr(mcorr), hw, float(self.thres_close), ptr(merge_q), ptr(merge_slot),
+                                    ptr(run_off), ptr(append_q), ptr(counts), self._h_counts[c].data_ptr(), ptr(pws),
+                                    pws.numel(), st), 'bank_plan')
+            check(lib.vfn_bank_merge(C.byref(bank), ptr(nck), ptr(ncv), ptr(merge_q), ptr(merge_slot), ptr(run_off),
+                                     ptr(counts), hw, float(update_rate), st), 'bank_merge')
+            self.launches += 6
+            per.append(dict(hw=hw, ck=ck, cv=cv, nck=nck, append_q=append_q, counts=counts, midx=midx, mcorr=mcorr,
+                            merge_q=merge_q, merge_slot=merge_slot, run_off=run_off))
+        torch.cuda.current_stream().synchronize()          # one host sync: |merge|, |runs|, |append| per object
+        hc = self._h_counts.numpy()
+        evicting = []
+        for c in range(self.obj_n):
+            n_app = int(hc[c, 2])
+            per[c]['n_app'] = n_app
+            if self.class_budget < self._n[c] + n_app:                         # FeatureBank.py:102
+                self._launch_evict_plan(c, n_app, frame_idx)
+                evicting.append(c)
+        if evicting:
+            torch.cuda.current_stream().synchronize()
+            for c in evicting:
+                self._finish_evict(c, per[c]['n_app'])
+        for c in range(self.obj_n):
+            s, p = self._slabs[c], per[c]
+            n_app = p['n_app']
+            self._ensure_capacity(c, self._n[c] + n_app, s.d_key, s.d_val)
+            s = self._slabs[c]
+            bank = s.struct(self._n[c])
+            if n_app > 0:
+                check(lib.vfn_bank_append_rows(C.byref(bank), ptr(p['ck']), ptr(p['cv']), ptr(p['nck']),
+                                               ptr(p['append_q']), n_app, None, float(frame_idx), 0.0, st),
+                      'append_rows')                                               # FeatureBank.py:105-111
+                self.launches += 1
+            self._n[c] += n_app
+            self.peak_n[c] = max(self.peak_n[c], self._n[c])                       # FeatureBank.py:113
+            bank = s.struct(self._n[c])
+            check(lib.vfn_bank_clamp_info(C.byref(bank), self._n[c], st), 'clamp_info')   # FeatureBank.py:115
+            self.launches += 1
+            self.last_decisions[c] = dict(match_idx=p['midx'], match_corr=p['mcorr'], n_merge=int(hc[c, 0]),
+                                          n_runs=int(hc[c, 1]), n_append=n_app, merge_q=p['merge_q'],
+                                          merge_slot=p['merge_slot'], run_off=p['run_off'], append_q=p['append_q'],
+                                          evicted=c in evicting)
+
+    def _launch_evict_plan(self, c: int, request_n: int, frame_idx):
+        lib, st = self._lib, stream_ptr()
+        s, n = self._slabs[c], self._n[c]
+        lfu = self._buf(f'lfu{c}', (max(n, 1),), torch.float32)
+        plan = self._buf(f'plan{c}', (72,), torch.int32)
+        bank = s.struct(n)
+        check(lib.vfn_bank_evict_plan(C.byref(bank), float(frame_idx), float(self.class_budget), int(request_n),
+                                      ptr(plan), self._h_plan[c].data_ptr(), ptr(lfu), st), 'evict_plan')
+        self.launches += 1
+
+    def _finish_evict(self, c: int, request_n: int):
+        lib, st = self._lib, stream_ptr()
+        hp = self._h_plan.numpy()[c]
+        status, kept, n_iter = int(hp[0]), int(hp[1]), int(hp[2])
+        self.last_thresholds = [int(v) for v in hp[4:4 + n_iter]]
+        if status == 1:
+            raise RuntimeError('FeatureBank.remove: every entry was evicted and the budget is still exceeded '
+                               '(the reference raises on LFU.min() of an empty tensor, FeatureBank.py:136)')
+        if status == 2:
+            raise ValueError('FeatureBank.remove: LFU minimum is not finite (the reference raises in int(), '
+                             'FeatureBank.py:123)')
+        s, n = self._slabs[c], self._n[c]
+        alt = self._alt[c]
+        if alt is None or alt.cap < s.cap:
+            alt = _Slab(s.d_key, s.d_val, s.cap, self.device, s.kh is not None)
+        src, dst = s.struct(n), alt.struct(0)
+        lfu = self._scratch[f'lfu{c}']
+        plan = self._scratch[f'plan{c}']
+        cws = self._buf(f'cws{c}', (lib.vfn_bank_compact_workspace_bytes(n),), torch.uint8)
+        check(lib.vfn_bank_compact(C.byref(src), C.byref(dst), ptr(lfu), ptr(plan), ptr(cws), cws.numel(), st),
+              'bank_compact')
+        self.launches += 3
+        self._slabs[c], self._alt[c] = alt, s
+        self._n[c] = kept
+        self.replace_n[c] += n - kept                                             # FeatureBank.py:140-141
+        return (self.class_budget - kept) - request_n
+
+    def remove(self, class_idx, request_n, frame_idx):
+        """FeatureBank.py:117-143; returns `balance`."""
+        self._launch_evict_plan(class_idx, request_n, frame_idx)
+        torch.cuda.current_stream().synchronize()
+        return self._finish_evict(class_idx, request_n)
+
+    def print_peak_mem(self):
+        ur = self.peak_n / self.class_budget
+        rr = self.replace_n / self.class_budget
+        print(f'Obj num: {self.obj_n}.', f'Budget / obj: {self.class_budget}.', f'UR: {ur}.', f'Replace: {rr}.')
+
+    # ---- test / parity helpers (not in the reference) ---------------------------------------------
+    def load_state(self, keys, values, info):
+        """Teacher forcing: overwrite the bank with (d,N) keys/values and (N,2) info tensors."""
+        for c in range(self.obj_n):
+            self._slabs[c], self._alt[c], self._n[c] = None, None, 0
+            self._ingest(c, keys[c], values[c], 0.0, 0.0)
+            self._slabs[c].info[:self._n[c]].copy_(info[c].to(self.device, torch.float32))
