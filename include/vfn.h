@@ -150,7 +150,8 @@ int vfn_urr_post(const float* d_p_up, const float* d_unc, const float* d_conf, c
                  int32_t h, int32_t w, float* d_prob, void* stream);
 
 /* ---- self-test hooks for the tcgen05/TMA building blocks (used by tests/, not by the product path) ---- */
-int vfn_debug_umma_ss(const uint16_t* d_a, const uint16_t* d_b, float* d_c, int32_t n_tiles, void* stream);
+/* d_ptr != NULL: the next tcgen05 read launches dump the first S^T tile of CTA 0 (128 x tile floats) there. */
+int vfn_debug_set_dump(float* d_ptr);
 
 #ifdef __cplusplus
 }

@@ -174,9 +174,13 @@ def test_update_vs_oracle_decisions(vfn, n, hw, seed, budget):
     ofb, fb = _run_update_pair(vfn, n, hw, seed, budget)
     for c in range(2):
         d, dg = ofb.last_decisions[c], fb.last_decisions[c]
-        # synthetic margins are far above fp32 rounding noise: decisions must be identical
-        assert float(d.margin.min()) > 1e-5
-        assert torch.equal(dg['match_idx'].cpu().long(), d.match_idx)
+        # decisions must be identical wherever the top-1/top-2 cosine margin exceeds fp32 summation noise (4e-6);
+        # inside that band either candidate is a legitimate fp32 arg-max (cuBLAS and MKL disagree there too)
+        gidx = dg['match_idx'].cpu().long()
+        clear = d.margin > 4e-6
+        assert float(clear.float().mean()) > 0.99
+        assert torch.equal(gidx[clear], d.match_idx[clear])
+        assert torch.equal(gidx, d.match_idx), 'near-tie flip (margin <= 4e-6); seeds are chosen to have none'
         np.testing.assert_allclose(dg['match_corr'].cpu().numpy(), d.match_corr.numpy(), rtol=0, atol=2e-6)
         nm, na = dg['n_merge'], dg['n_append']
         assert nm == len(d.merge_q) and na == len(d.append_q) and dg['n_runs'] == len(d.touched)

@@ -44,7 +44,7 @@ SIGNATURES = {
     'vfn_bank_clamp_info': (c_i32, [BANK_P, c_i64, c_vp]),
     'vfn_urr_pre': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vfn_urr_post': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
-    'vfn_debug_umma_ss': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp]),
+    'vfn_debug_set_dump': (c_i32, [c_vp]),
 }
 
 _lib = None

@@ -1,10 +1,789 @@
-// placeholder until the tcgen05 kernels land
+// tcgen05 / TMEM / TMA implementation of the memory read (Matcher.forward, AFB_URR.py:136-178) for sm_100a.
+//
+//   phase A  S^T[j,i] = <q_j, k_i> * log2(e)/sqrt(128)   -> per-query running (max, sum 2^(s-max)) over the slots
+//   phase B  S^T recomputed, P = 2^(S - lse2_j) (already normalised: no online rescale), usage counts
+//            cnt_i += [P_ij > thres], O^T[j,c] += sum_i P_ij V_ic with the fp32 accumulator resident in TMEM.
+//
+// Orientation (both phases): TMEM lanes = queries (M = 128), columns = bank slots (S) / value channels (O).
+// A operands come from TMEM (Q for the S-MMA, P for the O-MMA), B operands from shared memory via TMA:
+//   K tiles  K-major  [slots x 128 d]   bf16, 128B swizzle, two 64-d boxes per piece
+//   V tiles  MN-major [slots x 256 ch]  bf16, 128B swizzle, four 64-channel boxes per piece
+// Precision: operands are bf16 hi+lo splits (x ~ hi + lo, 16 mantissa bits); every product uses
+// hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM (3 MMA passes), which keeps logits to ~2e-5 and the
+// readout far inside the 1e-3 tolerance (plain bf16 would give ~7e-3).
+// Work split: persistent CTAs (one per SM), static stream-K partition of the (object, query tile[, channel half])
+// x slot-tile space, so every CTA gets the same number of tile units; per-CTA partials are combined by
+// lse_combine_kernel / combine_out_kernel (vfn_simt.cu) in a fixed order (deterministic).
 #include "vfn_tc.cuh"
+
+#include <cuda.h>
+
 namespace vfn {
-bool tc_shapes_ok(int, int) { return false; }
-void tc_pick_splits(int, int64_t, int64_t, int* a, int* b) { *a = 1; *b = 1; }
-size_t tc_workspace_bytes(int, int64_t) { return 0; }
-int tc_phase_a(const vfn_bank*, int, const float*, int64_t, int, float2*, char*, cudaStream_t) { return VFN_E_UNSUPPORTED; }
-int tc_phase_b(const vfn_bank*, int, int64_t, int, const float*, float, int, float*, char*, cudaStream_t) { return VFN_E_UNSUPPORTED; }
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-extern "C" int vfn_debug_umma_ss(const uint16_t*, const uint16_t*, float*, int32_t, void*) { return VFN_E_UNSUPPORTED; }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // bounded spin: a broken pipeline traps (launch error) instead of hanging the GPU
+  uint32_t done = 0;
+  for (uint32_t spins = 0;; ++spins) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrives on the mbarrier once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// descriptors
+// ------------------------------------------------------------------------------------------------
+// shared-memory matrix descriptor, 128B swizzle, Blackwell version bit
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor kind::f16: bf16 x bf16 -> f32
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int DK = 128, DV = 512;
+constexpr int QT = 128;                 // queries per tile (TMEM lanes)
+constexpr int TC_THREADS = 384;         // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 softmax WG0, 8-11 softmax WG1
+constexpr int TC_MAX_OBJ = 4;
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+
+// TMEM columns
+constexpr uint32_t TM_O = 0;            // phase B: O^T accumulator, 256 columns
+constexpr uint32_t TM_QH = 256, TM_QL = 320;   // Q hi / lo as A operand: 64 columns each (128 bf16)
+constexpr uint32_t TM_S = 384;          // phase B: 2 buffers x 64 columns ; phase A uses [0,256) as 2 x 128
+
+struct TcMaps {
+  CUtensorMap kh[TC_MAX_OBJ], kl[TC_MAX_OBJ], vh[TC_MAX_OBJ], vl[TC_MAX_OBJ];
+};
+struct TcArgs {
+  int obj_n, hw, q_tiles, pieces;       // pieces = partial slots per combo (P_MAX)
+  int n[TC_MAX_OBJ];                    // live slots per object
+  int tiles[TC_MAX_OBJ];                // slot tiles per object for this phase
+  const uint16_t* qh;                   // (q_tiles*128, 128) bf16 hi of q * log2e/sqrt(d)
+  const uint16_t* ql;
+  int32_t* cnt[TC_MAX_OBJ];
+  float* dbg;
+};
+
+// static stream-K partition: unit space = concat over combos of that combo's slot tiles
+struct Segment {
+  int combo, t0, t1, piece;
+};
+__device__ __forceinline__ long long part_lo(long long b, long long T, long long G) { return b * T / G; }
+__device__ __forceinline__ int owner_of(long long u, long long T, long long G) { return (int)(((u + 1) * G - 1) / T); }
+
+// ------------------------------------------------------------------------------------------------
+// phase A
+// ------------------------------------------------------------------------------------------------
+constexpr int A_TILE = 128;             // slots per S tile
+constexpr int A_STAGES = 3;
+constexpr int A_STAGE_BYTES = A_TILE * DK * 2 * 2;   // hi + lo = 64 KB
+constexpr int A_SMEM = A_STAGES * A_STAGE_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_a_kernel(const __grid_constant__ TcMaps maps, TcArgs args,
+                                                                   float2* __restrict__ part) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* kst = smem;                                           // A_STAGES x 64 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_STAGES * A_STAGE_BYTES);
+  uint64_t* k_full = bars;                 // [A_STAGES]
+  uint64_t* k_empty = bars + A_STAGES;     // [A_STAGES]
+  uint64_t* s_full = bars + 2 * A_STAGES;  // [2]
+  uint64_t* s_empty = s_full + 2;          // [2]
+  uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(s_empty + 2);
+  __shared__ float2 ml_x[QT];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_base_p, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_base_p;
+
+  // partition
+  const long long G = gridDim.x;
+  long long T = 0;
+  for (int o = 0; o < args.obj_n; ++o) T += (long long)args.tiles[o] * args.q_tiles;
+  const long long lo = part_lo(blockIdx.x, T, G), hi = part_lo(blockIdx.x + 1, T, G);
+
+  uint32_t k_it = 0;            // tiles streamed so far (producer & MMA agree)
+  uint32_t buf_it[2] = {0, 0};  // uses of each S buffer so far
+  long long u = lo;
+  while (u < hi) {
+    // locate the combo of unit u
+    int obj = 0;
+    long long start = 0;
+    while (u >= start + (long long)args.tiles[obj] * args.q_tiles) { start += (long long)args.tiles[obj] * args.q_tiles; ++obj; }
+    const int tiles_o = args.tiles[obj];
+    const int qt = (int)((u - start) / tiles_o);
+    const long long cstart = start + (long long)qt * tiles_o;
+    const int t0 = (int)(u - cstart);
+    const int t1 = (int)((hi - cstart) < tiles_o ? (hi - cstart) : tiles_o);
+    const int piece = blockIdx.x - owner_of(cstart, T, G);
+    const int n_obj = args.n[obj];
+    const int ntile = t1 - t0;
+
+    // (1) Q tile -> TMEM (WG0: hi, WG1: lo); one row (query) per thread
+    if (warp >= 4) {
+      const int wg = (warp - 4) >> 2;
+      const int row = ((warp & 3) << 5) + lane;
+      const uint16_t* src = (wg == 0 ? args.qh : args.ql) + ((size_t)qt * QT + row) * DK;
+      const uint32_t tbase = tmem + (((uint32_t)(warp & 3) * 32u) << 16) + (wg == 0 ? TM_QH : TM_QL);
+      uint32_t v[32];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 x = reinterpret_cast<const uint4*>(src)[h * 8 + i];
+          v[4 * i + 0] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+        }
+        tmem_st32(tbase + h * 32, v);
+      }
+      tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // (2) roles
+    if (warp == 0) {
+      for (int t = 0; t < ntile; ++t, ++k_it) {
+        const uint32_t st = k_it % A_STAGES, ph = (k_it / A_STAGES) & 1;
+        if (lane == 0) {
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[st], A_STAGE_BYTES);
+          uint8_t* dst = kst + st * A_STAGE_BYTES;
+          const int row0 = (t0 + t) * A_TILE;
+          tma_load_2d(dst, &maps.kh[obj], &k_full[st], 0, row0);
+          tma_load_2d(dst + 16384, &maps.kh[obj], &k_full[st], 64, row0);
+          tma_load_2d(dst + 32768, &maps.kl[obj], &k_full[st], 0, row0);
+          tma_load_2d(dst + 49152, &maps.kl[obj], &k_full[st], 64, row0);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      constexpr uint32_t idesc = make_idesc(128, A_TILE, 0, 0);
+      for (int t = 0; t < ntile; ++t, ++k_it) {
+        const uint32_t st = k_it % A_STAGES, ph = (k_it / A_STAGES) & 1;
+        const int b = t & 1;
+        if (lane == 0) {
+          mbar_wait(&s_empty[b], (buf_it[b] & 1) ^ 1);
+          mbar_wait(&k_full[st], ph);
+          tc_fence_after();
+          const uint32_t kbase = smem_u32(kst + st * A_STAGE_BYTES);
+          const uint32_t d_t = tmem + (uint32_t)b * A_TILE;
+          // passes: (Qh,Kh) (Ql,Kh) (Qh,Kl)
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a_col = (pass == 1) ? TM_QL : TM_QH;
+            const uint32_t kb = kbase + ((pass == 2) ? 32768u : 0u);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint64_t bd = make_sdesc(kb + (ks >> 2) * 16384u + (ks & 3) * 32u, 16, 1024);
+              mma_ts(d_t, tmem + a_col + ks * 8, bd, idesc, (pass | ks) ? 1u : 0u);
+            }
+          }
+          tc_commit(&k_empty[st]);
+          tc_commit(&s_full[b]);
+        }
+        __syncwarp();
+        ++buf_it[b];
+      }
+    } else if (warp >= 4) {
+      const int wg = (warp - 4) >> 2;
+      const int row = ((warp & 3) << 5) + lane;
+      const uint32_t tlane = tmem + (((uint32_t)(warp & 3) * 32u) << 16);
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int t = wg; t < ntile; t += 2) {
+        mbar_wait(&s_full[wg], buf_it[wg] & 1);
+        ++buf_it[wg];
+        tc_fence_after();
+        const int slot0 = (t0 + t) * A_TILE;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(tlane + (uint32_t)wg * A_TILE + ch * 32, v);
+          tmem_wait_ld();
+          if (args.dbg && blockIdx.x == 0 && u == lo && t == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) args.dbg[row * A_TILE + ch * 32 + i] = __uint_as_float(v[i]);
+          }
+          float cm = -INFINITY;
+          const int lim = n_obj - (slot0 + ch * 32);     // valid slots in this chunk
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float s = __uint_as_float(v[i]);
+            s = (i < lim) ? s : -INFINITY;
+            v[i] = __float_as_uint(s);
+            cm = fmaxf(cm, s);
+          }
+          const float m_new = fmaxf(m_run, cm);
+          if (m_new > -INFINITY) {
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc += ex2(__uint_as_float(v[i]) - m_new);
+            l_run = l_run * ex2(m_run - m_new) + acc;
+            m_run = m_new;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&s_empty[wg]);
+      }
+      // (3) combine the two warpgroups' statistics and publish the piece
+      if (wg == 1) ml_x[row] = make_float2(m_run, l_run);
+      named_bar_sync(1, 256);
+      if (wg == 0) {
+        const float2 o = ml_x[row];
+        const float m = fmaxf(m_run, o.x);
+        float l = 0.f;
+        if (m > -INFINITY) l = l_run * ex2(m_run - m) + o.y * ex2(o.x - m);
+        const int j = qt * QT + row;
+        if (j < args.hw) part[((size_t)obj * args.pieces + piece) * args.hw + j] = make_float2(m * LN2, l);
+      }
+    } else {
+      // warps 2,3 idle during the tile loop
+    }
+    // keep role-local counters consistent for warps that did not run the loops
+    if (warp != 0 && warp != 1) k_it += ntile;
+    if (warp != 1 && warp < 4) { buf_it[0] += (ntile + 1) >> 1; buf_it[1] += ntile >> 1; }
+    if (warp >= 4) { const int wgx = (warp - 4) >> 2; buf_it[wgx ^ 1] += (wgx ^ 1) == 0 ? (ntile + 1) >> 1 : ntile >> 1; }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    u = cstart + t1;
+  }
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase B
+// ------------------------------------------------------------------------------------------------
+constexpr int B_TILE = 64;                              // slots per tile
+constexpr int B_KSTAGES = 2, B_VSTAGES = 2;
+constexpr int B_KSTAGE_BYTES = B_TILE * DK * 2 * 2;     // 32 KB (hi + lo)
+constexpr int B_VSTAGE_BYTES = B_TILE * 256 * 2 * 2;    // 64 KB (hi + lo, 256 channels)
+constexpr int B_SMEM = B_KSTAGES * B_KSTAGE_BYTES + B_VSTAGES * B_VSTAGE_BYTES + 1024 + 1024;
+
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_constant__ TcMaps maps, TcArgs args,
+                                                                   const float* __restrict__ lse, float thres,
+                                                                   int do_count, float* __restrict__ po) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* kst = smem;
+  uint8_t* vst = smem + B_KSTAGES * B_KSTAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(vst + B_VSTAGES * B_VSTAGE_BYTES);
+  uint64_t* k_full = bars;            // [2]
+  uint64_t* k_empty = bars + 2;       // [2]
+  uint64_t* v_full = bars + 4;        // [2]
+  uint64_t* v_empty = bars + 6;       // [2]
+  uint64_t* s_full = bars + 8;        // [2]
+  uint64_t* p_full = bars + 10;       // [2]
+  uint64_t* o_full = bars + 12;       // [1]
+  uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(bars + 13);
+  int* cnt_s = reinterpret_cast<int*>(bars + 16);   // [2][64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128);
+    }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 128) cnt_s[threadIdx.x] = 0;
+  if (warp == 2) tmem_alloc(tmem_base_p, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_base_p;
+
+  const long long G = gridDim.x;
+  long long T = 0;
+  for (int o = 0; o < args.obj_n; ++o) T += (long long)args.tiles[o] * args.q_tiles * 2;
+  const long long lo = part_lo(blockIdx.x, T, G), hi = part_lo(blockIdx.x + 1, T, G);
+
+  uint32_t k_it = 0;            // tiles streamed so far
+  uint32_t buf_it[2] = {0, 0};  // uses of each S/P buffer
+  uint32_t seg_it = 0;          // segments finished (o_full phase)
+  long long u = lo;
+  while (u < hi) {
+    int obj = 0;
+    long long start = 0;
+    while (u >= start + (long long)args.tiles[obj] * args.q_tiles * 2) { start += (long long)args.tiles[obj] * args.q_tiles * 2; ++obj; }
+    const int tiles_o = args.tiles[obj];
+    const int cidx = (int)((u - start) / tiles_o);     // combo within object: qt * 2 + half
+    const int qt = cidx >> 1, half = cidx & 1;
+    const long long cstart = start + (long long)cidx * tiles_o;
+    const int t0 = (int)(u - cstart);
+    const int t1 = (int)((hi - cstart) < tiles_o ? (hi - cstart) : tiles_o);
+    const int piece = blockIdx.x - owner_of(cstart, T, G);
+    const int n_obj = args.n[obj];
+    const int ntile = t1 - t0;
+
+    if (warp >= 4) {
+      const int wg = (warp - 4) >> 2;
+      const int row = ((warp & 3) << 5) + lane;
+      const uint16_t* src = (wg == 0 ? args.qh : args.ql) + ((size_t)qt * QT + row) * DK;
+      const uint32_t tbase = tmem + (((uint32_t)(warp & 3) * 32u) << 16) + (wg == 0 ? TM_QH : TM_QL);
+      uint32_t v[32];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 x = reinterpret_cast<const uint4*>(src)[h * 8 + i];
+          v[4 * i + 0] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+        }
+        tmem_st32(tbase + h * 32, v);
+      }
+      tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == 0) {
+      for (int t = 0; t < ntile; ++t, ++k_it) {
+        const uint32_t st = k_it & 1, ph = (k_it >> 1) & 1;
+        if (lane == 0) {
+          const int row0 = (t0 + t) * B_TILE;
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[st], B_KSTAGE_BYTES);
+          uint8_t* kd = kst + st * B_KSTAGE_BYTES;
+          tma_load_2d(kd, &maps.kh[obj], &k_full[st], 0, row0);
+          tma_load_2d(kd + 8192, &maps.kh[obj], &k_full[st], 64, row0);
+          tma_load_2d(kd + 16384, &maps.kl[obj], &k_full[st], 0, row0);
+          tma_load_2d(kd + 24576, &maps.kl[obj], &k_full[st], 64, row0);
+          mbar_wait(&v_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&v_full[st], B_VSTAGE_BYTES);
+          uint8_t* vd = vst + st * B_VSTAGE_BYTES;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            tma_load_2d(vd + g * 8192, &maps.vh[obj], &v_full[st], half * 256 + g * 64, row0);
+            tma_load_2d(vd + 32768 + g * 8192, &maps.vl[obj], &v_full[st], half * 256 + g * 64, row0);
+          }
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      constexpr uint32_t idesc_s = make_idesc(128, B_TILE, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc(128, 256, 0, 1);
+      if (lane == 0) {
+        // software pipeline: S(0); for t: { S(t+1); wait P(t); O(t) }
+        auto issue_s = [&](int t, uint32_t kit) {
+          const uint32_t st = kit & 1, ph = (kit >> 1) & 1;
+          const int b = t & 1;
+          mbar_wait(&k_full[st], ph);
+          tc_fence_after();
+          const uint32_t kbase = smem_u32(kst + st * B_KSTAGE_BYTES);
+          const uint32_t d_t = tmem + TM_S + (uint32_t)b * 64;
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a_col = (pass == 1) ? TM_QL : TM_QH;
+            const uint32_t kb = kbase + ((pass == 2) ? 16384u : 0u);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint64_t bd = make_sdesc(kb + (ks >> 2) * 8192u + (ks & 3) * 32u, 16, 1024);
+              mma_ts(d_t, tmem + a_col + ks * 8, bd, idesc_s, (pass | ks) ? 1u : 0u);
+            }
+          }
+          tc_commit(&k_empty[st]);
+          tc_commit(&s_full[b]);
+        };
+        if (ntile > 0) issue_s(0, k_it);
+        for (int t = 0; t < ntile; ++t) {
+          if (t + 1 < ntile) issue_s(t + 1, k_it + t + 1);
+          const uint32_t kit = k_it + t;
+          const uint32_t st = kit & 1, ph = (kit >> 1) & 1;
+          const int b = t & 1;
+          mbar_wait(&p_full[b], buf_it[b] & 1);
+          ++buf_it[b];
+          mbar_wait(&v_full[st], ph);
+          tc_fence_after();
+          const uint32_t vbase = smem_u32(vst + st * B_VSTAGE_BYTES);
+          const uint32_t pcol = tmem + TM_S + (uint32_t)b * 64;
+          // passes: (Ph,Vh) (Ph,Vl) (Pl,Vh)
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a_col = pcol + ((pass == 2) ? 32u : 0u);
+            const uint32_t vb = vbase + ((pass == 1) ? 32768u : 0u);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t bd = make_sdesc(vb + ks * 2048u, 8192, 1024);
+              mma_ts(tmem + TM_O, a_col + ks * 8, bd, idesc_o, (t | pass | ks) ? 1u : 0u);
+            }
+          }
+          tc_commit(&v_empty[st]);
+        }
+        tc_commit(o_full);
+      } else {
+        for (int t = 0; t < ntile; ++t) ++buf_it[t & 1];
+      }
+      k_it += ntile;
+      __syncwarp();
+    } else if (warp >= 4) {
+      const int wg = (warp - 4) >> 2;
+      const int row = ((warp & 3) << 5) + lane;
+      const int wtid = threadIdx.x - 128 - wg * 128;       // 0..127 within the warpgroup
+      const uint32_t tlane = tmem + (((uint32_t)(warp & 3) * 32u) << 16);
+      const int j = qt * QT + row;
+      const float lse2 = (j < args.hw) ? lse[(size_t)obj * args.hw + j] * LOG2E : INFINITY;
+      int* mycnt = cnt_s + wg * 64;
+      const bool counting = do_count && (half == 0);
+      for (int t = wg; t < ntile; t += 2) {
+        mbar_wait(&s_full[wg], buf_it[wg] & 1);
+        ++buf_it[wg];
+        tc_fence_after();
+        const int slot0 = (t0 + t) * B_TILE;
+        const uint32_t sb = tlane + TM_S + (uint32_t)wg * 64;
+        uint32_t s0[32], s1[32];
+        tmem_ld32(sb, s0);
+        tmem_ld32(sb + 32, s1);
+        tmem_wait_ld();
+        if (args.dbg && blockIdx.x == 0 && u == lo && t == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            args.dbg[row * B_TILE + i] = __uint_as_float(s0[i]);
+            args.dbg[row * B_TILE + 32 + i] = __uint_as_float(s1[i]);
+          }
+        }
+        const int lim = n_obj - slot0;
+        uint32_t hi_w[32], lo_w[32];
+        unsigned long long bits = 0ull;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = ex2(__uint_as_float(s0[i]) - lse2), p1 = ex2(__uint_as_float(s0[i + 1]) - lse2);
+          p0 = (i < lim) ? p0 : 0.f;
+          p1 = (i + 1 < lim) ? p1 : 0.f;
+          bits |= (unsigned long long)(p0 > thres) << i;
+          bits |= (unsigned long long)(p1 > thres) << (i + 1);
+          const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+          const __nv_bfloat162 l = __floats2bfloat162_rn(p0 - __low2float(h), p1 - __high2float(h));
+          hi_w[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+          lo_w[i >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = ex2(__uint_as_float(s1[i]) - lse2), p1 = ex2(__uint_as_float(s1[i + 1]) - lse2);
+          p0 = (32 + i < lim) ? p0 : 0.f;
+          p1 = (33 + i < lim) ? p1 : 0.f;
+          bits |= (unsigned long long)(p0 > thres) << (32 + i);
+          bits |= (unsigned long long)(p1 > thres) << (33 + i);
+          const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+          const __nv_bfloat162 l = __floats2bfloat162_rn(p0 - __low2float(h), p1 - __high2float(h));
+          hi_w[16 + (i >> 1)] = *reinterpret_cast<const uint32_t*>(&h);
+          lo_w[16 + (i >> 1)] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        tmem_st32(sb, hi_w);          // P hi: 64 bf16 = 32 columns
+        tmem_st32(sb + 32, lo_w);     // P lo
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&p_full[wg]);
+        if (counting) {
+          if (j >= args.hw) bits = 0ull;
+          const int dense = __any_sync(0xffffffffu, __popcll(bits) > 6);
+          if (dense) {
+            int c_lo = 0, c_hi = 0;
+#pragma unroll 8
+            for (int c = 0; c < 32; ++c) {
+              const unsigned b0 = __ballot_sync(0xffffffffu, (bits >> c) & 1ull);
+              const unsigned b1 = __ballot_sync(0xffffffffu, (bits >> (32 + c)) & 1ull);
+              if (lane == c) { c_lo = __popc(b0); c_hi = __popc(b1); }
+            }
+            if (c_lo) atomicAdd(&mycnt[lane], c_lo);
+            if (c_hi) atomicAdd(&mycnt[32 + lane], c_hi);
+          } else {
+            while (bits) {
+              const int c = __ffsll((long long)bits) - 1;
+              bits &= bits - 1;
+              atomicAdd(&mycnt[c], 1);
+            }
+          }
+          named_bar_sync(1 + wg, 128);
+          if (wtid < 64) {
+            const int c = mycnt[wtid];
+            if (c) {
+              atomicAdd(&args.cnt[obj][slot0 + wtid], c);
+              mycnt[wtid] = 0;
+            }
+          }
+          named_bar_sync(1 + wg, 128);
+        }
+      }
+      // epilogue: O^T (128 queries x 256 channels) -> partial buffer, WG0 channels [0,128), WG1 [128,256)
+      mbar_wait(o_full, seg_it & 1);
+      tc_fence_after();
+      if (ntile > 0) {
+        float* dst = po + (((size_t)obj * args.pieces + piece) * DV + half * 256 + wg * 128) * (size_t)args.hw;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(tlane + TM_O + (uint32_t)wg * 128 + ch * 32, v);
+          tmem_wait_ld();
+          if (j < args.hw) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dst[(size_t)(ch * 32 + i) * args.hw + j] = __uint_as_float(v[i]);
+          }
+        }
+      }
+    }
+    if (warp != 0 && warp != 1) k_it += ntile;
+    if (warp < 4 && warp != 1) { buf_it[0] += (ntile + 1) >> 1; buf_it[1] += ntile >> 1; }
+    if (warp >= 4) { const int wgx = (warp - 4) >> 2; buf_it[wgx ^ 1] += (wgx ^ 1) == 0 ? (ntile + 1) >> 1 : ntile >> 1; }
+    ++seg_it;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    u = cstart + t1;
+  }
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+__global__ void fill_ml_kernel(float2* __restrict__ p, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = make_float2(-INFINITY, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor (rows, cols) row-major; box = (box_rows, 64 cols = 128 B), 128B swizzle, OOB rows -> 0
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return VFN_E_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return VFN_E_CUDA; }
+  return VFN_OK;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static float* g_dbg = nullptr;
+
+bool tc_shapes_ok(int d_key, int d_val) { return d_key == DK && d_val == DV; }
+
+void tc_pick_splits(int obj_n, int64_t n_max, int64_t hw, int* split_a, int* split_b) {
+  (void)obj_n; (void)n_max;
+  const int G = num_sms();
+  const int q_tiles = (int)cdiv(hw, QT);
+  *split_a = (int)cdiv(G, q_tiles) + 1;
+  *split_b = (int)cdiv(G, q_tiles * 2) + 1;
+}
+
+size_t tc_workspace_bytes(int obj_n, int64_t hw) {
+  (void)obj_n;
+  const size_t rows = (size_t)cdiv(hw, QT) * QT;
+  return 2 * align_up(rows * DK * sizeof(uint16_t), 256);
+}
+
+static int fill_args(const vfn_bank* banks, int obj_n, int64_t hw, int pieces, int tile, char* ws_tc, TcMaps* maps,
+                     TcArgs* a, bool need_v) {
+  VFN_CHECK_ARG(obj_n <= TC_MAX_OBJ, "tcgen05 read supports at most %d objects", TC_MAX_OBJ);
+  const size_t rows = (size_t)cdiv(hw, QT) * QT;
+  a->obj_n = obj_n; a->hw = (int)hw; a->q_tiles = (int)cdiv(hw, QT); a->pieces = pieces;
+  a->qh = reinterpret_cast<const uint16_t*>(ws_tc);
+  a->ql = reinterpret_cast<const uint16_t*>(ws_tc + align_up(rows * DK * sizeof(uint16_t), 256));
+  a->dbg = g_dbg;
+  for (int o = 0; o < obj_n; ++o) {
+    VFN_CHECK_ARG(banks[o].kh && banks[o].vh, "bank %d has no bf16 operand arrays", o);
+    VFN_CHECK_ARG(banks[o].n < (1ll << 31), "bank too large");
+    a->n[o] = (int)banks[o].n;
+    a->tiles[o] = (int)cdiv(banks[o].n, tile);
+    a->cnt[o] = banks[o].cnt;
+    if (int rc = make_map(&maps->kh[o], banks[o].kh, banks[o].n, DK, tile)) return rc;
+    if (int rc = make_map(&maps->kl[o], banks[o].kl, banks[o].n, DK, tile)) return rc;
+    if (need_v) {
+      if (int rc = make_map(&maps->vh[o], banks[o].vh, banks[o].n, DV, tile)) return rc;
+      if (int rc = make_map(&maps->vl[o], banks[o].vl, banks[o].n, DV, tile)) return rc;
+    }
+  }
+  return VFN_OK;
+}
+
+int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t hw, int split_a, float2* part,
+               char* ws_tc, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    VFN_CUDA_OK(cudaFuncSetAttribute(tc_phase_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
+    VFN_CUDA_OK(cudaFuncSetAttribute(tc_phase_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+    attr = true;
+  }
+  TcMaps maps;
+  TcArgs a;
+  if (int rc = fill_args(banks, obj_n, hw, split_a, A_TILE, ws_tc, &maps, &a, false)) return rc;
+  const size_t rows = (size_t)a.q_tiles * QT;
+  // Q hi/lo of q * log2(e)/sqrt(d): logits land in the log2 domain; pad rows zeroed
+  VFN_CUDA_OK(cudaMemsetAsync(ws_tc, 0, 2 * align_up(rows * DK * sizeof(uint16_t), 256), st));
+  const float scale = LOG2E / sqrtf((float)DK);
+  if (int rc = vfn_prep_rows(q_in_dm, DK, hw, nullptr, nullptr, const_cast<uint16_t*>(a.qh),
+                             const_cast<uint16_t*>(a.ql), scale, st))
+    return rc;
+  const size_t np = (size_t)obj_n * split_a * hw;
+  fill_ml_kernel<<<(unsigned)cdiv(np, 256), 256, 0, st>>>(part, np);
+  tc_phase_a_kernel<<<num_sms(), TC_THREADS, A_SMEM, st>>>(maps, a, part);
+  VFN_LAUNCH_OK();
+  return VFN_OK;
+}
+
+int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const float* lse, float thres_valid,
+               int update_bank, float* po, char* ws_tc, cudaStream_t st) {
+  TcMaps maps;
+  TcArgs a;
+  if (int rc = fill_args(banks, obj_n, hw, split_b, B_TILE, ws_tc, &maps, &a, true)) return rc;
+  VFN_CUDA_OK(cudaMemsetAsync(po, 0, (size_t)obj_n * split_b * DV * hw * sizeof(float), st));
+  tc_phase_b_kernel<<<num_sms(), TC_THREADS, B_SMEM, st>>>(maps, a, lse, thres_valid, update_bank, po);
+  VFN_LAUNCH_OK();
+  return VFN_OK;
+}
+
+}  // namespace vfn
+
+extern "C" int vfn_debug_set_dump(float* d_ptr) {
+  vfn::g_dbg = d_ptr;
+  return VFN_OK;
+}
