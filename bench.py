@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py - hot-path throughput of the AFB-URR memory propagation on B200 (contract: task prompt section 4).
+
+A "step" is one pass of the hot path over one synthetic 480p / 2-object / 100-frame clip at the drop-in boundary:
+per frame  read (Matcher.forward) -> URR pre/post -> bank update (match, merge, LFU evict, append), starting from
+init_bank.  `value` = frames/s with the clip resident in HBM; `e2e` = the same through the public Python API with
+HOST (pinned) inputs copied in and the refined mask copied out every frame.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (CUDA kernels)
+    python bench.py --impl reference ...                           # reference algorithm on the host cores (oracle port)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HW_H, HW_W = 30, 54          # r4 grid of a 480x864 padded frame  (HW = 1620)
+R1_H, R1_W = 240, 432
+D_KEY, D_VAL = 128, 512
+BUDGET = 250000               # test_video_seg.py:24  -> class_budget 100000.0
+METRIC = '480p frames/sec (1/2/4/8 B200); mem-read tensor util; bank-update HBM GB/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--frames', type=int, default=100)
+    ap.add_argument('--frac-merge', type=float, default=0.1)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--read-impl', type=int, default=0, help='0 auto (tcgen05), 1 fp32 SIMT, 2 tcgen05')
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------------
+def make_clip(seed, frames, frac_merge, pin):
+    from vfloodnet_b200 import synth
+    gen = synth.ClipGenerator(seed=seed, obj_n=2, hw=HW_H * HW_W, d_key=D_KEY, d_val=D_VAL, frac_merge=frac_merge)
+    keys0, vals0 = gen.init()
+    fr = []
+    for _ in range(frames):
+        q_in, q_out, pk, pv = gen.frame()
+        fr.append((q_in, q_out, pk, pv))
+    g = torch.Generator().manual_seed(seed + 1000)
+    urr = synth.gen_urr_inputs(g, 2, R1_H, R1_W)
+    if pin:
+        P = lambda t: t.pin_memory()
+        keys0, vals0 = [P(k) for k in keys0], [P(v) for v in vals0]
+        fr = [(P(a), P(b), [P(k) for k in pk], [P(v) for v in pv]) for a, b, pk, pv in fr]
+        urr = tuple(P(t) for t in urr)
+    return dict(keys0=keys0, vals0=vals0, frames=fr, urr=urr)
+
+
+def to_device(clip, dev):
+    D = lambda t: t.to(dev, non_blocking=True)
+    return dict(keys0=[D(k) for k in clip['keys0']], vals0=[D(v) for v in clip['vals0']],
+                frames=[(D(a), D(b), [D(k) for k in pk], [D(v) for v in pv]) for a, b, pk, pv in clip['frames']],
+                urr=tuple(D(t) for t in clip['urr']))
+
+
+def run_clip_gpu(vfn, clip, dev, read_impl, host_inputs=False, out_host=None):
+    """one step: the whole clip through the drop-in API.  Returns final bank sizes."""
+    fb = vfn.FeatureBank(2, BUDGET, dev, impl=read_impl)
+    m = vfn.Matcher(update_bank=True)
+    D = (lambda t: t.to(dev, non_blocking=True)) if host_inputs else (lambda t: t)
+    fb.init_bank([D(k) for k in clip['keys0']], [D(v) for v in clip['vals0']])
+    for t, (q_in, q_out, pk, pv) in enumerate(clip['frames']):
+        p, r1, q_local = (D(x) for x in clip['urr'])
+        out = m(fb, D(q_in), D(q_out))
+        p_up, unc, conf, local_match = vfn.urr_pre(p, r1.expand(2, -1, -1, -1), (1, 2, R1_H, R1_W))
+        prob = vfn.urr_post(p_up, unc, conf, q_local)
+        fb.update([D(k) for k in pk], [D(v) for v in pv], t + 1)
+        if out_host is not None:
+            out_host.copy_(prob, non_blocking=True)
+    return fb, out, prob
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i',
+                                    str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.samples.append([x.strip() for x in o.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': int(self.samples[0][1]), 'reasons': reasons,
+                'samples': len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port, torch CPU, all host threads) on a bounded sample
+# ---------------------------------------------------------------------------------------------------
+def expected_bank_size(frame, frac_merge):
+    hw = HW_H * HW_W
+    return int(min(hw + (1 - frac_merge) * hw * frame, 0.8 * (BUDGET // 2)))
+
+
+def cpu_sample(frac_merge, sample_frames=(25, 50, 75, 100), seed=0):
+    """Times oracle read + URR + update at the bank sizes the clip has at `sample_frames` (synthetic bank contents of
+    the clip's analytic size trajectory).  Returns (frames_per_sec, description, seconds)."""
+    from oracle import afb_oracle as O
+    from vfloodnet_b200 import synth
+    torch.set_num_threads(os.cpu_count())
+    hw = HW_H * HW_W
+    total = 0.0
+    for f in sample_frames:
+        g = torch.Generator().manual_seed(seed + f)
+        n = expected_bank_size(f, frac_merge)
+        fb = O.OracleFeatureBank(2, BUDGET, 'cpu')
+        keys, vals = zip(*[synth.gen_bank(g, n) for _ in range(2)])
+        fb.init_bank(list(keys), list(vals))
+        for c in range(2):
+            fb.info[c] = synth.gen_info(g, n, f)
+        q_in, q_out = synth.gen_query(g, hw)
+        pk, pv = zip(*[synth.gen_candidates(g, keys[c], vals[c], hw, frac_merge) for c in range(2)])
+        p, r1, q_local = synth.gen_urr_inputs(g, 2, R1_H, R1_W)
+        t0 = time.perf_counter()
+        O.hot_path_step(fb, q_in, q_out, list(pk), list(pv), f,
+                        urr_in=(p, r1.expand(2, -1, -1, -1), q_local, (1, 2, R1_H, R1_W)))
+        total += time.perf_counter() - t0
+    desc = (f'oracle port (torch CPU fp32) of read+URR+update on frames {list(sample_frames)} of the clip, bank sizes '
+            f'{[expected_bank_size(f, frac_merge) for f in sample_frames]} slots/object (analytic trajectory)')
+    return len(sample_frames) / total, desc, total
+
+
+def main_reference(args, rank, world):
+    if rank != 0:
+        return
+    for _ in range(args.warmup and 1):
+        cpu_sample(args.frac_merge, sample_frames=(5,))
+    t0 = time.perf_counter()
+    n_frames = 0
+    for _ in range(args.steps):
+        fps, desc, secs = cpu_sample(args.frac_merge)
+        n_frames += 4
+    el = time.perf_counter() - t0
+    v = n_frames / el
+    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'frames/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * el / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': '480p-2obj-100frame-clip-hotpath', 'hw': HW_H * HW_W, 'budget': BUDGET,
+                       'frames': args.frames, 'frac_merge': args.frac_merge},
+            'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': desc},
+            'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def main_ours(args, rank, world, local_rank):
+    import ctypes
+    import vfloodnet_b200 as vfn
+    from vfloodnet_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # one independent stream (clip) per GPU: weak scaling, no data-path collective (stream-parallel)
+    host_clip = make_clip(seed=100 + rank, frames=args.frames, frac_merge=args.frac_merge, pin=True)
+    dev_clip = to_device(host_clip, dev)
+    out_host = torch.empty((2, 2 * R1_H, 2 * R1_W), dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        run_clip_gpu(vfn, dev_clip, dev, args.read_impl)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.vfn_profile_enable(1)
+    l0 = lib.vfn_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        fb, out, prob = run_clip_gpu(vfn, dev_clip, dev, args.read_impl)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.vfn_launch_count() - l0
+    prof = (ctypes.c_double * 24)()
+    _lib.check(lib.vfn_profile_collect(prof, 8), 'profile_collect')
+    lib.vfn_profile_enable(0)
+    sampler.stop_flag = True
+    final_n = [fb.bank_n(c) for c in range(2)]
+
+    # e2e: host inputs, copies inside the timed region
+    for _ in range(1):
+        run_clip_gpu(vfn, host_clip, dev, args.read_impl, host_inputs=True, out_host=out_host)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        run_clip_gpu(vfn, host_clip, dev, args.read_impl, host_inputs=True, out_host=out_host)
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+
+    t_ms = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t_ms.tolist()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    frames_total = args.frames * args.steps * world
+    value = frames_total / (ms / 1e3)
+    e2e = frames_total / (ms_e2e / 1e3)
+    numel = lambda ts: sum(t.numel() for t in ts)
+    fr = host_clip['frames'][0]
+    h2d_frame = 4 * (fr[0].numel() + fr[1].numel() + numel(fr[2]) + numel(fr[3]) + numel(host_clip['urr']))
+    h2d = args.frames * h2d_frame + 4 * (numel(host_clip['keys0']) + numel(host_clip['vals0']))
+    d2h = args.frames * out_host.numel() * 4
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    tf_peak = peaks.get('bf16_tflops_sustained', 1400.0)
+    peak_src = 'bf16_tflops_sustained of MEASURED_PEAKS.json' if peaks else 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
+    hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    k = lambda i: (prof[3 * i], prof[3 * i + 1], prof[3 * i + 2])
+    nb, msb, wb = k(1)
+    na, msa, wa = k(0)
+    ach = (wb / (msb * 1e-3) / 1e12) if msb > 0 else 0.0
+    roofline = {'bound': 'tensor', 'kernel': 'tc_phase_b_kernel (read phase B: P=softmax, O+=P.V, usage counts)',
+                'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': ach / tf_peak if tf_peak else None,
+                'traffic': None, 'peak_source': peak_src, 'launches': int(nb), 'avg_ms': msb / nb if nb else None,
+                'algorithmic_flop_per_launch': wb / nb if nb else None,
+                'read_total': {'achieved': ((wa + wb) / ((msa + msb) * 1e-3) / 1e12) if msa + msb > 0 else 0.0,
+                               'phase_a_avg_ms': msa / na if na else None, 'unit': 'TFLOP/s'}}
+    extra = {}
+    names = {2: 'match', 3: 'compact_move', 4: 'merge', 5: 'append', 6: 'urr_local'}
+    for i, nm in names.items():
+        n_i, ms_i, w_i = k(i)
+        if n_i:
+            d = {'launches': int(n_i), 'avg_ms': ms_i / n_i}
+            if w_i > 0:
+                rate = w_i / (ms_i * 1e-3)
+                if i == 2:
+                    d.update(achieved=rate / 1e12, unit='TFLOP/s')
+                else:
+                    d.update(achieved=rate / 1e9, unit='GB/s', frac_of_hbm_peak=rate / 1e9 / hbm_peak)
+            extra[nm] = d
+    line = {'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'bf16x3-split operands, f32 accumulate (read); f32 (match, update, URR)',
+            'data': 'synthetic',
+            'config': {'workload': '480p-2obj-100frame-clip-hotpath', 'hw': HW_H * HW_W, 'budget': BUDGET,
+                       'frames': args.frames, 'frac_merge': args.frac_merge, 'streams_per_gpu': 1,
+                       'final_bank_slots': final_n, 'l2_policy': 'inputs_exceed_l2 (bank operands 0.5-1.1 GB >> 126 MB)',
+                       'read_impl': args.read_impl},
+            'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+            'gpu_launches': int(launches), 'roofline': roofline, 'kernels': extra, 'clocks': sampler.summary()}
+    if not args.no_cpu_baseline and world == 1:
+        fps, desc, secs = cpu_sample(args.frac_merge)
+        line['cpu_baseline'] = {'value': fps, 'unit': 'frames/s', 'cores': os.cpu_count(), 'kind': 'port',
+                                'sample': desc, 'seconds': secs}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        main_reference(args, rank, world)
+    else:
+        if world != args.gpus and world == 1 and args.gpus > 1:
+            # convenience: re-launch under torchrun when asked for N>1 GPUs directly
+            cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
+                   '--master-addr', '127.0.0.1', '--master-port', '29517', os.path.abspath(__file__)] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+        main_ours(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

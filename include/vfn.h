@@ -149,6 +149,16 @@ int vfn_urr_pre(const float* d_p, const float* d_r1, int64_t r1_obj_stride, int3
 int vfn_urr_post(const float* d_p_up, const float* d_unc, const float* d_conf, const float* d_q_local, int32_t obj_n,
                  int32_t h, int32_t w, float* d_prob, void* stream);
 
+/* ---- measurement hooks (bench.py) ----------------------------------------------------------------
+ * While enabled, the library brackets its dominant kernels with CUDA events recorded on the launching stream.
+ * kinds: 0 read phase A, 1 read phase B, 2 match, 3 compaction move, 4 merge, 5 append, 6 URR local.
+ * collect: h_out[3*k + {0,1,2}] = {launches, total ms, total algorithmic work (flop or bytes)} (host sync on the events).
+ * vfn_launch_count(): number of kernels this library has launched in this process. */
+int vfn_profile_enable(int32_t on);
+int vfn_profile_collect(double* h_out, int32_t n_kinds);
+int vfn_profile_add_work(int32_t kind, double work);
+int64_t vfn_launch_count(void);
+
 /* ---- self-test hooks for the tcgen05/TMA building blocks (used by tests/, not by the product path) ---- */
 /* d_ptr != NULL: the next tcgen05 read launches dump the first S^T tile of CTA 0 (128 x tile floats) there. */
 int vfn_debug_set_dump(float* d_ptr);

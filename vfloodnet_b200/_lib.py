@@ -44,6 +44,10 @@ SIGNATURES = {
     'vfn_bank_clamp_info': (c_i32, [BANK_P, c_i64, c_vp]),
     'vfn_urr_pre': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vfn_urr_post': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    'vfn_profile_enable': (c_i32, [c_i32]),
+    'vfn_profile_collect': (c_i32, [c_vp, c_i32]),
+    'vfn_profile_add_work': (c_i32, [c_i32, c_f64]),
+    'vfn_launch_count': (c_i64, []),
     'vfn_debug_set_dump': (c_i32, [c_vp]),
 }
 

@@ -3,8 +3,7 @@
 // Reference behaviour restated: video_module/model/FeatureBank.py:27-143 (see include/vfn.h per entry point).
 #include "vfn_common.cuh"
 
-#include <mutex>
-#include <string>
+#include <vector>
 
 namespace vfn {
 
@@ -15,6 +14,35 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+// ------------------------------------------------------------------------------------------------
+// measurement hooks
+// ------------------------------------------------------------------------------------------------
+struct ProfRec { cudaEvent_t a, b; int kind; double work; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_ev_pool;
+static cudaEvent_t g_open[PROF_KINDS];
+static long long g_launches = 0;
+
+static cudaEvent_t get_event() {
+  if (!g_ev_pool.empty()) { cudaEvent_t e = g_ev_pool.back(); g_ev_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+void prof_begin(int kind, cudaStream_t st) {
+  if (!g_prof_on) return;
+  g_open[kind] = get_event();
+  cudaEventRecord(g_open[kind], st);
+}
+void prof_end(int kind, cudaStream_t st, double work) {
+  if (!g_prof_on) return;
+  cudaEvent_t e = get_event();
+  cudaEventRecord(e, st);
+  g_prof.push_back({g_open[kind], e, kind, work});
+}
+void count_launches(int n) { g_launches += n; }
 
 // ------------------------------------------------------------------------------------------------
 // prep_rows: (d, n) dimension-major  ->  (n, d) entry-major raw / L2-normalised / bf16 hi+lo
@@ -519,6 +547,35 @@ extern "C" {
 int vfn_version(void) { return VFN_VERSION; }
 const char* vfn_last_error(void) { return g_err; }
 
+int vfn_profile_enable(int32_t on) {
+  for (auto& r : g_prof) { g_ev_pool.push_back(r.a); g_ev_pool.push_back(r.b); }
+  g_prof.clear();
+  g_prof_on = on != 0;
+  return VFN_OK;
+}
+
+int vfn_profile_collect(double* h_out, int32_t n_kinds) {
+  VFN_CHECK_ARG(h_out && n_kinds >= 1 && n_kinds <= PROF_KINDS, "profile_collect: bad args");
+  for (int k = 0; k < n_kinds * 3; ++k) h_out[k] = 0.0;
+  for (auto& r : g_prof) {
+    VFN_CUDA_OK(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    VFN_CUDA_OK(cudaEventElapsedTime(&ms, r.a, r.b));
+    if (r.kind < n_kinds) { h_out[3 * r.kind] += 1.0; h_out[3 * r.kind + 1] += ms; h_out[3 * r.kind + 2] += r.work; }
+  }
+  return VFN_OK;
+}
+
+int64_t vfn_launch_count(void) { return g_launches; }
+
+int vfn_profile_add_work(int32_t kind, double work) {
+  VFN_CHECK_ARG(kind >= 0 && kind < PROF_KINDS, "profile_add_work: bad kind");
+  if (!g_prof_on) return VFN_OK;
+  for (auto it = g_prof.rbegin(); it != g_prof.rend(); ++it)
+    if (it->kind == kind) { it->work += work; break; }
+  return VFN_OK;
+}
+
 int vfn_device_is_sm100(void) {
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -534,6 +591,7 @@ int vfn_prep_rows(const float* d_src_dm, int32_t d, int64_t n, float* d_raw_em, 
   prep_rows_kernel<<<(unsigned)cdiv(n, 32), block, 0, as_stream(stream)>>>(d_src_dm, d, n, d_raw_em, d_normed_em,
                                                                            d_hi_em, d_lo_em, scale);
   VFN_LAUNCH_OK();
+  count_launches(1);
   return VFN_OK;
 }
 
@@ -549,9 +607,13 @@ int vfn_bank_append_rows(const vfn_bank* bank, const float* d_ck_em, const float
   }
   if (n_sel_upper == 0) return VFN_OK;
   const unsigned grid = (unsigned)(n_sel_upper < 148 * 16 ? n_sel_upper : 148 * 16);
+  prof_begin(PROF_APPEND, as_stream(stream));
   append_rows_kernel<<<grid, 128, 0, as_stream(stream)>>>(*bank, d_ck_em, d_cv_em, d_nck_em, d_sel, d_n_sel,
                                                           n_sel_upper, info0, info1);
+  // algorithmic bytes: read + write of the appended rows (keys, values, info)
+  prof_end(PROF_APPEND, as_stream(stream), 2.0 * 4.0 * (bank->d_key + bank->d_val + 2) * (double)n_sel_upper);
   VFN_LAUNCH_OK();
+  count_launches(1);
   return VFN_OK;
 }
 
@@ -562,6 +624,7 @@ int vfn_bank_refresh(const vfn_bank* bank, int64_t first, int64_t count, void* s
   const unsigned grid = (unsigned)(count < 148 * 16 ? count : 148 * 16);
   refresh_rows_kernel<<<grid, 128, 0, as_stream(stream)>>>(*bank, first, count);
   VFN_LAUNCH_OK();
+  count_launches(1);
   return VFN_OK;
 }
 
@@ -585,6 +648,7 @@ int vfn_bank_plan(const int32_t* d_match_idx, const float* d_match_corr, int64_t
                                                          d_merge_slot, d_run_off, d_append_q, d_counts, h_counts,
                                                          reinterpret_cast<unsigned long long*>(d_ws));
   VFN_LAUNCH_OK();
+  count_launches(1);
   return VFN_OK;
 }
 
@@ -600,9 +664,12 @@ int vfn_bank_merge(const vfn_bank* bank, const float* d_nck_em, const float* d_n
   // (1 - update_rate) is evaluated in double by Python and rounded to fp32 when it meets the tensor
   const float omr = (float)(1.0 - (double)update_rate);
   const unsigned grid = (unsigned)(hw < 148 * 8 ? hw : 148 * 8);
+  prof_begin(PROF_MERGE, as_stream(stream));
   merge_runs_kernel<<<grid, MERGE_THREADS, 0, as_stream(stream)>>>(*bank, d_nck_em, d_ncv_em, d_merge_q, d_merge_slot,
                                                                    d_run_off, d_counts, omr, update_rate);
+  prof_end(PROF_MERGE, as_stream(stream), 0.0);
   VFN_LAUNCH_OK();
+  count_launches(1);
   return VFN_OK;
 }
 
@@ -613,6 +680,7 @@ int vfn_bank_evict_plan(const vfn_bank* bank, float frame_idx, double class_budg
   evict_plan_kernel<<<1, EV_THREADS, 0, as_stream(stream)>>>(bank->info, bank->n, frame_idx, class_budget, request_n,
                                                              d_plan, h_plan, d_lfu_scratch);
   VFN_LAUNCH_OK();
+  count_launches(1);
   return VFN_OK;
 }
 
@@ -635,8 +703,12 @@ int vfn_bank_compact(const vfn_bank* src, const vfn_bank* dst, const float* d_lf
   cudaStream_t st = as_stream(stream);
   compact_count_kernel<<<nb, CP_THREADS, 0, st>>>(d_lfu, src->n, d_plan, block_cnt);
   compact_scan_kernel<<<1, 1024, 0, st>>>(block_cnt, nb);
+  prof_begin(PROF_COMPACT, st);
   compact_move_kernel<<<nb, CP_THREADS, 0, st>>>(*src, *dst, d_lfu, d_plan, block_cnt);
+  // work is filled in by the host (kept count is only known after the plan is read back): see vfn_profile_add_work
+  prof_end(PROF_COMPACT, st, 0.0);
   VFN_LAUNCH_OK();
+  count_launches(3);
   return VFN_OK;
 }
 
@@ -646,6 +718,7 @@ int vfn_bank_clamp_info(const vfn_bank* bank, int64_t n, void* stream) {
   if (n == 0) return VFN_OK;
   clamp_info_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(bank->info, n);
   VFN_LAUNCH_OK();
+  count_launches(1);
   return VFN_OK;
 }
 

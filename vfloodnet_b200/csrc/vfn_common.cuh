@@ -12,6 +12,13 @@ namespace vfn {
 
 void set_error(const char* fmt, ...);
 
+// measurement hooks (vfn_profile_* in include/vfn.h): CUDA events on the launching stream around selected kernels
+enum ProfKind { PROF_READ_A = 0, PROF_READ_B = 1, PROF_MATCH = 2, PROF_COMPACT = 3, PROF_MERGE = 4, PROF_APPEND = 5,
+                PROF_URR = 6, PROF_KINDS = 8 };
+void prof_begin(int kind, cudaStream_t st);
+void prof_end(int kind, cudaStream_t st, double work);
+void count_launches(int n);
+
 #define VFN_CHECK_ARG(cond, ...)              \
   do {                                        \
     if (!(cond)) {                            \

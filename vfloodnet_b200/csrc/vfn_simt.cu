@@ -442,8 +442,13 @@ static int run_phase_a(const BankSet& set, const ReadPlan& p, const float* q_in_
   if (p.tc) return tc_phase_a(set.b, p.obj_n, q_in_dm, p.hw, p.split_a, part, ws + p.off_tc, st);
   if (int rc = vfn_prep_rows(q_in_dm, p.d_key, p.hw, Q, nullptr, nullptr, nullptr, 1.f, st)) return rc;
   dim3 grid(p.q_tiles, p.split_a, p.obj_n);
+  double work = 0;
+  for (int o = 0; o < p.obj_n; ++o) work += 2.0 * p.d_key * (double)set.b[o].n * (double)p.hw;
+  prof_begin(PROF_READ_A, st);
   simt_score_kernel<MODE_LSE><<<grid, ST_THREADS, 0, st>>>(set, Q, p.hw, p.split_a, part);
+  prof_end(PROF_READ_A, st, work);
   VFN_LAUNCH_OK();
+  count_launches(1);
   return VFN_OK;
 }
 
@@ -459,9 +464,14 @@ static int run_phase_b(const BankSet& set, const ReadPlan& p, const float* lse, 
     attr_set = true;
   }
   dim3 grid(p.q_tiles, p.split_b, p.obj_n * p.n_chunk);
+  double work = 0;
+  for (int o = 0; o < p.obj_n; ++o) work += 2.0 * p.d_val * (double)set.b[o].n * (double)p.hw;
+  prof_begin(PROF_READ_B, st);
   simt_readout_kernel<<<grid, ST_THREADS, sizeof(ReadoutSmem), st>>>(set, Q, p.hw, p.split_b, p.n_chunk, lse,
                                                                      thres_valid, update_bank, po);
+  prof_end(PROF_READ_B, st, work);
   VFN_LAUNCH_OK();
+  count_launches(1);
   return VFN_OK;
 }
 
@@ -564,6 +574,7 @@ int vfn_memread(const vfn_bank* banks, int32_t obj_n, const float* d_q_in_dm, co
     finalize_counts_kernel<<<g, 256, 0, st>>>(set, obj_n);
   }
   VFN_LAUNCH_OK();
+  count_launches(2 + (update_bank ? 1 : 0));
   return VFN_OK;
 }
 
@@ -584,8 +595,11 @@ int vfn_bank_match(const vfn_bank* bank, const float* d_nck_em, int64_t hw, int3
   if (ws_bytes < (size_t)split * hw * sizeof(float2)) { set_error("match: workspace too small"); return VFN_E_CAPACITY; }
   cudaStream_t st = as_stream(stream);
   dim3 grid(q_tiles, split, 1);
+  prof_begin(PROF_MATCH, st);
   simt_score_kernel<MODE_MATCH><<<grid, ST_THREADS, 0, st>>>(set, d_nck_em, hw, split,
                                                              reinterpret_cast<float2*>(d_ws));
+  prof_end(PROF_MATCH, st, 2.0 * set.b[0].d_key * (double)n_max * (double)hw);
+  count_launches(2);
   match_reduce_kernel<<<(unsigned)cdiv(hw, 256), 256, 0, st>>>(reinterpret_cast<float2*>(d_ws), split, hw, d_match_idx,
                                                                d_match_corr);
   VFN_LAUNCH_OK();

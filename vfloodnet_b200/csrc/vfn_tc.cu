@@ -765,8 +765,13 @@ int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t h
     return rc;
   const size_t np = (size_t)obj_n * split_a * hw;
   fill_ml_kernel<<<(unsigned)cdiv(np, 256), 256, 0, st>>>(part, np);
+  double work = 0;
+  for (int o = 0; o < obj_n; ++o) work += 2.0 * DK * (double)banks[o].n * (double)hw;
+  prof_begin(PROF_READ_A, st);
   tc_phase_a_kernel<<<num_sms(), TC_THREADS, A_SMEM, st>>>(maps, a, part);
+  prof_end(PROF_READ_A, st, work);
   VFN_LAUNCH_OK();
+  count_launches(3);
   return VFN_OK;
 }
 
@@ -776,8 +781,13 @@ int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const 
   TcArgs a;
   if (int rc = fill_args(banks, obj_n, hw, split_b, B_TILE, ws_tc, &maps, &a, true)) return rc;
   VFN_CUDA_OK(cudaMemsetAsync(po, 0, (size_t)obj_n * split_b * DV * hw * sizeof(float), st));
+  double work = 0;
+  for (int o = 0; o < obj_n; ++o) work += 2.0 * DV * (double)banks[o].n * (double)hw;
+  prof_begin(PROF_READ_B, st);
   tc_phase_b_kernel<<<num_sms(), TC_THREADS, B_SMEM, st>>>(maps, a, lse, thres_valid, update_bank, po);
+  prof_end(PROF_READ_B, st, work);
   VFN_LAUNCH_OK();
+  count_launches(1);
   return VFN_OK;
 }
 

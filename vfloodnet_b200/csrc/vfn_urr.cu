@@ -190,8 +190,12 @@ int vfn_urr_pre(const float* d_p, const float* d_r1, int64_t r1_obj_stride, int3
   dim3 g2((unsigned)cdiv(w, 128), h, obj_n);
   urr_window_kernel<<<g2, 128, 0, st>>>(d_seg, obj_n, h, w, d_conf, d_avg);
   dim3 g3((unsigned)cdiv(w, UT), (unsigned)cdiv(h, UT), obj_n * (c / CH_PER_CTA));
+  prof_begin(PROF_URR, st);
   urr_local_kernel<<<g3, 256, 0, st>>>(d_r1, r1_obj_stride, c, h, w, d_seg, d_avg, d_local_match);
+  // algorithmic bytes: read r1 once, write [r1 ; r1_local] per object, + small planes
+  prof_end(PROF_URR, st, 4.0 * (double)h * w * ((r1_obj_stride ? obj_n : 1) * (double)c + obj_n * (2.0 * c + 8.0)));
   VFN_LAUNCH_OK();
+  count_launches(3);
   return VFN_OK;
 }
 
@@ -202,6 +206,7 @@ int vfn_urr_post(const float* d_p_up, const float* d_unc, const float* d_conf, c
   dim3 g((unsigned)cdiv(2 * w, 128), 2 * h, obj_n);
   urr_post_kernel<<<g, 128, 0, as_stream(stream)>>>(d_p_up, d_unc, d_conf, d_q_local, obj_n, h, w, d_prob);
   VFN_LAUNCH_OK();
+  count_launches(1);
   return VFN_OK;
 }
 

@@ -303,6 +303,8 @@ class FeatureBank:
         cws = self._buf(f'cws{c}', (lib.vfn_bank_compact_workspace_bytes(n),), torch.uint8)
         check(lib.vfn_bank_compact(C.byref(src), C.byref(dst), ptr(lfu), ptr(plan), ptr(cws), cws.numel(), st),
               'bank_compact')
+        # algorithmic bytes of the compaction: evicted rows read once, kept rows read + written
+        lib.vfn_profile_add_work(3, 4.0 * (s.d_key + s.d_val + 2) * ((n - kept) + 2.0 * kept))
         self.launches += 3
         self._slabs[c], self._alt[c] = alt, s
         self._n[c] = kept
