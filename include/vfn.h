@@ -42,7 +42,8 @@ typedef struct vfn_bank {
   float* keys;     /* (cap, d_key)  raw keys      == reference fb.keys[i].T   */
   float* values;   /* (cap, d_val)  raw values    == reference fb.values[i].T */
   float* info;     /* (cap, 2)      [frame added, sum log(cnt+1)]  (FeatureBank.py:34-35) */
-  float* nkeys;    /* (cap, d_key)  keys / max(|key|,1e-12): cached NF.normalize(keys, dim=0) (FeatureBank.py:63) */
+  float* nkh;      /* (cap, d_key)  cached NF.normalize(keys, dim=0) (FeatureBank.py:63), split for the 3xTF32 match:   */
+  float* nkl;      /* (cap, d_key)  nkh = value with the low 13 mantissa bits cleared (exact in tf32), nkl = value - nkh  */
   uint16_t* kh;    /* (cap, d_key)  bf16 hi part of keys   - tensor-core operand, NULL if unused */
   uint16_t* kl;    /* (cap, d_key)  bf16 lo part (key - hi) */
   uint16_t* vh;    /* (cap, d_val)  bf16 hi part of values */
@@ -71,7 +72,7 @@ int vfn_bank_append_rows(const vfn_bank* bank, const float* d_ck_em, const float
                          const int32_t* d_sel, int64_t n_sel_upper, const int32_t* d_n_sel, float info0, float info1,
                          void* stream);
 
-/* Recompute derived arrays (nkeys, kh/kl, vh/vl) of slots [first, first+count) from keys/values. */
+/* Recompute derived arrays (nkh/nkl, kh/kl, vh/vl) of slots [first, first+count) from keys/values. */
 int vfn_bank_refresh(const vfn_bank* bank, int64_t first, int64_t count, void* stream);
 
 /* ---- memory read: Matcher.forward (AFB_URR.py:136-178) ------------------------------------------
@@ -98,7 +99,7 @@ int vfn_memread_phase_b(const vfn_bank* banks, int32_t obj_n, const float* d_q_i
 int vfn_lse_combine(const float* d_ml, int32_t n_parts, int64_t n_rows, float* d_lse, void* stream);
 
 /* ---- bank update: FeatureBank.update (FeatureBank.py:53-115) -----------------------------------
- * match: j*_q = argmax_i <nkeys_i, nck_q>, ties -> lowest i; c*_q = that maximum.  (FeatureBank.py:63-68) */
+ * match: j*_q = argmax_i <nkh_i + nkl_i, nck_q>, ties -> lowest i; c*_q = that maximum.  (FeatureBank.py:63-68) */
 size_t vfn_bank_match_workspace_bytes(int64_t n, int64_t hw);
 int vfn_bank_match(const vfn_bank* bank, const float* d_nck_em, int64_t hw, int32_t* d_match_idx, float* d_match_corr,
                    void* d_ws, size_t ws_bytes, int32_t impl, void* stream);

@@ -37,9 +37,9 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     from vfloodnet_b200._lib import VfnBank
-    # 2 x int32, 2 x int64, 9 pointers
-    assert ctypes.sizeof(VfnBank) == 8 + 16 + 9 * 8
-    assert VfnBank.keys.offset == 24 and VfnBank.cnt.offset == 24 + 8 * 8
+    # 2 x int32, 2 x int64, 10 pointers
+    assert ctypes.sizeof(VfnBank) == 8 + 16 + 10 * 8
+    assert VfnBank.keys.offset == 24 and VfnBank.cnt.offset == 24 + 9 * 8
 
 
 def test_argument_errors_are_reported_not_fatal():

@@ -104,11 +104,12 @@ def test_read_vs_oracle(vfn, n, hw, seed):
 # ---------------------------------------------------------------------------------------------------
 # update (teacher forced per frame against the reference-generated vectors)
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('name', ['small_evict', 'small_evict2', 'small_allmerge', 'small_allappend', 'real_dims'])
-def test_update_golden_teacher_forced(vfn, golden_dir, name):
+@pytest.mark.parametrize('name,impl', [('small_evict', 1), ('small_evict2', 1), ('small_allmerge', 1),
+                                       ('small_allappend', 1)] + [('real_dims', i) for i in IMPLS])
+def test_update_golden_teacher_forced(vfn, golden_dir, name, impl):
     g = load(golden_dir, f'update_{name}.npz')
     obj_n = int(g['obj_n'])
-    fb = vfn.FeatureBank(obj_n, int(g['budget']), 'cuda', update_rate=0.1, thres_close=float(g['thres_close']), impl=1)
+    fb = vfn.FeatureBank(obj_n, int(g['budget']), 'cuda', update_rate=0.1, thres_close=float(g['thres_close']), impl=impl)
     assert fb.class_budget == float(g['class_budget'])
     prev = dict(key=[g[f'key_init{c}'] for c in range(obj_n)], val=[g[f'val_init{c}'] for c in range(obj_n)])
     replace_prev = np.zeros(obj_n)
@@ -151,7 +152,7 @@ def test_loop_golden_free_running(vfn, golden_dir, name):
 # ---------------------------------------------------------------------------------------------------
 # update vs oracle at 480p size, decisions bit-exact
 # ---------------------------------------------------------------------------------------------------
-def _run_update_pair(vfn, n, hw, seed, budget, frame_idx=12, frac_merge=0.5, thres=0.95):
+def _run_update_pair(vfn, n, hw, seed, budget, frame_idx=12, frac_merge=0.5, thres=0.95, impl=1):
     from vfloodnet_b200 import synth
     g = torch.Generator().manual_seed(seed)
     keys, vals = zip(*[synth.gen_bank(g, n) for _ in range(2)])
@@ -162,7 +163,7 @@ def _run_update_pair(vfn, n, hw, seed, budget, frame_idx=12, frac_merge=0.5, thr
     for c in range(2):
         ofb.info[c] = info[c].clone()
     ofb.update([k.clone() for k in pk], [v.clone() for v in pv], frame_idx)
-    fb = vfn.FeatureBank(2, budget, 'cuda', thres_close=thres, impl=1)
+    fb = vfn.FeatureBank(2, budget, 'cuda', thres_close=thres, impl=impl)
     fb.load_state(list(keys), list(vals), info)
     fb.update([k.cuda() for k in pk], [v.cuda() for v in pv], frame_idx)
     return ofb, fb
@@ -170,8 +171,10 @@ def _run_update_pair(vfn, n, hw, seed, budget, frame_idx=12, frac_merge=0.5, thr
 
 @pytest.mark.parametrize('n,hw,seed,budget', [(5000, 1620, 0, 10 ** 6), (20000, 1620, 1, 50000), (1620, 1620, 2, 4000),
                                               (3000, 257, 3, 10 ** 6)])
-def test_update_vs_oracle_decisions(vfn, n, hw, seed, budget):
-    ofb, fb = _run_update_pair(vfn, n, hw, seed, budget)
+@pytest.mark.parametrize('impl', IMPLS)
+def test_update_vs_oracle_decisions(vfn, n, hw, seed, budget, impl):
+    """impl 1: fp32 SIMT match; impl 2: 3xTF32 tcgen05 match.  Everything downstream (plan/merge/evict/append) is shared."""
+    ofb, fb = _run_update_pair(vfn, n, hw, seed, budget, impl=impl)
     for c in range(2):
         d, dg = ofb.last_decisions[c], fb.last_decisions[c]
         # decisions must be identical wherever the top-1/top-2 cosine margin exceeds fp32 summation noise (4e-6);
@@ -198,7 +201,8 @@ def test_update_vs_oracle_decisions(vfn, n, hw, seed, budget):
     np.testing.assert_array_equal(fb.peak_n[0:0], ofb.peak_n[0:0])
 
 
-def test_match_ties_lowest_index(vfn):
+@pytest.mark.parametrize('impl', IMPLS)
+def test_match_ties_lowest_index(vfn, impl):
     """exact duplicate bank columns: argmax must return the lowest slot (ATen semantics)."""
     from vfloodnet_b200 import synth
     g = torch.Generator().manual_seed(5)
@@ -207,7 +211,7 @@ def test_match_ties_lowest_index(vfn):
     k[:, 550] = k[:, 3]
     pk = torch.cat([k[:, 150:160], k[:, 450:460], k[:, 550:551], torch.randn(128, 9, generator=g)], dim=1).contiguous()
     pv = torch.randn(512, pk.shape[1], generator=g)
-    fb = vfn.FeatureBank(1, 10 ** 6, 'cuda', impl=1)
+    fb = vfn.FeatureBank(1, 10 ** 6, 'cuda', impl=impl)
     fb.init_bank([k], [v])
     fb.update([pk.cuda()], [pv.cuda()], 1)
     idx = fb.last_decisions[0]['match_idx'].cpu().long()

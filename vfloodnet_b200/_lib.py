@@ -14,7 +14,7 @@ c_i32, c_i64, c_f32, c_f64, c_vp, c_sz = C.c_int32, C.c_int64, C.c_float, C.c_do
 class VfnBank(C.Structure):
     """struct vfn_bank (include/vfn.h)"""
     _fields_ = [('d_key', c_i32), ('d_val', c_i32), ('cap', c_i64), ('n', c_i64),
-                ('keys', c_vp), ('values', c_vp), ('info', c_vp), ('nkeys', c_vp),
+                ('keys', c_vp), ('values', c_vp), ('info', c_vp), ('nkh', c_vp), ('nkl', c_vp),
                 ('kh', c_vp), ('kl', c_vp), ('vh', c_vp), ('vl', c_vp), ('cnt', c_vp)]
 
 

@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(128) append_rows_kernel(vfn_bank bank, const f
       float4 v = ks[f];
       reinterpret_cast<float4*>(bank.keys + dst * bank.d_key)[f] = v;
       if (bank.kh) store_split4(bank.kh, bank.kl, dst * bank.d_key + 4 * f, v);
-      if (nck) reinterpret_cast<float4*>(bank.nkeys + dst * bank.d_key)[f] =
-                   reinterpret_cast<const float4*>(nck + s * bank.d_key)[f];
+      if (nck) store_nk4(bank.nkh, bank.nkl, dst * bank.d_key + 4 * f,
+                         reinterpret_cast<const float4*>(nck + s * bank.d_key)[f]);
       ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
     }
     if (!nck) {   // derive the normalised key here (init_bank / append API path)
@@ -141,8 +141,7 @@ __global__ void __launch_bounds__(128) append_rows_kernel(vfn_bank bank, const f
       float den = fmaxf(sqrtf(tot), 1e-12f);
       for (int f = threadIdx.x; f < dk4; f += blockDim.x) {
         float4 v = ks[f];
-        reinterpret_cast<float4*>(bank.nkeys + dst * bank.d_key)[f] =
-            make_float4(v.x / den, v.y / den, v.z / den, v.w / den);
+        store_nk4(bank.nkh, bank.nkl, dst * bank.d_key + 4 * f, make_float4(v.x / den, v.y / den, v.z / den, v.w / den));
       }
     }
     for (int f = threadIdx.x; f < dv4; f += blockDim.x) {
@@ -172,7 +171,7 @@ __global__ void __launch_bounds__(128) refresh_rows_kernel(vfn_bank bank, int64_
     float den = fmaxf(sqrtf(block_sum(ss, red)), 1e-12f);
     for (int f = threadIdx.x; f < dk4; f += blockDim.x) {
       float4 v = ks[f];
-      reinterpret_cast<float4*>(bank.nkeys + u * bank.d_key)[f] = make_float4(v.x / den, v.y / den, v.z / den, v.w / den);
+      store_nk4(bank.nkh, bank.nkl, u * bank.d_key + 4 * f, make_float4(v.x / den, v.y / den, v.z / den, v.w / den));
       if (bank.kh) store_split4(bank.kh, bank.kl, u * bank.d_key + 4 * f, v);
     }
     if (bank.vh)
@@ -358,7 +357,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_runs_kernel(vfn_bank bank
     if (is_key) {
       reinterpret_cast<float4*>(bank.keys + u * bank.d_key)[f] = nw;
       const float d2 = fmaxf(sqrtf(ssk2), 1e-12f);
-      reinterpret_cast<float4*>(bank.nkeys + u * bank.d_key)[f] = make_float4(nw.x / d2, nw.y / d2, nw.z / d2, nw.w / d2);
+      store_nk4(bank.nkh, bank.nkl, u * bank.d_key + 4 * f, make_float4(nw.x / d2, nw.y / d2, nw.z / d2, nw.w / d2));
       if (bank.kh) store_split4(bank.kh, bank.kl, u * bank.d_key + 4 * f, nw);
     }
     if (is_val) {
@@ -503,7 +502,8 @@ __global__ void __launch_bounds__(CP_THREADS) compact_move_kernel(vfn_bank src, 
     const int64_t d = base_dst + e;
     warp_copy16(dst.keys + d * dk, src.keys + s * dk, dk / 4, lane);
     warp_copy16(dst.values + d * dv, src.values + s * dv, dv / 4, lane);
-    warp_copy16(dst.nkeys + d * dk, src.nkeys + s * dk, dk / 4, lane);
+    warp_copy16(dst.nkh + d * dk, src.nkh + s * dk, dk / 4, lane);
+    warp_copy16(dst.nkl + d * dk, src.nkl + s * dk, dk / 4, lane);
     if (src.kh) {
       warp_copy16(dst.kh + d * dk, src.kh + s * dk, dk / 8, lane);
       warp_copy16(dst.kl + d * dk, src.kl + s * dk, dk / 8, lane);
@@ -530,7 +530,7 @@ static int check_bank(const vfn_bank* b) {
   VFN_CHECK_ARG(b != nullptr, "bank is NULL");
   VFN_CHECK_ARG(b->d_key > 0 && b->d_val > 0 && b->d_key % 8 == 0 && b->d_val % 8 == 0,
                 "d_key/d_val must be positive multiples of 8 (got %d, %d)", b->d_key, b->d_val);
-  VFN_CHECK_ARG(b->keys && b->values && b->info && b->nkeys && b->cnt, "bank has NULL arrays");
+  VFN_CHECK_ARG(b->keys && b->values && b->info && b->nkh && b->nkl && b->cnt, "bank has NULL arrays");
   VFN_CHECK_ARG(b->n >= 0 && b->n <= b->cap, "bank n=%lld exceeds cap=%lld", (long long)b->n, (long long)b->cap);
   VFN_CHECK_ARG((b->kh == nullptr) == (b->kl == nullptr) && (b->kh == nullptr) == (b->vh == nullptr) &&
                     (b->kh == nullptr) == (b->vl == nullptr),

@@ -51,6 +51,19 @@ __device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& lo) 
   lo = __bfloat16_as_ushort(l);
 }
 
+// tf32 hi/lo split: hi keeps sign, exponent and the top 10 mantissa bits (exactly representable in tf32, whatever
+// the tensor core does with the discarded bits), lo = x - hi is exact in fp32
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = x - hi;
+}
+__device__ __forceinline__ void store_nk4(float* nkh, float* nkl, int64_t off, float4 v) {
+  float4 h, l;
+  split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+  *reinterpret_cast<float4*>(nkh + off) = h;
+  *reinterpret_cast<float4*>(nkl + off) = l;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -23,15 +23,24 @@ struct BankSet {
 enum ScoreMode { MODE_LSE = 0, MODE_MATCH = 1 };
 
 // Loads rows [r0, r0+128) x cols [k0, k0+16) of a row-major (n_rows, d) matrix into registers (2 float4 / thread).
-__device__ __forceinline__ void load_chunk(const float* __restrict__ A, int64_t n_rows, int d, int64_t r0, int k0,
-                                           float4 (&reg)[2]) {
+// A2 != nullptr: the matrix is stored as an exact two-term split (A + A2), e.g. the bank's nkh + nkl.
+__device__ __forceinline__ void load_chunk(const float* __restrict__ A, const float* __restrict__ A2, int64_t n_rows,
+                                           int d, int64_t r0, int k0, float4 (&reg)[2]) {
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int idx = threadIdx.x + ST_THREADS * r;
     const int row = idx >> 2, c4 = idx & 3;
     const int64_t gr = r0 + row;
     const int k = k0 + c4 * 4;
-    reg[r] = (gr < n_rows && k < d) ? *reinterpret_cast<const float4*>(A + gr * d + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gr < n_rows && k < d) {
+      v = *reinterpret_cast<const float4*>(A + gr * d + k);
+      if (A2) {
+        const float4 w = *reinterpret_cast<const float4*>(A2 + gr * d + k);
+        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;     // exact: lo was defined as value - hi
+      }
+    }
+    reg[r] = v;
   }
 }
 __device__ __forceinline__ void store_chunk_t(float (*S)[LDS_], const float4 (&reg)[2]) {
@@ -47,7 +56,8 @@ __device__ __forceinline__ void store_chunk_t(float (*S)[LDS_], const float4 (&r
 }
 
 // acc[a][b] = sum_k A[i_a][k] * B[j_b][k] for the thread's 8 rows (i) and 8 columns (j); sequential fp32 FMA over k.
-__device__ __forceinline__ void tile_scores(const float* __restrict__ A, int64_t n_a, const float* __restrict__ B,
+__device__ __forceinline__ void tile_scores(const float* __restrict__ A, const float* __restrict__ A2, int64_t n_a,
+                                            const float* __restrict__ B,
                                             int64_t n_b, int d, int64_t i0, int64_t j0, float (*As)[LDS_],
                                             float (*Bs)[LDS_], float (&acc)[8][8]) {
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -56,16 +66,16 @@ __device__ __forceinline__ void tile_scores(const float* __restrict__ A, int64_t
 #pragma unroll
     for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
   float4 ra[2], rb[2];
-  load_chunk(A, n_a, d, i0, 0, ra);
-  load_chunk(B, n_b, d, j0, 0, rb);
+  load_chunk(A, A2, n_a, d, i0, 0, ra);
+  load_chunk(B, nullptr, n_b, d, j0, 0, rb);
   for (int k0 = 0; k0 < d; k0 += TK) {
     __syncthreads();
     store_chunk_t(As, ra);
     store_chunk_t(Bs, rb);
     __syncthreads();
     if (k0 + TK < d) {
-      load_chunk(A, n_a, d, i0, k0 + TK, ra);
-      load_chunk(B, n_b, d, j0, k0 + TK, rb);
+      load_chunk(A, A2, n_a, d, i0, k0 + TK, ra);
+      load_chunk(B, nullptr, n_b, d, j0, k0 + TK, rb);
     }
 #pragma unroll
     for (int kk = 0; kk < TK; ++kk) {
@@ -100,7 +110,8 @@ __global__ void __launch_bounds__(ST_THREADS) simt_score_kernel(BankSet banks, c
   __shared__ float red1[16][TN];
   const vfn_bank bk = banks.b[blockIdx.z];
   const int d = bk.d_key;
-  const float* A = (MODE == MODE_MATCH) ? bk.nkeys : bk.keys;
+  const float* A = (MODE == MODE_MATCH) ? bk.nkh : bk.keys;
+  const float* A2 = (MODE == MODE_MATCH) ? bk.nkl : nullptr;
   const int64_t n = bk.n;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int64_t j0 = (int64_t)blockIdx.x * TN;
@@ -113,7 +124,7 @@ __global__ void __launch_bounds__(ST_THREADS) simt_score_kernel(BankSet banks, c
   float acc[8][8];
   for (int64_t t = t_begin; t < t_end; ++t) {
     const int64_t i0 = t * TM;
-    tile_scores(A, n, Q, hw, d, i0, j0, As, Bs, acc);
+    tile_scores(A, A2, n, Q, hw, d, i0, j0, As, Bs, acc);
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
       float m = -INFINITY;
@@ -286,7 +297,7 @@ __global__ void __launch_bounds__(ST_THREADS) simt_readout_kernel(BankSet banks,
     for (int b = 0; b < 8; ++b) o[a][b] = 0.f;
   for (int64_t t = t_begin; t < t_end; ++t) {
     const int64_t i0 = t * TM;
-    tile_scores(bk.keys, n, Q, hw, d, i0, j0, sm.As, sm.Bs, acc);
+    tile_scores(bk.keys, nullptr, n, Q, hw, d, i0, j0, sm.As, sm.Bs, acc);
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
       const int r = row_of(ty, a);
@@ -436,10 +447,10 @@ static int check_banks(const vfn_bank* banks, int obj_n, int64_t* n_max, BankSet
   return VFN_OK;
 }
 
-static int run_phase_a(const BankSet& set, const ReadPlan& p, const float* q_in_dm, char* ws, cudaStream_t st) {
+static int run_phase_a(const BankSet& set, ReadPlan& p, const float* q_in_dm, char* ws, cudaStream_t st) {
   float* Q = reinterpret_cast<float*>(ws + p.off_q);
   float2* part = reinterpret_cast<float2*>(ws + p.off_part);
-  if (p.tc) return tc_phase_a(set.b, p.obj_n, q_in_dm, p.hw, p.split_a, part, ws + p.off_tc, st);
+  if (p.tc) return tc_phase_a(set.b, p.obj_n, q_in_dm, p.hw, p.split_a, part, ws + p.off_tc, st, &p.split_a);
   if (int rc = vfn_prep_rows(q_in_dm, p.d_key, p.hw, Q, nullptr, nullptr, nullptr, 1.f, st)) return rc;
   dim3 grid(p.q_tiles, p.split_a, p.obj_n);
   double work = 0;
@@ -452,11 +463,12 @@ static int run_phase_a(const BankSet& set, const ReadPlan& p, const float* q_in_
   return VFN_OK;
 }
 
-static int run_phase_b(const BankSet& set, const ReadPlan& p, const float* lse, float thres_valid, int update_bank,
+static int run_phase_b(const BankSet& set, ReadPlan& p, const float* lse, float thres_valid, int update_bank,
                        char* ws, cudaStream_t st) {
   float* Q = reinterpret_cast<float*>(ws + p.off_q);
   float* po = reinterpret_cast<float*>(ws + p.off_po);
-  if (p.tc) return tc_phase_b(set.b, p.obj_n, p.hw, p.split_b, lse, thres_valid, update_bank, po, ws + p.off_tc, st);
+  if (p.tc) return tc_phase_b(set.b, p.obj_n, p.hw, p.split_b, lse, thres_valid, update_bank, po, ws + p.off_tc, st,
+                              &p.split_b);
   static bool attr_set = false;
   if (!attr_set) {
     VFN_CUDA_OK(cudaFuncSetAttribute(simt_readout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -589,17 +601,24 @@ int vfn_bank_match(const vfn_bank* bank, const float* d_nck_em, int64_t hw, int3
   int64_t n_max;
   if (int rc = check_banks(bank, 1, &n_max, &set)) return rc;
   VFN_CHECK_ARG(d_nck_em && d_match_idx && d_match_corr && d_ws && hw > 0, "match: bad args");
-  (void)impl;
-  const int q_tiles = (int)cdiv(hw, TN);
-  const int split = pick_split(cdiv(n_max, TM), q_tiles, 148 * 4);
-  if (ws_bytes < (size_t)split * hw * sizeof(float2)) { set_error("match: workspace too small"); return VFN_E_CAPACITY; }
   cudaStream_t st = as_stream(stream);
-  dim3 grid(q_tiles, split, 1);
-  prof_begin(PROF_MATCH, st);
-  simt_score_kernel<MODE_MATCH><<<grid, ST_THREADS, 0, st>>>(set, d_nck_em, hw, split,
-                                                             reinterpret_cast<float2*>(d_ws));
-  prof_end(PROF_MATCH, st, 2.0 * set.b[0].d_key * (double)n_max * (double)hw);
-  count_launches(2);
+  if (ws_bytes < vfn_bank_match_workspace_bytes(n_max, hw)) { set_error("match: workspace too small"); return VFN_E_CAPACITY; }
+  int split = 0;
+  const bool tc = (impl != 1) && set.b[0].d_key == 128 && vfn_device_is_sm100();
+  if (impl == 2 && !tc) { set_error("tcgen05 match needs d_key = 128 on an sm_100 device"); return VFN_E_UNSUPPORTED; }
+  if (tc) {
+    if (int rc = tc_match(&set.b[0], d_nck_em, hw, 64, reinterpret_cast<float2*>(d_ws), &split, st)) return rc;
+  } else {
+    const int q_tiles = (int)cdiv(hw, TN);
+    split = pick_split(cdiv(n_max, TM), q_tiles, 148 * 4);
+    dim3 grid(q_tiles, split, 1);
+    prof_begin(PROF_MATCH, st);
+    simt_score_kernel<MODE_MATCH><<<grid, ST_THREADS, 0, st>>>(set, d_nck_em, hw, split,
+                                                               reinterpret_cast<float2*>(d_ws));
+    prof_end(PROF_MATCH, st, 2.0 * set.b[0].d_key * (double)n_max * (double)hw);
+    count_launches(1);
+  }
+  count_launches(1);
   match_reduce_kernel<<<(unsigned)cdiv(hw, 256), 256, 0, st>>>(reinterpret_cast<float2*>(d_ws), split, hw, d_match_idx,
                                                                d_match_corr);
   VFN_LAUNCH_OK();

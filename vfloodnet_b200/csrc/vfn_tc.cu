@@ -88,6 +88,17 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
       : "memory");
 }
+__device__ __forceinline__ void mma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 // D[tmem] (+)= A[smem] * B[smem]
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -147,6 +158,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// instruction descriptor kind::tf32: tf32 x tf32 -> f32, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 constexpr int DK = 128, DV = 512;
 constexpr int QT = 128;                 // queries per tile (TMEM lanes)
 constexpr int TC_THREADS = 384;         // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 softmax WG0, 8-11 softmax WG1
@@ -171,12 +187,6 @@ struct TcArgs {
   float* dbg;
 };
 
-// static stream-K partition: unit space = concat over combos of that combo's slot tiles
-struct Segment {
-  int combo, t0, t1, piece;
-};
-__device__ __forceinline__ long long part_lo(long long b, long long T, long long G) { return b * T / G; }
-__device__ __forceinline__ int owner_of(long long u, long long T, long long G) { return (int)(((u + 1) * G - 1) / T); }
 
 // ------------------------------------------------------------------------------------------------
 // phase A
@@ -211,28 +221,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_a_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem = *tmem_base_p;
 
-  // partition
-  const long long G = gridDim.x;
-  long long T = 0;
-  for (int o = 0; o < args.obj_n; ++o) T += (long long)args.tiles[o] * args.q_tiles;
-  const long long lo = part_lo(blockIdx.x, T, G), hi = part_lo(blockIdx.x + 1, T, G);
-
+  // work items = (split, object, query tile), dealt round-robin to the persistent CTAs: in any round all CTAs
+  // stream the same few slot ranges, so the K tiles are served from L2 (ncu: 14x DRAM re-reads with a per-CTA
+  // contiguous partition, profiles/r1_*).
+  const int n_combos = args.obj_n * args.q_tiles;
+  const int n_items = n_combos * args.pieces;
   uint32_t k_it = 0;            // tiles streamed so far (producer & MMA agree)
   uint32_t buf_it[2] = {0, 0};  // uses of each S buffer so far
-  long long u = lo;
-  while (u < hi) {
-    // locate the combo of unit u
-    int obj = 0;
-    long long start = 0;
-    while (u >= start + (long long)args.tiles[obj] * args.q_tiles) { start += (long long)args.tiles[obj] * args.q_tiles; ++obj; }
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int piece = item / n_combos;
+    const int combo = item - piece * n_combos;
+    const int obj = combo / args.q_tiles;
+    const int qt = combo - obj * args.q_tiles;
     const int tiles_o = args.tiles[obj];
-    const int qt = (int)((u - start) / tiles_o);
-    const long long cstart = start + (long long)qt * tiles_o;
-    const int t0 = (int)(u - cstart);
-    const int t1 = (int)((hi - cstart) < tiles_o ? (hi - cstart) : tiles_o);
-    const int piece = blockIdx.x - owner_of(cstart, T, G);
+    const int t0 = (int)((long long)tiles_o * piece / args.pieces);
+    const int t1 = (int)((long long)tiles_o * (piece + 1) / args.pieces);
     const int n_obj = args.n[obj];
     const int ntile = t1 - t0;
+    const bool first_item = (item == (int)blockIdx.x);
 
     // (1) Q tile -> TMEM (WG0: hi, WG1: lo); one row (query) per thread
     if (warp >= 4) {
@@ -315,7 +321,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_a_kernel(const __grid_
           uint32_t v[32];
           tmem_ld32(tlane + (uint32_t)wg * A_TILE + ch * 32, v);
           tmem_wait_ld();
-          if (args.dbg && blockIdx.x == 0 && u == lo && t == 0) {
+          if (args.dbg && blockIdx.x == 0 && first_item && t == 0) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) args.dbg[row * A_TILE + ch * 32 + i] = __uint_as_float(v[i]);
           }
@@ -361,7 +367,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_a_kernel(const __grid_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    u = cstart + t1;
   }
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
@@ -411,28 +416,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem = *tmem_base_p;
 
-  const long long G = gridDim.x;
-  long long T = 0;
-  for (int o = 0; o < args.obj_n; ++o) T += (long long)args.tiles[o] * args.q_tiles * 2;
-  const long long lo = part_lo(blockIdx.x, T, G), hi = part_lo(blockIdx.x + 1, T, G);
-
+  // work items = (split, object, query tile, channel half), round-robin over the persistent CTAs (see phase A)
+  const int cpo = args.q_tiles * 2;
+  const int n_combos = args.obj_n * cpo;
+  const int n_items = n_combos * args.pieces;
   uint32_t k_it = 0;            // tiles streamed so far
   uint32_t buf_it[2] = {0, 0};  // uses of each S/P buffer
-  uint32_t seg_it = 0;          // segments finished (o_full phase)
-  long long u = lo;
-  while (u < hi) {
-    int obj = 0;
-    long long start = 0;
-    while (u >= start + (long long)args.tiles[obj] * args.q_tiles * 2) { start += (long long)args.tiles[obj] * args.q_tiles * 2; ++obj; }
-    const int tiles_o = args.tiles[obj];
-    const int cidx = (int)((u - start) / tiles_o);     // combo within object: qt * 2 + half
+  uint32_t seg_it = 0;          // items finished (o_full phase)
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int piece = item / n_combos;
+    const int combo = item - piece * n_combos;
+    const int obj = combo / cpo;
+    const int cidx = combo - obj * cpo;                // qt * 2 + half
     const int qt = cidx >> 1, half = cidx & 1;
-    const long long cstart = start + (long long)cidx * tiles_o;
-    const int t0 = (int)(u - cstart);
-    const int t1 = (int)((hi - cstart) < tiles_o ? (hi - cstart) : tiles_o);
-    const int piece = blockIdx.x - owner_of(cstart, T, G);
+    const int tiles_o = args.tiles[obj];
+    const int t0 = (int)((long long)tiles_o * piece / args.pieces);
+    const int t1 = (int)((long long)tiles_o * (piece + 1) / args.pieces);
     const int n_obj = args.n[obj];
     const int ntile = t1 - t0;
+    const bool first_item = (item == (int)blockIdx.x);
 
     if (warp >= 4) {
       const int wg = (warp - 4) >> 2;
@@ -553,7 +555,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
         tmem_ld32(sb, s0);
         tmem_ld32(sb + 32, s1);
         tmem_wait_ld();
-        if (args.dbg && blockIdx.x == 0 && u == lo && t == 0) {
+        if (args.dbg && blockIdx.x == 0 && first_item && t == 0) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             args.dbg[row * B_TILE + i] = __uint_as_float(s0[i]);
@@ -647,15 +649,185 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    u = cstart + t1;
   }
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
-__global__ void fill_ml_kernel(float2* __restrict__ p, size_t n) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = make_float2(-INFINITY, 0.f);
+
+// ------------------------------------------------------------------------------------------------
+// cosine match on the tensor cores (FeatureBank.py:63-68): corr = <nk_i, nck_j> as 3xTF32
+// (hi*hi + lo*hi + hi*lo, fp32 accumulate: ~2^-21 relative, i.e. fp32-GEMM-grade), per-query arg-max with
+// ties -> lowest slot.  Same pipeline as phase A; lanes = candidates (queries), columns = bank slots.
+// ------------------------------------------------------------------------------------------------
+constexpr int M_TILE = 64;
+constexpr int M_STAGES = 3;
+constexpr int M_STAGE_BYTES = M_TILE * DK * 4 * 2;      // fp32 hi + lo = 64 KB
+constexpr int M_SMEM = M_STAGES * M_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t TMM_QH = 0, TMM_QL = 128, TMM_S = 256;
+
+struct MatchArgs {
+  int hw, q_tiles, pieces, n, tiles;
+  const float* nck;        // (hw, 128) normalised candidates, entry-major
+  float* dbg;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_match_kernel(const __grid_constant__ CUtensorMap map_h,
+                                                                 const __grid_constant__ CUtensorMap map_l,
+                                                                 MatchArgs args, float2* __restrict__ part) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* kst = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + M_STAGES * M_STAGE_BYTES);
+  uint64_t* k_full = bars;
+  uint64_t* k_empty = bars + M_STAGES;
+  uint64_t* s_full = bars + 2 * M_STAGES;
+  uint64_t* s_empty = s_full + 2;
+  uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(s_empty + 2);
+  __shared__ float2 best_x[QT];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < M_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_base_p, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_base_p;
+
+  const int n_items = args.q_tiles * args.pieces;
+  uint32_t k_it = 0;
+  uint32_t buf_it[2] = {0, 0};
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int piece = item / args.q_tiles;
+    const int qt = item - piece * args.q_tiles;
+    const int t0 = (int)((long long)args.tiles * piece / args.pieces);
+    const int t1 = (int)((long long)args.tiles * (piece + 1) / args.pieces);
+    const int ntile = t1 - t0;
+
+    // (1) candidate tile -> TMEM as tf32 hi (WG0) / lo (WG1); one candidate per lane, 128 columns each
+    if (warp >= 4) {
+      const int wg = (warp - 4) >> 2;
+      const int row = ((warp & 3) << 5) + lane;
+      const int j = qt * QT + row;
+      const float* src = args.nck + (size_t)j * DK;
+      const uint32_t tbase = tmem + (((uint32_t)(warp & 3) * 32u) << 16) + (wg == 0 ? TMM_QH : TMM_QL);
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (j < args.hw) x = reinterpret_cast<const float4*>(src)[ch * 8 + i];
+          float h, l;
+          split_tf32(x.x, h, l); v[4 * i + 0] = __float_as_uint(wg == 0 ? h : l);
+          split_tf32(x.y, h, l); v[4 * i + 1] = __float_as_uint(wg == 0 ? h : l);
+          split_tf32(x.z, h, l); v[4 * i + 2] = __float_as_uint(wg == 0 ? h : l);
+          split_tf32(x.w, h, l); v[4 * i + 3] = __float_as_uint(wg == 0 ? h : l);
+        }
+        tmem_st32(tbase + ch * 32, v);
+      }
+      tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == 0) {
+      for (int t = 0; t < ntile; ++t, ++k_it) {
+        const uint32_t st = k_it % M_STAGES, ph = (k_it / M_STAGES) & 1;
+        if (lane == 0) {
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[st], M_STAGE_BYTES);
+          uint8_t* dst = kst + st * M_STAGE_BYTES;
+          const int row0 = (t0 + t) * M_TILE;
+#pragma unroll
+          for (int blk = 0; blk < 4; ++blk) {
+            tma_load_2d(dst + blk * 8192, &map_h, &k_full[st], blk * 32, row0);
+            tma_load_2d(dst + 32768 + blk * 8192, &map_l, &k_full[st], blk * 32, row0);
+          }
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      constexpr uint32_t idesc = make_idesc_tf32(128, M_TILE);
+      for (int t = 0; t < ntile; ++t, ++k_it) {
+        const uint32_t st = k_it % M_STAGES, ph = (k_it / M_STAGES) & 1;
+        const int b = t & 1;
+        if (lane == 0) {
+          mbar_wait(&s_empty[b], (buf_it[b] & 1) ^ 1);
+          mbar_wait(&k_full[st], ph);
+          tc_fence_after();
+          const uint32_t kbase = smem_u32(kst + st * M_STAGE_BYTES);
+          const uint32_t d_t = tmem + TMM_S + (uint32_t)b * M_TILE;
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a_col = (pass == 1) ? TMM_QL : TMM_QH;
+            const uint32_t kb = kbase + ((pass == 2) ? 32768u : 0u);
+#pragma unroll
+            for (int ks = 0; ks < 16; ++ks) {
+              const uint64_t bd = make_sdesc(kb + (ks >> 2) * 8192u + (ks & 3) * 32u, 16, 1024);
+              mma_ts_tf32(d_t, tmem + a_col + ks * 8, bd, idesc, (pass | ks) ? 1u : 0u);
+            }
+          }
+          tc_commit(&k_empty[st]);
+          tc_commit(&s_full[b]);
+        }
+        __syncwarp();
+        ++buf_it[b];
+      }
+    } else if (warp >= 4) {
+      const int wg = (warp - 4) >> 2;
+      const int row = ((warp & 3) << 5) + lane;
+      const uint32_t tlane = tmem + (((uint32_t)(warp & 3) * 32u) << 16);
+      float best = -INFINITY;
+      int bidx = 0x7fffffff;
+      for (int t = wg; t < ntile; t += 2) {
+        mbar_wait(&s_full[wg], buf_it[wg] & 1);
+        ++buf_it[wg];
+        tc_fence_after();
+        const int slot0 = (t0 + t) * M_TILE;
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(tlane + TMM_S + (uint32_t)wg * M_TILE + ch * 32, v);
+          tmem_wait_ld();
+          if (args.dbg && blockIdx.x == 0 && item == (int)blockIdx.x && t == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) args.dbg[row * M_TILE + ch * 32 + i] = __uint_as_float(v[i]);
+          }
+          const int lim = args.n - (slot0 + ch * 32);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float sv = __uint_as_float(v[i]);
+            if (i < lim && sv > best) { best = sv; bidx = slot0 + ch * 32 + i; }   // ascending scan + strict > : lowest index wins
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&s_empty[wg]);
+      }
+      if (wg == 1) best_x[row] = make_float2(best, __int_as_float(bidx));
+      named_bar_sync(1, 256);
+      if (wg == 0) {
+        const float2 o = best_x[row];
+        const int oi = __float_as_int(o.y);
+        if (o.x > best || (o.x == best && oi < bidx)) { best = o.x; bidx = oi; }
+        const int j = qt * QT + row;
+        if (j < args.hw) part[(size_t)piece * args.hw + j] = make_float2(best, __int_as_float(bidx));
+      }
+    }
+    if (warp != 0 && warp != 1) k_it += ntile;
+    if (warp != 1 && warp < 4) { buf_it[0] += (ntile + 1) >> 1; buf_it[1] += ntile >> 1; }
+    if (warp >= 4) { const int wgx = (warp - 4) >> 2; buf_it[wgx ^ 1] += (wgx ^ 1) == 0 ? (ntile + 1) >> 1 : ntile >> 1; }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -677,15 +849,17 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D bf16 tensor (rows, cols) row-major; box = (box_rows, 64 cols = 128 B), 128B swizzle, OOB rows -> 0
-static int make_map(CUtensorMap* m, const void* base, int64_t rows, int cols, int box_rows) {
+// 2-D tensor (rows, cols) row-major, bf16 (elem_bytes 2) or fp32 (4); box = (box_rows, 128 B of columns), 128B swizzle,
+// OOB rows -> 0
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int cols, int box_rows, int elem_bytes = 2) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return VFN_E_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return VFN_E_CUDA; }
@@ -707,12 +881,27 @@ static float* g_dbg = nullptr;
 
 bool tc_shapes_ok(int d_key, int d_val) { return d_key == DK && d_val == DV; }
 
-void tc_pick_splits(int obj_n, int64_t n_max, int64_t hw, int* split_a, int* split_b) {
-  (void)obj_n; (void)n_max;
+constexpr int TC_MAX_SPLIT = 24;
+
+// number of slot splits per (object, query tile[, half]) combo: minimise rounds x (tiles per item + fixed per-item
+// overhead) for `combos` combos dealt round-robin to G persistent CTAs; every item keeps at least one tile.
+static int best_split(int combos, int64_t tiles_min, int64_t tiles_max, int overhead_tiles) {
   const int G = num_sms();
-  const int q_tiles = (int)cdiv(hw, QT);
-  *split_a = (int)cdiv(G, q_tiles) + 1;
-  *split_b = (int)cdiv(G, q_tiles * 2) + 1;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int s = 1; s <= TC_MAX_SPLIT && s <= tiles_min; ++s) {
+    const int64_t rounds = cdiv((int64_t)combos * s, G);
+    const double cost = (double)rounds * (double)(cdiv(tiles_max, s) + overhead_tiles);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
+void tc_pick_splits(int obj_n, int64_t n_max, int64_t hw, int* split_a, int* split_b) {
+  // upper bounds used to size the workspace; the per-launch choice (<= these) is made in tc_phase_a / tc_phase_b
+  (void)obj_n; (void)n_max; (void)hw;
+  *split_a = TC_MAX_SPLIT;
+  *split_b = TC_MAX_SPLIT;
 }
 
 size_t tc_workspace_bytes(int obj_n, int64_t hw) {
@@ -746,7 +935,7 @@ static int fill_args(const vfn_bank* banks, int obj_n, int64_t hw, int pieces, i
 }
 
 int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t hw, int split_a, float2* part,
-               char* ws_tc, cudaStream_t st) {
+               char* ws_tc, cudaStream_t st, int* pieces_out) {
   static bool attr = false;
   if (!attr) {
     VFN_CUDA_OK(cudaFuncSetAttribute(tc_phase_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
@@ -755,7 +944,16 @@ int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t h
   }
   TcMaps maps;
   TcArgs a;
-  if (int rc = fill_args(banks, obj_n, hw, split_a, A_TILE, ws_tc, &maps, &a, false)) return rc;
+  int64_t tmin = INT64_MAX, tmax = 0;
+  for (int o = 0; o < obj_n; ++o) {
+    const int64_t t = cdiv(banks[o].n, A_TILE);
+    tmin = t < tmin ? t : tmin;
+    tmax = t > tmax ? t : tmax;
+  }
+  const int pieces = best_split(obj_n * (int)cdiv(hw, QT), tmin, tmax, 3);
+  if (pieces > split_a) { set_error("phase A: split %d exceeds workspace bound %d", pieces, split_a); return VFN_E_CAPACITY; }
+  *pieces_out = pieces;
+  if (int rc = fill_args(banks, obj_n, hw, pieces, A_TILE, ws_tc, &maps, &a, false)) return rc;
   const size_t rows = (size_t)a.q_tiles * QT;
   // Q hi/lo of q * log2(e)/sqrt(d): logits land in the log2 domain; pad rows zeroed
   VFN_CUDA_OK(cudaMemsetAsync(ws_tc, 0, 2 * align_up(rows * DK * sizeof(uint16_t), 256), st));
@@ -763,29 +961,61 @@ int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t h
   if (int rc = vfn_prep_rows(q_in_dm, DK, hw, nullptr, nullptr, const_cast<uint16_t*>(a.qh),
                              const_cast<uint16_t*>(a.ql), scale, st))
     return rc;
-  const size_t np = (size_t)obj_n * split_a * hw;
-  fill_ml_kernel<<<(unsigned)cdiv(np, 256), 256, 0, st>>>(part, np);
   double work = 0;
   for (int o = 0; o < obj_n; ++o) work += 2.0 * DK * (double)banks[o].n * (double)hw;
   prof_begin(PROF_READ_A, st);
   tc_phase_a_kernel<<<num_sms(), TC_THREADS, A_SMEM, st>>>(maps, a, part);
   prof_end(PROF_READ_A, st, work);
   VFN_LAUNCH_OK();
-  count_launches(3);
+  count_launches(2);
   return VFN_OK;
 }
 
 int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const float* lse, float thres_valid,
-               int update_bank, float* po, char* ws_tc, cudaStream_t st) {
+               int update_bank, float* po, char* ws_tc, cudaStream_t st, int* pieces_out) {
   TcMaps maps;
   TcArgs a;
-  if (int rc = fill_args(banks, obj_n, hw, split_b, B_TILE, ws_tc, &maps, &a, true)) return rc;
-  VFN_CUDA_OK(cudaMemsetAsync(po, 0, (size_t)obj_n * split_b * DV * hw * sizeof(float), st));
+  int64_t tmin = INT64_MAX, tmax = 0;
+  for (int o = 0; o < obj_n; ++o) {
+    const int64_t t = cdiv(banks[o].n, B_TILE);
+    tmin = t < tmin ? t : tmin;
+    tmax = t > tmax ? t : tmax;
+  }
+  const int pieces = best_split(obj_n * 2 * (int)cdiv(hw, QT), tmin, tmax, 4);
+  if (pieces > split_b) { set_error("phase B: split %d exceeds workspace bound %d", pieces, split_b); return VFN_E_CAPACITY; }
+  *pieces_out = pieces;
+  if (int rc = fill_args(banks, obj_n, hw, pieces, B_TILE, ws_tc, &maps, &a, true)) return rc;
   double work = 0;
   for (int o = 0; o < obj_n; ++o) work += 2.0 * DV * (double)banks[o].n * (double)hw;
   prof_begin(PROF_READ_B, st);
   tc_phase_b_kernel<<<num_sms(), TC_THREADS, B_SMEM, st>>>(maps, a, lse, thres_valid, update_bank, po);
   prof_end(PROF_READ_B, st, work);
+  VFN_LAUNCH_OK();
+  count_launches(1);
+  return VFN_OK;
+}
+
+int tc_match(const vfn_bank* bank, const float* nck_em, int64_t hw, int max_pieces, float2* part, int* pieces_out,
+             cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    VFN_CUDA_OK(cudaFuncSetAttribute(tc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, M_SMEM));
+    attr = true;
+  }
+  VFN_CHECK_ARG(bank->d_key == DK && bank->n < (1ll << 31), "tcgen05 match needs d_key = 128");
+  CUtensorMap mh, ml;
+  if (int rc = make_map(&mh, bank->nkh, bank->n, DK, M_TILE, 4)) return rc;
+  if (int rc = make_map(&ml, bank->nkl, bank->n, DK, M_TILE, 4)) return rc;
+  MatchArgs a;
+  a.hw = (int)hw; a.q_tiles = (int)cdiv(hw, QT); a.n = (int)bank->n; a.tiles = (int)cdiv(bank->n, M_TILE);
+  a.nck = nck_em; a.dbg = g_dbg;
+  int pieces = best_split(a.q_tiles, a.tiles, a.tiles, 3);
+  if (pieces > max_pieces) pieces = max_pieces;
+  a.pieces = pieces;
+  *pieces_out = pieces;
+  prof_begin(PROF_MATCH, st);
+  tc_match_kernel<<<num_sms(), TC_THREADS, M_SMEM, st>>>(mh, ml, a, part);
+  prof_end(PROF_MATCH, st, 2.0 * DK * (double)bank->n * (double)hw);
   VFN_LAUNCH_OK();
   count_launches(1);
   return VFN_OK;

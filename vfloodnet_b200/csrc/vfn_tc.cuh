@@ -9,10 +9,16 @@ bool tc_shapes_ok(int d_key, int d_val);
 void tc_pick_splits(int obj_n, int64_t n_max, int64_t hw, int* split_a, int* split_b);
 size_t tc_workspace_bytes(int obj_n, int64_t hw);
 // phase A: (m, l) partials [natural-log domain] for every (object, split, query): part[(obj*split_a + s)*hw + j]
+// split_a / split_b are the workspace bounds; the number of pieces actually used comes back in *pieces_out and is the
+// n_split the combine kernels must use.
 int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t hw, int split_a, float2* part,
-               char* ws_tc, cudaStream_t st);
+               char* ws_tc, cudaStream_t st, int* pieces_out);
 // phase B: partial readouts po[((obj*split_b + s)*d_val + c)*hw + j] and usage counts into bank.cnt
 int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const float* lse, float thres_valid,
-               int update_bank, float* po, char* ws_tc, cudaStream_t st);
+               int update_bank, float* po, char* ws_tc, cudaStream_t st, int* pieces_out);
+
+// cosine match (3xTF32): per-piece (max, argmax bits) partials part[piece*hw + j]; *pieces_out pieces were written
+int tc_match(const vfn_bank* bank, const float* nck_em, int64_t hw, int max_pieces, float2* part, int* pieces_out,
+             cudaStream_t st);
 
 }  // namespace vfn

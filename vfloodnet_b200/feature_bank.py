@@ -28,7 +28,8 @@ class _Slab:
         self.keys = torch.empty((cap, d_key), **f32)
         self.values = torch.empty((cap, d_val), **f32)
         self.info = torch.zeros((cap, 2), **f32)
-        self.nkeys = torch.empty((cap, d_key), **f32)
+        self.nkh = torch.empty((cap, d_key), **f32)
+        self.nkl = torch.empty((cap, d_key), **f32)
         self.cnt = torch.zeros((cap,), dtype=torch.int32, device=device)
         if operands:
             bf = dict(dtype=torch.bfloat16, device=device)
@@ -41,10 +42,10 @@ class _Slab:
 
     def struct(self, n: int) -> VfnBank:
         return VfnBank(self.d_key, self.d_val, self.cap, n, ptr(self.keys), ptr(self.values), ptr(self.info),
-                       ptr(self.nkeys), ptr(self.kh), ptr(self.kl), ptr(self.vh), ptr(self.vl), ptr(self.cnt))
+                       ptr(self.nkh), ptr(self.nkl), ptr(self.kh), ptr(self.kl), ptr(self.vh), ptr(self.vl), ptr(self.cnt))
 
     def copy_rows_from(self, other: '_Slab', n: int):
-        for name in ('keys', 'values', 'info', 'nkeys', 'kh', 'kl', 'vh', 'vl', 'cnt'):
+        for name in ('keys', 'values', 'info', 'nkh', 'nkl', 'kh', 'kl', 'vh', 'vl', 'cnt'):
             a, b = getattr(self, name), getattr(other, name)
             if a is not None:
                 a[:n].copy_(b[:n])
