@@ -550,6 +550,14 @@ const char* vfn_last_error(void) { return g_err; }
 int vfn_profile_enable(int32_t on) {
   for (auto& r : g_prof) { g_ev_pool.push_back(r.a); g_ev_pool.push_back(r.b); }
   g_prof.clear();
+  if (on) {   // pre-create events so that recording inside a timed region never calls cudaEventCreate
+    while (g_ev_pool.size() < 16384) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) break;
+      g_ev_pool.push_back(e);
+    }
+    g_prof.reserve(8192);
+  }
   g_prof_on = on != 0;
   return VFN_OK;
 }

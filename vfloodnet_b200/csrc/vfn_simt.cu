@@ -592,7 +592,7 @@ int vfn_memread(const vfn_bank* banks, int32_t obj_n, const float* d_q_in_dm, co
 
 size_t vfn_bank_match_workspace_bytes(int64_t n, int64_t hw) {
   (void)n;
-  return align_up((size_t)64 * hw * sizeof(float2), 256);
+  return align_up((size_t)64 * hw * 4 * sizeof(float2), 256);   // 64 pieces x top-4 candidates
 }
 
 int vfn_bank_match(const vfn_bank* bank, const float* d_nck_em, int64_t hw, int32_t* d_match_idx, float* d_match_corr,
@@ -606,9 +606,8 @@ int vfn_bank_match(const vfn_bank* bank, const float* d_nck_em, int64_t hw, int3
   int split = 0;
   const bool tc = (impl != 1) && set.b[0].d_key == 128 && vfn_device_is_sm100();
   if (impl == 2 && !tc) { set_error("tcgen05 match needs d_key = 128 on an sm_100 device"); return VFN_E_UNSUPPORTED; }
-  if (tc) {
-    if (int rc = tc_match(&set.b[0], d_nck_em, hw, 64, reinterpret_cast<float2*>(d_ws), &split, st)) return rc;
-  } else {
+  if (tc) return tc_match(&set.b[0], d_nck_em, hw, 64, reinterpret_cast<float2*>(d_ws), d_match_idx, d_match_corr, st);
+  {
     const int q_tiles = (int)cdiv(hw, TN);
     split = pick_split(cdiv(n_max, TM), q_tiles, 148 * 4);
     dim3 grid(q_tiles, split, 1);

@@ -666,6 +666,36 @@ constexpr int M_STAGE_BYTES = M_TILE * DK * 4 * 2;      // fp32 hi + lo = 64 KB
 constexpr int M_SMEM = M_STAGES * M_STAGE_BYTES + 1024 + 256;
 constexpr uint32_t TMM_QH = 0, TMM_QL = 128, TMM_S = 256;
 
+constexpr int MATCH_TOPK = 4;   // approximate candidates kept per (piece, query) for the exact fp32 re-score
+
+// insert (v, i) into a descending top-4 list; the caller scans slots in ascending order, so strict '>' keeps the
+// lowest slot first among equal values
+__device__ __forceinline__ void top4_insert(float (&tv)[MATCH_TOPK], int (&ti)[MATCH_TOPK], float v, int i) {
+  if (v > tv[3]) {
+    tv[3] = v; ti[3] = i;
+#pragma unroll
+    for (int r = 3; r > 0; --r) {
+      if (tv[r] > tv[r - 1]) {
+        const float fv = tv[r]; tv[r] = tv[r - 1]; tv[r - 1] = fv;
+        const int fi = ti[r]; ti[r] = ti[r - 1]; ti[r - 1] = fi;
+      }
+    }
+  }
+}
+// general insert with explicit (value desc, slot asc) order, for merging lists that were not scanned in slot order
+__device__ __forceinline__ void top4_merge(float (&tv)[MATCH_TOPK], int (&ti)[MATCH_TOPK], float v, int i) {
+  if (v > tv[3] || (v == tv[3] && i < ti[3])) {
+    tv[3] = v; ti[3] = i;
+#pragma unroll
+    for (int r = 3; r > 0; --r) {
+      if (tv[r] > tv[r - 1] || (tv[r] == tv[r - 1] && ti[r] < ti[r - 1])) {
+        const float fv = tv[r]; tv[r] = tv[r - 1]; tv[r - 1] = fv;
+        const int fi = ti[r]; ti[r] = ti[r - 1]; ti[r - 1] = fi;
+      }
+    }
+  }
+}
+
 struct MatchArgs {
   int hw, q_tiles, pieces, n, tiles;
   const float* nck;        // (hw, 128) normalised candidates, entry-major
@@ -684,7 +714,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_match_kernel(const __grid_co
   uint64_t* s_full = bars + 2 * M_STAGES;
   uint64_t* s_empty = s_full + 2;
   uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(s_empty + 2);
-  __shared__ float2 best_x[QT];
+  __shared__ float2 best_x[QT][MATCH_TOPK];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -783,8 +813,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_match_kernel(const __grid_co
       const int wg = (warp - 4) >> 2;
       const int row = ((warp & 3) << 5) + lane;
       const uint32_t tlane = tmem + (((uint32_t)(warp & 3) * 32u) << 16);
-      float best = -INFINITY;
-      int bidx = 0x7fffffff;
+      float tv[MATCH_TOPK];
+      int ti[MATCH_TOPK];
+#pragma unroll
+      for (int r = 0; r < MATCH_TOPK; ++r) { tv[r] = -INFINITY; ti[r] = 0x7fffffff; }
       for (int t = wg; t < ntile; t += 2) {
         mbar_wait(&s_full[wg], buf_it[wg] & 1);
         ++buf_it[wg];
@@ -803,20 +835,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_match_kernel(const __grid_co
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float sv = __uint_as_float(v[i]);
-            if (i < lim && sv > best) { best = sv; bidx = slot0 + ch * 32 + i; }   // ascending scan + strict > : lowest index wins
+            if (i < lim) top4_insert(tv, ti, sv, slot0 + ch * 32 + i);
           }
         }
         tc_fence_before();
         mbar_arrive(&s_empty[wg]);
       }
-      if (wg == 1) best_x[row] = make_float2(best, __int_as_float(bidx));
+      if (wg == 1) {
+#pragma unroll
+        for (int r = 0; r < MATCH_TOPK; ++r) best_x[row][r] = make_float2(tv[r], __int_as_float(ti[r]));
+      }
       named_bar_sync(1, 256);
       if (wg == 0) {
-        const float2 o = best_x[row];
-        const int oi = __float_as_int(o.y);
-        if (o.x > best || (o.x == best && oi < bidx)) { best = o.x; bidx = oi; }
+#pragma unroll
+        for (int r = 0; r < MATCH_TOPK; ++r) {
+          const float2 o = best_x[row][r];
+          top4_merge(tv, ti, o.x, __float_as_int(o.y));
+        }
         const int j = qt * QT + row;
-        if (j < args.hw) part[(size_t)piece * args.hw + j] = make_float2(best, __int_as_float(bidx));
+        if (j < args.hw) {
+#pragma unroll
+          for (int r = 0; r < MATCH_TOPK; ++r)
+            part[((size_t)piece * args.hw + j) * MATCH_TOPK + r] = make_float2(tv[r], __int_as_float(ti[r]));
+        }
       }
     }
     if (warp != 0 && warp != 1) k_it += ntile;
@@ -828,6 +869,84 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_match_kernel(const __grid_co
   }
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// Exact fp32 re-score of the tensor-core candidates: one warp per candidate query.  The 3xTF32 scores carry the
+// tensor core's truncating accumulation (measured: ~4e-6 systematic bias), so every slot whose approximate score is
+// within MATCH_BAND of the approximate maximum is re-evaluated with the sequential fp32 FMA chain the SIMT kernel uses
+// (bit-identical values and ordering).  If some piece's whole top-4 lies inside the band there may be hidden
+// candidates: that query falls back to an exact scan of all slots (rare: needs >= 4 near-duplicate slots).
+constexpr float MATCH_BAND = 2e-5f;
+
+__device__ __forceinline__ float exact_dot128(const float* __restrict__ nkh, const float* __restrict__ nkl,
+                                              const float* __restrict__ q, int64_t slot) {
+  const float4* h = reinterpret_cast<const float4*>(nkh + slot * DK);
+  const float4* l = reinterpret_cast<const float4*>(nkl + slot * DK);
+  const float4* b = reinterpret_cast<const float4*>(q);
+  float acc = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < DK / 4; ++k) {
+    const float4 hv = h[k], lv = l[k], bv = b[k];
+    acc = fmaf(hv.x + lv.x, bv.x, acc);
+    acc = fmaf(hv.y + lv.y, bv.y, acc);
+    acc = fmaf(hv.z + lv.z, bv.z, acc);
+    acc = fmaf(hv.w + lv.w, bv.w, acc);
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(256) match_rescore_kernel(const float2* __restrict__ part, int pieces, int hw, int n,
+                                                            const float* __restrict__ nkh,
+                                                            const float* __restrict__ nkl,
+                                                            const float* __restrict__ nck,
+                                                            int32_t* __restrict__ idx_out,
+                                                            float* __restrict__ corr_out) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= hw) return;
+  const int n_cand = pieces * MATCH_TOPK;
+  const float* q = nck + (size_t)j * DK;
+  // approximate maximum over all pieces
+  float amax = -INFINITY;
+  for (int c = lane; c < n_cand; c += 32) {
+    const int pc = c / MATCH_TOPK, r = c - pc * MATCH_TOPK;
+    amax = fmaxf(amax, part[((size_t)pc * hw + j) * MATCH_TOPK + r].x);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  const float band = amax - MATCH_BAND;
+  float best = -INFINITY;
+  int bidx = 0x7fffffff;
+  int overflow = 0;
+  for (int c = lane; c < n_cand; c += 32) {
+    const int pc = c / MATCH_TOPK, r = c - pc * MATCH_TOPK;
+    const float2 e = part[((size_t)pc * hw + j) * MATCH_TOPK + r];
+    const int slot = __float_as_int(e.y);
+    if (e.x >= band && slot < n) {
+      if (r == MATCH_TOPK - 1) overflow = 1;
+      const float v = exact_dot128(nkh, nkl, q, slot);
+      if (v > best || (v == best && slot < bidx)) { best = v; bidx = slot; }
+    }
+  }
+  overflow = __any_sync(0xffffffffu, overflow);
+  if (overflow) {
+    best = -INFINITY;
+    bidx = 0x7fffffff;
+    for (int slot = lane; slot < n; slot += 32) {
+      const float v = exact_dot128(nkh, nkl, q, slot);
+      if (v > best) { best = v; bidx = slot; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+  }
+  if (lane == 0) {
+    idx_out[j] = bidx;
+    corr_out[j] = best;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -995,8 +1114,8 @@ int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const 
   return VFN_OK;
 }
 
-int tc_match(const vfn_bank* bank, const float* nck_em, int64_t hw, int max_pieces, float2* part, int* pieces_out,
-             cudaStream_t st) {
+int tc_match(const vfn_bank* bank, const float* nck_em, int64_t hw, int max_pieces, float2* part, int32_t* idx_out,
+             float* corr_out, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     VFN_CUDA_OK(cudaFuncSetAttribute(tc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, M_SMEM));
@@ -1012,12 +1131,13 @@ int tc_match(const vfn_bank* bank, const float* nck_em, int64_t hw, int max_piec
   int pieces = best_split(a.q_tiles, a.tiles, a.tiles, 3);
   if (pieces > max_pieces) pieces = max_pieces;
   a.pieces = pieces;
-  *pieces_out = pieces;
   prof_begin(PROF_MATCH, st);
   tc_match_kernel<<<num_sms(), TC_THREADS, M_SMEM, st>>>(mh, ml, a, part);
   prof_end(PROF_MATCH, st, 2.0 * DK * (double)bank->n * (double)hw);
+  match_rescore_kernel<<<(unsigned)cdiv(hw, 8), 256, 0, st>>>(part, pieces, (int)hw, (int)bank->n, bank->nkh, bank->nkl,
+                                                              nck_em, idx_out, corr_out);
   VFN_LAUNCH_OK();
-  count_launches(1);
+  count_launches(2);
   return VFN_OK;
 }
 

@@ -17,8 +17,9 @@ int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t h
 int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const float* lse, float thres_valid,
                int update_bank, float* po, char* ws_tc, cudaStream_t st, int* pieces_out);
 
-// cosine match (3xTF32): per-piece (max, argmax bits) partials part[piece*hw + j]; *pieces_out pieces were written
-int tc_match(const vfn_bank* bank, const float* nck_em, int64_t hw, int max_pieces, float2* part, int* pieces_out,
-             cudaStream_t st);
+// cosine match: 3xTF32 tcgen05 scores -> per-piece top-4 candidates in `part` (max_pieces*hw*4 float2) -> exact fp32
+// re-score (same FMA chain as the SIMT kernel) -> idx_out / corr_out
+int tc_match(const vfn_bank* bank, const float* nck_em, int64_t hw, int max_pieces, float2* part, int32_t* idx_out,
+             float* corr_out, cudaStream_t st);
 
 }  // namespace vfn
