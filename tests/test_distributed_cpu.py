@@ -1,0 +1,96 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: the sharded-bank exchange steps (LSE combine, partial
+readout reduction, arg-max combine with global tie-break) and the stream-parallel partition used by bench.py."""
+import math
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from vfloodnet_b200 import sharded
+        g = torch.Generator().manual_seed(7)          # same data on every rank
+        n, hw, dk, dv = 301, 37, 16, 24
+        K = torch.randn(dk, n, generator=g) * 1.58
+        V = torch.randn(dv, n, generator=g)
+        Q = torch.randn(dk, hw, generator=g) * 1.58
+        s_full = (K.t() @ Q) / math.sqrt(dk)
+        p_full = torch.softmax(s_full, dim=0)
+        mem_full = V @ p_full
+        lo, hi = sharded.shard_range(n, rank, world)
+        s = s_full[lo:hi]
+        m = s.max(dim=0).values
+        l = torch.exp(s - m).sum(dim=0)
+        lse = sharded.combine_lse(torch.stack([m, l], dim=-1))
+        ok_lse = torch.allclose(lse, torch.logsumexp(s_full, dim=0), atol=1e-5)
+        p_loc = torch.exp(s - lse)                      # normalised with the GLOBAL lse
+        cnt_loc = (p_loc > 1e-3).sum(dim=1)
+        ok_cnt = torch.equal(cnt_loc, (p_full[lo:hi] > 1e-3).sum(dim=1))
+        mem = sharded.reduce_readout(V[:, lo:hi] @ p_loc)
+        ok_mem = torch.allclose(mem, mem_full, atol=1e-5)
+        # arg-max combine with exact duplicates across shards: lowest global slot must win
+        Kn = torch.nn.functional.normalize(K, dim=0)
+        Kn[:, n - 5] = Kn[:, 3]                        # duplicate of slot 3 lives in the last shard
+        cand = Kn[:, [3, 100, 200]]
+        corr = Kn.t() @ cand
+        c_loc, i_loc = corr[lo:hi].max(dim=0)
+        best, idx = sharded.combine_match(c_loc, i_loc + lo)
+        ok_match = idx.tolist() == corr.argmax(dim=0).tolist() and idx[0].item() == 3
+        # empty shard (-inf, 0) must not poison the combine
+        ml_e = torch.stack([m, l], dim=-1) if rank == 0 else torch.stack([torch.full_like(m, -math.inf), torch.zeros_like(l)], -1)
+        lse_e = sharded.combine_lse(ml_e)
+        ok_empty = torch.allclose(lse_e, torch.logsumexp(s_full[:sharded.shard_range(n, 0, world)[1]], dim=0), atol=1e-5)
+        q.put((rank, bool(ok_lse), bool(ok_cnt), bool(ok_mem), bool(ok_match), bool(ok_empty)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_exchange_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in res:
+        assert all(r[1:]), f'rank {r[0]}: lse/cnt/mem/match/empty = {r[1:]}'
+
+
+def test_shard_ranges_cover_and_preserve_order():
+    from vfloodnet_b200.sharded import shard_range
+    for n in (0, 1, 7, 100000):
+        for w in (1, 2, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+
+
+def test_bench_reference_arm_rank_gating(monkeypatch, capsys):
+    """under torchrun only rank 0 runs and prints the reference arm; other ranks exit without work"""
+    import bench
+    import argparse
+    args = argparse.Namespace(gpus=2, steps=1, warmup=0, frames=100, frac_merge=0.1)
+    called = []
+    monkeypatch.setattr(bench, 'cpu_sample', lambda *a, **k: (called.append(1) or (1.0, 'stub', 1.0)))
+    bench.main_reference(args, rank=1, world=2)
+    assert not called and capsys.readouterr().out == ''
+    bench.main_reference(args, rank=0, world=2)
+    out = capsys.readouterr().out
+    assert called and '"impl": "reference"' in out

@@ -285,3 +285,57 @@ def test_urr_vs_oracle_480p(vfn):
     a, b = out.cpu()[1] > 0.5, out_o[1] > 0.5
     iou = (a & b).sum().item() / max((a | b).sum().item(), 1)
     assert iou >= 0.999
+
+
+# ---------------------------------------------------------------------------------------------------
+# split-memory read (sharded bank): phase A / LSE combine / phase B on two shards == single-bank read
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('impl', IMPLS)
+def test_split_memory_read_two_shards_one_gpu(vfn, impl):
+    import ctypes as C
+    from vfloodnet_b200 import synth, _lib
+    from vfloodnet_b200._lib import check, ptr, stream_ptr
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(11)
+    n, hw = 7001, 1620
+    keys, vals = zip(*[synth.gen_bank(g, n) for _ in range(2)])
+    info = [synth.gen_info(g, n, 9) for _ in range(2)]
+    q_in, q_out = synth.gen_query(g, hw)
+    full = vfn.FeatureBank(2, 10 ** 6, 'cuda', impl=impl)
+    full.load_state(list(keys), list(vals), info)
+    m = vfn.Matcher(update_bank=True)
+    m.want_lse = True
+    out_full = m(full, q_in.cuda(), q_out.cuda())
+    cut = 3000
+    shards, mls = [], []
+    for lo, hi in ((0, cut), (cut, n)):
+        fb = vfn.FeatureBank(2, 10 ** 6, 'cuda', impl=impl)
+        fb.load_state([k[:, lo:hi] for k in keys], [v[:, lo:hi] for v in vals], [i[lo:hi] for i in info])
+        shards.append(fb)
+    qd = q_in.cuda().contiguous()
+    wss = []
+    for fb in shards:
+        ws = torch.empty(lib.vfn_memread_workspace_bytes(2, max(s.cap for s in fb._slabs), hw, 128, 512), dtype=torch.uint8,
+                         device='cuda')
+        ml = torch.empty((2, hw, 2), device='cuda')
+        check(lib.vfn_memread_phase_a(fb.bank_array(), 2, ptr(qd), hw, ptr(ml), ptr(ws), ws.numel(), impl, stream_ptr()))
+        wss.append(ws); mls.append(ml)
+    ml = torch.stack(mls)
+    M = ml[..., 0].max(dim=0).values
+    lse = (M + torch.log((ml[..., 1] * torch.exp(ml[..., 0] - M)).sum(dim=0))).contiguous()
+    # same reduction through the C entry point
+    lse_c = torch.empty_like(lse)
+    check(lib.vfn_lse_combine(ptr(ml.contiguous()), 2, 2 * hw, ptr(lse_c), stream_ptr()))
+    assert (lse_c - lse).abs().max().item() < 1e-5
+    assert (lse - m.last_lse).abs().max().item() < 1e-4
+    total = torch.zeros((2, 512, hw), device='cuda')
+    for fb, ws in zip(shards, wss):
+        part = torch.empty((2, 512, hw), device='cuda')
+        check(lib.vfn_memread_phase_b(fb.bank_array(), 2, ptr(qd), hw, ptr(lse), 1e-3, 1, ptr(part), ptr(ws), ws.numel(),
+                                      impl, stream_ptr()))
+        total += part
+    assert (total - out_full[0, :, :512]).abs().max().item() <= (2e-5 if impl == 1 else 2e-4)
+    for c in range(2):
+        got = torch.cat([shards[0].info[c], shards[1].info[c]])
+        d = (got[:, 1] - full.info[c][:, 1]).abs()
+        assert int((d > 1e-6).sum()) <= 2       # counts are local and exact up to threshold-band flips
