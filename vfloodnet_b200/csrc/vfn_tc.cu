@@ -133,6 +133,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2(float x) {
@@ -404,7 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
-      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128);
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 256);
     }
     mbar_init(o_full, 1);
     fence_barrier_init();
@@ -517,15 +525,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
           tc_fence_after();
           const uint32_t vbase = smem_u32(vst + st * B_VSTAGE_BYTES);
           const uint32_t pcol = tmem + TM_S + (uint32_t)b * 64;
-          // passes: (Ph,Vh) (Ph,Vl) (Pl,Vh)
+          // passes: (Ph,Vh) (Ph,Vl) (Pl,Vh).  P layout inside the 64-column buffer (written by the two softmax
+          // warpgroups, 32 slots each): [Ph(0-31) | Pl(0-31) | Ph(32-63) | Pl(32-63)], 16 columns per block
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t a_col = pcol + ((pass == 2) ? 32u : 0u);
+            const uint32_t lo_off = (pass == 2) ? 16u : 0u;
             const uint32_t vb = vbase + ((pass == 1) ? 32768u : 0u);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint64_t bd = make_sdesc(vb + ks * 2048u, 8192, 1024);
-              mma_ts(tmem + TM_O, a_col + ks * 8, bd, idesc_o, (t | pass | ks) ? 1u : 0u);
+              const uint32_t a_col = pcol + (uint32_t)(ks >> 1) * 32u + lo_off + (uint32_t)(ks & 1) * 8u;
+              mma_ts(tmem + TM_O, a_col, bd, idesc_o, (t | pass | ks) ? 1u : 0u);
             }
           }
           tc_commit(&v_empty[st]);
@@ -543,79 +553,64 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
       const uint32_t tlane = tmem + (((uint32_t)(warp & 3) * 32u) << 16);
       const int j = qt * QT + row;
       const float lse2 = (j < args.hw) ? lse[(size_t)obj * args.hw + j] * LOG2E : INFINITY;
-      int* mycnt = cnt_s + wg * 64;
+      int* mycnt = cnt_s + wg * 32;
       const bool counting = do_count && (half == 0);
-      for (int t = wg; t < ntile; t += 2) {
-        mbar_wait(&s_full[wg], buf_it[wg] & 1);
-        ++buf_it[wg];
+      // both warpgroups work on every tile: WG0 takes slots [0,32) of the tile, WG1 slots [32,64).  Halving the
+      // per-tile softmax latency is what keeps the tensor pipe fed (S(t+1) is only 768 clk of cover).
+      for (int t = 0; t < ntile; ++t) {
+        const int b = t & 1;
+        mbar_wait(&s_full[b], buf_it[b] & 1);
+        ++buf_it[b];
         tc_fence_after();
-        const int slot0 = (t0 + t) * B_TILE;
-        const uint32_t sb = tlane + TM_S + (uint32_t)wg * 64;
-        uint32_t s0[32], s1[32];
+        const int slot0 = (t0 + t) * B_TILE + wg * 32;
+        const uint32_t sb = tlane + TM_S + (uint32_t)b * 64 + (uint32_t)wg * 32;
+        uint32_t s0[32];
         tmem_ld32(sb, s0);
-        tmem_ld32(sb + 32, s1);
         tmem_wait_ld();
         if (args.dbg && blockIdx.x == 0 && first_item && t == 0) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            args.dbg[row * B_TILE + i] = __uint_as_float(s0[i]);
-            args.dbg[row * B_TILE + 32 + i] = __uint_as_float(s1[i]);
-          }
+          for (int i = 0; i < 32; ++i) args.dbg[row * B_TILE + wg * 32 + i] = __uint_as_float(s0[i]);
         }
         const int lim = n_obj - slot0;
-        uint32_t hi_w[32], lo_w[32];
-        unsigned long long bits = 0ull;
+        uint32_t hi_w[16], lo_w[16];
+        uint32_t bits = 0u;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           float p0 = ex2(__uint_as_float(s0[i]) - lse2), p1 = ex2(__uint_as_float(s0[i + 1]) - lse2);
           p0 = (i < lim) ? p0 : 0.f;
           p1 = (i + 1 < lim) ? p1 : 0.f;
-          bits |= (unsigned long long)(p0 > thres) << i;
-          bits |= (unsigned long long)(p1 > thres) << (i + 1);
+          bits |= (uint32_t)(p0 > thres) << i;
+          bits |= (uint32_t)(p1 > thres) << (i + 1);
           const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
           const __nv_bfloat162 l = __floats2bfloat162_rn(p0 - __low2float(h), p1 - __high2float(h));
           hi_w[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
           lo_w[i >> 1] = *reinterpret_cast<const uint32_t*>(&l);
         }
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2(__uint_as_float(s1[i]) - lse2), p1 = ex2(__uint_as_float(s1[i + 1]) - lse2);
-          p0 = (32 + i < lim) ? p0 : 0.f;
-          p1 = (33 + i < lim) ? p1 : 0.f;
-          bits |= (unsigned long long)(p0 > thres) << (32 + i);
-          bits |= (unsigned long long)(p1 > thres) << (33 + i);
-          const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-          const __nv_bfloat162 l = __floats2bfloat162_rn(p0 - __low2float(h), p1 - __high2float(h));
-          hi_w[16 + (i >> 1)] = *reinterpret_cast<const uint32_t*>(&h);
-          lo_w[16 + (i >> 1)] = *reinterpret_cast<const uint32_t*>(&l);
-        }
-        tmem_st32(sb, hi_w);          // P hi: 64 bf16 = 32 columns
-        tmem_st32(sb + 32, lo_w);     // P lo
+        tmem_st16(sb, hi_w);          // P hi: 32 bf16 = 16 columns
+        tmem_st16(sb + 16, lo_w);     // P lo
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(&p_full[wg]);
+        mbar_arrive(&p_full[b]);
         if (counting) {
-          if (j >= args.hw) bits = 0ull;
-          const int dense = __any_sync(0xffffffffu, __popcll(bits) > 6);
+          if (j >= args.hw) bits = 0u;
+          const int dense = __any_sync(0xffffffffu, __popc(bits) > 4);
           if (dense) {
-            int c_lo = 0, c_hi = 0;
+            int c_mine = 0;
 #pragma unroll 8
             for (int c = 0; c < 32; ++c) {
-              const unsigned b0 = __ballot_sync(0xffffffffu, (bits >> c) & 1ull);
-              const unsigned b1 = __ballot_sync(0xffffffffu, (bits >> (32 + c)) & 1ull);
-              if (lane == c) { c_lo = __popc(b0); c_hi = __popc(b1); }
+              const unsigned bal = __ballot_sync(0xffffffffu, (bits >> c) & 1u);
+              if (lane == c) c_mine = __popc(bal);
             }
-            if (c_lo) atomicAdd(&mycnt[lane], c_lo);
-            if (c_hi) atomicAdd(&mycnt[32 + lane], c_hi);
+            if (c_mine) atomicAdd(&mycnt[lane], c_mine);
           } else {
             while (bits) {
-              const int c = __ffsll((long long)bits) - 1;
+              const int c = __ffs((int)bits) - 1;
               bits &= bits - 1;
               atomicAdd(&mycnt[c], 1);
             }
           }
           named_bar_sync(1 + wg, 128);
-          if (wtid < 64) {
+          if (wtid < 32) {
             const int c = mycnt[wtid];
             if (c) {
               atomicAdd(&args.cnt[obj][slot0 + wtid], c);
@@ -644,7 +639,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
     }
     if (warp != 0 && warp != 1) k_it += ntile;
     if (warp < 4 && warp != 1) { buf_it[0] += (ntile + 1) >> 1; buf_it[1] += ntile >> 1; }
-    if (warp >= 4) { const int wgx = (warp - 4) >> 2; buf_it[wgx ^ 1] += (wgx ^ 1) == 0 ? (ntile + 1) >> 1 : ntile >> 1; }
     ++seg_it;
     tc_fence_before();
     __syncthreads();
