@@ -42,12 +42,14 @@ typedef struct vfn_bank {
   float* keys;     /* (cap, d_key)  raw keys      == reference fb.keys[i].T   */
   float* values;   /* (cap, d_val)  raw values    == reference fb.values[i].T */
   float* info;     /* (cap, 2)      [frame added, sum log(cnt+1)]  (FeatureBank.py:34-35) */
-  float* nkh;      /* (cap, d_key)  cached NF.normalize(keys, dim=0) (FeatureBank.py:63), split for the 3xTF32 match:   */
-  float* nkl;      /* (cap, d_key)  nkh = value with the low 13 mantissa bits cleared (exact in tf32), nkl = value - nkh  */
-  uint16_t* kh;    /* (cap, d_key)  bf16 hi part of keys   - tensor-core operand, NULL if unused */
-  uint16_t* kl;    /* (cap, d_key)  bf16 lo part (key - hi) */
-  uint16_t* vh;    /* (cap, d_val)  bf16 hi part of values */
-  uint16_t* vl;    /* (cap, d_val)  bf16 lo part */
+  float* nk;       /* (cap, d_key)  cached NF.normalize(keys, dim=0) (FeatureBank.py:63), exact fp32: SIMT match + re-score */
+  uint16_t* nkh;   /* (cap, d_key)  fp16 hi of 16*nk  - tensor-core match operand, NULL if unused */
+  uint16_t* nkl;   /* (cap, d_key)  fp16 lo  (16*nk - hi) */
+  uint16_t* kh;    /* (cap, d_key)  fp16 hi of keys   - tensor-core read operand, NULL if unused */
+  uint16_t* kl;    /* (cap, d_key)  fp16 lo  (key - hi) */
+  uint16_t* vh;    /* (cap, d_val)  fp16 hi of values */
+  uint8_t* v8;     /* (cap, d_val)  e4m3(value)        - partner of the P-residual pass */
+  uint8_t* vl;     /* (cap, d_val)  e5m2(value - vh)   - partner of the e4m3(P) pass */
   int32_t* cnt;    /* (cap)         usage-count scratch, all zero between reads */
 } vfn_bank;
 
@@ -57,7 +59,8 @@ const char* vfn_last_error(void);
 int vfn_device_is_sm100(void);
 
 /* ---- candidate / query preparation ------------------------------------------------------------
- * (d, n) dm  ->  (n, d) em copies: raw and L2-normalised (x / max(|x|, 1e-12)), + optional bf16 hi/lo of raw*scale.
+ * (d, n) dm  ->  (n, d) em copies: raw and L2-normalised (x / max(|x|, 1e-12)), + optional fp16 hi/lo of raw*scale
+ * (of normalised*scale when d_normed_em is non-NULL: the tensor-core match operand).
  * Replaces NF.normalize(prev_key, dim=0) / NF.normalize(prev_value, dim=0) (FeatureBank.py:64,88) and the
  * transposes implied by keys[i].transpose(0,1) (AFB_URR.py:144).  Any output pointer may be NULL. */
 int vfn_prep_rows(const float* d_src_dm, int32_t d, int64_t n, float* d_raw_em, float* d_normed_em,
@@ -72,7 +75,7 @@ int vfn_bank_append_rows(const vfn_bank* bank, const float* d_ck_em, const float
                          const int32_t* d_sel, int64_t n_sel_upper, const int32_t* d_n_sel, float info0, float info1,
                          void* stream);
 
-/* Recompute derived arrays (nkh/nkl, kh/kl, vh/vl) of slots [first, first+count) from keys/values. */
+/* Recompute derived arrays (nk, nkh/nkl, kh/kl, vh/v8/vl) of slots [first, first+count) from keys/values. */
 int vfn_bank_refresh(const vfn_bank* bank, int64_t first, int64_t count, void* stream);
 
 /* ---- memory read: Matcher.forward (AFB_URR.py:136-178) ------------------------------------------
@@ -99,7 +102,7 @@ int vfn_memread_phase_b(const vfn_bank* banks, int32_t obj_n, const float* d_q_i
 int vfn_lse_combine(const float* d_ml, int32_t n_parts, int64_t n_rows, float* d_lse, void* stream);
 
 /* ---- bank update: FeatureBank.update (FeatureBank.py:53-115) -----------------------------------
- * match: j*_q = argmax_i <nkh_i + nkl_i, nck_q>, ties -> lowest i; c*_q = that maximum.  (FeatureBank.py:63-68) */
+ * match: j*_q = argmax_i <nk_i, nck_q>, ties -> lowest i; c*_q = that maximum.  (FeatureBank.py:63-68) */
 size_t vfn_bank_match_workspace_bytes(int64_t n, int64_t hw);
 int vfn_bank_match(const vfn_bank* bank, const float* d_nck_em, int64_t hw, int32_t* d_match_idx, float* d_match_corr,
                    void* d_ws, size_t ws_bytes, int32_t impl, void* stream);
@@ -135,6 +138,41 @@ int vfn_bank_compact(const vfn_bank* src, const vfn_bank* dst, const float* d_lf
 
 /* info[:,1] = clamp(info[:,1], 0, 1e5) over slots [0, n)  (FeatureBank.py:115) */
 int vfn_bank_clamp_info(const vfn_bank* bank, int64_t n, void* stream);
+
+/* ---- whole update in one call: FeatureBank.update (FeatureBank.py:53-115) for all objects ----------
+ * Runs, for every object: candidate preparation, match, plan, merge, [LFU eviction if class_budget < n + |A|:
+ * evict plan + compaction into alts[c]], append, clamp - the exact sequence of the fine-grained entry points above,
+ * issued from C++ so that a frame costs one host call instead of ~25.  This entry point DOES synchronise the stream
+ * (once for the append counts, once more if any object evicts): those are the reference's own implicit syncs
+ * (`nonzero`, `int(LFU.min())`, FeatureBank.py:71,100,123).
+ * banks[c].n is updated in place.  If object c evicted, its live data moved into alts[c]: the two structs are
+ * swapped and io[c].swapped = 1 so the caller swaps its buffer ownership.  Capacity contract: banks[c].cap >= n + hw,
+ * alts[c].cap >= n (alts[c].keys may be NULL when the caller knows no eviction can happen: then an eviction is an error).
+ * io[c].d_* are caller-owned device buffers of hw (run_off: hw + 1) elements holding the decisions of this update. */
+typedef struct vfn_update_io {
+  const float* d_prev_key_dm;    /* (d_key, hw) candidate keys    (memorize() output, AFB_URR.py:255-272) */
+  const float* d_prev_value_dm;  /* (d_val, hw) candidate values */
+  int32_t* d_match_idx;          /* (hw) j*            */
+  float* d_match_corr;           /* (hw) c*            */
+  int32_t* d_merge_q;            /* (hw) merge pairs sorted by (slot, q) */
+  int32_t* d_merge_slot;         /* (hw) */
+  int32_t* d_run_off;            /* (hw + 1) */
+  int32_t* d_append_q;           /* (hw) append set, ascending */
+  /* host results */
+  int32_t n_merge, n_runs, n_append;
+  int32_t evicted;               /* 1 if remove() ran for this object */
+  int32_t swapped;               /* 1 if banks[c] / alts[c] were exchanged */
+  int32_t evict_status;          /* 0 ok, 1 = survivors empty (reference raises), 2 = non-finite LFU minimum */
+  int32_t kept, n_iter;
+  int32_t thresholds[64];        /* T sequence of remove() */
+  int64_t n_before;              /* bank size before this update */
+} vfn_update_io;
+
+size_t vfn_bank_update_workspace_bytes(int32_t obj_n, int64_t n_max, int64_t hw, int32_t d_key, int32_t d_val);
+/* h_pinned: obj_n * 80 int32 of pinned host memory (counts + eviction plans land there). */
+int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_io* io, int64_t hw, float frame_idx,
+                    float update_rate, float thres_close, double class_budget, void* d_ws, size_t ws_bytes,
+                    int32_t* h_pinned, int32_t impl, void* stream);
 
 /* ---- URR: non-convolution parts of Decoder.forward (AFB_URR.py:214-237, myutils/data.py:42-48) -----
  * pre:  p (obj_n,2,h/2,w/2) coarse logits from pred2, r1 (obj_n or 1, c, h, w)  ->

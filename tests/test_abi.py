@@ -36,10 +36,13 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    from vfloodnet_b200._lib import VfnBank
-    # 2 x int32, 2 x int64, 10 pointers
-    assert ctypes.sizeof(VfnBank) == 8 + 16 + 10 * 8
-    assert VfnBank.keys.offset == 24 and VfnBank.cnt.offset == 24 + 9 * 8
+    from vfloodnet_b200._lib import VfnBank, VfnUpdateIO
+    # 2 x int32, 2 x int64, 12 pointers
+    assert ctypes.sizeof(VfnBank) == 8 + 16 + 12 * 8
+    assert VfnBank.keys.offset == 24 and VfnBank.cnt.offset == 24 + 11 * 8
+    # 8 pointers, 8 + 64 int32, 1 int64
+    assert ctypes.sizeof(VfnUpdateIO) == 8 * 8 + 72 * 4 + 8
+    assert VfnUpdateIO.thresholds.offset == 8 * 8 + 8 * 4 and VfnUpdateIO.n_before.offset == 8 * 8 + 72 * 4
 
 
 def test_argument_errors_are_reported_not_fatal():

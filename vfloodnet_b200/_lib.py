@@ -14,11 +14,21 @@ c_i32, c_i64, c_f32, c_f64, c_vp, c_sz = C.c_int32, C.c_int64, C.c_float, C.c_do
 class VfnBank(C.Structure):
     """struct vfn_bank (include/vfn.h)"""
     _fields_ = [('d_key', c_i32), ('d_val', c_i32), ('cap', c_i64), ('n', c_i64),
-                ('keys', c_vp), ('values', c_vp), ('info', c_vp), ('nkh', c_vp), ('nkl', c_vp),
-                ('kh', c_vp), ('kl', c_vp), ('vh', c_vp), ('vl', c_vp), ('cnt', c_vp)]
+                ('keys', c_vp), ('values', c_vp), ('info', c_vp), ('nk', c_vp), ('nkh', c_vp), ('nkl', c_vp),
+                ('kh', c_vp), ('kl', c_vp), ('vh', c_vp), ('v8', c_vp), ('vl', c_vp), ('cnt', c_vp)]
+
+
+class VfnUpdateIO(C.Structure):
+    """struct vfn_update_io (include/vfn.h)"""
+    _fields_ = [('d_prev_key_dm', c_vp), ('d_prev_value_dm', c_vp), ('d_match_idx', c_vp), ('d_match_corr', c_vp),
+                ('d_merge_q', c_vp), ('d_merge_slot', c_vp), ('d_run_off', c_vp), ('d_append_q', c_vp),
+                ('n_merge', c_i32), ('n_runs', c_i32), ('n_append', c_i32), ('evicted', c_i32), ('swapped', c_i32),
+                ('evict_status', c_i32), ('kept', c_i32), ('n_iter', c_i32), ('thresholds', c_i32 * 64),
+                ('n_before', c_i64)]
 
 
 BANK_P = C.POINTER(VfnBank)
+IO_P = C.POINTER(VfnUpdateIO)
 
 # name -> (restype, argtypes); mirrors include/vfn.h one to one
 SIGNATURES = {
@@ -42,6 +52,9 @@ SIGNATURES = {
     'vfn_bank_compact_workspace_bytes': (c_sz, [c_i64]),
     'vfn_bank_compact': (c_i32, [BANK_P, BANK_P, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'vfn_bank_clamp_info': (c_i32, [BANK_P, c_i64, c_vp]),
+    'vfn_bank_update_workspace_bytes': (c_sz, [c_i32, c_i64, c_i64, c_i32, c_i32]),
+    'vfn_bank_update': (c_i32, [BANK_P, BANK_P, c_i32, IO_P, c_i64, c_f32, c_f32, c_f32, c_f64, c_vp, c_sz, c_vp,
+                                c_i32, c_vp]),
     'vfn_urr_pre': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vfn_urr_post': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     'vfn_profile_enable': (c_i32, [c_i32]),

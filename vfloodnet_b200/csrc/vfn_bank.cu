@@ -45,33 +45,42 @@ void prof_end(int kind, cudaStream_t st, double work) {
 void count_launches(int n) { g_launches += n; }
 
 // ------------------------------------------------------------------------------------------------
-// prep_rows: (d, n) dimension-major  ->  (n, d) entry-major raw / L2-normalised / bf16 hi+lo
+// prep_rows: (d, n) dimension-major  ->  (n, d) entry-major raw / L2-normalised / fp16 hi+lo.
+// One launch serves several independent jobs (blockIdx.y): all candidate tensors of a frame in one go.
+// hi/lo receive the split of raw*scale, or of normalised*scale when `split_normed` is set.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) prep_rows_kernel(const float* __restrict__ src, int d, int64_t n,
-                                                        float* __restrict__ raw, float* __restrict__ normed,
-                                                        uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
-                                                        float scale) {
+constexpr int PREP_MAX_JOBS = 16;
+struct PrepJobs { PrepJob j[PREP_MAX_JOBS]; };
+
+__global__ void __launch_bounds__(256) prep_rows_kernel(const __grid_constant__ PrepJobs jobs) {
   __shared__ float tile[32][33];
   __shared__ float part[8][32];
   __shared__ float denom[32];
+  const PrepJob& jb = jobs.j[blockIdx.y];
+  const float* __restrict__ src = jb.src;
+  const int d = jb.d;
+  const int64_t n = jb.n;
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int64_t q0 = (int64_t)blockIdx.x * 32;
+  if (q0 >= n) return;
   const int64_t q = q0 + tx;
-  float ss = 0.f;
-  if (q < n)
-    for (int k = ty; k < d; k += 8) {
-      float v = src[(int64_t)k * n + q];
-      ss = fmaf(v, v, ss);
-    }
-  part[ty][tx] = ss;
-  __syncthreads();
-  if (ty == 0) {
-    float t = 0.f;
+  if (jb.normed || jb.split_normed) {
+    float ss = 0.f;
+    if (q < n)
+      for (int k = ty; k < d; k += 8) {
+        float v = src[(int64_t)k * n + q];
+        ss = fmaf(v, v, ss);
+      }
+    part[ty][tx] = ss;
+    __syncthreads();
+    if (ty == 0) {
+      float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += part[i][tx];
-    denom[tx] = fmaxf(sqrtf(t), 1e-12f);   // NF.normalize eps
+      for (int i = 0; i < 8; ++i) t += part[i][tx];
+      denom[tx] = fmaxf(sqrtf(t), 1e-12f);   // NF.normalize eps
+    }
+    __syncthreads();
   }
-  __syncthreads();
   for (int k0 = 0; k0 < d; k0 += 32) {
     for (int r = ty; r < 32; r += 8) {
       int k = k0 + r;
@@ -84,13 +93,15 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const float* __restrict_
       if (qq < n && k < d) {
         float v = tile[tx][r];
         int64_t o = qq * d + k;
-        if (raw) raw[o] = v;
-        if (normed) normed[o] = v / denom[r];
-        if (hi) {
+        if (jb.raw) jb.raw[o] = v;
+        float nv = 0.f;
+        if (jb.normed || jb.split_normed) nv = v / denom[r];
+        if (jb.normed) jb.normed[o] = nv;
+        if (jb.hi) {
           uint16_t h, l;
-          split_bf16(v * scale, h, l);
-          hi[o] = h;
-          if (lo) lo[o] = l;
+          split_f16((jb.split_normed ? nv : v) * jb.scale, h, l);
+          jb.hi[o] = h;
+          if (jb.lo) jb.lo[o] = l;
         }
       }
     }
@@ -98,21 +109,22 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const float* __restrict_
   }
 }
 
+int launch_prep(const PrepJob* jobs, int n_jobs, cudaStream_t st) {
+  VFN_CHECK_ARG(n_jobs >= 1 && n_jobs <= PREP_MAX_JOBS, "prep: too many jobs");
+  PrepJobs pj;
+  int64_t n_max = 0;
+  for (int i = 0; i < n_jobs; ++i) { pj.j[i] = jobs[i]; if (jobs[i].n > n_max) n_max = jobs[i].n; }
+  if (n_max == 0) return VFN_OK;
+  dim3 block(32, 8), grid((unsigned)cdiv(n_max, 32), n_jobs);
+  prep_rows_kernel<<<grid, block, 0, st>>>(pj);
+  VFN_LAUNCH_OK();
+  count_launches(1);
+  return VFN_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // row helpers: one block owns one bank slot
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_split4(uint16_t* hi, uint16_t* lo, int64_t off, float4 v) {
-  uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
-  split_bf16(v.x, h0, l0);
-  split_bf16(v.y, h1, l1);
-  split_bf16(v.z, h2, l2);
-  split_bf16(v.w, h3, l3);
-  uint2 H = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
-  uint2 L = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
-  *reinterpret_cast<uint2*>(hi + off) = H;
-  *reinterpret_cast<uint2*>(lo + off) = L;
-}
-
 // append: grid.x = upper bound on selected rows; block = 128 threads; row i -> slot bank.n + i
 __global__ void __launch_bounds__(128) append_rows_kernel(vfn_bank bank, const float* __restrict__ ck,
                                                           const float* __restrict__ cv, const float* __restrict__ nck,
@@ -131,8 +143,8 @@ __global__ void __launch_bounds__(128) append_rows_kernel(vfn_bank bank, const f
     for (int f = threadIdx.x; f < dk4; f += blockDim.x) {
       float4 v = ks[f];
       reinterpret_cast<float4*>(bank.keys + dst * bank.d_key)[f] = v;
-      if (bank.kh) store_split4(bank.kh, bank.kl, dst * bank.d_key + 4 * f, v);
-      if (nck) store_nk4(bank.nkh, bank.nkl, dst * bank.d_key + 4 * f,
+      if (bank.kh) store_key_ops4(bank.kh, bank.kl, dst * bank.d_key + 4 * f, v);
+      if (nck) store_nk4(bank.nk, bank.nkh, bank.nkl, dst * bank.d_key + 4 * f,
                          reinterpret_cast<const float4*>(nck + s * bank.d_key)[f]);
       ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
     }
@@ -141,13 +153,14 @@ __global__ void __launch_bounds__(128) append_rows_kernel(vfn_bank bank, const f
       float den = fmaxf(sqrtf(tot), 1e-12f);
       for (int f = threadIdx.x; f < dk4; f += blockDim.x) {
         float4 v = ks[f];
-        store_nk4(bank.nkh, bank.nkl, dst * bank.d_key + 4 * f, make_float4(v.x / den, v.y / den, v.z / den, v.w / den));
+        store_nk4(bank.nk, bank.nkh, bank.nkl, dst * bank.d_key + 4 * f,
+                  make_float4(v.x / den, v.y / den, v.z / den, v.w / den));
       }
     }
     for (int f = threadIdx.x; f < dv4; f += blockDim.x) {
       float4 v = vs[f];
       reinterpret_cast<float4*>(bank.values + dst * bank.d_val)[f] = v;
-      if (bank.vh) store_split4(bank.vh, bank.vl, dst * bank.d_val + 4 * f, v);
+      if (bank.vh) store_val_ops4(bank.vh, bank.v8, bank.vl, dst * bank.d_val + 4 * f, v);
     }
     if (threadIdx.x == 0) {
       bank.info[dst * 2 + 0] = info0;
@@ -171,13 +184,14 @@ __global__ void __launch_bounds__(128) refresh_rows_kernel(vfn_bank bank, int64_
     float den = fmaxf(sqrtf(block_sum(ss, red)), 1e-12f);
     for (int f = threadIdx.x; f < dk4; f += blockDim.x) {
       float4 v = ks[f];
-      store_nk4(bank.nkh, bank.nkl, u * bank.d_key + 4 * f, make_float4(v.x / den, v.y / den, v.z / den, v.w / den));
-      if (bank.kh) store_split4(bank.kh, bank.kl, u * bank.d_key + 4 * f, v);
+      store_nk4(bank.nk, bank.nkh, bank.nkl, u * bank.d_key + 4 * f,
+                make_float4(v.x / den, v.y / den, v.z / den, v.w / den));
+      if (bank.kh) store_key_ops4(bank.kh, bank.kl, u * bank.d_key + 4 * f, v);
     }
     if (bank.vh)
       for (int f = threadIdx.x; f < dv4; f += blockDim.x)
-        store_split4(bank.vh, bank.vl, u * bank.d_val + 4 * f,
-                     reinterpret_cast<const float4*>(bank.values + u * bank.d_val)[f]);
+        store_val_ops4(bank.vh, bank.v8, bank.vl, u * bank.d_val + 4 * f,
+                       reinterpret_cast<const float4*>(bank.values + u * bank.d_val)[f]);
   }
 }
 
@@ -357,12 +371,13 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_runs_kernel(vfn_bank bank
     if (is_key) {
       reinterpret_cast<float4*>(bank.keys + u * bank.d_key)[f] = nw;
       const float d2 = fmaxf(sqrtf(ssk2), 1e-12f);
-      store_nk4(bank.nkh, bank.nkl, u * bank.d_key + 4 * f, make_float4(nw.x / d2, nw.y / d2, nw.z / d2, nw.w / d2));
-      if (bank.kh) store_split4(bank.kh, bank.kl, u * bank.d_key + 4 * f, nw);
+      store_nk4(bank.nk, bank.nkh, bank.nkl, u * bank.d_key + 4 * f,
+                make_float4(nw.x / d2, nw.y / d2, nw.z / d2, nw.w / d2));
+      if (bank.kh) store_key_ops4(bank.kh, bank.kl, u * bank.d_key + 4 * f, nw);
     }
     if (is_val) {
       reinterpret_cast<float4*>(bank.values + u * bank.d_val)[f - dk4] = nw;
-      if (bank.vh) store_split4(bank.vh, bank.vl, u * bank.d_val + 4 * (f - dk4), nw);
+      if (bank.vh) store_val_ops4(bank.vh, bank.v8, bank.vl, u * bank.d_val + 4 * (f - dk4), nw);
     }
   }
 }
@@ -502,13 +517,15 @@ __global__ void __launch_bounds__(CP_THREADS) compact_move_kernel(vfn_bank src, 
     const int64_t d = base_dst + e;
     warp_copy16(dst.keys + d * dk, src.keys + s * dk, dk / 4, lane);
     warp_copy16(dst.values + d * dv, src.values + s * dv, dv / 4, lane);
-    warp_copy16(dst.nkh + d * dk, src.nkh + s * dk, dk / 4, lane);
-    warp_copy16(dst.nkl + d * dk, src.nkl + s * dk, dk / 4, lane);
+    warp_copy16(dst.nk + d * dk, src.nk + s * dk, dk / 4, lane);
     if (src.kh) {
+      warp_copy16(dst.nkh + d * dk, src.nkh + s * dk, dk / 8, lane);
+      warp_copy16(dst.nkl + d * dk, src.nkl + s * dk, dk / 8, lane);
       warp_copy16(dst.kh + d * dk, src.kh + s * dk, dk / 8, lane);
       warp_copy16(dst.kl + d * dk, src.kl + s * dk, dk / 8, lane);
       warp_copy16(dst.vh + d * dv, src.vh + s * dv, dv / 8, lane);
-      warp_copy16(dst.vl + d * dv, src.vl + s * dv, dv / 8, lane);
+      warp_copy16(dst.v8 + d * dv, src.v8 + s * dv, dv / 16, lane);
+      warp_copy16(dst.vl + d * dv, src.vl + s * dv, dv / 16, lane);
     }
     if (lane == 0) {
       reinterpret_cast<float2*>(dst.info)[d] = reinterpret_cast<const float2*>(src.info)[s];
@@ -530,11 +547,12 @@ static int check_bank(const vfn_bank* b) {
   VFN_CHECK_ARG(b != nullptr, "bank is NULL");
   VFN_CHECK_ARG(b->d_key > 0 && b->d_val > 0 && b->d_key % 8 == 0 && b->d_val % 8 == 0,
                 "d_key/d_val must be positive multiples of 8 (got %d, %d)", b->d_key, b->d_val);
-  VFN_CHECK_ARG(b->keys && b->values && b->info && b->nkh && b->nkl && b->cnt, "bank has NULL arrays");
+  VFN_CHECK_ARG(b->keys && b->values && b->info && b->nk && b->cnt, "bank has NULL arrays");
   VFN_CHECK_ARG(b->n >= 0 && b->n <= b->cap, "bank n=%lld exceeds cap=%lld", (long long)b->n, (long long)b->cap);
   VFN_CHECK_ARG((b->kh == nullptr) == (b->kl == nullptr) && (b->kh == nullptr) == (b->vh == nullptr) &&
-                    (b->kh == nullptr) == (b->vl == nullptr),
-                "bf16 operand arrays must be all set or all NULL");
+                    (b->kh == nullptr) == (b->vl == nullptr) && (b->kh == nullptr) == (b->v8 == nullptr) &&
+                    (b->kh == nullptr) == (b->nkh == nullptr) && (b->kh == nullptr) == (b->nkl == nullptr),
+                "tensor-core operand arrays must be all set or all NULL");
   return VFN_OK;
 }
 
@@ -595,12 +613,8 @@ int vfn_prep_rows(const float* d_src_dm, int32_t d, int64_t n, float* d_raw_em, 
                   uint16_t* d_lo_em, float scale, void* stream) {
   VFN_CHECK_ARG(d_src_dm && d > 0 && n >= 0, "prep_rows: bad args");
   if (n == 0) return VFN_OK;
-  dim3 block(32, 8);
-  prep_rows_kernel<<<(unsigned)cdiv(n, 32), block, 0, as_stream(stream)>>>(d_src_dm, d, n, d_raw_em, d_normed_em,
-                                                                           d_hi_em, d_lo_em, scale);
-  VFN_LAUNCH_OK();
-  count_launches(1);
-  return VFN_OK;
+  PrepJob jb{d_src_dm, d, n, d_raw_em, d_normed_em, d_hi_em, d_lo_em, scale, d_normed_em ? 1 : 0};
+  return launch_prep(&jb, 1, as_stream(stream));
 }
 
 int vfn_bank_append_rows(const vfn_bank* bank, const float* d_ck_em, const float* d_cv_em, const float* d_nck_em,

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -18,6 +20,13 @@ enum ProfKind { PROF_READ_A = 0, PROF_READ_B = 1, PROF_MATCH = 2, PROF_COMPACT =
 void prof_begin(int kind, cudaStream_t st);
 void prof_end(int kind, cudaStream_t st, double work);
 void count_launches(int n);
+
+// several (d, n) -> (n, d) preparation jobs in one launch (vfn_bank.cu)
+struct PrepJob {
+  const float* src; int d; int64_t n;
+  float* raw; float* normed; uint16_t* hi; uint16_t* lo; float scale; int split_normed;
+};
+int launch_prep(const PrepJob* jobs, int n_jobs, cudaStream_t st);
 
 #define VFN_CHECK_ARG(cond, ...)              \
   do {                                        \
@@ -42,26 +51,53 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// bf16 hi/lo split: x ~= hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi)   (16 mantissa bits kept)
-__device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& lo) {
-  __nv_bfloat16 h = __float2bfloat16_rn(x);
-  float r = x - __bfloat162float(h);
-  __nv_bfloat16 l = __float2bfloat16_rn(r);
-  hi = __bfloat16_as_ushort(h);
-  lo = __bfloat16_as_ushort(l);
+// ---- tensor-core operand formats --------------------------------------------------------------
+// fp16 hi/lo split: x ~= hi + lo with hi = f16_rn(x), lo = f16_rn(x - hi): ~22 significant bits.  satfinite: a value
+// beyond the fp16 range clamps (finite garbage for |x| > 6.5e4) instead of producing inf/NaN inside an MMA.
+__device__ __forceinline__ uint16_t f16_sat(float x) {
+  uint16_t h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  return h;
 }
+__device__ __forceinline__ float f16_to_f32(uint16_t h) { return __half2float(__ushort_as_half(h)); }
+__device__ __forceinline__ void split_f16(float x, uint16_t& hi, uint16_t& lo) {
+  hi = f16_sat(x);
+  lo = f16_sat(x - f16_to_f32(hi));
+}
+// two floats -> packed fp8 pair, a in the LOW byte (memory order a, b)
+__device__ __forceinline__ uint16_t e4m3x2(float a, float b) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ uint16_t e5m2x2(float a, float b) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(r) : "f"(b), "f"(a));
+  return r;
+}
+// normalised keys are stored x16 in fp16 hi/lo so that the lo part stays in the normal range (|nk| <= 1)
+constexpr float NK_SCALE = 16.f;
 
-// tf32 hi/lo split: hi keeps sign, exponent and the top 10 mantissa bits (exactly representable in tf32, whatever
-// the tensor core does with the discarded bits), lo = x - hi is exact in fp32
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-  lo = x - hi;
+// keys: fp16 hi + fp16 lo (3-pass product, ~2^-22)
+__device__ __forceinline__ void store_key_ops4(uint16_t* kh, uint16_t* kl, int64_t off, float4 v) {
+  uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+  split_f16(v.x, h0, l0); split_f16(v.y, h1, l1); split_f16(v.z, h2, l2); split_f16(v.w, h3, l3);
+  *reinterpret_cast<uint2*>(kh + off) = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+  *reinterpret_cast<uint2*>(kl + off) = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
 }
-__device__ __forceinline__ void store_nk4(float* nkh, float* nkl, int64_t off, float4 v) {
-  float4 h, l;
-  split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-  *reinterpret_cast<float4*>(nkh + off) = h;
-  *reinterpret_cast<float4*>(nkl + off) = l;
+// values: fp16 hi, e4m3 of the value (partner of the P-residual pass), e5m2 of the residual v - hi
+__device__ __forceinline__ void store_val_ops4(uint16_t* vh, uint8_t* v8, uint8_t* vl, int64_t off, float4 v) {
+  const uint16_t h0 = f16_sat(v.x), h1 = f16_sat(v.y), h2 = f16_sat(v.z), h3 = f16_sat(v.w);
+  *reinterpret_cast<uint2*>(vh + off) = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+  *reinterpret_cast<uint32_t*>(v8 + off) = (uint32_t)e4m3x2(v.x, v.y) | ((uint32_t)e4m3x2(v.z, v.w) << 16);
+  *reinterpret_cast<uint32_t*>(vl + off) =
+      (uint32_t)e5m2x2(v.x - f16_to_f32(h0), v.y - f16_to_f32(h1)) |
+      ((uint32_t)e5m2x2(v.z - f16_to_f32(h2), v.w - f16_to_f32(h3)) << 16);
+}
+// normalised key: exact fp32 copy (re-score / SIMT match) + fp16 hi/lo of 16*nk (tensor-core match), if present
+__device__ __forceinline__ void store_nk4(float* nk, uint16_t* nkh, uint16_t* nkl, int64_t off, float4 v) {
+  *reinterpret_cast<float4*>(nk + off) = v;
+  if (nkh) store_key_ops4(nkh, nkl, off, make_float4(v.x * NK_SCALE, v.y * NK_SCALE, v.z * NK_SCALE, v.w * NK_SCALE));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

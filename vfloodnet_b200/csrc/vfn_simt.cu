@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(ST_THREADS) simt_score_kernel(BankSet banks, c
   __shared__ float red1[16][TN];
   const vfn_bank bk = banks.b[blockIdx.z];
   const int d = bk.d_key;
-  const float* A = (MODE == MODE_MATCH) ? bk.nkh : bk.keys;
-  const float* A2 = (MODE == MODE_MATCH) ? bk.nkl : nullptr;
+  const float* A = (MODE == MODE_MATCH) ? bk.nk : bk.keys;
+  const float* A2 = nullptr;
   const int64_t n = bk.n;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int64_t j0 = (int64_t)blockIdx.x * TN;
@@ -592,7 +592,9 @@ int vfn_memread(const vfn_bank* banks, int32_t obj_n, const float* d_q_in_dm, co
 
 size_t vfn_bank_match_workspace_bytes(int64_t n, int64_t hw) {
   (void)n;
-  return align_up((size_t)64 * hw * 4 * sizeof(float2), 256);   // 64 pieces x top-4 candidates
+  const size_t simt = align_up((size_t)64 * hw * sizeof(float2), 256);
+  const size_t tc = tc_match_workspace_bytes(1, hw);
+  return simt > tc ? simt : tc;
 }
 
 int vfn_bank_match(const vfn_bank* bank, const float* d_nck_em, int64_t hw, int32_t* d_match_idx, float* d_match_corr,
@@ -604,9 +606,9 @@ int vfn_bank_match(const vfn_bank* bank, const float* d_nck_em, int64_t hw, int3
   cudaStream_t st = as_stream(stream);
   if (ws_bytes < vfn_bank_match_workspace_bytes(n_max, hw)) { set_error("match: workspace too small"); return VFN_E_CAPACITY; }
   int split = 0;
-  const bool tc = (impl != 1) && set.b[0].d_key == 128 && vfn_device_is_sm100();
+  const bool tc = (impl != 1) && set.b[0].d_key == 128 && set.b[0].nkh != nullptr && vfn_device_is_sm100();
   if (impl == 2 && !tc) { set_error("tcgen05 match needs d_key = 128 on an sm_100 device"); return VFN_E_UNSUPPORTED; }
-  if (tc) return tc_match(&set.b[0], d_nck_em, hw, 64, reinterpret_cast<float2*>(d_ws), d_match_idx, d_match_corr, st);
+  if (tc) return tc_match(&set.b[0], 1, &d_nck_em, hw, reinterpret_cast<char*>(d_ws), 0, &d_match_idx, &d_match_corr, st);
   {
     const int q_tiles = (int)cdiv(hw, TN);
     split = pick_split(cdiv(n_max, TM), q_tiles, 148 * 4);

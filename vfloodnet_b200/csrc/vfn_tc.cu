@@ -1,19 +1,22 @@
-// tcgen05 / TMEM / TMA implementation of the memory read (Matcher.forward, AFB_URR.py:136-178) for sm_100a.
+// tcgen05 / TMEM / TMA implementation of the memory read (Matcher.forward, AFB_URR.py:136-178) and of the cosine
+// match (FeatureBank.py:63-68) for sm_100a.
 //
 //   phase A  S^T[j,i] = <q_j, k_i> * log2(e)/sqrt(128)   -> per-query running (max, sum 2^(s-max)) over the slots
 //   phase B  S^T recomputed, P = 2^(S - lse2_j) (already normalised: no online rescale), usage counts
 //            cnt_i += [P_ij > thres], O^T[j,c] += sum_i P_ij V_ic with the fp32 accumulator resident in TMEM.
+//   match    corr[j,i] = <nck_j, nk_i> -> per-query candidate slots within a band of the maximum -> exact fp32 re-score.
 //
-// Orientation (both phases): TMEM lanes = queries (M = 128), columns = bank slots (S) / value channels (O).
-// A operands come from TMEM (Q for the S-MMA, P for the O-MMA), B operands from shared memory via TMA:
-//   K tiles  K-major  [slots x 128 d]   bf16, 128B swizzle, two 64-d boxes per piece
-//   V tiles  MN-major [slots x 256 ch]  bf16, 128B swizzle, four 64-channel boxes per piece
-// Precision: operands are bf16 hi+lo splits (x ~ hi + lo, 16 mantissa bits); every product uses
-// hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM (3 MMA passes), which keeps logits to ~2e-5 and the
-// readout far inside the 1e-3 tolerance (plain bf16 would give ~7e-3).
-// Work split: persistent CTAs (one per SM), static stream-K partition of the (object, query tile[, channel half])
-// x slot-tile space, so every CTA gets the same number of tile units; per-CTA partials are combined by
-// lse_combine_kernel / combine_out_kernel (vfn_simt.cu) in a fixed order (deterministic).
+// Orientation (all kernels): TMEM lanes = queries / candidates (M = 128), columns = bank slots (S) / value channels (O).
+// A operands come from TMEM (Q for the S-MMA, P for the O-MMA), B operands from shared memory via TMA (128B swizzle):
+//   K tiles  K-major  [slots x 128 d]   fp16 hi, fp16 lo
+//   V tiles  MN-major [slots x 256 ch]  fp16 hi, e4m3(value), e5m2(value - hi)
+// Precision (scripts/precision_study.py):
+//   affinity / match scores: fp16 hi/lo splits, hi*hi + lo*hi + hi*lo (kind::f16, 3 passes, ~2^-21 relative):
+//     logits and LSE are fp32-grade, so the usage-count threshold P > 1e-3 decides like the reference;
+//   readout: P' = 256*P = hi(fp16) + lo, O' = hi*Vhi (kind::f16) + e4m3(lo)*e4m3(V) + e4m3(P')*e5m2(V - Vhi)
+//     (kind::f8f6f4, double rate): 2 bf16-equivalent passes instead of 3, readout error ~1e-4 (tolerance 1e-3).
+// Work split: persistent CTAs (one per SM), work items = (slot split x object x query tile[, channel half]) dealt
+// round-robin; per-item partials are combined in a fixed order (vfn_simt.cu), deterministic.
 #include "vfn_tc.cuh"
 
 #include <cuda.h>
@@ -152,6 +155,47 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+
+// kind::f8f6f4: A (tmem) and B (smem) are 8-bit floats (formats in the instruction descriptor), K = 32 per instruction
+__device__ __forceinline__ void mma_ts_f8(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3])
+               : "memory");
+}
+__device__ __forceinline__ uint32_t f16x2_rn(float lo, float hi) {   // lo -> low half
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 f16x2_to_f32(uint32_t h) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&h));
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
 // ------------------------------------------------------------------------------------------------
 // descriptors
 // ------------------------------------------------------------------------------------------------
@@ -160,67 +204,93 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor kind::f16: bf16 x bf16 -> f32
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// instruction descriptor, fp32 accumulate.  kind::f16: fmt 0 = f16, 1 = bf16; kind::f8f6f4: fmt 0 = e4m3, 1 = e5m2.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_fmt, int b_fmt, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-
-// instruction descriptor kind::tf32: tf32 x tf32 -> f32, both operands K-major
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
+constexpr int FMT_F16 = 0, FMT_E4M3 = 0, FMT_E5M2 = 1;
 
 constexpr int DK = 128, DV = 512;
 constexpr int QT = 128;                 // queries per tile (TMEM lanes)
-constexpr int TC_THREADS = 384;         // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 softmax WG0, 8-11 softmax WG1
+// warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4..19 sixteen epilogue / softmax warps
+// (warp w owns TMEM lanes 32*(w%4)..+32; the four warps sharing a lane quarter split the columns)
+constexpr int TC_THREADS = 640;
+constexpr int EPI_WARPS = 16, EPI_THREADS = EPI_WARPS * 32;
 constexpr int TC_MAX_OBJ = 4;
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 
-// TMEM columns
-constexpr uint32_t TM_O = 0;            // phase B: O^T accumulator, 256 columns
-constexpr uint32_t TM_QH = 256, TM_QL = 320;   // Q hi / lo as A operand: 64 columns each (128 bf16)
-constexpr uint32_t TM_S = 384;          // phase B: 2 buffers x 64 columns ; phase A uses [0,256) as 2 x 128
-
 struct TcMaps {
-  CUtensorMap kh[TC_MAX_OBJ], kl[TC_MAX_OBJ], vh[TC_MAX_OBJ], vl[TC_MAX_OBJ];
+  CUtensorMap kh[TC_MAX_OBJ], kl[TC_MAX_OBJ], vh[TC_MAX_OBJ], v8[TC_MAX_OBJ], vl[TC_MAX_OBJ];
 };
 struct TcArgs {
-  int obj_n, hw, q_tiles, pieces;       // pieces = partial slots per combo (P_MAX)
+  int obj_n, hw, q_tiles, pieces;       // pieces = partial slots per combo
   int n[TC_MAX_OBJ];                    // live slots per object
   int tiles[TC_MAX_OBJ];                // slot tiles per object for this phase
-  const uint16_t* qh;                   // (q_tiles*128, 128) bf16 hi of q * log2e/sqrt(d)
+  const uint16_t* qh;                   // (rows, 128) fp16 hi of the A operand (q * log2e/sqrt(d), or 16 * normalised candidate)
   const uint16_t* ql;
+  long long a_obj_stride;               // elements between objects in qh/ql (0: one query set for all objects)
   int32_t* cnt[TC_MAX_OBJ];
+  float band;                           // match: candidate band in the (scaled) score domain
   float* dbg;
 };
 
+// A operand (128 rows x 128 d, fp16 hi and lo) -> TMEM columns [col_h, col_h+64) and [col_l, col_l+64).
+// Epilogue warp (quarter q, column group cg): cg 0,1 -> hi halves, cg 2,3 -> lo halves; 32 columns (64 fp16) each.
+__device__ __forceinline__ void load_a_operand(const TcArgs& args, int obj, int qt, uint32_t tmem, uint32_t col_h,
+                                               uint32_t col_l, int warp, int lane) {
+  const int quarter = warp & 3, cg = (warp - 4) >> 2;
+  const int row = (quarter << 5) + lane;
+  const uint16_t* base = (cg < 2 ? args.qh : args.ql) + (size_t)obj * args.a_obj_stride;
+  const uint4* src = reinterpret_cast<const uint4*>(base + ((size_t)qt * QT + row) * DK + (cg & 1) * 64);
+  const uint32_t taddr = tmem + (((uint32_t)quarter * 32u) << 16) + (cg < 2 ? col_h : col_l) + (uint32_t)(cg & 1) * 32u;
+  uint32_t v[32];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint4 x = src[i];
+    v[4 * i + 0] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+  }
+  tmem_st32(taddr, v);
+  tmem_wait_st();
+}
 
 // ------------------------------------------------------------------------------------------------
-// phase A
+// score scan: phase A of the read (MODE_LSE) and the cosine match (MODE_MATCH).
+//   TMEM: A hi [0,64) | A lo [64,128) | three S buffers of 128 columns at 128 + 128 b
+//   smem: three 64 KB stages, each one 128-slot tile of the B operand: [hi: 2 boxes of 64 d | lo: 2 boxes]
+// Every epilogue warp processes its 32 columns of EVERY tile; a buffer is released as soon as its values are in
+// registers, so the MMA stream runs up to two tiles ahead of the epilogue.
 // ------------------------------------------------------------------------------------------------
-constexpr int A_TILE = 128;             // slots per S tile
-constexpr int A_STAGES = 3;
-constexpr int A_STAGE_BYTES = A_TILE * DK * 2 * 2;   // hi + lo = 64 KB
-constexpr int A_SMEM = A_STAGES * A_STAGE_BYTES + 1024 + 256;
+constexpr int SC_TILE = 128;
+constexpr int SC_STAGES = 3, SC_BUFS = 3;
+constexpr int SC_STAGE_BYTES = SC_TILE * DK * 2 * 2;   // hi + lo = 64 KB
+constexpr int SC_AUX_BYTES = EPI_THREADS * 4 * 8;      // match: 4-entry candidate ring per epilogue thread; LSE: (m,l) exchange
+constexpr int SC_SMEM = SC_STAGES * SC_STAGE_BYTES + 1024 + 256 + SC_AUX_BYTES;
+constexpr uint32_t TS_AH = 0, TS_AL = 64, TS_S = 128;
+constexpr int MODE_LSE = 0, MODE_MATCH = 1;
+constexpr int MATCH_RING = 4;           // near-tie candidates kept per (item, query, column group)
+constexpr int MATCH_CAND = 4 * MATCH_RING;   // candidate entries per (item, query)
 
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_a_kernel(const __grid_constant__ TcMaps maps, TcArgs args,
-                                                                   float2* __restrict__ part) {
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const __grid_constant__ TcMaps maps, TcArgs args,
+                                                                float2* __restrict__ part) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* kst = smem;                                           // A_STAGES x 64 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_STAGES * A_STAGE_BYTES);
-  uint64_t* k_full = bars;                 // [A_STAGES]
-  uint64_t* k_empty = bars + A_STAGES;     // [A_STAGES]
-  uint64_t* s_full = bars + 2 * A_STAGES;  // [2]
-  uint64_t* s_empty = s_full + 2;          // [2]
-  uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(s_empty + 2);
-  __shared__ float2 ml_x[QT];
+  uint8_t* kst = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SC_STAGES * SC_STAGE_BYTES);
+  uint64_t* k_full = bars;                   // [3]
+  uint64_t* k_empty = bars + 3;              // [3]
+  uint64_t* s_full = bars + 6;               // [3]
+  uint64_t* s_empty = bars + 9;              // [3]
+  uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(bars + 12);
+  float2* aux = reinterpret_cast<float2*>(smem + SC_STAGES * SC_STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128); }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], EPI_WARPS);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_base_p, 512);
@@ -230,12 +300,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_a_kernel(const __grid_
   const uint32_t tmem = *tmem_base_p;
 
   // work items = (split, object, query tile), dealt round-robin to the persistent CTAs: in any round all CTAs
-  // stream the same few slot ranges, so the K tiles are served from L2 (ncu: 14x DRAM re-reads with a per-CTA
-  // contiguous partition, profiles/r1_*).
+  // stream the same few slot ranges, so the tiles are served from L2 (profiles/r1a_summary.md).
   const int n_combos = args.obj_n * args.q_tiles;
   const int n_items = n_combos * args.pieces;
-  uint32_t k_it = 0;            // tiles streamed so far (producer & MMA agree)
-  uint32_t buf_it[2] = {0, 0};  // uses of each S buffer so far
+  uint32_t tile_ctr = 0;        // tiles streamed so far by this CTA (all roles agree)
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int piece = item / n_combos;
     const int combo = item - piece * n_combos;
@@ -248,59 +316,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_a_kernel(const __grid_
     const int ntile = t1 - t0;
     const bool first_item = (item == (int)blockIdx.x);
 
-    // (1) Q tile -> TMEM (WG0: hi, WG1: lo); one row (query) per thread
-    if (warp >= 4) {
-      const int wg = (warp - 4) >> 2;
-      const int row = ((warp & 3) << 5) + lane;
-      const uint16_t* src = (wg == 0 ? args.qh : args.ql) + ((size_t)qt * QT + row) * DK;
-      const uint32_t tbase = tmem + (((uint32_t)(warp & 3) * 32u) << 16) + (wg == 0 ? TM_QH : TM_QL);
-      uint32_t v[32];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint4 x = reinterpret_cast<const uint4*>(src)[h * 8 + i];
-          v[4 * i + 0] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
-        }
-        tmem_st32(tbase + h * 32, v);
-      }
-      tmem_wait_st();
-    }
+    if (warp >= 4) load_a_operand(args, obj, qt, tmem, TS_AH, TS_AL, warp, lane);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
 
-    // (2) roles
     if (warp == 0) {
-      for (int t = 0; t < ntile; ++t, ++k_it) {
-        const uint32_t st = k_it % A_STAGES, ph = (k_it / A_STAGES) & 1;
-        if (lane == 0) {
+      if (lane == 0) {
+        for (int t = 0; t < ntile; ++t) {
+          const uint32_t c = tile_ctr + t, st = c % SC_STAGES, ph = (c / SC_STAGES) & 1;
           mbar_wait(&k_empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&k_full[st], A_STAGE_BYTES);
-          uint8_t* dst = kst + st * A_STAGE_BYTES;
-          const int row0 = (t0 + t) * A_TILE;
+          mbar_arrive_expect_tx(&k_full[st], SC_STAGE_BYTES);
+          uint8_t* dst = kst + st * SC_STAGE_BYTES;
+          const int row0 = (t0 + t) * SC_TILE;
           tma_load_2d(dst, &maps.kh[obj], &k_full[st], 0, row0);
           tma_load_2d(dst + 16384, &maps.kh[obj], &k_full[st], 64, row0);
           tma_load_2d(dst + 32768, &maps.kl[obj], &k_full[st], 0, row0);
           tma_load_2d(dst + 49152, &maps.kl[obj], &k_full[st], 64, row0);
         }
-        __syncwarp();
       }
+      __syncwarp();
     } else if (warp == 1) {
-      constexpr uint32_t idesc = make_idesc(128, A_TILE, 0, 0);
-      for (int t = 0; t < ntile; ++t, ++k_it) {
-        const uint32_t st = k_it % A_STAGES, ph = (k_it / A_STAGES) & 1;
-        const int b = t & 1;
-        if (lane == 0) {
-          mbar_wait(&s_empty[b], (buf_it[b] & 1) ^ 1);
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc(128, SC_TILE, FMT_F16, FMT_F16, 0, 0);
+        for (int t = 0; t < ntile; ++t) {
+          const uint32_t c = tile_ctr + t, st = c % SC_STAGES, ph = (c / SC_STAGES) & 1;
+          mbar_wait(&s_empty[st], ph ^ 1);
           mbar_wait(&k_full[st], ph);
           tc_fence_after();
-          const uint32_t kbase = smem_u32(kst + st * A_STAGE_BYTES);
-          const uint32_t d_t = tmem + (uint32_t)b * A_TILE;
-          // passes: (Qh,Kh) (Ql,Kh) (Qh,Kl)
+          const uint32_t kbase = smem_u32(kst + st * SC_STAGE_BYTES);
+          const uint32_t d_t = tmem + TS_S + st * SC_TILE;
+          // passes: (Ah,Bh) (Al,Bh) (Ah,Bl)
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t a_col = (pass == 1) ? TM_QL : TM_QH;
+            const uint32_t a_col = (pass == 1) ? TS_AL : TS_AH;
             const uint32_t kb = kbase + ((pass == 2) ? 32768u : 0u);
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
@@ -309,69 +358,110 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_a_kernel(const __grid_
             }
           }
           tc_commit(&k_empty[st]);
-          tc_commit(&s_full[b]);
+          tc_commit(&s_full[st]);
         }
-        __syncwarp();
-        ++buf_it[b];
       }
+      __syncwarp();
     } else if (warp >= 4) {
-      const int wg = (warp - 4) >> 2;
-      const int row = ((warp & 3) << 5) + lane;
-      const uint32_t tlane = tmem + (((uint32_t)(warp & 3) * 32u) << 16);
+      const int quarter = warp & 3, cg = (warp - 4) >> 2;
+      const int row = (quarter << 5) + lane;
+      const int et = threadIdx.x - 128;                       // 0..511
+      const uint32_t tlane = tmem + (((uint32_t)quarter * 32u) << 16) + TS_S + (uint32_t)cg * 32u;
       float m_run = -INFINITY, l_run = 0.f;
-      for (int t = wg; t < ntile; t += 2) {
-        mbar_wait(&s_full[wg], buf_it[wg] & 1);
-        ++buf_it[wg];
+      int cnt = 0;
+      float2* ring = aux + et * MATCH_RING;
+      for (int t = 0; t < ntile; ++t) {
+        const uint32_t c = tile_ctr + t, st = c % SC_BUFS, ph = (c / SC_BUFS) & 1;
+        mbar_wait(&s_full[st], ph);
         tc_fence_after();
-        const int slot0 = (t0 + t) * A_TILE;
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t v[32];
-          tmem_ld32(tlane + (uint32_t)wg * A_TILE + ch * 32, v);
-          tmem_wait_ld();
-          if (args.dbg && blockIdx.x == 0 && first_item && t == 0) {
+        uint32_t v[32];
+        tmem_ld32(tlane + st * SC_TILE, v);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[st]);             // values are in registers: the buffer is free
+        if (args.dbg && blockIdx.x == 0 && first_item && t == 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) args.dbg[row * A_TILE + ch * 32 + i] = __uint_as_float(v[i]);
-          }
-          float cm = -INFINITY;
-          const int lim = n_obj - (slot0 + ch * 32);     // valid slots in this chunk
+          for (int i = 0; i < 32; ++i) args.dbg[row * SC_TILE + cg * 32 + i] = __uint_as_float(v[i]);
+        }
+        const int slot0 = (t0 + t) * SC_TILE + cg * 32;
+        const int lim = n_obj - slot0;                        // valid slots in this thread's 32 columns
+        if (lim <= 0) continue;
+        if (lim < 32) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float s = __uint_as_float(v[i]);
-            s = (i < lim) ? s : -INFINITY;
-            v[i] = __float_as_uint(s);
-            cm = fmaxf(cm, s);
-          }
+          for (int i = 0; i < 32; ++i)
+            if (i >= lim) v[i] = __float_as_uint(-INFINITY);
+        }
+        float cm = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) cm = fmax3(cm, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+        if (MODE == MODE_LSE) {
           const float m_new = fmaxf(m_run, cm);
           if (m_new > -INFINITY) {
-            float acc = 0.f;
+            float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) acc += ex2(__uint_as_float(v[i]) - m_new);
-            l_run = l_run * ex2(m_run - m_new) + acc;
+            for (int i = 0; i < 32; i += 2) {
+              a0 += ex2(__uint_as_float(v[i]) - m_new);
+              a1 += ex2(__uint_as_float(v[i + 1]) - m_new);
+            }
+            l_run = l_run * ex2(m_run - m_new) + (a0 + a1);
             m_run = m_new;
           }
+        } else {
+          // candidates = every slot whose score is within `band` of the running maximum at its time; a jump of the
+          // maximum by more than the band invalidates everything before it
+          if (cm > m_run + args.band) cnt = 0;
+          const float m_new = fmaxf(m_run, cm);
+          const float thr = m_new - args.band;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float sv = __uint_as_float(v[i]);
+            if (sv >= thr) {
+              ring[cnt & (MATCH_RING - 1)] = make_float2(sv, __int_as_float(slot0 + i));
+              ++cnt;
+            }
+          }
+          m_run = m_new;
         }
-        tc_fence_before();
-        mbar_arrive(&s_empty[wg]);
       }
-      // (3) combine the two warpgroups' statistics and publish the piece
-      if (wg == 1) ml_x[row] = make_float2(m_run, l_run);
-      named_bar_sync(1, 256);
-      if (wg == 0) {
-        const float2 o = ml_x[row];
-        const float m = fmaxf(m_run, o.x);
-        float l = 0.f;
-        if (m > -INFINITY) l = l_run * ex2(m_run - m) + o.y * ex2(o.x - m);
-        const int j = qt * QT + row;
-        if (j < args.hw) part[((size_t)obj * args.pieces + piece) * args.hw + j] = make_float2(m * LN2, l);
+      const int j = qt * QT + row;
+      if (MODE == MODE_LSE) {
+        // combine the four column groups' statistics and publish the piece
+        aux[cg * QT + row] = make_float2(m_run, l_run);
+        named_bar_sync(1, EPI_THREADS);
+        if (cg == 0) {
+          float m = m_run;
+#pragma unroll
+          for (int g = 1; g < 4; ++g) m = fmaxf(m, aux[g * QT + row].x);
+          float l = 0.f;
+          if (m > -INFINITY) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float2 o = aux[g * QT + row];
+              if (o.x > -INFINITY) l += o.y * ex2(o.x - m);
+            }
+          }
+          if (j < args.hw) part[((size_t)obj * args.pieces + piece) * args.hw + j] = make_float2(m * LN2, l);
+        }
+        named_bar_sync(1, EPI_THREADS);                      // aux is reused by the next item
+      } else {
+        if (j < args.hw) {
+          float2 e[MATCH_RING];
+          const float thr = m_run - args.band;
+#pragma unroll
+          for (int r = 0; r < MATCH_RING; ++r) {
+            const float2 x = ring[r];
+            e[r] = (r < cnt && x.x >= thr) ? x : make_float2(-INFINITY, __int_as_float(0x7fffffff));
+          }
+          if (cnt > MATCH_RING) e[0] = make_float2(m_run, __int_as_float(-1));     // overflow: exact scan needed
+          float4* dst = reinterpret_cast<float4*>(
+              part + (((size_t)obj * args.pieces + piece) * args.hw + j) * MATCH_CAND + cg * MATCH_RING);
+          dst[0] = make_float4(e[0].x, e[0].y, e[1].x, e[1].y);
+          dst[1] = make_float4(e[2].x, e[2].y, e[3].x, e[3].y);
+        }
       }
-    } else {
-      // warps 2,3 idle during the tile loop
     }
-    // keep role-local counters consistent for warps that did not run the loops
-    if (warp != 0 && warp != 1) k_it += ntile;
-    if (warp != 1 && warp < 4) { buf_it[0] += (ntile + 1) >> 1; buf_it[1] += ntile >> 1; }
-    if (warp >= 4) { const int wgx = (warp - 4) >> 2; buf_it[wgx ^ 1] += (wgx ^ 1) == 0 ? (ntile + 1) >> 1 : ntile >> 1; }
+    tile_ctr += ntile;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -382,12 +472,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_a_kernel(const __grid_
 
 // ------------------------------------------------------------------------------------------------
 // phase B
+//   TMEM: O^T accumulator [0,256) | Q hi [256,320) | Q lo [320,384) | two S/P buffers of 64 columns at 384 + 64 b
+//   smem: K stages 32 KB [kh: 2 boxes of 64 d | kl: 2 boxes], V stages 64 KB [vh: 4 boxes of 64 ch | v8: 2 boxes of
+//         128 ch | vl: 2 boxes], 64 slots per tile
+//   MMA order  S(0) S(1) | O(0) S(2) | O(1) S(3) | ...: softmax(t) has a whole tile period (O(t-1) + S(t+1)) of cover.
+//   Softmax warps: parity = tile & 1 picks the group of 8 warps (= S/P buffer), half picks 32 of the 64 slots.
+//   P layout per 32-slot half (32 columns, written in place over S): [P hi fp16: 16 | e4m3(P - hi): 8 | e4m3(P): 8]
+//   with P scaled by 256 (the scale is removed in the epilogue).
 // ------------------------------------------------------------------------------------------------
-constexpr int B_TILE = 64;                              // slots per tile
-constexpr int B_KSTAGES = 2, B_VSTAGES = 2;
-constexpr int B_KSTAGE_BYTES = B_TILE * DK * 2 * 2;     // 32 KB (hi + lo)
-constexpr int B_VSTAGE_BYTES = B_TILE * 256 * 2 * 2;    // 64 KB (hi + lo, 256 channels)
-constexpr int B_SMEM = B_KSTAGES * B_KSTAGE_BYTES + B_VSTAGES * B_VSTAGE_BYTES + 1024 + 1024;
+constexpr int B_TILE = 64;
+constexpr int B_KSTAGE_BYTES = B_TILE * DK * 2 * 2;                 // 32 KB
+constexpr int B_VSTAGE_BYTES = B_TILE * 256 * (2 + 1 + 1);          // 64 KB
+constexpr int B_SMEM = 2 * B_KSTAGE_BYTES + 2 * B_VSTAGE_BYTES + 1024 + 1024;
+constexpr uint32_t TM_O = 0, TM_QH = 256, TM_QL = 320, TM_S = 384;
+constexpr float P_SCALE_LOG2 = 8.f, P_SCALE = 256.f;
+
+// 16 logits -> P' = 2^(s - lse2 + 8); returns packed fp16 hi (8 regs), e4m3 residual (4), e4m3 P' (4), threshold bits
+__device__ __forceinline__ uint32_t softmax_chunk16(const uint32_t (&s)[16], float lse2m, float thres_s, int lim,
+                                                    uint32_t (&hi)[8], uint32_t (&lo)[4], uint32_t (&p8)[4]) {
+  uint32_t bits = 0u;
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    float p0 = ex2(__uint_as_float(s[i]) - lse2m), p1 = ex2(__uint_as_float(s[i + 1]) - lse2m);
+    p0 = (i < lim) ? p0 : 0.f;
+    p1 = (i + 1 < lim) ? p1 : 0.f;
+    bits |= (uint32_t)(p0 > thres_s) << i;
+    bits |= (uint32_t)(p1 > thres_s) << (i + 1);
+    const uint32_t h = f16x2_rn(p0, p1);
+    const float2 hf = f16x2_to_f32(h);
+    hi[i >> 1] = h;
+    const uint32_t l = e4m3x2(p0 - hf.x, p1 - hf.y), q = e4m3x2(p0, p1);
+    if ((i & 2) == 0) { lo[i >> 2] = l; p8[i >> 2] = q; }
+    else { lo[i >> 2] |= l << 16; p8[i >> 2] |= q << 16; }
+  }
+  return bits;
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_constant__ TcMaps maps, TcArgs args,
                                                                    const float* __restrict__ lse, float thres,
@@ -395,8 +514,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* kst = smem;
-  uint8_t* vst = smem + B_KSTAGES * B_KSTAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(vst + B_VSTAGES * B_VSTAGE_BYTES);
+  uint8_t* vst = smem + 2 * B_KSTAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(vst + 2 * B_VSTAGE_BYTES);
   uint64_t* k_full = bars;            // [2]
   uint64_t* k_empty = bars + 2;       // [2]
   uint64_t* v_full = bars + 4;        // [2]
@@ -405,14 +524,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
   uint64_t* p_full = bars + 10;       // [2]
   uint64_t* o_full = bars + 12;       // [1]
   uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(bars + 13);
-  int* cnt_s = reinterpret_cast<int*>(bars + 16);   // [2][64]
+  int* cnt_s = reinterpret_cast<int*>(bars + 16);   // [4 groups][32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
-      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 256);
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8);
     }
     mbar_init(o_full, 1);
     fence_barrier_init();
@@ -424,12 +543,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem = *tmem_base_p;
 
-  // work items = (split, object, query tile, channel half), round-robin over the persistent CTAs (see phase A)
+  // work items = (split, object, query tile, channel half), round-robin over the persistent CTAs
   const int cpo = args.q_tiles * 2;
   const int n_combos = args.obj_n * cpo;
   const int n_items = n_combos * args.pieces;
-  uint32_t k_it = 0;            // tiles streamed so far
-  uint32_t buf_it[2] = {0, 0};  // uses of each S/P buffer
+  uint32_t k_it = 0;            // tiles streamed so far (K/V stage = k_it & 1)
+  uint32_t buf_it[2] = {0, 0};  // uses of each S/P buffer so far
   uint32_t seg_it = 0;          // items finished (o_full phase)
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int piece = item / n_combos;
@@ -444,31 +563,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
     const int ntile = t1 - t0;
     const bool first_item = (item == (int)blockIdx.x);
 
-    if (warp >= 4) {
-      const int wg = (warp - 4) >> 2;
-      const int row = ((warp & 3) << 5) + lane;
-      const uint16_t* src = (wg == 0 ? args.qh : args.ql) + ((size_t)qt * QT + row) * DK;
-      const uint32_t tbase = tmem + (((uint32_t)(warp & 3) * 32u) << 16) + (wg == 0 ? TM_QH : TM_QL);
-      uint32_t v[32];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint4 x = reinterpret_cast<const uint4*>(src)[h * 8 + i];
-          v[4 * i + 0] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
-        }
-        tmem_st32(tbase + h * 32, v);
-      }
-      tmem_wait_st();
-    }
+    if (warp >= 4) load_a_operand(args, obj, qt, tmem, TM_QH, TM_QL, warp, lane);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
 
     if (warp == 0) {
-      for (int t = 0; t < ntile; ++t, ++k_it) {
-        const uint32_t st = k_it & 1, ph = (k_it >> 1) & 1;
-        if (lane == 0) {
+      if (lane == 0) {
+        for (int t = 0; t < ntile; ++t) {
+          const uint32_t kit = k_it + t, st = kit & 1, ph = (kit >> 1) & 1;
           const int row0 = (t0 + t) * B_TILE;
           mbar_wait(&k_empty[st], ph ^ 1);
           mbar_arrive_expect_tx(&k_full[st], B_KSTAGE_BYTES);
@@ -481,20 +584,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
           mbar_arrive_expect_tx(&v_full[st], B_VSTAGE_BYTES);
           uint8_t* vd = vst + st * B_VSTAGE_BYTES;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            tma_load_2d(vd + g * 8192, &maps.vh[obj], &v_full[st], half * 256 + g * 64, row0);
-            tma_load_2d(vd + 32768 + g * 8192, &maps.vl[obj], &v_full[st], half * 256 + g * 64, row0);
+          for (int g = 0; g < 4; ++g) tma_load_2d(vd + g * 8192, &maps.vh[obj], &v_full[st], half * 256 + g * 64, row0);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            tma_load_2d(vd + 32768 + g * 8192, &maps.v8[obj], &v_full[st], half * 256 + g * 128, row0);
+            tma_load_2d(vd + 49152 + g * 8192, &maps.vl[obj], &v_full[st], half * 256 + g * 128, row0);
           }
         }
-        __syncwarp();
       }
+      __syncwarp();
     } else if (warp == 1) {
-      constexpr uint32_t idesc_s = make_idesc(128, B_TILE, 0, 0);
-      constexpr uint32_t idesc_o = make_idesc(128, 256, 0, 1);
       if (lane == 0) {
-        // software pipeline: S(0); for t: { S(t+1); wait P(t); O(t) }
-        auto issue_s = [&](int t, uint32_t kit) {
-          const uint32_t st = kit & 1, ph = (kit >> 1) & 1;
+        constexpr uint32_t idesc_s = make_idesc(128, B_TILE, FMT_F16, FMT_F16, 0, 0);
+        constexpr uint32_t idesc_o = make_idesc(128, 256, FMT_F16, FMT_F16, 0, 1);
+        constexpr uint32_t idesc_o8 = make_idesc(128, 256, FMT_E4M3, FMT_E4M3, 0, 1);    // e4m3(P - hi) x e4m3(V)
+        constexpr uint32_t idesc_ol = make_idesc(128, 256, FMT_E4M3, FMT_E5M2, 0, 1);    // e4m3(P) x e5m2(V - Vhi)
+        auto issue_s = [&](int t) {
+          const uint32_t kit = k_it + t, st = kit & 1, ph = (kit >> 1) & 1;
           const int b = t & 1;
           mbar_wait(&k_full[st], ph);
           tc_fence_after();
@@ -513,11 +619,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
           tc_commit(&k_empty[st]);
           tc_commit(&s_full[b]);
         };
-        if (ntile > 0) issue_s(0, k_it);
+        if (ntile > 0) issue_s(0);
+        if (ntile > 1) issue_s(1);
         for (int t = 0; t < ntile; ++t) {
-          if (t + 1 < ntile) issue_s(t + 1, k_it + t + 1);
-          const uint32_t kit = k_it + t;
-          const uint32_t st = kit & 1, ph = (kit >> 1) & 1;
+          const uint32_t kit = k_it + t, st = kit & 1, ph = (kit >> 1) & 1;
           const int b = t & 1;
           mbar_wait(&p_full[b], buf_it[b] & 1);
           ++buf_it[b];
@@ -525,72 +630,70 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
           tc_fence_after();
           const uint32_t vbase = smem_u32(vst + st * B_VSTAGE_BYTES);
           const uint32_t pcol = tmem + TM_S + (uint32_t)b * 64;
-          // passes: (Ph,Vh) (Ph,Vl) (Pl,Vh).  P layout inside the 64-column buffer (written by the two softmax
-          // warpgroups, 32 slots each): [Ph(0-31) | Pl(0-31) | Ph(32-63) | Pl(32-63)], 16 columns per block
+          // main pass: fp16 P hi x fp16 V hi, 16 slots per instruction
 #pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t lo_off = (pass == 2) ? 16u : 0u;
-            const uint32_t vb = vbase + ((pass == 1) ? 32768u : 0u);
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t bd = make_sdesc(vbase + ks * 2048u, 8192, 1024);
+            mma_ts(tmem + TM_O, pcol + (uint32_t)(ks >> 1) * 32u + (uint32_t)(ks & 1) * 8u, bd, idesc_o, (t | ks) ? 1u : 0u);
+          }
+          // correction passes (fp8, 32 slots per instruction)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t bd = make_sdesc(vb + ks * 2048u, 8192, 1024);
-              const uint32_t a_col = pcol + (uint32_t)(ks >> 1) * 32u + lo_off + (uint32_t)(ks & 1) * 8u;
-              mma_ts(tmem + TM_O, a_col, bd, idesc_o, (t | pass | ks) ? 1u : 0u);
-            }
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t b8 = make_sdesc(vbase + 32768u + h * 4096u, 8192, 1024);
+            mma_ts_f8(tmem + TM_O, pcol + (uint32_t)h * 32u + 16u, b8, idesc_o8, 1u);
+            const uint64_t bl = make_sdesc(vbase + 49152u + h * 4096u, 8192, 1024);
+            mma_ts_f8(tmem + TM_O, pcol + (uint32_t)h * 32u + 24u, bl, idesc_ol, 1u);
           }
           tc_commit(&v_empty[st]);
+          if (t + 2 < ntile) issue_s(t + 2);   // in-order MMA pipe: S(t+2) overwrites buffer b only after O(t) read it
         }
         tc_commit(o_full);
       } else {
         for (int t = 0; t < ntile; ++t) ++buf_it[t & 1];
       }
-      k_it += ntile;
       __syncwarp();
     } else if (warp >= 4) {
-      const int wg = (warp - 4) >> 2;
-      const int row = ((warp & 3) << 5) + lane;
-      const int wtid = threadIdx.x - 128 - wg * 128;       // 0..127 within the warpgroup
-      const uint32_t tlane = tmem + (((uint32_t)(warp & 3) * 32u) << 16);
+      const int quarter = warp & 3, grp = (warp - 4) >> 2;      // grp 0..3
+      const int parity = grp >> 1, hsel = grp & 1;
+      const int row = (quarter << 5) + lane;
+      const int gtid = (quarter << 5) + lane;                    // 0..127 within the group
+      const uint32_t tlane = tmem + (((uint32_t)quarter * 32u) << 16);
       const int j = qt * QT + row;
-      const float lse2 = (j < args.hw) ? lse[(size_t)obj * args.hw + j] * LOG2E : INFINITY;
-      int* mycnt = cnt_s + wg * 32;
+      const float lse2m = (j < args.hw) ? (lse[(size_t)obj * args.hw + j] * LOG2E - P_SCALE_LOG2) : INFINITY;
+      const float thres_s = thres * P_SCALE;
+      int* mycnt = cnt_s + grp * 32;
       const bool counting = do_count && (half == 0);
-      // both warpgroups work on every tile: WG0 takes slots [0,32) of the tile, WG1 slots [32,64).  Halving the
-      // per-tile softmax latency is what keeps the tensor pipe fed (S(t+1) is only 768 clk of cover).
-      for (int t = 0; t < ntile; ++t) {
-        const int b = t & 1;
-        mbar_wait(&s_full[b], buf_it[b] & 1);
-        ++buf_it[b];
+      for (int t = parity; t < ntile; t += 2) {
+        mbar_wait(&s_full[parity], buf_it[parity] & 1);
+        ++buf_it[parity];
         tc_fence_after();
-        const int slot0 = (t0 + t) * B_TILE + wg * 32;
-        const uint32_t sb = tlane + TM_S + (uint32_t)b * 64 + (uint32_t)wg * 32;
-        uint32_t s0[32];
-        tmem_ld32(sb, s0);
+        const int slot0 = (t0 + t) * B_TILE + hsel * 32;
+        const uint32_t sb = tlane + TM_S + (uint32_t)parity * 64 + (uint32_t)hsel * 32;
+        uint32_t s0[16], s1[16];
+        tmem_ld16(sb, s0);
+        tmem_ld16(sb + 16, s1);
         tmem_wait_ld();
         if (args.dbg && blockIdx.x == 0 && first_item && t == 0) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) args.dbg[row * B_TILE + wg * 32 + i] = __uint_as_float(s0[i]);
+          for (int i = 0; i < 16; ++i) {
+            args.dbg[row * B_TILE + hsel * 32 + i] = __uint_as_float(s0[i]);
+            args.dbg[row * B_TILE + hsel * 32 + 16 + i] = __uint_as_float(s1[i]);
+          }
         }
         const int lim = n_obj - slot0;
-        uint32_t hi_w[16], lo_w[16];
-        uint32_t bits = 0u;
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2(__uint_as_float(s0[i]) - lse2), p1 = ex2(__uint_as_float(s0[i + 1]) - lse2);
-          p0 = (i < lim) ? p0 : 0.f;
-          p1 = (i + 1 < lim) ? p1 : 0.f;
-          bits |= (uint32_t)(p0 > thres) << i;
-          bits |= (uint32_t)(p1 > thres) << (i + 1);
-          const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-          const __nv_bfloat162 l = __floats2bfloat162_rn(p0 - __low2float(h), p1 - __high2float(h));
-          hi_w[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-          lo_w[i >> 1] = *reinterpret_cast<const uint32_t*>(&l);
-        }
-        tmem_st16(sb, hi_w);          // P hi: 32 bf16 = 16 columns
-        tmem_st16(sb + 16, lo_w);     // P lo
+        uint32_t hi[8], lo[4], p8[4];
+        uint32_t bits = softmax_chunk16(s0, lse2m, thres_s, lim, hi, lo, p8);
+        tmem_st8(sb, hi);
+        tmem_st4(sb + 16, lo);
+        tmem_st4(sb + 24, p8);
+        bits |= softmax_chunk16(s1, lse2m, thres_s, lim - 16, hi, lo, p8) << 16;
+        tmem_st8(sb + 8, hi);
+        tmem_st4(sb + 20, lo);
+        tmem_st4(sb + 28, p8);
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(&p_full[b]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[parity]);
         if (counting) {
           if (j >= args.hw) bits = 0u;
           const int dense = __any_sync(0xffffffffu, __popc(bits) > 4);
@@ -609,35 +712,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
               atomicAdd(&mycnt[c], 1);
             }
           }
-          named_bar_sync(1 + wg, 128);
-          if (wtid < 32) {
-            const int c = mycnt[wtid];
+          named_bar_sync(1 + grp, 128);
+          if (gtid < 32) {
+            const int c = mycnt[gtid];
             if (c) {
-              atomicAdd(&args.cnt[obj][slot0 + wtid], c);
-              mycnt[wtid] = 0;
+              atomicAdd(&args.cnt[obj][slot0 + gtid], c);
+              mycnt[gtid] = 0;
             }
           }
-          named_bar_sync(1 + wg, 128);
+          named_bar_sync(1 + grp, 128);
         }
       }
-      // epilogue: O^T (128 queries x 256 channels) -> partial buffer, WG0 channels [0,128), WG1 [128,256)
+      buf_it[parity ^ 1] += (uint32_t)((ntile + 1 - (parity ^ 1)) >> 1);
+      // epilogue: O^T (128 queries x 256 channels) * 2^-8 -> partial buffer; group g takes channels [64 g, 64 g + 64)
       mbar_wait(o_full, seg_it & 1);
       tc_fence_after();
       if (ntile > 0) {
-        float* dst = po + (((size_t)obj * args.pieces + piece) * DV + half * 256 + wg * 128) * (size_t)args.hw;
+        float* dst = po + (((size_t)obj * args.pieces + piece) * DV + half * 256 + grp * 64) * (size_t)args.hw;
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < 2; ++ch) {
           uint32_t v[32];
-          tmem_ld32(tlane + TM_O + (uint32_t)wg * 128 + ch * 32, v);
+          tmem_ld32(tlane + TM_O + (uint32_t)grp * 64 + ch * 32, v);
           tmem_wait_ld();
           if (j < args.hw) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) dst[(size_t)(ch * 32 + i) * args.hw + j] = __uint_as_float(v[i]);
+            for (int i = 0; i < 32; ++i) dst[(size_t)(ch * 32 + i) * args.hw + j] = __uint_as_float(v[i]) * (1.f / P_SCALE);
           }
         }
       }
     }
-    if (warp != 0 && warp != 1) k_it += ntile;
+    k_it += ntile;
     if (warp < 4 && warp != 1) { buf_it[0] += (ntile + 1) >> 1; buf_it[1] += ntile >> 1; }
     ++seg_it;
     tc_fence_before();
@@ -648,277 +752,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
-
 // ------------------------------------------------------------------------------------------------
-// cosine match on the tensor cores (FeatureBank.py:63-68): corr = <nk_i, nck_j> as 3xTF32
-// (hi*hi + lo*hi + hi*lo, fp32 accumulate: ~2^-21 relative, i.e. fp32-GEMM-grade), per-query arg-max with
-// ties -> lowest slot.  Same pipeline as phase A; lanes = candidates (queries), columns = bank slots.
+// Exact fp32 re-score of the tensor-core candidates (FeatureBank.py:66-68): one warp per candidate query.
+// The fp16x3 scores carry the tensor core's truncating accumulation (measured: ~4e-6 systematic bias), so every slot
+// whose approximate score lies within MATCH_BAND of the approximate maximum is re-evaluated with the sequential fp32
+// FMA chain the SIMT kernel uses (bit-identical values and ordering, ties -> lowest slot).  An overflow marker (more
+// than four near-ties in one column group of one item) sends that query to an exact scan of all slots.
 // ------------------------------------------------------------------------------------------------
-constexpr int M_TILE = 64;
-constexpr int M_STAGES = 3;
-constexpr int M_STAGE_BYTES = M_TILE * DK * 4 * 2;      // fp32 hi + lo = 64 KB
-constexpr int M_SMEM = M_STAGES * M_STAGE_BYTES + 1024 + 256;
-constexpr uint32_t TMM_QH = 0, TMM_QL = 128, TMM_S = 256;
-
-constexpr int MATCH_TOPK = 4;   // approximate candidates kept per (piece, query) for the exact fp32 re-score
-
-// insert (v, i) into a descending top-4 list; the caller scans slots in ascending order, so strict '>' keeps the
-// lowest slot first among equal values
-__device__ __forceinline__ void top4_insert(float (&tv)[MATCH_TOPK], int (&ti)[MATCH_TOPK], float v, int i) {
-  if (v > tv[3]) {
-    tv[3] = v; ti[3] = i;
-#pragma unroll
-    for (int r = 3; r > 0; --r) {
-      if (tv[r] > tv[r - 1]) {
-        const float fv = tv[r]; tv[r] = tv[r - 1]; tv[r - 1] = fv;
-        const int fi = ti[r]; ti[r] = ti[r - 1]; ti[r - 1] = fi;
-      }
-    }
-  }
-}
-// general insert with explicit (value desc, slot asc) order, for merging lists that were not scanned in slot order
-__device__ __forceinline__ void top4_merge(float (&tv)[MATCH_TOPK], int (&ti)[MATCH_TOPK], float v, int i) {
-  if (v > tv[3] || (v == tv[3] && i < ti[3])) {
-    tv[3] = v; ti[3] = i;
-#pragma unroll
-    for (int r = 3; r > 0; --r) {
-      if (tv[r] > tv[r - 1] || (tv[r] == tv[r - 1] && ti[r] < ti[r - 1])) {
-        const float fv = tv[r]; tv[r] = tv[r - 1]; tv[r - 1] = fv;
-        const int fi = ti[r]; ti[r] = ti[r - 1]; ti[r - 1] = fi;
-      }
-    }
-  }
-}
-
-struct MatchArgs {
-  int hw, q_tiles, pieces, n, tiles;
-  const float* nck;        // (hw, 128) normalised candidates, entry-major
-  float* dbg;
-};
-
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_match_kernel(const __grid_constant__ CUtensorMap map_h,
-                                                                 const __grid_constant__ CUtensorMap map_l,
-                                                                 MatchArgs args, float2* __restrict__ part) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* kst = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + M_STAGES * M_STAGE_BYTES);
-  uint64_t* k_full = bars;
-  uint64_t* k_empty = bars + M_STAGES;
-  uint64_t* s_full = bars + 2 * M_STAGES;
-  uint64_t* s_empty = s_full + 2;
-  uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(s_empty + 2);
-  __shared__ float2 best_x[QT][MATCH_TOPK];
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < M_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128); }
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_base_p, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_base_p;
-
-  const int n_items = args.q_tiles * args.pieces;
-  uint32_t k_it = 0;
-  uint32_t buf_it[2] = {0, 0};
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int piece = item / args.q_tiles;
-    const int qt = item - piece * args.q_tiles;
-    const int t0 = (int)((long long)args.tiles * piece / args.pieces);
-    const int t1 = (int)((long long)args.tiles * (piece + 1) / args.pieces);
-    const int ntile = t1 - t0;
-
-    // (1) candidate tile -> TMEM as tf32 hi (WG0) / lo (WG1); one candidate per lane, 128 columns each
-    if (warp >= 4) {
-      const int wg = (warp - 4) >> 2;
-      const int row = ((warp & 3) << 5) + lane;
-      const int j = qt * QT + row;
-      const float* src = args.nck + (size_t)j * DK;
-      const uint32_t tbase = tmem + (((uint32_t)(warp & 3) * 32u) << 16) + (wg == 0 ? TMM_QH : TMM_QL);
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t v[32];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (j < args.hw) x = reinterpret_cast<const float4*>(src)[ch * 8 + i];
-          float h, l;
-          split_tf32(x.x, h, l); v[4 * i + 0] = __float_as_uint(wg == 0 ? h : l);
-          split_tf32(x.y, h, l); v[4 * i + 1] = __float_as_uint(wg == 0 ? h : l);
-          split_tf32(x.z, h, l); v[4 * i + 2] = __float_as_uint(wg == 0 ? h : l);
-          split_tf32(x.w, h, l); v[4 * i + 3] = __float_as_uint(wg == 0 ? h : l);
-        }
-        tmem_st32(tbase + ch * 32, v);
-      }
-      tmem_wait_st();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-
-    if (warp == 0) {
-      for (int t = 0; t < ntile; ++t, ++k_it) {
-        const uint32_t st = k_it % M_STAGES, ph = (k_it / M_STAGES) & 1;
-        if (lane == 0) {
-          mbar_wait(&k_empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&k_full[st], M_STAGE_BYTES);
-          uint8_t* dst = kst + st * M_STAGE_BYTES;
-          const int row0 = (t0 + t) * M_TILE;
-#pragma unroll
-          for (int blk = 0; blk < 4; ++blk) {
-            tma_load_2d(dst + blk * 8192, &map_h, &k_full[st], blk * 32, row0);
-            tma_load_2d(dst + 32768 + blk * 8192, &map_l, &k_full[st], blk * 32, row0);
-          }
-        }
-        __syncwarp();
-      }
-    } else if (warp == 1) {
-      constexpr uint32_t idesc = make_idesc_tf32(128, M_TILE);
-      for (int t = 0; t < ntile; ++t, ++k_it) {
-        const uint32_t st = k_it % M_STAGES, ph = (k_it / M_STAGES) & 1;
-        const int b = t & 1;
-        if (lane == 0) {
-          mbar_wait(&s_empty[b], (buf_it[b] & 1) ^ 1);
-          mbar_wait(&k_full[st], ph);
-          tc_fence_after();
-          const uint32_t kbase = smem_u32(kst + st * M_STAGE_BYTES);
-          const uint32_t d_t = tmem + TMM_S + (uint32_t)b * M_TILE;
-#pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t a_col = (pass == 1) ? TMM_QL : TMM_QH;
-            const uint32_t kb = kbase + ((pass == 2) ? 32768u : 0u);
-#pragma unroll
-            for (int ks = 0; ks < 16; ++ks) {
-              const uint64_t bd = make_sdesc(kb + (ks >> 2) * 8192u + (ks & 3) * 32u, 16, 1024);
-              mma_ts_tf32(d_t, tmem + a_col + ks * 8, bd, idesc, (pass | ks) ? 1u : 0u);
-            }
-          }
-          tc_commit(&k_empty[st]);
-          tc_commit(&s_full[b]);
-        }
-        __syncwarp();
-        ++buf_it[b];
-      }
-    } else if (warp >= 4) {
-      const int wg = (warp - 4) >> 2;
-      const int row = ((warp & 3) << 5) + lane;
-      const uint32_t tlane = tmem + (((uint32_t)(warp & 3) * 32u) << 16);
-      float tv[MATCH_TOPK];
-      int ti[MATCH_TOPK];
-#pragma unroll
-      for (int r = 0; r < MATCH_TOPK; ++r) { tv[r] = -INFINITY; ti[r] = 0x7fffffff; }
-      for (int t = wg; t < ntile; t += 2) {
-        mbar_wait(&s_full[wg], buf_it[wg] & 1);
-        ++buf_it[wg];
-        tc_fence_after();
-        const int slot0 = (t0 + t) * M_TILE;
-#pragma unroll 1
-        for (int ch = 0; ch < 2; ++ch) {
-          uint32_t v[32];
-          tmem_ld32(tlane + TMM_S + (uint32_t)wg * M_TILE + ch * 32, v);
-          tmem_wait_ld();
-          if (args.dbg && blockIdx.x == 0 && item == (int)blockIdx.x && t == 0) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) args.dbg[row * M_TILE + ch * 32 + i] = __uint_as_float(v[i]);
-          }
-          const int lim = args.n - (slot0 + ch * 32);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float sv = __uint_as_float(v[i]);
-            if (i < lim) top4_insert(tv, ti, sv, slot0 + ch * 32 + i);
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(&s_empty[wg]);
-      }
-      if (wg == 1) {
-#pragma unroll
-        for (int r = 0; r < MATCH_TOPK; ++r) best_x[row][r] = make_float2(tv[r], __int_as_float(ti[r]));
-      }
-      named_bar_sync(1, 256);
-      if (wg == 0) {
-#pragma unroll
-        for (int r = 0; r < MATCH_TOPK; ++r) {
-          const float2 o = best_x[row][r];
-          top4_merge(tv, ti, o.x, __float_as_int(o.y));
-        }
-        const int j = qt * QT + row;
-        if (j < args.hw) {
-#pragma unroll
-          for (int r = 0; r < MATCH_TOPK; ++r)
-            part[((size_t)piece * args.hw + j) * MATCH_TOPK + r] = make_float2(tv[r], __int_as_float(ti[r]));
-        }
-      }
-    }
-    if (warp != 0 && warp != 1) k_it += ntile;
-    if (warp != 1 && warp < 4) { buf_it[0] += (ntile + 1) >> 1; buf_it[1] += ntile >> 1; }
-    if (warp >= 4) { const int wgx = (warp - 4) >> 2; buf_it[wgx ^ 1] += (wgx ^ 1) == 0 ? (ntile + 1) >> 1 : ntile >> 1; }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-  }
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 512);
-}
-
-// Exact fp32 re-score of the tensor-core candidates: one warp per candidate query.  The 3xTF32 scores carry the
-// tensor core's truncating accumulation (measured: ~4e-6 systematic bias), so every slot whose approximate score is
-// within MATCH_BAND of the approximate maximum is re-evaluated with the sequential fp32 FMA chain the SIMT kernel uses
-// (bit-identical values and ordering).  If some piece's whole top-4 lies inside the band there may be hidden
-// candidates: that query falls back to an exact scan of all slots (rare: needs >= 4 near-duplicate slots).
 constexpr float MATCH_BAND = 2e-5f;
 
-__device__ __forceinline__ float exact_dot128(const float* __restrict__ nkh, const float* __restrict__ nkl,
-                                              const float* __restrict__ q, int64_t slot) {
-  const float4* h = reinterpret_cast<const float4*>(nkh + slot * DK);
-  const float4* l = reinterpret_cast<const float4*>(nkl + slot * DK);
+__device__ __forceinline__ float exact_dot128(const float* __restrict__ nk, const float* __restrict__ q, int64_t slot) {
+  const float4* a = reinterpret_cast<const float4*>(nk + slot * DK);
   const float4* b = reinterpret_cast<const float4*>(q);
   float acc = 0.f;
 #pragma unroll 8
   for (int k = 0; k < DK / 4; ++k) {
-    const float4 hv = h[k], lv = l[k], bv = b[k];
-    acc = fmaf(hv.x + lv.x, bv.x, acc);
-    acc = fmaf(hv.y + lv.y, bv.y, acc);
-    acc = fmaf(hv.z + lv.z, bv.z, acc);
-    acc = fmaf(hv.w + lv.w, bv.w, acc);
+    const float4 av = a[k], bv = b[k];
+    acc = fmaf(av.x, bv.x, acc);
+    acc = fmaf(av.y, bv.y, acc);
+    acc = fmaf(av.z, bv.z, acc);
+    acc = fmaf(av.w, bv.w, acc);
   }
   return acc;
 }
 
-__global__ void __launch_bounds__(256) match_rescore_kernel(const float2* __restrict__ part, int pieces, int hw, int n,
-                                                            const float* __restrict__ nkh,
-                                                            const float* __restrict__ nkl,
-                                                            const float* __restrict__ nck,
-                                                            int32_t* __restrict__ idx_out,
-                                                            float* __restrict__ corr_out) {
+struct RescoreArgs {
+  int obj_n, pieces, hw;
+  int n[TC_MAX_OBJ];
+  const float* nk[TC_MAX_OBJ];
+  const float* nck[TC_MAX_OBJ];
+  int32_t* idx_out[TC_MAX_OBJ];
+  float* corr_out[TC_MAX_OBJ];
+  float band;
+};
+
+__global__ void __launch_bounds__(256) match_rescore_kernel(const float2* __restrict__ part, RescoreArgs a) {
   const int lane = threadIdx.x & 31;
+  const int obj = blockIdx.y;
   const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (j >= hw) return;
-  const int n_cand = pieces * MATCH_TOPK;
-  const float* q = nck + (size_t)j * DK;
-  // approximate maximum over all pieces
+  if (j >= a.hw) return;
+  const int n = a.n[obj];
+  const float* nk = a.nk[obj];
+  const int n_cand = a.pieces * MATCH_CAND;
+  const float* q = a.nck[obj] + (size_t)j * DK;
+  auto entry = [&](int c) {
+    const int pc = c / MATCH_CAND, r = c - pc * MATCH_CAND;
+    return part[(((size_t)obj * a.pieces + pc) * a.hw + j) * MATCH_CAND + r];
+  };
+  // approximate maximum over all pieces (overflow markers carry their group's maximum)
   float amax = -INFINITY;
-  for (int c = lane; c < n_cand; c += 32) {
-    const int pc = c / MATCH_TOPK, r = c - pc * MATCH_TOPK;
-    amax = fmaxf(amax, part[((size_t)pc * hw + j) * MATCH_TOPK + r].x);
-  }
+  for (int c = lane; c < n_cand; c += 32) amax = fmaxf(amax, entry(c).x);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-  const float band = amax - MATCH_BAND;
+  const float band = amax - a.band;
   float best = -INFINITY;
   int bidx = 0x7fffffff;
   int overflow = 0;
   for (int c = lane; c < n_cand; c += 32) {
-    const int pc = c / MATCH_TOPK, r = c - pc * MATCH_TOPK;
-    const float2 e = part[((size_t)pc * hw + j) * MATCH_TOPK + r];
+    const float2 e = entry(c);
     const int slot = __float_as_int(e.y);
-    if (e.x >= band && slot < n) {
-      if (r == MATCH_TOPK - 1) overflow = 1;
-      const float v = exact_dot128(nkh, nkl, q, slot);
+    if (e.x >= band) {
+      if (slot < 0) { overflow = 1; continue; }
+      if (slot >= n) continue;
+      const float v = exact_dot128(nk, q, slot);
       if (v > best || (v == best && slot < bidx)) { best = v; bidx = slot; }
     }
   }
@@ -927,7 +823,7 @@ __global__ void __launch_bounds__(256) match_rescore_kernel(const float2* __rest
     best = -INFINITY;
     bidx = 0x7fffffff;
     for (int slot = lane; slot < n; slot += 32) {
-      const float v = exact_dot128(nkh, nkl, q, slot);
+      const float v = exact_dot128(nk, q, slot);
       if (v > best) { best = v; bidx = slot; }
     }
   }
@@ -938,8 +834,8 @@ __global__ void __launch_bounds__(256) match_rescore_kernel(const float2* __rest
     if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
   }
   if (lane == 0) {
-    idx_out[j] = bidx;
-    corr_out[j] = best;
+    a.idx_out[obj][j] = bidx;
+    a.corr_out[obj][j] = best;
   }
 }
 
@@ -962,16 +858,16 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D tensor (rows, cols) row-major, bf16 (elem_bytes 2) or fp32 (4); box = (box_rows, 128 B of columns), 128B swizzle,
-// OOB rows -> 0
-static int make_map(CUtensorMap* m, const void* base, int64_t rows, int cols, int box_rows, int elem_bytes = 2) {
+// 2-D tensor (rows, cols) row-major of 2-byte (fp16) or 1-byte (fp8) elements; box = (box_rows, 128 B of columns),
+// 128B swizzle, OOB rows -> 0
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int cols, int box_rows, int elem_bytes) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return VFN_E_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * elem_bytes};
   cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+  CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
                    const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1017,31 +913,45 @@ void tc_pick_splits(int obj_n, int64_t n_max, int64_t hw, int* split_a, int* spl
   *split_b = TC_MAX_SPLIT;
 }
 
+static size_t a_operand_bytes(int64_t hw) { return align_up((size_t)cdiv(hw, QT) * QT * DK * sizeof(uint16_t), 256); }
+
 size_t tc_workspace_bytes(int obj_n, int64_t hw) {
   (void)obj_n;
-  const size_t rows = (size_t)cdiv(hw, QT) * QT;
-  return 2 * align_up(rows * DK * sizeof(uint16_t), 256);
+  return 2 * a_operand_bytes(hw);
+}
+
+static int set_attrs() {
+  static bool attr = false;
+  if (!attr) {
+    VFN_CUDA_OK(cudaFuncSetAttribute(tc_scan_kernel<MODE_LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
+    VFN_CUDA_OK(cudaFuncSetAttribute(tc_scan_kernel<MODE_MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
+    VFN_CUDA_OK(cudaFuncSetAttribute(tc_phase_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+    attr = true;
+  }
+  return VFN_OK;
 }
 
 static int fill_args(const vfn_bank* banks, int obj_n, int64_t hw, int pieces, int tile, char* ws_tc, TcMaps* maps,
                      TcArgs* a, bool need_v) {
   VFN_CHECK_ARG(obj_n <= TC_MAX_OBJ, "tcgen05 read supports at most %d objects", TC_MAX_OBJ);
-  const size_t rows = (size_t)cdiv(hw, QT) * QT;
   a->obj_n = obj_n; a->hw = (int)hw; a->q_tiles = (int)cdiv(hw, QT); a->pieces = pieces;
   a->qh = reinterpret_cast<const uint16_t*>(ws_tc);
-  a->ql = reinterpret_cast<const uint16_t*>(ws_tc + align_up(rows * DK * sizeof(uint16_t), 256));
+  a->ql = reinterpret_cast<const uint16_t*>(ws_tc + a_operand_bytes(hw));
+  a->a_obj_stride = 0;
+  a->band = 0.f;
   a->dbg = g_dbg;
   for (int o = 0; o < obj_n; ++o) {
-    VFN_CHECK_ARG(banks[o].kh && banks[o].vh, "bank %d has no bf16 operand arrays", o);
+    VFN_CHECK_ARG(banks[o].kh && banks[o].vh, "bank %d has no tensor-core operand arrays", o);
     VFN_CHECK_ARG(banks[o].n < (1ll << 31), "bank too large");
     a->n[o] = (int)banks[o].n;
     a->tiles[o] = (int)cdiv(banks[o].n, tile);
     a->cnt[o] = banks[o].cnt;
-    if (int rc = make_map(&maps->kh[o], banks[o].kh, banks[o].n, DK, tile)) return rc;
-    if (int rc = make_map(&maps->kl[o], banks[o].kl, banks[o].n, DK, tile)) return rc;
+    if (int rc = make_map(&maps->kh[o], banks[o].kh, banks[o].n, DK, tile, 2)) return rc;
+    if (int rc = make_map(&maps->kl[o], banks[o].kl, banks[o].n, DK, tile, 2)) return rc;
     if (need_v) {
-      if (int rc = make_map(&maps->vh[o], banks[o].vh, banks[o].n, DV, tile)) return rc;
-      if (int rc = make_map(&maps->vl[o], banks[o].vl, banks[o].n, DV, tile)) return rc;
+      if (int rc = make_map(&maps->vh[o], banks[o].vh, banks[o].n, DV, tile, 2)) return rc;
+      if (int rc = make_map(&maps->v8[o], banks[o].v8, banks[o].n, DV, tile, 1)) return rc;
+      if (int rc = make_map(&maps->vl[o], banks[o].vl, banks[o].n, DV, tile, 1)) return rc;
     }
   }
   return VFN_OK;
@@ -1049,27 +959,21 @@ static int fill_args(const vfn_bank* banks, int obj_n, int64_t hw, int pieces, i
 
 int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t hw, int split_a, float2* part,
                char* ws_tc, cudaStream_t st, int* pieces_out) {
-  static bool attr = false;
-  if (!attr) {
-    VFN_CUDA_OK(cudaFuncSetAttribute(tc_phase_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
-    VFN_CUDA_OK(cudaFuncSetAttribute(tc_phase_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
-    attr = true;
-  }
+  if (int rc = set_attrs()) return rc;
   TcMaps maps;
   TcArgs a;
   int64_t tmin = INT64_MAX, tmax = 0;
   for (int o = 0; o < obj_n; ++o) {
-    const int64_t t = cdiv(banks[o].n, A_TILE);
+    const int64_t t = cdiv(banks[o].n, SC_TILE);
     tmin = t < tmin ? t : tmin;
     tmax = t > tmax ? t : tmax;
   }
-  const int pieces = best_split(obj_n * (int)cdiv(hw, QT), tmin, tmax, 3);
+  const int pieces = best_split(obj_n * (int)cdiv(hw, QT), tmin, tmax, 2);
   if (pieces > split_a) { set_error("phase A: split %d exceeds workspace bound %d", pieces, split_a); return VFN_E_CAPACITY; }
   *pieces_out = pieces;
-  if (int rc = fill_args(banks, obj_n, hw, pieces, A_TILE, ws_tc, &maps, &a, false)) return rc;
-  const size_t rows = (size_t)a.q_tiles * QT;
+  if (int rc = fill_args(banks, obj_n, hw, pieces, SC_TILE, ws_tc, &maps, &a, false)) return rc;
   // Q hi/lo of q * log2(e)/sqrt(d): logits land in the log2 domain; pad rows zeroed
-  VFN_CUDA_OK(cudaMemsetAsync(ws_tc, 0, 2 * align_up(rows * DK * sizeof(uint16_t), 256), st));
+  VFN_CUDA_OK(cudaMemsetAsync(ws_tc, 0, 2 * a_operand_bytes(hw), st));
   const float scale = LOG2E / sqrtf((float)DK);
   if (int rc = vfn_prep_rows(q_in_dm, DK, hw, nullptr, nullptr, const_cast<uint16_t*>(a.qh),
                              const_cast<uint16_t*>(a.ql), scale, st))
@@ -1077,7 +981,7 @@ int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t h
   double work = 0;
   for (int o = 0; o < obj_n; ++o) work += 2.0 * DK * (double)banks[o].n * (double)hw;
   prof_begin(PROF_READ_A, st);
-  tc_phase_a_kernel<<<num_sms(), TC_THREADS, A_SMEM, st>>>(maps, a, part);
+  tc_scan_kernel<MODE_LSE><<<num_sms(), TC_THREADS, SC_SMEM, st>>>(maps, a, part);
   prof_end(PROF_READ_A, st, work);
   VFN_LAUNCH_OK();
   count_launches(2);
@@ -1086,6 +990,7 @@ int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t h
 
 int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const float* lse, float thres_valid,
                int update_bank, float* po, char* ws_tc, cudaStream_t st, int* pieces_out) {
+  if (int rc = set_attrs()) return rc;
   TcMaps maps;
   TcArgs a;
   int64_t tmin = INT64_MAX, tmax = 0;
@@ -1108,28 +1013,74 @@ int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const 
   return VFN_OK;
 }
 
-int tc_match(const vfn_bank* bank, const float* nck_em, int64_t hw, int max_pieces, float2* part, int32_t* idx_out,
-             float* corr_out, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    VFN_CUDA_OK(cudaFuncSetAttribute(tc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, M_SMEM));
-    attr = true;
+size_t tc_match_workspace_bytes(int obj_n, int64_t hw) {
+  return align_up((size_t)obj_n * TC_MAX_SPLIT * hw * MATCH_CAND * sizeof(float2), 256) + 2 * (size_t)obj_n * a_operand_bytes(hw);
+}
+
+// fp32 (hw, 128) entry-major normalised candidates -> fp16 hi/lo of 16x (single-object API path)
+__global__ void split_rows_kernel(const float* __restrict__ src, int64_t n, float scale, uint16_t* __restrict__ hi,
+                                  uint16_t* __restrict__ lo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint16_t h, l;
+  split_f16(src[i] * scale, h, l);
+  hi[i] = h;
+  lo[i] = l;
+}
+
+// cand_split != 0: the fp16 hi/lo of 16 * normalised candidates are already in the workspace (written by the fused
+// preparation kernel at tc_match_cand_hi/lo); otherwise they are derived here from nck.
+uint16_t* tc_match_cand_hi(char* ws, int obj_n, int64_t hw, int obj) {
+  return reinterpret_cast<uint16_t*>(ws + align_up((size_t)obj_n * TC_MAX_SPLIT * hw * MATCH_CAND * sizeof(float2), 256) +
+                                     (size_t)obj * a_operand_bytes(hw));
+}
+uint16_t* tc_match_cand_lo(char* ws, int obj_n, int64_t hw, int obj) {
+  return tc_match_cand_hi(ws, obj_n, hw, obj_n) + (size_t)obj * a_operand_bytes(hw) / sizeof(uint16_t);
+}
+
+int tc_match(const vfn_bank* banks, int obj_n, const float* const* nck_em, int64_t hw, char* ws, int cand_split,
+             int32_t* const* idx_out, float* const* corr_out, cudaStream_t st) {
+  if (int rc = set_attrs()) return rc;
+  VFN_CHECK_ARG(obj_n >= 1 && obj_n <= TC_MAX_OBJ, "tcgen05 match supports at most %d objects", TC_MAX_OBJ);
+  TcMaps maps;
+  TcArgs a;
+  RescoreArgs r;
+  int64_t tmin = INT64_MAX, tmax = 0;
+  double work = 0;
+  for (int o = 0; o < obj_n; ++o) {
+    VFN_CHECK_ARG(banks[o].d_key == DK && banks[o].n < (1ll << 31) && banks[o].nkh, "tcgen05 match needs d_key = 128");
+    const int64_t t = cdiv(banks[o].n, SC_TILE);
+    tmin = t < tmin ? t : tmin;
+    tmax = t > tmax ? t : tmax;
+    if (int rc = make_map(&maps.kh[o], banks[o].nkh, banks[o].n, DK, SC_TILE, 2)) return rc;
+    if (int rc = make_map(&maps.kl[o], banks[o].nkl, banks[o].n, DK, SC_TILE, 2)) return rc;
+    a.n[o] = (int)banks[o].n; a.tiles[o] = (int)t; a.cnt[o] = nullptr;
+    r.n[o] = (int)banks[o].n; r.nk[o] = banks[o].nk; r.nck[o] = nck_em[o]; r.idx_out[o] = idx_out[o]; r.corr_out[o] = corr_out[o];
+    work += 2.0 * DK * (double)banks[o].n * (double)hw;
   }
-  VFN_CHECK_ARG(bank->d_key == DK && bank->n < (1ll << 31), "tcgen05 match needs d_key = 128");
-  CUtensorMap mh, ml;
-  if (int rc = make_map(&mh, bank->nkh, bank->n, DK, M_TILE, 4)) return rc;
-  if (int rc = make_map(&ml, bank->nkl, bank->n, DK, M_TILE, 4)) return rc;
-  MatchArgs a;
-  a.hw = (int)hw; a.q_tiles = (int)cdiv(hw, QT); a.n = (int)bank->n; a.tiles = (int)cdiv(bank->n, M_TILE);
-  a.nck = nck_em; a.dbg = g_dbg;
-  int pieces = best_split(a.q_tiles, a.tiles, a.tiles, 3);
-  if (pieces > max_pieces) pieces = max_pieces;
-  a.pieces = pieces;
+  const int pieces = best_split(obj_n * (int)cdiv(hw, QT), tmin, tmax, 2);
+  a.obj_n = obj_n; a.hw = (int)hw; a.q_tiles = (int)cdiv(hw, QT); a.pieces = pieces;
+  a.qh = tc_match_cand_hi(ws, obj_n, hw, 0);
+  a.ql = tc_match_cand_lo(ws, obj_n, hw, 0);
+  a.a_obj_stride = (long long)(a_operand_bytes(hw) / sizeof(uint16_t));
+  a.band = MATCH_BAND * NK_SCALE * NK_SCALE;
+  a.dbg = g_dbg;
+  if (!cand_split) {
+    VFN_CUDA_OK(cudaMemsetAsync(const_cast<uint16_t*>(a.qh), 0, 2 * (size_t)obj_n * a_operand_bytes(hw), st));
+    for (int o = 0; o < obj_n; ++o) {
+      const int64_t ne = hw * DK;
+      split_rows_kernel<<<(unsigned)cdiv(ne, 256), 256, 0, st>>>(nck_em[o], ne, NK_SCALE, tc_match_cand_hi(ws, obj_n, hw, o),
+                                                                tc_match_cand_lo(ws, obj_n, hw, o));
+    }
+    count_launches(obj_n);
+  }
+  float2* part = reinterpret_cast<float2*>(ws);
   prof_begin(PROF_MATCH, st);
-  tc_match_kernel<<<num_sms(), TC_THREADS, M_SMEM, st>>>(mh, ml, a, part);
-  prof_end(PROF_MATCH, st, 2.0 * DK * (double)bank->n * (double)hw);
-  match_rescore_kernel<<<(unsigned)cdiv(hw, 8), 256, 0, st>>>(part, pieces, (int)hw, (int)bank->n, bank->nkh, bank->nkl,
-                                                              nck_em, idx_out, corr_out);
+  tc_scan_kernel<MODE_MATCH><<<num_sms(), TC_THREADS, SC_SMEM, st>>>(maps, a, part);
+  prof_end(PROF_MATCH, st, work);
+  r.obj_n = obj_n; r.pieces = pieces; r.hw = (int)hw; r.band = a.band;
+  dim3 grid((unsigned)cdiv(hw, 8), obj_n);
+  match_rescore_kernel<<<grid, 256, 0, st>>>(part, r);
   VFN_LAUNCH_OK();
   count_launches(2);
   return VFN_OK;

@@ -17,9 +17,14 @@ int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t h
 int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const float* lse, float thres_valid,
                int update_bank, float* po, char* ws_tc, cudaStream_t st, int* pieces_out);
 
-// cosine match: 3xTF32 tcgen05 scores -> per-piece top-4 candidates in `part` (max_pieces*hw*4 float2) -> exact fp32
-// re-score (same FMA chain as the SIMT kernel) -> idx_out / corr_out
-int tc_match(const vfn_bank* bank, const float* nck_em, int64_t hw, int max_pieces, float2* part, int32_t* idx_out,
-             float* corr_out, cudaStream_t st);
+// cosine match for obj_n banks in one launch: fp16x3 tcgen05 scores -> per-(piece, query, column group) near-tie
+// candidates in the workspace -> exact fp32 re-score (same FMA chain as the SIMT kernel) -> idx_out[o] / corr_out[o].
+// ws: tc_match_workspace_bytes(obj_n, hw).  cand_split != 0: the fp16 hi/lo of 16 * normalised candidates were already
+// written to tc_match_cand_hi/lo(ws, ...) (zero padded to a multiple of 128 rows) by the preparation kernel.
+size_t tc_match_workspace_bytes(int obj_n, int64_t hw);
+uint16_t* tc_match_cand_hi(char* ws, int obj_n, int64_t hw, int obj);
+uint16_t* tc_match_cand_lo(char* ws, int obj_n, int64_t hw, int obj);
+int tc_match(const vfn_bank* banks, int obj_n, const float* const* nck_em, int64_t hw, char* ws, int cand_split,
+             int32_t* const* idx_out, float* const* corr_out, cudaStream_t st);
 
 }  // namespace vfn

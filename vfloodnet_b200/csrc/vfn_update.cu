@@ -1,0 +1,166 @@
+// FeatureBank.update for all objects in one host call (FeatureBank.py:53-115): the sequence
+//   prepare candidates -> match -> plan -> merge -> [sync: |A|] -> (evict plan -> [sync] -> compaction) -> append -> clamp
+// issued from C++.  The arithmetic lives in the kernels of vfn_bank.cu / vfn_tc.cu / vfn_simt.cu; this file only
+// orders the launches, so a frame costs one ctypes call instead of ~25 (profiles/r1a_summary.md: the Python launch
+// path was 38 % of the frame).
+#include "vfn_common.cuh"
+#include "vfn_tc.cuh"
+
+namespace vfn {
+
+struct UpdLayout {
+  size_t ck, cv, nck, ncv;     // per-object strides apply: base + obj * stride
+  size_t s_ck, s_cv;
+  size_t counts, plan, lfu, s_lfu, pws, s_pws, cws, s_cws, match, total;
+};
+
+static UpdLayout upd_layout(int obj_n, int64_t n_max, int64_t hw, int d_key, int d_val) {
+  UpdLayout L{};
+  size_t o = 0;
+  L.s_ck = align_up((size_t)hw * d_key * sizeof(float), 256);
+  L.s_cv = align_up((size_t)hw * d_val * sizeof(float), 256);
+  L.ck = o;  o += obj_n * L.s_ck;
+  L.nck = o; o += obj_n * L.s_ck;
+  L.cv = o;  o += obj_n * L.s_cv;
+  L.ncv = o; o += obj_n * L.s_cv;
+  L.counts = o; o += align_up((size_t)obj_n * 4 * sizeof(int32_t), 256);
+  L.plan = o;   o += align_up((size_t)obj_n * 72 * sizeof(int32_t), 256);
+  L.s_lfu = align_up((size_t)(n_max > 0 ? n_max : 1) * sizeof(float), 256);
+  L.lfu = o;    o += obj_n * L.s_lfu;
+  L.s_pws = align_up(vfn_bank_plan_workspace_bytes(hw), 256);
+  L.pws = o;    o += obj_n * L.s_pws;
+  L.s_cws = align_up(vfn_bank_compact_workspace_bytes(n_max > 0 ? n_max : 1), 256);
+  L.cws = o;    o += obj_n * L.s_cws;
+  L.match = o;
+  size_t m_tc = tc_match_workspace_bytes(obj_n, hw);
+  size_t m_simt = vfn_bank_match_workspace_bytes(n_max, hw);
+  o += align_up(m_tc > m_simt ? m_tc : m_simt, 256);
+  L.total = o;
+  return L;
+}
+
+}  // namespace vfn
+
+using namespace vfn;
+
+extern "C" {
+
+size_t vfn_bank_update_workspace_bytes(int32_t obj_n, int64_t n_max, int64_t hw, int32_t d_key, int32_t d_val) {
+  if (obj_n < 1 || hw < 1 || d_key < 1 || d_val < 1) return 0;
+  return upd_layout(obj_n, n_max, hw, d_key, d_val).total;
+}
+
+int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_io* io, int64_t hw, float frame_idx,
+                    float update_rate, float thres_close, double class_budget, void* d_ws, size_t ws_bytes,
+                    int32_t* h_pinned, int32_t impl, void* stream) {
+  VFN_CHECK_ARG(banks && alts && io && d_ws && h_pinned && obj_n >= 1 && obj_n <= 4 && hw >= 1, "bank_update: bad args");
+  const int d_key = banks[0].d_key, d_val = banks[0].d_val;
+  int64_t n_max = 0;
+  for (int c = 0; c < obj_n; ++c) {
+    VFN_CHECK_ARG(banks[c].d_key == d_key && banks[c].d_val == d_val, "bank_update: banks differ in dims");
+    VFN_CHECK_ARG(banks[c].n >= 1 && banks[c].n + hw <= banks[c].cap, "bank_update: bank %d needs cap >= n + hw", c);
+    VFN_CHECK_ARG(io[c].d_prev_key_dm && io[c].d_prev_value_dm && io[c].d_match_idx && io[c].d_match_corr &&
+                      io[c].d_merge_q && io[c].d_merge_slot && io[c].d_run_off && io[c].d_append_q,
+                  "bank_update: io[%d] has NULL buffers", c);
+    if (banks[c].n > n_max) n_max = banks[c].n;
+    io[c].n_before = banks[c].n;
+    io[c].evicted = io[c].swapped = io[c].evict_status = io[c].kept = io[c].n_iter = 0;
+  }
+  const UpdLayout L = upd_layout(obj_n, n_max, hw, d_key, d_val);
+  if (ws_bytes < L.total) { set_error("bank_update: workspace %zu < %zu", ws_bytes, L.total); return VFN_E_CAPACITY; }
+  cudaStream_t st = as_stream(stream);
+  char* ws = reinterpret_cast<char*>(d_ws);
+  auto CK = [&](int c) { return reinterpret_cast<float*>(ws + L.ck + c * L.s_ck); };
+  auto NCK = [&](int c) { return reinterpret_cast<float*>(ws + L.nck + c * L.s_ck); };
+  auto CV = [&](int c) { return reinterpret_cast<float*>(ws + L.cv + c * L.s_cv); };
+  auto NCV = [&](int c) { return reinterpret_cast<float*>(ws + L.ncv + c * L.s_cv); };
+  int32_t* counts = reinterpret_cast<int32_t*>(ws + L.counts);
+  int32_t* plan = reinterpret_cast<int32_t*>(ws + L.plan);
+  char* mws = ws + L.match;
+  int32_t* h_counts = h_pinned;                 // obj_n * 4
+  int32_t* h_plan = h_pinned + 4 * obj_n;       // obj_n * 72   (caller provides obj_n * 80 ints)
+
+  const bool tc = (impl != 1) && d_key == 128 && banks[0].nkh != nullptr && vfn_device_is_sm100();
+  if (impl == 2 && !tc) { set_error("tcgen05 match needs d_key = 128 operands on an sm_100 device"); return VFN_E_UNSUPPORTED; }
+
+  // (1) candidates: (d, hw) -> entry-major raw + normalised (FeatureBank.py:64,88), + fp16 split of 16 * normalised keys
+  PrepJob jobs[8];
+  if (tc) VFN_CUDA_OK(cudaMemsetAsync(tc_match_cand_hi(mws, obj_n, hw, 0), 0,
+                                      (size_t)((char*)tc_match_cand_lo(mws, obj_n, hw, obj_n) - (char*)tc_match_cand_hi(mws, obj_n, hw, 0)), st));
+  for (int c = 0; c < obj_n; ++c) {
+    jobs[2 * c] = PrepJob{io[c].d_prev_key_dm, d_key, hw, CK(c), NCK(c), tc ? tc_match_cand_hi(mws, obj_n, hw, c) : nullptr,
+                          tc ? tc_match_cand_lo(mws, obj_n, hw, c) : nullptr, NK_SCALE, 1};
+    jobs[2 * c + 1] = PrepJob{io[c].d_prev_value_dm, d_val, hw, CV(c), NCV(c), nullptr, nullptr, 1.f, 0};
+  }
+  if (int rc = launch_prep(jobs, 2 * obj_n, st)) return rc;
+
+  // (2) match (FeatureBank.py:63-68): all objects in one tensor-core launch, or the fp32 SIMT kernels per object
+  if (tc) {
+    const float* nck[4]; int32_t* idx[4]; float* corr[4];
+    for (int c = 0; c < obj_n; ++c) { nck[c] = NCK(c); idx[c] = io[c].d_match_idx; corr[c] = io[c].d_match_corr; }
+    if (int rc = tc_match(banks, obj_n, nck, hw, mws, 1, idx, corr, st)) return rc;
+  } else {
+    for (int c = 0; c < obj_n; ++c)
+      if (int rc = vfn_bank_match(&banks[c], NCK(c), hw, io[c].d_match_idx, io[c].d_match_corr, mws,
+                                  ws_bytes - L.match, 1, stream))
+        return rc;
+  }
+  // (3) plan + merge per object (FeatureBank.py:71-97)
+  for (int c = 0; c < obj_n; ++c) {
+    if (int rc = vfn_bank_plan(io[c].d_match_idx, io[c].d_match_corr, hw, thres_close, io[c].d_merge_q, io[c].d_merge_slot,
+                               io[c].d_run_off, io[c].d_append_q, counts + 4 * c, h_counts + 4 * c,
+                               ws + L.pws + c * L.s_pws, L.s_pws, stream))
+      return rc;
+    if (int rc = vfn_bank_merge(&banks[c], NCK(c), NCV(c), io[c].d_merge_q, io[c].d_merge_slot, io[c].d_run_off,
+                                counts + 4 * c, hw, update_rate, stream))
+      return rc;
+  }
+  VFN_CUDA_OK(cudaStreamSynchronize(st));                 // |merge|, |runs|, |append| per object (nonzero/unique syncs)
+  bool any_evict = false;
+  for (int c = 0; c < obj_n; ++c) {
+    io[c].n_merge = h_counts[4 * c + 0];
+    io[c].n_runs = h_counts[4 * c + 1];
+    io[c].n_append = h_counts[4 * c + 2];
+    if (class_budget < (double)(banks[c].n + io[c].n_append)) {            // FeatureBank.py:102
+      io[c].evicted = 1;
+      any_evict = true;
+      if (int rc = vfn_bank_evict_plan(&banks[c], frame_idx, class_budget, io[c].n_append, plan + 72 * c, h_plan + 72 * c,
+                                       reinterpret_cast<float*>(ws + L.lfu + c * L.s_lfu), stream))
+        return rc;
+    }
+  }
+  if (any_evict) {
+    VFN_CUDA_OK(cudaStreamSynchronize(st));               // int(LFU.min()) syncs of remove()
+    for (int c = 0; c < obj_n; ++c) {
+      if (!io[c].evicted) continue;
+      const int32_t* hp = h_plan + 72 * c;
+      io[c].evict_status = hp[0]; io[c].kept = hp[1]; io[c].n_iter = hp[2];
+      for (int k = 0; k < 64; ++k) io[c].thresholds[k] = (k < hp[2]) ? hp[4 + k] : 0;
+      if (hp[0] != 0) continue;                             // the caller raises like the reference
+      VFN_CHECK_ARG(alts[c].keys != nullptr && alts[c].cap >= hp[1] + hw, "bank_update: eviction needs alts[%d] with cap >= kept + hw", c);
+      alts[c].n = 0;
+      if (int rc = vfn_bank_compact(&banks[c], &alts[c], reinterpret_cast<float*>(ws + L.lfu + c * L.s_lfu), plan + 72 * c,
+                                    ws + L.cws + c * L.s_cws, L.s_cws, stream))
+        return rc;
+      // algorithmic bytes of the compaction: evicted rows read once, kept rows read + written
+      vfn_profile_add_work(PROF_COMPACT, 4.0 * (d_key + d_val + 2) * ((double)(banks[c].n - hp[1]) + 2.0 * hp[1]));
+      vfn_bank tmp = banks[c]; banks[c] = alts[c]; alts[c] = tmp;
+      banks[c].n = hp[1];
+      io[c].swapped = 1;
+    }
+  }
+  // (4) append + clamp (FeatureBank.py:105-115)
+  for (int c = 0; c < obj_n; ++c) {
+    if (io[c].evict_status != 0) continue;
+    const int64_t n_app = io[c].n_append;
+    if (n_app > 0)
+      if (int rc = vfn_bank_append_rows(&banks[c], CK(c), CV(c), NCK(c), io[c].d_append_q, n_app, nullptr, frame_idx, 0.f,
+                                        stream))
+        return rc;
+    banks[c].n += n_app;
+    if (int rc = vfn_bank_clamp_info(&banks[c], banks[c].n, stream)) return rc;
+  }
+  return VFN_OK;
+}
+
+}  // extern "C"

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import VfnBank, check, ptr, stream_ptr
+from ._lib import VfnBank, VfnUpdateIO, check, ptr, stream_ptr
 
 
 class _Slab:
@@ -28,24 +28,31 @@ class _Slab:
         self.keys = torch.empty((cap, d_key), **f32)
         self.values = torch.empty((cap, d_val), **f32)
         self.info = torch.zeros((cap, 2), **f32)
-        self.nkh = torch.empty((cap, d_key), **f32)
-        self.nkl = torch.empty((cap, d_key), **f32)
+        self.nk = torch.empty((cap, d_key), **f32)
         self.cnt = torch.zeros((cap,), dtype=torch.int32, device=device)
         if operands:
-            bf = dict(dtype=torch.bfloat16, device=device)
-            self.kh = torch.empty((cap, d_key), **bf)
-            self.kl = torch.empty((cap, d_key), **bf)
-            self.vh = torch.empty((cap, d_val), **bf)
-            self.vl = torch.empty((cap, d_val), **bf)
+            # tensor-core operands: zero-filled so that rows beyond n never hold NaN/Inf bit patterns
+            f16 = dict(dtype=torch.float16, device=device)
+            u8 = dict(dtype=torch.uint8, device=device)
+            self.nkh = torch.zeros((cap, d_key), **f16)
+            self.nkl = torch.zeros((cap, d_key), **f16)
+            self.kh = torch.zeros((cap, d_key), **f16)
+            self.kl = torch.zeros((cap, d_key), **f16)
+            self.vh = torch.zeros((cap, d_val), **f16)
+            self.v8 = torch.zeros((cap, d_val), **u8)
+            self.vl = torch.zeros((cap, d_val), **u8)
         else:
-            self.kh = self.kl = self.vh = self.vl = None
+            self.nkh = self.nkl = self.kh = self.kl = self.vh = self.v8 = self.vl = None
+
+    _ARRAYS = ('keys', 'values', 'info', 'nk', 'nkh', 'nkl', 'kh', 'kl', 'vh', 'v8', 'vl', 'cnt')
 
     def struct(self, n: int) -> VfnBank:
         return VfnBank(self.d_key, self.d_val, self.cap, n, ptr(self.keys), ptr(self.values), ptr(self.info),
-                       ptr(self.nkh), ptr(self.nkl), ptr(self.kh), ptr(self.kl), ptr(self.vh), ptr(self.vl), ptr(self.cnt))
+                       ptr(self.nk), ptr(self.nkh), ptr(self.nkl), ptr(self.kh), ptr(self.kl), ptr(self.vh),
+                       ptr(self.v8), ptr(self.vl), ptr(self.cnt))
 
     def copy_rows_from(self, other: '_Slab', n: int):
-        for name in ('keys', 'values', 'info', 'nkh', 'nkl', 'kh', 'kl', 'vh', 'vl', 'cnt'):
+        for name in self._ARRAYS:
             a, b = getattr(self, name), getattr(other, name)
             if a is not None:
                 a[:n].copy_(b[:n])
@@ -104,8 +111,8 @@ class FeatureBank:
         self._alt: List[Optional[_Slab]] = [None] * obj_n      # ping-pong target of eviction compaction
         self._n = [0] * obj_n
         self._scratch = {}
-        self._h_counts = torch.zeros((obj_n, 4), dtype=torch.int32).pin_memory()
         self._h_plan = torch.zeros((obj_n, 72), dtype=torch.int32).pin_memory()
+        self._h_pinned = torch.zeros((obj_n * 80,), dtype=torch.int32).pin_memory()
         self.last_decisions = [None] * obj_n    # device tensors of the last update (tests / debugging)
         self.launches = 0                       # kernels launched by this bank (bench accounting)
 
@@ -141,15 +148,17 @@ class FeatureBank:
     def _budget_cap(self):
         return int(math.ceil(self.class_budget))
 
-    def _ensure_capacity(self, c: int, needed: int, d_key: int, d_val: int):
+    def _ensure_capacity(self, c: int, needed: int, d_key: int, d_val: int, slack: int = 0):
+        """grow geometrically up to the budget (+ one frame of candidates: update() needs cap >= n + hw)"""
         s = self._slabs[c]
         if s is not None and s.cap >= needed:
             return
         cap = max(needed, 4096)
+        limit = max(self._budget_cap() + slack, needed)
         if s is not None:
-            cap = max(cap, min(2 * s.cap, max(self._budget_cap(), needed)))
+            cap = max(cap, min(2 * s.cap, limit))
         else:
-            cap = max(cap, min(4 * needed, max(self._budget_cap(), needed)))
+            cap = max(cap, min(4 * needed, limit))
         new = _Slab(d_key, d_val, cap, self.device, self._use_operands(d_key, d_val))
         if s is not None:
             new.copy_rows_from(s, self._n[c])
@@ -199,79 +208,71 @@ class FeatureBank:
             self.init_bank(keys, values, frame_idx)
 
     def update(self, prev_key, prev_value, frame_idx, update_rate=-1):
-        """FeatureBank.py:53-115: cosine match -> merge -> (LFU evict) -> append -> clamp."""
+        """FeatureBank.py:53-115: cosine match -> merge -> (LFU evict) -> append -> clamp, for all objects, as ONE call
+        into the library (vfn_bank_update orders the kernel launches in C++)."""
         if update_rate == -1:
             update_rate = self.update_rate
         lib, st = self._lib, stream_ptr()
-        per = []
-        for c in range(self.obj_n):
+        obj_n = self.obj_n
+        pk = [prev_key[c].to(self.device, torch.float32).contiguous() for c in range(obj_n)]
+        pv = [prev_value[c].to(self.device, torch.float32).contiguous() for c in range(obj_n)]
+        d_key, hw = pk[0].shape
+        d_val = pv[0].shape[0]
+        banks, alts = (VfnBank * obj_n)(), (VfnBank * obj_n)()
+        io = (VfnUpdateIO * obj_n)()
+        dec = []
+        for c in range(obj_n):
             s = self._slabs[c]
-            n = self._n[c]
-            pk = prev_key[c].to(self.device, torch.float32).contiguous()
-            pv = prev_value[c].to(self.device, torch.float32).contiguous()
-            d_key, hw = pk.shape
-            d_val = pv.shape[0]
-            if d_key != s.d_key or d_val != s.d_val:
+            if pk[c].shape != (s.d_key, hw) or pv[c].shape != (s.d_val, hw):
                 raise ValueError('candidate dims do not match the bank')
-            ck = self._buf(f'ck{c}', (hw, d_key), torch.float32)
-            nck = self._buf(f'nck{c}', (hw, d_key), torch.float32)
-            cv = self._buf(f'cv{c}', (hw, d_val), torch.float32)
-            ncv = self._buf(f'ncv{c}', (hw, d_val), torch.float32)
-            check(lib.vfn_prep_rows(ptr(pk), d_key, hw, ptr(ck), ptr(nck), None, None, 1.0, st), 'prep_rows')
-            check(lib.vfn_prep_rows(ptr(pv), d_val, hw, ptr(cv), ptr(ncv), None, None, 1.0, st), 'prep_rows')
-            midx = self._buf(f'midx{c}', (hw,), torch.int32)
-            mcorr = self._buf(f'mcorr{c}', (hw,), torch.float32)
-            mws = self._buf(f'mws{c}', (lib.vfn_bank_match_workspace_bytes(n, hw),), torch.uint8)
-            bank = s.struct(n)
-            check(lib.vfn_bank_match(C.byref(bank), ptr(nck), hw, ptr(midx), ptr(mcorr), ptr(mws), mws.numel(),
-                                     self.impl, st), 'bank_match')
-            merge_q = self._buf(f'merge_q{c}', (hw,), torch.int32)
-            merge_slot = self._buf(f'merge_slot{c}', (hw,), torch.int32)
-            run_off = self._buf(f'run_off{c}', (hw + 1,), torch.int32)
-            append_q = self._buf(f'append_q{c}', (hw,), torch.int32)
-            counts = self._buf(f'counts{c}', (4,), torch.int32)
-            pws = self._buf(f'pws{c}', (lib.vfn_bank_plan_workspace_bytes(hw),), torch.uint8)
-            check(lib.vfn_bank_plan(ptr(midx), ptr(mcorr), hw, float(self.thres_close), ptr(merge_q), ptr(merge_slot),
-                                    ptr(run_off), ptr(append_q), ptr(counts), self._h_counts[c].data_ptr(), ptr(pws),
-                                    pws.numel(), st), 'bank_plan')
-            check(lib.vfn_bank_merge(C.byref(bank), ptr(nck), ptr(ncv), ptr(merge_q), ptr(merge_slot), ptr(run_off),
-                                     ptr(counts), hw, float(update_rate), st), 'bank_merge')
-            self.launches += 6
-            per.append(dict(hw=hw, ck=ck, cv=cv, nck=nck, append_q=append_q, counts=counts, midx=midx, mcorr=mcorr,
-                            merge_q=merge_q, merge_slot=merge_slot, run_off=run_off))
-        torch.cuda.current_stream().synchronize()          # one host sync: |merge|, |runs|, |append| per object
-        hc = self._h_counts.numpy()
-        evicting = []
-        for c in range(self.obj_n):
-            n_app = int(hc[c, 2])
-            per[c]['n_app'] = n_app
-            if self.class_budget < self._n[c] + n_app:                         # FeatureBank.py:102
-                self._launch_evict_plan(c, n_app, frame_idx)
-                evicting.append(c)
-        if evicting:
-            torch.cuda.current_stream().synchronize()
-            for c in evicting:
-                self._finish_evict(c, per[c]['n_app'])
-        for c in range(self.obj_n):
-            s, p = self._slabs[c], per[c]
-            n_app = p['n_app']
-            self._ensure_capacity(c, self._n[c] + n_app, s.d_key, s.d_val)
+            self._ensure_capacity(c, self._n[c] + hw, s.d_key, s.d_val, slack=hw)
             s = self._slabs[c]
-            bank = s.struct(self._n[c])
-            if n_app > 0:
-                check(lib.vfn_bank_append_rows(C.byref(bank), ptr(p['ck']), ptr(p['cv']), ptr(p['nck']),
-                                               ptr(p['append_q']), n_app, None, float(frame_idx), 0.0, st),
-                      'append_rows')                                               # FeatureBank.py:105-111
-                self.launches += 1
-            self._n[c] += n_app
+            if self.class_budget < self._n[c] + hw:           # remove() may run: keep the ping-pong slab ready
+                alt = self._alt[c]
+                if alt is None or alt.cap < s.cap:
+                    self._alt[c] = _Slab(s.d_key, s.d_val, s.cap, self.device, s.kh is not None)
+            banks[c] = s.struct(self._n[c])
+            alts[c] = self._alt[c].struct(0) if self._alt[c] is not None else VfnBank()
+            d = dict(match_idx=self._buf(f'midx{c}', (hw,), torch.int32),
+                     match_corr=self._buf(f'mcorr{c}', (hw,), torch.float32),
+                     merge_q=self._buf(f'merge_q{c}', (hw,), torch.int32),
+                     merge_slot=self._buf(f'merge_slot{c}', (hw,), torch.int32),
+                     run_off=self._buf(f'run_off{c}', (hw + 1,), torch.int32),
+                     append_q=self._buf(f'append_q{c}', (hw,), torch.int32))
+            dec.append(d)
+            io[c].d_prev_key_dm, io[c].d_prev_value_dm = ptr(pk[c]), ptr(pv[c])
+            io[c].d_match_idx, io[c].d_match_corr = ptr(d['match_idx']), ptr(d['match_corr'])
+            io[c].d_merge_q, io[c].d_merge_slot = ptr(d['merge_q']), ptr(d['merge_slot'])
+            io[c].d_run_off, io[c].d_append_q = ptr(d['run_off']), ptr(d['append_q'])
+        n_max = max(self._n)
+        ws_bytes = lib.vfn_bank_update_workspace_bytes(obj_n, n_max, hw, d_key, d_val)
+        ws = self._buf('upd_ws', (ws_bytes,), torch.uint8)
+        l0 = lib.vfn_launch_count()
+        check(lib.vfn_bank_update(banks, alts, obj_n, io, hw, float(frame_idx), float(update_rate),
+                                  float(self.thres_close), float(self.class_budget), ptr(ws), ws.numel(),
+                                  self._h_pinned.data_ptr(), self.impl, st), 'bank_update')
+        self.launches += lib.vfn_launch_count() - l0
+        err = None
+        for c in range(obj_n):
+            r = io[c]
+            if r.evicted:
+                self.last_thresholds = [int(r.thresholds[k]) for k in range(r.n_iter)]
+                if r.evict_status == 1:
+                    err = err or RuntimeError('FeatureBank.remove: every entry was evicted and the budget is still '
+                                              'exceeded (the reference raises on LFU.min() of an empty tensor, '
+                                              'FeatureBank.py:136)')
+                elif r.evict_status == 2:
+                    err = err or ValueError('FeatureBank.remove: LFU minimum is not finite (the reference raises in '
+                                            'int(), FeatureBank.py:123)')
+            if r.swapped:
+                self._slabs[c], self._alt[c] = self._alt[c], self._slabs[c]
+                self.replace_n[c] += r.n_before - r.kept                         # FeatureBank.py:140-141
+            self._n[c] = int(banks[c].n)
             self.peak_n[c] = max(self.peak_n[c], self._n[c])                       # FeatureBank.py:113
-            bank = s.struct(self._n[c])
-            check(lib.vfn_bank_clamp_info(C.byref(bank), self._n[c], st), 'clamp_info')   # FeatureBank.py:115
-            self.launches += 1
-            self.last_decisions[c] = dict(match_idx=p['midx'], match_corr=p['mcorr'], n_merge=int(hc[c, 0]),
-                                          n_runs=int(hc[c, 1]), n_append=n_app, merge_q=p['merge_q'],
-                                          merge_slot=p['merge_slot'], run_off=p['run_off'], append_q=p['append_q'],
-                                          evicted=c in evicting)
+            self.last_decisions[c] = dict(n_merge=int(r.n_merge), n_runs=int(r.n_runs), n_append=int(r.n_append),
+                                          evicted=bool(r.evicted), **dec[c])
+        if err is not None:
+            raise err
 
     def _launch_evict_plan(self, c: int, request_n: int, frame_idx):
         lib, st = self._lib, stream_ptr()
