@@ -71,52 +71,116 @@ def to_device(clip, dev):
 
 
 def run_clip_gpu(vfn, clip, dev, read_impl, host_inputs=False, out_host=None):
-    """one step: the whole clip through the drop-in API.  Returns final bank sizes."""
+    """one step: the whole clip through the drop-in API.  Returns (bank, last readout, last refined mask).
+    host_inputs: every frame's tensors start in pinned HOST memory; their H2D copies are issued on a side stream one
+    frame ahead (double buffering) and the refined mask is copied back to the host every frame."""
     fb = vfn.FeatureBank(2, BUDGET, dev, impl=read_impl)
     m = vfn.Matcher(update_bank=True)
-    D = (lambda t: t.to(dev, non_blocking=True)) if host_inputs else (lambda t: t)
-    fb.init_bank([D(k) for k in clip['keys0']], [D(v) for v in clip['vals0']])
-    for t, (q_in, q_out, pk, pv) in enumerate(clip['frames']):
-        p, r1, q_local = (D(x) for x in clip['urr'])
-        out = m(fb, D(q_in), D(q_out))
+    cur = torch.cuda.current_stream(dev)
+    if host_inputs:
+        copy_stream = _copy_stream(dev)
+        H = lambda t: t.to(dev, non_blocking=True)
+
+        def stage(t):
+            copy_stream.wait_stream(cur) if t == 0 else None
+            with torch.cuda.stream(copy_stream):
+                q_in, q_out, pk, pv = clip['frames'][t]
+                tens = (H(q_in), H(q_out), [H(k) for k in pk], [H(v) for v in pv], tuple(H(x) for x in clip['urr']))
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return tens, ev
+
+        fb.init_bank([H(k) for k in clip['keys0']], [H(v) for v in clip['vals0']])
+        nxt = stage(0)
+    out = prob = None
+    for t in range(len(clip['frames'])):
+        if host_inputs:
+            (q_in, q_out, pk, pv, urr), ev = nxt
+            if t + 1 < len(clip['frames']):
+                nxt = stage(t + 1)
+            cur.wait_event(ev)
+            for x in (q_in, q_out, *pk, *pv, *urr):
+                x.record_stream(cur)
+        else:
+            if t == 0:
+                fb.init_bank(list(clip['keys0']), list(clip['vals0']))
+            q_in, q_out, pk, pv = clip['frames'][t]
+            urr = clip['urr']
+        p, r1, q_local = urr
+        out = m(fb, q_in, q_out)
         p_up, unc, conf, local_match = vfn.urr_pre(p, r1.expand(2, -1, -1, -1), (1, 2, R1_H, R1_W))
         prob = vfn.urr_post(p_up, unc, conf, q_local)
-        fb.update([D(k) for k in pk], [D(v) for v in pv], t + 1)
+        fb.update(pk, pv, t + 1)
         if out_host is not None:
             out_host.copy_(prob, non_blocking=True)
     return fb, out, prob
+
+
+_COPY_STREAMS = {}
+
+
+def _copy_stream(dev):
+    if dev not in _COPY_STREAMS:
+        _COPY_STREAMS[dev] = torch.cuda.Stream(dev)
+    return _COPY_STREAMS[dev]
 
 
 # ---------------------------------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons DURING the timed region.  Samples through NVML in-process (the library behind
+    nvidia-smi; no fork of a CUDA process inside the timed region), falling back to the nvidia-smi CLI."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    BITS = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4}
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + uuid) if not uuid.startswith('GPU-') else uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def run(self):
         while not self.stop_flag:
             try:
-                o = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i',
-                                    str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.samples.append([x.strip() for x in o.split(',')])
+                if self.nvml is not None:
+                    n = self.nvml
+                    sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                    try:
+                        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                    except Exception:
+                        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                    self.samples.append([str(sm), str(self.sm_max)] +
+                                        [('Active' if r & b else 'Not Active') for b in self.BITS.values()])
+                else:
+                    o = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i',
+                                        str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                    if o:
+                        self.samples.append([x.strip() for x in o.split(',')])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05 if self.nvml is not None else 0.5)
 
     def summary(self):
         if not self.samples:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['clock query unavailable']}
         sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        names = list(self.BITS)
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples)]
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': int(self.samples[0][1]), 'reasons': reasons,
-                'samples': len(self.samples)}
+                'samples': len(self.samples), 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -289,7 +353,7 @@ def main_ours(args, rank, world, local_rank):
             extra[nm] = d
     line = {'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'bf16x3-split operands, f32 accumulate (read); f32 (match, update, URR)',
+            'vs_baseline': None, 'dtype': 'f16 hi/lo + f8 split operands, f32 accumulate (read, match); f32 (update, URR)',
             'data': 'synthetic',
             'config': {'workload': '480p-2obj-100frame-clip-hotpath', 'hw': HW_H * HW_W, 'budget': BUDGET,
                        'frames': args.frames, 'frac_merge': args.frac_merge, 'streams_per_gpu': 1,

@@ -201,6 +201,8 @@ int64_t vfn_launch_count(void);
 /* ---- self-test hooks for the tcgen05/TMA building blocks (used by tests/, not by the product path) ---- */
 /* d_ptr != NULL: the next tcgen05 read launches dump the first S^T tile of CTA 0 (128 x tile floats) there. */
 int vfn_debug_set_dump(float* d_ptr);
+/* 1 (default): CTA-pair (cta_group::2) tcgen05 kernels; 0: the single-CTA kernels (cross-check in tests/) */
+int vfn_debug_set_pair(int32_t on);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,147 @@
+// tcgen05.mma issue-rate microbenchmark (sm_100a): cycles per instruction for the shapes the read kernels use.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mma_rate mma_rate.cu && ./mma_rate
+// One CTA (or CTA pair) per SM; one thread issues `reps` back-to-back MMAs into the same accumulator and commits;
+// operands are zero-filled smem / TMEM (timing does not depend on the values).
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t a, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((a >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int af, int bf, int amn, int bmn) {
+  return (1u << 4) | ((uint32_t)af << 7) | ((uint32_t)bf << 10) | ((uint32_t)amn << 15) | ((uint32_t)bmn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+enum { K_F16 = 0, K_F8 = 1, K_TF32 = 2 };
+
+template <int KIND, int PAIR, int SS>
+__device__ __forceinline__ void mma(uint32_t d, uint32_t a_t, uint64_t a_d, uint64_t b_d, uint32_t idesc) {
+  if (SS) {
+    if (KIND == K_F16) {
+      if (PAIR) asm volatile("{.reg .pred p; setp.ne.b32 p, 1, 0; tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;}" ::"r"(d), "l"(a_d), "l"(b_d), "r"(idesc) : "memory");
+      else asm volatile("{.reg .pred p; setp.ne.b32 p, 1, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;}" ::"r"(d), "l"(a_d), "l"(b_d), "r"(idesc) : "memory");
+    } else {
+      if (PAIR) asm volatile("{.reg .pred p; setp.ne.b32 p, 1, 0; tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;}" ::"r"(d), "l"(a_d), "l"(b_d), "r"(idesc) : "memory");
+      else asm volatile("{.reg .pred p; setp.ne.b32 p, 1, 0; tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;}" ::"r"(d), "l"(a_d), "l"(b_d), "r"(idesc) : "memory");
+    }
+  } else {
+    if (KIND == K_F16) {
+      if (PAIR) asm volatile("{.reg .pred p; setp.ne.b32 p, 1, 0; tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;}" ::"r"(d), "r"(a_t), "l"(b_d), "r"(idesc) : "memory");
+      else asm volatile("{.reg .pred p; setp.ne.b32 p, 1, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;}" ::"r"(d), "r"(a_t), "l"(b_d), "r"(idesc) : "memory");
+    } else {
+      if (PAIR) asm volatile("{.reg .pred p; setp.ne.b32 p, 1, 0; tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], [%1], %2, %3, p;}" ::"r"(d), "r"(a_t), "l"(b_d), "r"(idesc) : "memory");
+      else asm volatile("{.reg .pred p; setp.ne.b32 p, 1, 0; tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;}" ::"r"(d), "r"(a_t), "l"(b_d), "r"(idesc) : "memory");
+    }
+  }
+}
+
+// B layout: bmn = 0: K-major SW128 (rows = N, 128 B of K per row); bmn = 1: MN-major SW128 (rows = K, 128 B of N per row)
+template <int KIND, int PAIR, int SS>
+__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int bmn, int reps, int same_b, long long* out_cycles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_p;
+  for (int i = threadIdx.x; i < 160 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  uint32_t rank = 0;
+  if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 32) {
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_p)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_p)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  if (PAIR) { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+  else __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_p;
+  // zero the A region of TMEM (columns 256..383) so that no NaN patterns are multiplied
+  {
+    const uint32_t taddr = tmem + (((threadIdx.x >> 5) * 32u) << 16) + 256;
+    for (int c = 0; c < 128; c += 8)
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr + c), "r"(0) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  if (PAIR) { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+  else __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const int M = PAIR ? 256 : 128;
+  const uint32_t idesc = make_idesc(M, N, KIND == K_F8 ? 0 : 0, 0, 0, bmn);
+  const uint32_t a_smem = smem_u32(smem), b_smem = smem_u32(smem + 65536);
+  if (threadIdx.x == 0 && rank == 0) {
+    long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      const int ks = same_b ? 0 : (r & 3);
+      // K-major: advance 32 B inside the 128 B row per k-step; MN-major: advance 16 (f16) / 32 (f8) rows of 128 B
+      const uint64_t bd = bmn ? make_sdesc(b_smem + ks * (KIND == K_F8 ? 4096u : 2048u), 8192, 1024)
+                              : make_sdesc(b_smem + ks * 32u, 16, 1024);
+      const uint64_t ad = make_sdesc(a_smem + ks * 32u, 16, 1024);
+      mma<KIND, PAIR, SS>(tmem, tmem + 256 + ks * 8, ad, bd, idesc);
+    }
+    if (PAIR) asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    else asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{.reg .pred P1; mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], 0; selp.u32 %0, 1, 0, P1;}" : "=r"(done) : "r"(smem_u32(&bar)) : "memory");
+    long long t1 = clock64();
+    if (blockIdx.x == 0) *out_cycles = t1 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  if (PAIR) { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+  else __syncthreads();
+  if (threadIdx.x < 32) {
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+template <int KIND, int PAIR, int SS>
+void run(const char* name, int N, int bmn, int same_b = 0) {
+  long long* d;
+  cudaMalloc(&d, 8);
+  const int reps = 4096, smem = 160 * 1024 + 2048;
+  auto k = rate_kernel<KIND, PAIR, SS>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(148); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = PAIR ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  for (int it = 0; it < 2; ++it) cudaLaunchKernelEx(&cfg, k, N, bmn, reps, same_b, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long h = 0;
+  cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+  const int M = PAIR ? 256 : 128, K = KIND == K_F8 ? 32 : 16;
+  const double cyc = (double)h / reps;
+  const double ideal = (double)128 * N * K / (KIND == K_F8 ? 8192.0 : 4096.0);   // per SM: 128 rows
+  printf("%-34s M=%3d N=%3d K=%2d %s  %8.1f cyc/instr  (floor %6.1f, %5.1f%%)  %s\n", name, M, N, K, bmn ? "B MN-major" : "B K-major ", cyc,
+         ideal, 100.0 * ideal / cyc, e == cudaSuccess ? "" : cudaGetErrorString(e));
+  cudaFree(d);
+}
+
+int main() {
+  for (int N : {64, 128, 256}) run<K_F16, 0, 0>("TS f16 1-CTA", N, 0);
+  for (int N : {64, 128, 256}) run<K_F16, 0, 0>("TS f16 1-CTA same B", N, 0, 1);
+  for (int N : {64, 128, 256}) run<K_F16, 0, 1>("SS f16 1-CTA", N, 0);
+  for (int N : {128, 256}) run<K_F16, 0, 0>("TS f16 1-CTA", N, 1);
+  for (int N : {128, 256}) run<K_F8, 0, 0>("TS f8  1-CTA", N, 1);
+  for (int N : {64, 128, 256}) run<K_F8, 0, 0>("TS f8  1-CTA", N, 0);
+  for (int N : {64, 128, 256}) run<K_F16, 1, 0>("TS f16 pair", N, 0);
+  for (int N : {64, 128, 256}) run<K_F16, 1, 1>("SS f16 pair", N, 0);
+  for (int N : {128, 256}) run<K_F16, 1, 0>("TS f16 pair", N, 1);
+  for (int N : {128, 256}) run<K_F8, 1, 0>("TS f8  pair", N, 1);
+  return 0;
+}

@@ -339,3 +339,35 @@ def test_split_memory_read_two_shards_one_gpu(vfn, impl):
         got = torch.cat([shards[0].info[c], shards[1].info[c]])
         d = (got[:, 1] - full.info[c][:, 1]).abs()
         assert int((d > 1e-6).sum()) <= 2       # counts are local and exact up to threshold-band flips
+
+
+# ---------------------------------------------------------------------------------------------------
+# CTA-pair (cta_group::2) and single-CTA tcgen05 read kernels must agree with each other and with the oracle
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('n,hw', [(5000, 1620), (20000, 300)])
+def test_read_pair_and_single_cta_kernels(vfn, n, hw):
+    from vfloodnet_b200 import synth, _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(11)
+    ns = [n, n - 129]
+    keys, vals = zip(*[synth.gen_bank(g, k) for k in ns])
+    info = [synth.gen_info(g, k, 10) for k in ns]
+    q_in, q_out = synth.gen_query(g, hw)
+    rr, _ = _oracle_read(list(keys), list(vals), info, q_in, q_out)
+    outs, infos = [], []
+    try:
+        for pair in (1, 0):
+            lib.vfn_debug_set_pair(pair)
+            fb = vfn.FeatureBank(2, 10 ** 6, 'cuda', impl=2)
+            fb.load_state(list(keys), list(vals), info)
+            out = vfn.Matcher(update_bank=True)(fb, q_in.cuda(), q_out.cuda())
+            torch.cuda.synchronize()
+            assert (out.cpu() - rr.out).abs().max().item() <= 1e-3, pair
+            outs.append(out.cpu())
+            infos.append([fb.info[c].cpu().clone() for c in range(2)])
+    finally:
+        lib.vfn_debug_set_pair(1)
+    assert (outs[0] - outs[1]).abs().max().item() <= 2e-4
+    for c in range(2):
+        # same logits and LSE in both kernels: identical usage counts up to threshold-band flips
+        assert (infos[0][c] - infos[1][c]).abs().gt(1e-5).sum().item() <= 2

@@ -126,12 +126,22 @@ int launch_prep(const PrepJob* jobs, int n_jobs, cudaStream_t st) {
 // row helpers: one block owns one bank slot
 // ------------------------------------------------------------------------------------------------
 // append: grid.x = upper bound on selected rows; block = 128 threads; row i -> slot bank.n + i
-__global__ void __launch_bounds__(128) append_rows_kernel(vfn_bank bank, const float* __restrict__ ck,
-                                                          const float* __restrict__ cv, const float* __restrict__ nck,
-                                                          const int32_t* __restrict__ sel,
-                                                          const int32_t* __restrict__ n_sel_dev, int64_t n_sel_upper,
-                                                          float info0, float info1) {
+struct AppendObj {
+  vfn_bank bank; const float *ck, *cv, *nck; const int32_t *sel, *n_sel_dev; int64_t n_sel_upper;
+};
+struct AppendSet { AppendObj o[4]; };
+// grid (rows, objects)
+__global__ void __launch_bounds__(128) append_rows_kernel(const __grid_constant__ AppendSet set, float info0,
+                                                          float info1) {
   __shared__ float red[32];
+  const AppendObj& ao = set.o[blockIdx.y];
+  const vfn_bank& bank = ao.bank;
+  const float* __restrict__ ck = ao.ck;
+  const float* __restrict__ cv = ao.cv;
+  const float* __restrict__ nck = ao.nck;
+  const int32_t* __restrict__ sel = ao.sel;
+  const int32_t* __restrict__ n_sel_dev = ao.n_sel_dev;
+  const int64_t n_sel_upper = ao.n_sel_upper;
   const int64_t n_sel = n_sel_dev ? (int64_t)*n_sel_dev : n_sel_upper;
   const int dk4 = bank.d_key >> 2, dv4 = bank.d_val >> 2;
   for (int64_t i = blockIdx.x; i < n_sel; i += gridDim.x) {
@@ -230,14 +240,11 @@ __device__ __forceinline__ int block_excl_scan(int v, int* warp_tot /*[33]*/, in
   return warp_tot[wid] + inc - v;
 }
 
-__global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(const int32_t* __restrict__ match_idx,
-                                                            const float* __restrict__ match_corr, int hw, float thres,
-                                                            int32_t* __restrict__ merge_q,
-                                                            int32_t* __restrict__ merge_slot,
-                                                            int32_t* __restrict__ run_off,
-                                                            int32_t* __restrict__ append_q, int32_t* __restrict__ counts,
-                                                            int32_t* __restrict__ h_counts,
-                                                            unsigned long long* __restrict__ gkeys) {
+__device__ __forceinline__ void plan_body(const int32_t* __restrict__ match_idx, const float* __restrict__ match_corr,
+                                          int hw, float thres, int32_t* __restrict__ merge_q,
+                                          int32_t* __restrict__ merge_slot, int32_t* __restrict__ run_off,
+                                          int32_t* __restrict__ append_q, int32_t* __restrict__ counts,
+                                          int32_t* __restrict__ h_counts, unsigned long long* __restrict__ gkeys) {
   __shared__ unsigned long long skeys[PLAN_SMEM_KEYS];
   __shared__ int wt[33];
   const int tid = threadIdx.x;
@@ -315,19 +322,39 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(const int32_t* __res
   }
 }
 
+struct PlanObj {
+  const int32_t* match_idx; const float* match_corr; int32_t *merge_q, *merge_slot, *run_off, *append_q, *counts, *h_counts;
+  unsigned long long* gkeys;
+};
+struct PlanSet { PlanObj o[4]; };
+// one CTA per object (blockIdx.x)
+__global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(const __grid_constant__ PlanSet set, int hw, float thres) {
+  const PlanObj& p = set.o[blockIdx.x];
+  plan_body(p.match_idx, p.match_corr, hw, thres, p.merge_q, p.merge_slot, p.run_off, p.append_q, p.counts, p.h_counts,
+            p.gkeys);
+}
+
 // ------------------------------------------------------------------------------------------------
 // merge: one block per run of equal slot.  192 threads, one float4 of the [key | value] row per thread.
 // ------------------------------------------------------------------------------------------------
 constexpr int MERGE_THREADS = 192;
 
-__global__ void __launch_bounds__(MERGE_THREADS) merge_runs_kernel(vfn_bank bank, const float* __restrict__ nck,
-                                                                   const float* __restrict__ ncv,
-                                                                   const int32_t* __restrict__ merge_q,
-                                                                   const int32_t* __restrict__ merge_slot,
-                                                                   const int32_t* __restrict__ run_off,
-                                                                   const int32_t* __restrict__ counts, float omr,
+struct MergeObj {
+  vfn_bank bank; const float *nck, *ncv; const int32_t *merge_q, *merge_slot, *run_off, *counts;
+};
+struct MergeSet { MergeObj o[4]; };
+// grid (runs, objects)
+__global__ void __launch_bounds__(MERGE_THREADS) merge_runs_kernel(const __grid_constant__ MergeSet set, float omr,
                                                                    float r) {
   __shared__ float red[32];
+  const MergeObj& mo = set.o[blockIdx.y];
+  const vfn_bank& bank = mo.bank;
+  const float* __restrict__ nck = mo.nck;
+  const float* __restrict__ ncv = mo.ncv;
+  const int32_t* __restrict__ merge_q = mo.merge_q;
+  const int32_t* __restrict__ merge_slot = mo.merge_slot;
+  const int32_t* __restrict__ run_off = mo.run_off;
+  const int32_t* __restrict__ counts = mo.counts;
   const int n_runs = counts[1];
   const int dk4 = bank.d_key >> 2, dv4 = bank.d_val >> 2;
   const int f = threadIdx.x;
@@ -534,7 +561,11 @@ __global__ void __launch_bounds__(CP_THREADS) compact_move_kernel(vfn_bank src, 
   }
 }
 
-__global__ void clamp_info_kernel(float* __restrict__ info, int64_t n) {
+struct ClampSet { float* info[4]; int64_t n[4]; };
+// grid (rows / 256, objects)
+__global__ void clamp_info_kernel(const __grid_constant__ ClampSet set) {
+  float* __restrict__ info = set.info[blockIdx.y];
+  const int64_t n = set.n[blockIdx.y];
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     float v = info[2 * i + 1];
@@ -553,6 +584,90 @@ static int check_bank(const vfn_bank* b) {
                     (b->kh == nullptr) == (b->vl == nullptr) && (b->kh == nullptr) == (b->v8 == nullptr) &&
                     (b->kh == nullptr) == (b->nkh == nullptr) && (b->kh == nullptr) == (b->nkl == nullptr),
                 "tensor-core operand arrays must be all set or all NULL");
+  return VFN_OK;
+}
+
+int launch_plan(const UpdObj* o, int n_obj, int64_t hw, float thres_close, cudaStream_t st) {
+  VFN_CHECK_ARG(n_obj >= 1 && n_obj <= 4, "plan: 1..4 objects per launch");
+  VFN_CHECK_ARG(hw > 0 && hw <= 65536, "plan: hw=%lld out of range (1..65536)", (long long)hw);
+  PlanSet set;
+  for (int c = 0; c < n_obj; ++c) {
+    VFN_CHECK_ARG(o[c].match_idx && o[c].match_corr && o[c].merge_q && o[c].merge_slot && o[c].run_off && o[c].append_q &&
+                      o[c].counts && o[c].plan_ws, "plan: NULL argument");
+    set.o[c] = PlanObj{o[c].match_idx, o[c].match_corr, o[c].merge_q, o[c].merge_slot, o[c].run_off, o[c].append_q,
+                       o[c].counts, o[c].h_counts, reinterpret_cast<unsigned long long*>(o[c].plan_ws)};
+  }
+  plan_kernel<<<n_obj, PLAN_THREADS, 0, st>>>(set, (int)hw, thres_close);
+  VFN_LAUNCH_OK();
+  count_launches(1);
+  return VFN_OK;
+}
+
+int launch_merge(const UpdObj* o, int n_obj, int64_t hw, float update_rate, cudaStream_t st) {
+  VFN_CHECK_ARG(n_obj >= 1 && n_obj <= 4, "merge: 1..4 objects per launch");
+  MergeSet set;
+  for (int c = 0; c < n_obj; ++c) {
+    if (int rc = check_bank(&o[c].bank)) return rc;
+    VFN_CHECK_ARG(o[c].nck && o[c].ncv && o[c].merge_q && o[c].merge_slot && o[c].run_off && o[c].counts, "merge: bad args");
+    if ((o[c].bank.d_key + o[c].bank.d_val) / 4 > MERGE_THREADS) {
+      set_error("merge: d_key + d_val = %d exceeds %d", o[c].bank.d_key + o[c].bank.d_val, MERGE_THREADS * 4);
+      return VFN_E_UNSUPPORTED;
+    }
+    set.o[c] = MergeObj{o[c].bank, o[c].nck, o[c].ncv, o[c].merge_q, o[c].merge_slot, o[c].run_off, o[c].counts};
+  }
+  // (1 - update_rate) is evaluated in double by Python and rounded to fp32 when it meets the tensor
+  const float omr = (float)(1.0 - (double)update_rate);
+  dim3 grid((unsigned)(hw < 148 * 8 ? hw : 148 * 8), n_obj);
+  prof_begin(PROF_MERGE, st);
+  merge_runs_kernel<<<grid, MERGE_THREADS, 0, st>>>(set, omr, update_rate);
+  prof_end(PROF_MERGE, st, 0.0);
+  VFN_LAUNCH_OK();
+  count_launches(1);
+  return VFN_OK;
+}
+
+int launch_append(const UpdObj* o, int n_obj, float info0, float info1, cudaStream_t st) {
+  VFN_CHECK_ARG(n_obj >= 1 && n_obj <= 4, "append: 1..4 objects per launch");
+  AppendSet set;
+  int64_t n_max = 0;
+  double bytes = 0;
+  for (int c = 0; c < n_obj; ++c) {
+    if (int rc = check_bank(&o[c].bank)) return rc;
+    VFN_CHECK_ARG(o[c].ck && o[c].cv && o[c].n_sel >= 0, "append_rows: bad args");
+    if (o[c].bank.n + o[c].n_sel > o[c].bank.cap) {
+      set_error("append_rows: n=%lld + %lld exceeds cap=%lld", (long long)o[c].bank.n, (long long)o[c].n_sel,
+                (long long)o[c].bank.cap);
+      return VFN_E_CAPACITY;
+    }
+    set.o[c] = AppendObj{o[c].bank, o[c].ck, o[c].cv, o[c].nck, o[c].sel, o[c].n_sel_dev, o[c].n_sel};
+    if (o[c].n_sel > n_max) n_max = o[c].n_sel;
+    bytes += 2.0 * 4.0 * (o[c].bank.d_key + o[c].bank.d_val + 2) * (double)o[c].n_sel;
+  }
+  if (n_max == 0) return VFN_OK;
+  dim3 grid((unsigned)(n_max < 148 * 16 ? n_max : 148 * 16), n_obj);
+  prof_begin(PROF_APPEND, st);
+  append_rows_kernel<<<grid, 128, 0, st>>>(set, info0, info1);
+  // algorithmic bytes: read + write of the appended rows (keys, values, info)
+  prof_end(PROF_APPEND, st, bytes);
+  VFN_LAUNCH_OK();
+  count_launches(1);
+  return VFN_OK;
+}
+
+int launch_clamp(const vfn_bank* banks, int n_obj, cudaStream_t st) {
+  VFN_CHECK_ARG(n_obj >= 1 && n_obj <= 4, "clamp: 1..4 objects per launch");
+  ClampSet set;
+  int64_t n_max = 0;
+  for (int c = 0; c < n_obj; ++c) {
+    set.info[c] = banks[c].info;
+    set.n[c] = banks[c].n;
+    if (banks[c].n > n_max) n_max = banks[c].n;
+  }
+  if (n_max == 0) return VFN_OK;
+  dim3 grid((unsigned)cdiv(n_max, 256), n_obj);
+  clamp_info_kernel<<<grid, 256, 0, st>>>(set);
+  VFN_LAUNCH_OK();
+  count_launches(1);
   return VFN_OK;
 }
 
@@ -620,23 +735,10 @@ int vfn_prep_rows(const float* d_src_dm, int32_t d, int64_t n, float* d_raw_em, 
 int vfn_bank_append_rows(const vfn_bank* bank, const float* d_ck_em, const float* d_cv_em, const float* d_nck_em,
                          const int32_t* d_sel, int64_t n_sel_upper, const int32_t* d_n_sel, float info0, float info1,
                          void* stream) {
-  if (int rc = check_bank(bank)) return rc;
-  VFN_CHECK_ARG(d_ck_em && d_cv_em && n_sel_upper >= 0, "append_rows: bad args");
-  if (bank->n + n_sel_upper > bank->cap) {
-    set_error("append_rows: n=%lld + %lld exceeds cap=%lld", (long long)bank->n, (long long)n_sel_upper,
-              (long long)bank->cap);
-    return VFN_E_CAPACITY;
-  }
-  if (n_sel_upper == 0) return VFN_OK;
-  const unsigned grid = (unsigned)(n_sel_upper < 148 * 16 ? n_sel_upper : 148 * 16);
-  prof_begin(PROF_APPEND, as_stream(stream));
-  append_rows_kernel<<<grid, 128, 0, as_stream(stream)>>>(*bank, d_ck_em, d_cv_em, d_nck_em, d_sel, d_n_sel,
-                                                          n_sel_upper, info0, info1);
-  // algorithmic bytes: read + write of the appended rows (keys, values, info)
-  prof_end(PROF_APPEND, as_stream(stream), 2.0 * 4.0 * (bank->d_key + bank->d_val + 2) * (double)n_sel_upper);
-  VFN_LAUNCH_OK();
-  count_launches(1);
-  return VFN_OK;
+  VFN_CHECK_ARG(bank != nullptr, "bank is NULL");
+  UpdObj o{};
+  o.bank = *bank; o.ck = d_ck_em; o.cv = d_cv_em; o.nck = d_nck_em; o.sel = d_sel; o.n_sel_dev = d_n_sel; o.n_sel = n_sel_upper;
+  return launch_append(&o, 1, info0, info1, as_stream(stream));
 }
 
 int vfn_bank_refresh(const vfn_bank* bank, int64_t first, int64_t count, void* stream) {
@@ -659,40 +761,25 @@ size_t vfn_bank_plan_workspace_bytes(int64_t hw) {
 int vfn_bank_plan(const int32_t* d_match_idx, const float* d_match_corr, int64_t hw, float thres_close,
                   int32_t* d_merge_q, int32_t* d_merge_slot, int32_t* d_run_off, int32_t* d_append_q, int32_t* d_counts,
                   int32_t* h_counts, void* d_ws, size_t ws_bytes, void* stream) {
-  VFN_CHECK_ARG(d_match_idx && d_match_corr && d_merge_q && d_merge_slot && d_run_off && d_append_q && d_counts,
-                "plan: NULL argument");
-  VFN_CHECK_ARG(hw > 0 && hw <= 65536, "plan: hw=%lld out of range (1..65536)", (long long)hw);
   if (ws_bytes < vfn_bank_plan_workspace_bytes(hw) || !d_ws) {
     set_error("plan: workspace too small");
     return VFN_E_CAPACITY;
   }
-  plan_kernel<<<1, PLAN_THREADS, 0, as_stream(stream)>>>(d_match_idx, d_match_corr, (int)hw, thres_close, d_merge_q,
-                                                         d_merge_slot, d_run_off, d_append_q, d_counts, h_counts,
-                                                         reinterpret_cast<unsigned long long*>(d_ws));
-  VFN_LAUNCH_OK();
-  count_launches(1);
-  return VFN_OK;
+  UpdObj o{};
+  o.match_idx = d_match_idx; o.match_corr = d_match_corr; o.merge_q = d_merge_q; o.merge_slot = d_merge_slot;
+  o.run_off = d_run_off; o.append_q = d_append_q; o.counts = d_counts; o.h_counts = h_counts; o.plan_ws = d_ws;
+  return launch_plan(&o, 1, hw, thres_close, as_stream(stream));
 }
 
 int vfn_bank_merge(const vfn_bank* bank, const float* d_nck_em, const float* d_ncv_em, const int32_t* d_merge_q,
                    const int32_t* d_merge_slot, const int32_t* d_run_off, const int32_t* d_counts, int64_t hw,
                    float update_rate, void* stream) {
-  if (int rc = check_bank(bank)) return rc;
-  VFN_CHECK_ARG(d_nck_em && d_ncv_em && d_merge_q && d_merge_slot && d_run_off && d_counts && hw > 0, "merge: bad args");
-  if ((bank->d_key + bank->d_val) / 4 > MERGE_THREADS) {
-    set_error("merge: d_key + d_val = %d exceeds %d", bank->d_key + bank->d_val, MERGE_THREADS * 4);
-    return VFN_E_UNSUPPORTED;
-  }
-  // (1 - update_rate) is evaluated in double by Python and rounded to fp32 when it meets the tensor
-  const float omr = (float)(1.0 - (double)update_rate);
-  const unsigned grid = (unsigned)(hw < 148 * 8 ? hw : 148 * 8);
-  prof_begin(PROF_MERGE, as_stream(stream));
-  merge_runs_kernel<<<grid, MERGE_THREADS, 0, as_stream(stream)>>>(*bank, d_nck_em, d_ncv_em, d_merge_q, d_merge_slot,
-                                                                   d_run_off, d_counts, omr, update_rate);
-  prof_end(PROF_MERGE, as_stream(stream), 0.0);
-  VFN_LAUNCH_OK();
-  count_launches(1);
-  return VFN_OK;
+  VFN_CHECK_ARG(bank != nullptr && hw > 0, "merge: bad args");
+  UpdObj o{};
+  o.bank = *bank; o.nck = d_nck_em; o.ncv = d_ncv_em; o.merge_q = const_cast<int32_t*>(d_merge_q);
+  o.merge_slot = const_cast<int32_t*>(d_merge_slot); o.run_off = const_cast<int32_t*>(d_run_off);
+  o.counts = const_cast<int32_t*>(d_counts);
+  return launch_merge(&o, 1, hw, update_rate, as_stream(stream));
 }
 
 int vfn_bank_evict_plan(const vfn_bank* bank, float frame_idx, double class_budget, int64_t request_n, int32_t* d_plan,
@@ -737,11 +824,9 @@ int vfn_bank_compact(const vfn_bank* src, const vfn_bank* dst, const float* d_lf
 int vfn_bank_clamp_info(const vfn_bank* bank, int64_t n, void* stream) {
   if (int rc = check_bank(bank)) return rc;
   VFN_CHECK_ARG(n >= 0 && n <= bank->cap, "clamp_info: n out of range");
-  if (n == 0) return VFN_OK;
-  clamp_info_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(bank->info, n);
-  VFN_LAUNCH_OK();
-  count_launches(1);
-  return VFN_OK;
+  vfn_bank b = *bank;
+  b.n = n;
+  return launch_clamp(&b, 1, as_stream(stream));
 }
 
 }  // extern "C"

@@ -28,6 +28,20 @@ struct PrepJob {
 };
 int launch_prep(const PrepJob* jobs, int n_jobs, cudaStream_t st);
 
+// per-object arguments of the update's bookkeeping kernels; the launch_* helpers run one launch for all objects
+struct UpdObj {
+  vfn_bank bank;
+  const float *ck, *cv, *nck, *ncv;            // (hw, d) entry-major candidates: raw / normalised
+  const int32_t* match_idx; const float* match_corr;
+  int32_t *merge_q, *merge_slot, *run_off, *append_q, *counts, *h_counts;
+  void* plan_ws;
+  const int32_t* sel; const int32_t* n_sel_dev; int64_t n_sel;   // append: rows to ingest
+};
+int launch_plan(const UpdObj* o, int n_obj, int64_t hw, float thres_close, cudaStream_t st);
+int launch_merge(const UpdObj* o, int n_obj, int64_t hw, float update_rate, cudaStream_t st);
+int launch_append(const UpdObj* o, int n_obj, float info0, float info1, cudaStream_t st);
+int launch_clamp(const vfn_bank* banks, int n_obj, cudaStream_t st);
+
 #define VFN_CHECK_ARG(cond, ...)              \
   do {                                        \
     if (!(cond)) {                            \

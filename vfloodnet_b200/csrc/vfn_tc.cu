@@ -39,8 +39,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  // bounded spin: a broken pipeline traps (launch error) instead of hanging the GPU
+  // bounded wait: a broken pipeline traps (launch error) after ~2 s instead of hanging the GPU
   uint32_t done = 0;
+  uint64_t t_start = 0;
   for (uint32_t spins = 0;; ++spins) {
     asm volatile(
         "{\n\t"
@@ -52,7 +53,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     if (done) break;
-    if (spins > (1u << 26)) __trap();
+    if ((spins & 0x3FF) == 0x3FF) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t_start == 0) t_start = now;
+      else if (now - t_start > 2000000000ull) __trap();
+    }
   }
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -194,7 +200,86 @@ __device__ __forceinline__ uint32_t f16x2_rn(float lo, float hi) {   // lo -> lo
 __device__ __forceinline__ float2 f16x2_to_f32(uint32_t h) {
   return __half22float2(*reinterpret_cast<const __half2*>(&h));
 }
+// one elected lane of a converged warp (the CUTLASS idiom: keeps the enclosing code warp-uniform, so that MMA
+// descriptors live in uniform registers without a per-instruction ELECT / R2UR.BROADCAST waterfall loop)
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "@px mov.s32 %0, 1;\n\t"
+      "}"
+      : "+r"(pred));
+  return pred;
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// ---- CTA-pair (cta_group::2) helpers -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into this CTA's smem whose completion bytes are counted on a barrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t mbar_cluster_addr, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+// arrives on the barrier at this smem offset in BOTH CTAs of the pair once all prior MMAs of this thread completed
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts_f8_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------------
 // descriptors
@@ -337,15 +422,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const __grid_con
       }
       __syncwarp();
     } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc(128, SC_TILE, FMT_F16, FMT_F16, 0, 0);
-        for (int t = 0; t < ntile; ++t) {
-          const uint32_t c = tile_ctr + t, st = c % SC_STAGES, ph = (c / SC_STAGES) & 1;
-          mbar_wait(&s_empty[st], ph ^ 1);
-          mbar_wait(&k_full[st], ph);
-          tc_fence_after();
-          const uint32_t kbase = smem_u32(kst + st * SC_STAGE_BYTES);
-          const uint32_t d_t = tmem + TS_S + st * SC_TILE;
+      // the whole warp runs the loop (uniform control flow and operands); one elected lane issues
+      constexpr uint32_t idesc = make_idesc(128, SC_TILE, FMT_F16, FMT_F16, 0, 0);
+      for (int t = 0; t < ntile; ++t) {
+        const uint32_t c = tile_ctr + t, st = c % SC_STAGES, ph = (c / SC_STAGES) & 1;
+        mbar_wait(&s_empty[st], ph ^ 1);
+        mbar_wait(&k_full[st], ph);
+        tc_fence_after();
+        const uint32_t kbase = smem_u32(kst + st * SC_STAGE_BYTES);
+        const uint32_t d_t = tmem + TS_S + st * SC_TILE;
+        if (elect_one()) {
           // passes: (Ah,Bh) (Al,Bh) (Ah,Bl)
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
@@ -360,8 +446,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const __grid_con
           tc_commit(&k_empty[st]);
           tc_commit(&s_full[st]);
         }
+        __syncwarp();
       }
-      __syncwarp();
     } else if (warp >= 4) {
       const int quarter = warp & 3, cg = (warp - 4) >> 2;
       const int row = (quarter << 5) + lane;
@@ -531,7 +617,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
-      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8);
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], EPI_WARPS);
     }
     mbar_init(o_full, 1);
     fence_barrier_init();
@@ -594,18 +680,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
       }
       __syncwarp();
     } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc_s = make_idesc(128, B_TILE, FMT_F16, FMT_F16, 0, 0);
-        constexpr uint32_t idesc_o = make_idesc(128, 256, FMT_F16, FMT_F16, 0, 1);
-        constexpr uint32_t idesc_o8 = make_idesc(128, 256, FMT_E4M3, FMT_E4M3, 0, 1);    // e4m3(P - hi) x e4m3(V)
-        constexpr uint32_t idesc_ol = make_idesc(128, 256, FMT_E4M3, FMT_E5M2, 0, 1);    // e4m3(P) x e5m2(V - Vhi)
-        auto issue_s = [&](int t) {
-          const uint32_t kit = k_it + t, st = kit & 1, ph = (kit >> 1) & 1;
-          const int b = t & 1;
-          mbar_wait(&k_full[st], ph);
-          tc_fence_after();
-          const uint32_t kbase = smem_u32(kst + st * B_KSTAGE_BYTES);
-          const uint32_t d_t = tmem + TM_S + (uint32_t)b * 64;
+      // the whole warp runs the loop (uniform control flow and operands); one elected lane issues
+      constexpr uint32_t idesc_s = make_idesc(128, B_TILE, FMT_F16, FMT_F16, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc(128, 256, FMT_F16, FMT_F16, 0, 1);
+      constexpr uint32_t idesc_o8 = make_idesc(128, 256, FMT_E4M3, FMT_E4M3, 0, 1);    // e4m3(P - hi) x e4m3(V)
+      constexpr uint32_t idesc_ol = make_idesc(128, 256, FMT_E4M3, FMT_E5M2, 0, 1);    // e4m3(P) x e5m2(V - Vhi)
+      auto issue_s = [&](int t) {
+        const uint32_t kit = k_it + t, st = kit & 1, ph = (kit >> 1) & 1;
+        const int b = t & 1;
+        mbar_wait(&k_full[st], ph);
+        tc_fence_after();
+        const uint32_t kbase = smem_u32(kst + st * B_KSTAGE_BYTES);
+        const uint32_t d_t = tmem + TM_S + (uint32_t)b * 64;
+        if (elect_one()) {
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
             const uint32_t a_col = (pass == 1) ? TM_QL : TM_QH;
@@ -618,18 +705,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
           }
           tc_commit(&k_empty[st]);
           tc_commit(&s_full[b]);
-        };
-        if (ntile > 0) issue_s(0);
-        if (ntile > 1) issue_s(1);
-        for (int t = 0; t < ntile; ++t) {
-          const uint32_t kit = k_it + t, st = kit & 1, ph = (kit >> 1) & 1;
-          const int b = t & 1;
-          mbar_wait(&p_full[b], buf_it[b] & 1);
-          ++buf_it[b];
-          mbar_wait(&v_full[st], ph);
-          tc_fence_after();
-          const uint32_t vbase = smem_u32(vst + st * B_VSTAGE_BYTES);
-          const uint32_t pcol = tmem + TM_S + (uint32_t)b * 64;
+        }
+        __syncwarp();
+      };
+      if (ntile > 0) issue_s(0);
+      if (ntile > 1) issue_s(1);
+      for (int t = 0; t < ntile; ++t) {
+        const uint32_t kit = k_it + t, st = kit & 1, ph = (kit >> 1) & 1;
+        const int b = t & 1;
+        mbar_wait(&p_full[b], buf_it[b] & 1);
+        ++buf_it[b];
+        mbar_wait(&v_full[st], ph);
+        tc_fence_after();
+        const uint32_t vbase = smem_u32(vst + st * B_VSTAGE_BYTES);
+        const uint32_t pcol = tmem + TM_S + (uint32_t)b * 64;
+        if (elect_one()) {
           // main pass: fp16 P hi x fp16 V hi, 16 slots per instruction
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
@@ -645,62 +735,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
             mma_ts_f8(tmem + TM_O, pcol + (uint32_t)h * 32u + 24u, bl, idesc_ol, 1u);
           }
           tc_commit(&v_empty[st]);
-          if (t + 2 < ntile) issue_s(t + 2);   // in-order MMA pipe: S(t+2) overwrites buffer b only after O(t) read it
         }
-        tc_commit(o_full);
-      } else {
-        for (int t = 0; t < ntile; ++t) ++buf_it[t & 1];
+        __syncwarp();
+        if (t + 2 < ntile) issue_s(t + 2);   // in-order MMA pipe: S(t+2) overwrites buffer b only after O(t) read it
       }
+      if (elect_one()) tc_commit(o_full);
       __syncwarp();
     } else if (warp >= 4) {
-      const int quarter = warp & 3, grp = (warp - 4) >> 2;      // grp 0..3
-      const int parity = grp >> 1, hsel = grp & 1;
+      // every softmax warp works on every tile: slot group sg = 16 of the tile's 64 slots, for its 32 query rows
+      const int quarter = warp & 3, sg = (warp - 4) >> 2;
+      const int hsel = sg >> 1, sub = sg & 1;
       const int row = (quarter << 5) + lane;
-      const int gtid = (quarter << 5) + lane;                    // 0..127 within the group
+      const int gtid = row;                                      // 0..127 within the slot group
       const uint32_t tlane = tmem + (((uint32_t)quarter * 32u) << 16);
       const int j = qt * QT + row;
       const float lse2m = (j < args.hw) ? (lse[(size_t)obj * args.hw + j] * LOG2E - P_SCALE_LOG2) : INFINITY;
       const float thres_s = thres * P_SCALE;
-      int* mycnt = cnt_s + grp * 32;
+      int* mycnt = cnt_s + sg * 16;
       const bool counting = do_count && (half == 0);
-      for (int t = parity; t < ntile; t += 2) {
-        mbar_wait(&s_full[parity], buf_it[parity] & 1);
-        ++buf_it[parity];
+      for (int t = 0; t < ntile; ++t) {
+        const int b = t & 1;
+        mbar_wait(&s_full[b], buf_it[b] & 1);
+        ++buf_it[b];
         tc_fence_after();
-        const int slot0 = (t0 + t) * B_TILE + hsel * 32;
-        const uint32_t sb = tlane + TM_S + (uint32_t)parity * 64 + (uint32_t)hsel * 32;
-        uint32_t s0[16], s1[16];
-        tmem_ld16(sb, s0);
-        tmem_ld16(sb + 16, s1);
+        const int slot0 = (t0 + t) * B_TILE + sg * 16;
+        const uint32_t pb = tlane + TM_S + (uint32_t)b * 64 + (uint32_t)hsel * 32;   // this half's 32-column S / P region
+        uint32_t sv[16];
+        tmem_ld16(pb + (uint32_t)sub * 16, sv);
         tmem_wait_ld();
         if (args.dbg && blockIdx.x == 0 && first_item && t == 0) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            args.dbg[row * B_TILE + hsel * 32 + i] = __uint_as_float(s0[i]);
-            args.dbg[row * B_TILE + hsel * 32 + 16 + i] = __uint_as_float(s1[i]);
-          }
+          for (int i = 0; i < 16; ++i) args.dbg[row * B_TILE + sg * 16 + i] = __uint_as_float(sv[i]);
         }
-        const int lim = n_obj - slot0;
+        // P is written in place over S and the fp8 operands of the two 16-slot groups of a half interleave: all four
+        // warps of this lane quarter must hold their logits in registers before any of them stores
+        tc_fence_before();
+        named_bar_sync(5 + quarter, 128);
+        tc_fence_after();
         uint32_t hi[8], lo[4], p8[4];
-        uint32_t bits = softmax_chunk16(s0, lse2m, thres_s, lim, hi, lo, p8);
-        tmem_st8(sb, hi);
-        tmem_st4(sb + 16, lo);
-        tmem_st4(sb + 24, p8);
-        bits |= softmax_chunk16(s1, lse2m, thres_s, lim - 16, hi, lo, p8) << 16;
-        tmem_st8(sb + 8, hi);
-        tmem_st4(sb + 20, lo);
-        tmem_st4(sb + 28, p8);
+        uint32_t bits = softmax_chunk16(sv, lse2m, thres_s, n_obj - slot0, hi, lo, p8);
+        tmem_st8(pb + (uint32_t)sub * 8, hi);
+        tmem_st4(pb + 16 + (uint32_t)sub * 4, lo);
+        tmem_st4(pb + 24 + (uint32_t)sub * 4, p8);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[parity]);
+        if (lane == 0) mbar_arrive(&p_full[b]);
         if (counting) {
           if (j >= args.hw) bits = 0u;
-          const int dense = __any_sync(0xffffffffu, __popc(bits) > 4);
+          const int dense = __any_sync(0xffffffffu, __popc(bits) > 2);
           if (dense) {
             int c_mine = 0;
-#pragma unroll 8
-            for (int c = 0; c < 32; ++c) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
               const unsigned bal = __ballot_sync(0xffffffffu, (bits >> c) & 1u);
               if (lane == c) c_mine = __popc(bal);
             }
@@ -712,27 +799,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
               atomicAdd(&mycnt[c], 1);
             }
           }
-          named_bar_sync(1 + grp, 128);
-          if (gtid < 32) {
+          named_bar_sync(1 + sg, 128);
+          if (gtid < 16) {
             const int c = mycnt[gtid];
             if (c) {
               atomicAdd(&args.cnt[obj][slot0 + gtid], c);
               mycnt[gtid] = 0;
             }
           }
-          named_bar_sync(1 + grp, 128);
+          named_bar_sync(1 + sg, 128);
         }
       }
-      buf_it[parity ^ 1] += (uint32_t)((ntile + 1 - (parity ^ 1)) >> 1);
       // epilogue: O^T (128 queries x 256 channels) * 2^-8 -> partial buffer; group g takes channels [64 g, 64 g + 64)
       mbar_wait(o_full, seg_it & 1);
       tc_fence_after();
       if (ntile > 0) {
-        float* dst = po + (((size_t)obj * args.pieces + piece) * DV + half * 256 + grp * 64) * (size_t)args.hw;
+        float* dst = po + (((size_t)obj * args.pieces + piece) * DV + half * 256 + sg * 64) * (size_t)args.hw;
 #pragma unroll 1
         for (int ch = 0; ch < 2; ++ch) {
           uint32_t v[32];
-          tmem_ld32(tlane + TM_O + (uint32_t)grp * 64 + ch * 32, v);
+          tmem_ld32(tlane + TM_O + (uint32_t)sg * 64 + ch * 32, v);
           tmem_wait_ld();
           if (j < args.hw) {
 #pragma unroll
@@ -750,6 +836,269 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
   }
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase B on CTA pairs (cta_group::2, M = 256): the two CTAs of a cluster take two adjacent query tiles of the same
+// (object, slot split, channel half) and SHARE every K / V tile - each CTA TMA-loads half of it (K: 32 of the 64
+// slots, V: 128 of the 256 channels) and the pair's tensor cores read both halves.  Per CTA this halves the L2 -> smem
+// traffic and the smem bandwidth per MMA (the single-CTA kernel needs ~118 B/clk of shared memory, profiles/r1b).
+// Everything per CTA (TMEM layout, softmax, epilogue) is as in tc_phase_b_kernel; only the leader CTA (rank 0) issues
+// MMAs, its "full" barriers count the bytes of both CTAs' loads, and commits are multicast to both CTAs' barriers.
+// ------------------------------------------------------------------------------------------------
+constexpr int P_STAGES = 4;
+constexpr int P_KSTAGE_BYTES = 32 * DK * 2 * 2;                 // this CTA's 32 slots, hi + lo: 16 KB
+constexpr int P_VSTAGE_BYTES = B_TILE * 128 * (2 + 1 + 1);      // 64 slots x this CTA's 128 channels: 32 KB
+constexpr int P_SMEM = P_STAGES * (P_KSTAGE_BYTES + P_VSTAGE_BYTES) + 1024 + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+    tc_phase_b_pair_kernel(const __grid_constant__ TcMaps maps, TcArgs args, const float* __restrict__ lse, float thres,
+                           int do_count, float* __restrict__ po) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* kst = smem;
+  uint8_t* vst = smem + P_STAGES * P_KSTAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(vst + P_STAGES * P_VSTAGE_BYTES);
+  uint64_t* k_full = bars;             // [4]  (used on the leader)
+  uint64_t* k_empty = bars + 4;        // [4]
+  uint64_t* v_full = bars + 8;         // [4]  (used on the leader)
+  uint64_t* v_empty = bars + 12;       // [4]
+  uint64_t* s_full = bars + 16;        // [2]
+  uint64_t* p_full = bars + 18;        // [2]  (used on the leader: 8 local + 8 remote warps)
+  uint64_t* o_full = bars + 20;        // [1]
+  uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(bars + 21);
+  int* cnt_s = reinterpret_cast<int*>(bars + 24);   // [4 groups][32]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P_STAGES; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 2 * EPI_WARPS); }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 128) cnt_s[threadIdx.x] = 0;
+  if (warp == 2) tmem_alloc_pair(tmem_base_p, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_base_p;
+
+  // work items = (split, object, query-tile pair, channel half), round-robin over the clusters
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int qpairs = (args.q_tiles + 1) >> 1;
+  const int cpo = qpairs * 2;
+  const int n_combos = args.obj_n * cpo;
+  const int n_items = n_combos * args.pieces;
+  uint32_t k_it = 0;            // tiles streamed so far (stage = k_it & 3)
+  uint32_t buf_it[2] = {0, 0};  // uses of each S/P buffer so far
+  uint32_t seg_it = 0;          // items finished (o_full phase)
+  for (int item = cluster_id; item < n_items; item += n_clusters) {
+    const int piece = item / n_combos;
+    const int combo = item - piece * n_combos;
+    const int obj = combo / cpo;
+    const int cidx = combo - obj * cpo;                // qp * 2 + half
+    const int qt = (cidx >> 1) * 2 + (int)rank, half = cidx & 1;
+    const int tiles_o = args.tiles[obj];
+    const int t0 = (int)((long long)tiles_o * piece / args.pieces);
+    const int t1 = (int)((long long)tiles_o * (piece + 1) / args.pieces);
+    const int n_obj = args.n[obj];
+    const int ntile = t1 - t0;
+    const bool first_item = (item == cluster_id);
+
+    if (warp >= 4) load_a_operand(args, obj, qt, tmem, TM_QH, TM_QL, warp, lane);
+    tc_fence_before();
+    cluster_sync_all();      // both CTAs' Q tiles are in TMEM, both epilogues of the previous item are done
+    tc_fence_after();
+
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int t = 0; t < ntile; ++t) {
+          const uint32_t kit = k_it + t, st = kit & 3, ph = (kit >> 2) & 1;
+          const int row0 = (t0 + t) * B_TILE;
+          mbar_wait(&k_empty[st], ph ^ 1);
+          if (leader) mbar_arrive_expect_tx(&k_full[st], 2 * P_KSTAGE_BYTES);
+          const uint32_t kf = mapa_u32(smem_u32(&k_full[st]), 0);
+          uint8_t* kd = kst + st * P_KSTAGE_BYTES;
+          const int krow = row0 + (int)rank * 32;
+          tma_load_2d_pair(kd, &maps.kh[obj], kf, 0, krow);
+          tma_load_2d_pair(kd + 4096, &maps.kh[obj], kf, 64, krow);
+          tma_load_2d_pair(kd + 8192, &maps.kl[obj], kf, 0, krow);
+          tma_load_2d_pair(kd + 12288, &maps.kl[obj], kf, 64, krow);
+          mbar_wait(&v_empty[st], ph ^ 1);
+          if (leader) mbar_arrive_expect_tx(&v_full[st], 2 * P_VSTAGE_BYTES);
+          const uint32_t vf = mapa_u32(smem_u32(&v_full[st]), 0);
+          uint8_t* vd = vst + st * P_VSTAGE_BYTES;
+          const int ch0 = half * 256 + (int)rank * 128;
+          tma_load_2d_pair(vd, &maps.vh[obj], vf, ch0, row0);
+          tma_load_2d_pair(vd + 8192, &maps.vh[obj], vf, ch0 + 64, row0);
+          tma_load_2d_pair(vd + 16384, &maps.v8[obj], vf, ch0, row0);
+          tma_load_2d_pair(vd + 24576, &maps.vl[obj], vf, ch0, row0);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (leader) {
+        constexpr uint32_t idesc_s = make_idesc(256, B_TILE, FMT_F16, FMT_F16, 0, 0);
+        constexpr uint32_t idesc_o = make_idesc(256, 256, FMT_F16, FMT_F16, 0, 1);
+        constexpr uint32_t idesc_o8 = make_idesc(256, 256, FMT_E4M3, FMT_E4M3, 0, 1);
+        constexpr uint32_t idesc_ol = make_idesc(256, 256, FMT_E4M3, FMT_E5M2, 0, 1);
+        auto issue_s = [&](int t) {
+          const uint32_t kit = k_it + t, st = kit & 3, ph = (kit >> 2) & 1;
+          const int b = t & 1;
+          mbar_wait(&k_full[st], ph);
+          tc_fence_after();
+          const uint32_t kbase = smem_u32(kst + st * P_KSTAGE_BYTES);
+          const uint32_t d_t = tmem + TM_S + (uint32_t)b * 64;
+          if (elect_one()) {
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint32_t a_col = (pass == 1) ? TM_QL : TM_QH;
+              const uint32_t kb = kbase + ((pass == 2) ? 8192u : 0u);
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                const uint64_t bd = make_sdesc(kb + (ks >> 2) * 4096u + (ks & 3) * 32u, 16, 1024);
+                mma_ts_pair(d_t, tmem + a_col + ks * 8, bd, idesc_s, (pass | ks) ? 1u : 0u);
+              }
+            }
+            tc_commit_pair(&k_empty[st]);
+            tc_commit_pair(&s_full[b]);
+          }
+          __syncwarp();
+        };
+        if (ntile > 0) issue_s(0);
+        if (ntile > 1) issue_s(1);
+        for (int t = 0; t < ntile; ++t) {
+          const uint32_t kit = k_it + t, st = kit & 3, ph = (kit >> 2) & 1;
+          const int b = t & 1;
+          mbar_wait(&p_full[b], buf_it[b] & 1);
+          ++buf_it[b];
+          mbar_wait(&v_full[st], ph);
+          tc_fence_after();
+          const uint32_t vbase = smem_u32(vst + st * P_VSTAGE_BYTES);
+          const uint32_t pcol = tmem + TM_S + (uint32_t)b * 64;
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t bd = make_sdesc(vbase + ks * 2048u, 8192, 1024);
+              mma_ts_pair(tmem + TM_O, pcol + (uint32_t)(ks >> 1) * 32u + (uint32_t)(ks & 1) * 8u, bd, idesc_o,
+                          (t | ks) ? 1u : 0u);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint64_t b8 = make_sdesc(vbase + 16384u + h * 4096u, 8192, 1024);
+              mma_ts_f8_pair(tmem + TM_O, pcol + (uint32_t)h * 32u + 16u, b8, idesc_o8, 1u);
+              const uint64_t bl = make_sdesc(vbase + 24576u + h * 4096u, 8192, 1024);
+              mma_ts_f8_pair(tmem + TM_O, pcol + (uint32_t)h * 32u + 24u, bl, idesc_ol, 1u);
+            }
+            tc_commit_pair(&v_empty[st]);
+          }
+          __syncwarp();
+          if (t + 2 < ntile) issue_s(t + 2);
+        }
+        if (elect_one()) tc_commit_pair(o_full);
+        __syncwarp();
+      }
+    } else if (warp >= 4) {
+      // every softmax warp works on every tile: slot group sg = 16 of the tile's 64 slots, for its 32 query rows
+      const int quarter = warp & 3, sg = (warp - 4) >> 2;
+      const int hsel = sg >> 1, sub = sg & 1;
+      const int row = (quarter << 5) + lane;
+      const int gtid = row;                                      // 0..127 within the slot group
+      const uint32_t tlane = tmem + (((uint32_t)quarter * 32u) << 16);
+      const int j = qt * QT + row;
+      const float lse2m = (j < args.hw) ? (lse[(size_t)obj * args.hw + j] * LOG2E - P_SCALE_LOG2) : INFINITY;
+      const float thres_s = thres * P_SCALE;
+      int* mycnt = cnt_s + sg * 16;
+      const bool counting = do_count && (half == 0);
+      const uint32_t pf_leader0 = mapa_u32(smem_u32(&p_full[0]), 0), pf_leader1 = mapa_u32(smem_u32(&p_full[1]), 0);
+      for (int t = 0; t < ntile; ++t) {
+        const int b = t & 1;
+        const uint32_t pf_leader = b ? pf_leader1 : pf_leader0;
+        mbar_wait(&s_full[b], buf_it[b] & 1);
+        ++buf_it[b];
+        tc_fence_after();
+        const int slot0 = (t0 + t) * B_TILE + sg * 16;
+        const uint32_t pb = tlane + TM_S + (uint32_t)b * 64 + (uint32_t)hsel * 32;   // this half's 32-column S / P region
+        uint32_t sv[16];
+        tmem_ld16(pb + (uint32_t)sub * 16, sv);
+        tmem_wait_ld();
+        if (args.dbg && blockIdx.x == 0 && first_item && t == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) args.dbg[row * B_TILE + sg * 16 + i] = __uint_as_float(sv[i]);
+        }
+        // P is written in place over S and the fp8 operands of the two 16-slot groups of a half interleave: all four
+        // warps of this lane quarter must hold their logits in registers before any of them stores
+        tc_fence_before();
+        named_bar_sync(5 + quarter, 128);
+        tc_fence_after();
+        uint32_t hi[8], lo[4], p8[4];
+        uint32_t bits = softmax_chunk16(sv, lse2m, thres_s, n_obj - slot0, hi, lo, p8);
+        tmem_st8(pb + (uint32_t)sub * 8, hi);
+        tmem_st4(pb + 16 + (uint32_t)sub * 4, lo);
+        tmem_st4(pb + 24 + (uint32_t)sub * 4, p8);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(pf_leader);
+        if (counting) {
+          if (j >= args.hw) bits = 0u;
+          const int dense = __any_sync(0xffffffffu, __popc(bits) > 2);
+          if (dense) {
+            int c_mine = 0;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              const unsigned bal = __ballot_sync(0xffffffffu, (bits >> c) & 1u);
+              if (lane == c) c_mine = __popc(bal);
+            }
+            if (c_mine) atomicAdd(&mycnt[lane], c_mine);
+          } else {
+            while (bits) {
+              const int c = __ffs((int)bits) - 1;
+              bits &= bits - 1;
+              atomicAdd(&mycnt[c], 1);
+            }
+          }
+          named_bar_sync(1 + sg, 128);
+          if (gtid < 16) {
+            const int c = mycnt[gtid];
+            if (c) {
+              atomicAdd(&args.cnt[obj][slot0 + gtid], c);
+              mycnt[gtid] = 0;
+            }
+          }
+          named_bar_sync(1 + sg, 128);
+        }
+      }
+      mbar_wait(o_full, seg_it & 1);
+      tc_fence_after();
+      if (ntile > 0) {
+        float* dst = po + (((size_t)obj * args.pieces + piece) * DV + half * 256 + sg * 64) * (size_t)args.hw;
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(tlane + TM_O + (uint32_t)sg * 64 + ch * 32, v);
+          tmem_wait_ld();
+          if (j < args.hw) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dst[(size_t)(ch * 32 + i) * args.hw + j] = __uint_as_float(v[i]) * (1.f / P_SCALE);
+          }
+        }
+      }
+    }
+    k_it += ntile;
+    ++seg_it;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_pair(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -887,6 +1236,7 @@ static int num_sms() {
 }
 
 static float* g_dbg = nullptr;
+static int g_pair = 1;    // CTA-pair (cta_group::2) kernels where available; vfn_debug_set_pair(0) selects the single-CTA ones
 
 bool tc_shapes_ok(int d_key, int d_val) { return d_key == DK && d_val == DV; }
 
@@ -894,8 +1244,8 @@ constexpr int TC_MAX_SPLIT = 24;
 
 // number of slot splits per (object, query tile[, half]) combo: minimise rounds x (tiles per item + fixed per-item
 // overhead) for `combos` combos dealt round-robin to G persistent CTAs; every item keeps at least one tile.
-static int best_split(int combos, int64_t tiles_min, int64_t tiles_max, int overhead_tiles) {
-  const int G = num_sms();
+static int best_split(int combos, int64_t tiles_min, int64_t tiles_max, int overhead_tiles, int G = 0) {
+  if (G <= 0) G = num_sms();
   int best = 1;
   double best_cost = 1e30;
   for (int s = 1; s <= TC_MAX_SPLIT && s <= tiles_min; ++s) {
@@ -913,7 +1263,8 @@ void tc_pick_splits(int obj_n, int64_t n_max, int64_t hw, int* split_a, int* spl
   *split_b = TC_MAX_SPLIT;
 }
 
-static size_t a_operand_bytes(int64_t hw) { return align_up((size_t)cdiv(hw, QT) * QT * DK * sizeof(uint16_t), 256); }
+// rows padded to a whole number of query-tile PAIRS (the pair kernels read two adjacent tiles)
+static size_t a_operand_bytes(int64_t hw) { return align_up((size_t)cdiv(hw, 2 * QT) * 2 * QT * DK * sizeof(uint16_t), 256); }
 
 size_t tc_workspace_bytes(int obj_n, int64_t hw) {
   (void)obj_n;
@@ -926,13 +1277,15 @@ static int set_attrs() {
     VFN_CUDA_OK(cudaFuncSetAttribute(tc_scan_kernel<MODE_LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
     VFN_CUDA_OK(cudaFuncSetAttribute(tc_scan_kernel<MODE_MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
     VFN_CUDA_OK(cudaFuncSetAttribute(tc_phase_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+    VFN_CUDA_OK(cudaFuncSetAttribute(tc_phase_b_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
     attr = true;
   }
   return VFN_OK;
 }
 
 static int fill_args(const vfn_bank* banks, int obj_n, int64_t hw, int pieces, int tile, char* ws_tc, TcMaps* maps,
-                     TcArgs* a, bool need_v) {
+                     TcArgs* a, bool need_v, int k_box_rows = 0) {
+  if (k_box_rows <= 0) k_box_rows = tile;
   VFN_CHECK_ARG(obj_n <= TC_MAX_OBJ, "tcgen05 read supports at most %d objects", TC_MAX_OBJ);
   a->obj_n = obj_n; a->hw = (int)hw; a->q_tiles = (int)cdiv(hw, QT); a->pieces = pieces;
   a->qh = reinterpret_cast<const uint16_t*>(ws_tc);
@@ -946,8 +1299,8 @@ static int fill_args(const vfn_bank* banks, int obj_n, int64_t hw, int pieces, i
     a->n[o] = (int)banks[o].n;
     a->tiles[o] = (int)cdiv(banks[o].n, tile);
     a->cnt[o] = banks[o].cnt;
-    if (int rc = make_map(&maps->kh[o], banks[o].kh, banks[o].n, DK, tile, 2)) return rc;
-    if (int rc = make_map(&maps->kl[o], banks[o].kl, banks[o].n, DK, tile, 2)) return rc;
+    if (int rc = make_map(&maps->kh[o], banks[o].kh, banks[o].n, DK, k_box_rows, 2)) return rc;
+    if (int rc = make_map(&maps->kl[o], banks[o].kl, banks[o].n, DK, k_box_rows, 2)) return rc;
     if (need_v) {
       if (int rc = make_map(&maps->vh[o], banks[o].vh, banks[o].n, DV, tile, 2)) return rc;
       if (int rc = make_map(&maps->v8[o], banks[o].v8, banks[o].n, DV, tile, 1)) return rc;
@@ -999,14 +1352,19 @@ int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const 
     tmin = t < tmin ? t : tmin;
     tmax = t > tmax ? t : tmax;
   }
-  const int pieces = best_split(obj_n * 2 * (int)cdiv(hw, QT), tmin, tmax, 4);
+  const bool pair = g_pair && (num_sms() % 2 == 0);
+  const int combos = pair ? obj_n * 2 * (int)cdiv(hw, 2 * QT) : obj_n * 2 * (int)cdiv(hw, QT);
+  const int pieces = best_split(combos, tmin, tmax, 4, pair ? num_sms() / 2 : num_sms());
   if (pieces > split_b) { set_error("phase B: split %d exceeds workspace bound %d", pieces, split_b); return VFN_E_CAPACITY; }
   *pieces_out = pieces;
-  if (int rc = fill_args(banks, obj_n, hw, pieces, B_TILE, ws_tc, &maps, &a, true)) return rc;
+  if (int rc = fill_args(banks, obj_n, hw, pieces, B_TILE, ws_tc, &maps, &a, true, pair ? 32 : B_TILE)) return rc;
   double work = 0;
   for (int o = 0; o < obj_n; ++o) work += 2.0 * DV * (double)banks[o].n * (double)hw;
   prof_begin(PROF_READ_B, st);
-  tc_phase_b_kernel<<<num_sms(), TC_THREADS, B_SMEM, st>>>(maps, a, lse, thres_valid, update_bank, po);
+  if (pair)
+    tc_phase_b_pair_kernel<<<num_sms(), TC_THREADS, P_SMEM, st>>>(maps, a, lse, thres_valid, update_bank, po);
+  else
+    tc_phase_b_kernel<<<num_sms(), TC_THREADS, B_SMEM, st>>>(maps, a, lse, thres_valid, update_bank, po);
   prof_end(PROF_READ_B, st, work);
   VFN_LAUNCH_OK();
   count_launches(1);
@@ -1087,6 +1445,11 @@ int tc_match(const vfn_bank* banks, int obj_n, const float* const* nck_em, int64
 }
 
 }  // namespace vfn
+
+extern "C" int vfn_debug_set_pair(int32_t on) {
+  vfn::g_pair = on ? 1 : 0;
+  return VFN_OK;
+}
 
 extern "C" int vfn_debug_set_dump(float* d_ptr) {
   vfn::g_dbg = d_ptr;

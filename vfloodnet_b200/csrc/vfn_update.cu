@@ -105,16 +105,19 @@ int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_i
                                   ws_bytes - L.match, 1, stream))
         return rc;
   }
-  // (3) plan + merge per object (FeatureBank.py:71-97)
+  // (3) plan + merge, one launch each for all objects (FeatureBank.py:71-97)
+  UpdObj uo[4];
   for (int c = 0; c < obj_n; ++c) {
-    if (int rc = vfn_bank_plan(io[c].d_match_idx, io[c].d_match_corr, hw, thres_close, io[c].d_merge_q, io[c].d_merge_slot,
-                               io[c].d_run_off, io[c].d_append_q, counts + 4 * c, h_counts + 4 * c,
-                               ws + L.pws + c * L.s_pws, L.s_pws, stream))
-      return rc;
-    if (int rc = vfn_bank_merge(&banks[c], NCK(c), NCV(c), io[c].d_merge_q, io[c].d_merge_slot, io[c].d_run_off,
-                                counts + 4 * c, hw, update_rate, stream))
-      return rc;
+    uo[c] = UpdObj{};
+    uo[c].bank = banks[c];
+    uo[c].ck = CK(c); uo[c].cv = CV(c); uo[c].nck = NCK(c); uo[c].ncv = NCV(c);
+    uo[c].match_idx = io[c].d_match_idx; uo[c].match_corr = io[c].d_match_corr;
+    uo[c].merge_q = io[c].d_merge_q; uo[c].merge_slot = io[c].d_merge_slot; uo[c].run_off = io[c].d_run_off;
+    uo[c].append_q = io[c].d_append_q; uo[c].counts = counts + 4 * c; uo[c].h_counts = h_counts + 4 * c;
+    uo[c].plan_ws = ws + L.pws + c * L.s_pws;
   }
+  if (int rc = launch_plan(uo, obj_n, hw, thres_close, st)) return rc;
+  if (int rc = launch_merge(uo, obj_n, hw, update_rate, st)) return rc;
   VFN_CUDA_OK(cudaStreamSynchronize(st));                 // |merge|, |runs|, |append| per object (nonzero/unique syncs)
   bool any_evict = false;
   for (int c = 0; c < obj_n; ++c) {
@@ -149,17 +152,26 @@ int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_i
       io[c].swapped = 1;
     }
   }
-  // (4) append + clamp (FeatureBank.py:105-115)
+  // (4) append + clamp (FeatureBank.py:105-115), one launch each
+  UpdObj ao[4];
+  vfn_bank cb[4];
+  int n_a = 0, n_c = 0;
   for (int c = 0; c < obj_n; ++c) {
     if (io[c].evict_status != 0) continue;
     const int64_t n_app = io[c].n_append;
-    if (n_app > 0)
-      if (int rc = vfn_bank_append_rows(&banks[c], CK(c), CV(c), NCK(c), io[c].d_append_q, n_app, nullptr, frame_idx, 0.f,
-                                        stream))
-        return rc;
+    if (n_app > 0) {
+      ao[n_a] = uo[c];
+      ao[n_a].bank = banks[c];                // after a possible ping-pong swap
+      ao[n_a].sel = io[c].d_append_q; ao[n_a].n_sel_dev = nullptr; ao[n_a].n_sel = n_app;
+      ++n_a;
+    }
     banks[c].n += n_app;
-    if (int rc = vfn_bank_clamp_info(&banks[c], banks[c].n, stream)) return rc;
+    cb[n_c++] = banks[c];
   }
+  if (n_a > 0)
+    if (int rc = launch_append(ao, n_a, frame_idx, 0.f, st)) return rc;
+  if (n_c > 0)
+    if (int rc = launch_clamp(cb, n_c, st)) return rc;
   return VFN_OK;
 }
 

@@ -80,57 +80,80 @@ __global__ void urr_window_kernel(const float* __restrict__ seg, int obj_n, int 
 }
 
 // stage 3: local_match[o][ch] = r1[ch] ; local_match[o][C+ch] = box7(r1[ch]*seg[o])/49 / (avg[o] + 1e-8)
-// CTA: 32x32 output tile, loops over CH_PER_CTA channels re-using the seg tile. 256 threads.
-constexpr int UT = 32, UH = UT + 6, CH_PER_CTA = 8;
-__global__ void __launch_bounds__(256) urr_local_kernel(const float* __restrict__ r1, int64_t r1_obj_stride, int c_n,
-                                                        int h, int w, const float* __restrict__ seg,
-                                                        const float* __restrict__ avg, float* __restrict__ lm) {
-  __shared__ float sseg[UH][UH + 1];
-  __shared__ float prod[UH][UH + 1];
-  __shared__ float hsum[UH][UT + 1];
-  const int o = blockIdx.z / (c_n / CH_PER_CTA);
-  const int cg = blockIdx.z % (c_n / CH_PER_CTA);
-  const int x0 = blockIdx.x * UT, y0 = blockIdx.y * UT;
-  const float* segp = seg + (int64_t)o * h * w;
-  for (int i = threadIdx.x; i < UH * UH; i += 256) {
-    const int ly = i / UH, lx = i % UH;
-    const int yy = y0 + ly - 3, xx = x0 + lx - 3;
-    sseg[ly][lx] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? segp[(int64_t)yy * w + xx] : 0.f;
-  }
-  __syncthreads();
-  for (int cc = 0; cc < CH_PER_CTA; ++cc) {
-    const int ch = cg * CH_PER_CTA + cc;
-    const float* rp = r1 + (int64_t)o * r1_obj_stride + (int64_t)ch * h * w;
-    for (int i = threadIdx.x; i < UH * UH; i += 256) {
-      const int ly = i / UH, lx = i % UH;
-      const int yy = y0 + ly - 3, xx = x0 + lx - 3;
-      const float v = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? rp[(int64_t)yy * w + xx] : 0.f;
-      prod[ly][lx] = v * sseg[ly][lx];                 // r1 * rough_seg                   AFB_URR.py:226
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < UH * UT; i += 256) {  // horizontal 7-tap
-      const int ly = i / UT, lx = i % UT;
-      float s = 0.f;
-#pragma unroll
-      for (int k = 0; k < 7; ++k) s += prod[ly][lx + k];
-      hsum[ly][lx] = s;
-    }
-    __syncthreads();
-    float* out_raw = lm + ((int64_t)o * 2 * c_n + ch) * h * w;
-    float* out_loc = lm + ((int64_t)o * 2 * c_n + c_n + ch) * h * w;
-    for (int i = threadIdx.x; i < UT * UT; i += 256) {  // vertical 7-tap + epilogue
-      const int ly = i / UT, lx = i % UT;
-      const int yy = y0 + ly, xx = x0 + lx;
-      if (yy < h && xx < w) {
-        float s = 0.f;
-#pragma unroll
-        for (int k = 0; k < 7; ++k) s += hsum[ly + k][lx];
+// CTA = one channel x one 16-row x 128-column tile, ALL objects (r1 is read once and shared by the objects, the
+// reference's `expand`).  Stage 1 puts r1 and r1*seg[o] (with a 3-pixel halo) in shared memory; stage 2 gives each
+// thread one column: horizontal 7-tap from shared memory, vertical 7-tap from a register ring - no further barriers.
+constexpr int UT_W = 128, UT_H = 16, UHALO = 3, UW = UT_W + 2 * UHALO, UHH = UT_H + 2 * UHALO;
+constexpr int URR_LOCAL_MAX_OBJ = 2;     // objects per pass (more objects: several passes over the tile)
+constexpr int URR_LOCAL_THREADS = UT_W * URR_LOCAL_MAX_OBJ;
+__global__ void __launch_bounds__(URR_LOCAL_THREADS) urr_local_kernel(const float* __restrict__ r1, int64_t r1_obj_stride,
+                                                                      int c_n, int obj_n, int h, int w,
+                                                                      const float* __restrict__ seg,
+                                                                      const float* __restrict__ avg,
+                                                                      float* __restrict__ lm) {
+  __shared__ float sr1[UHH][UW];
+  __shared__ float prod[URR_LOCAL_MAX_OBJ][UHH][UW];
+  const int ch = blockIdx.z;
+  const int x0 = blockIdx.x * UT_W, y0 = blockIdx.y * UT_H;
+  const int64_t plane = (int64_t)h * w;
+  for (int ob = 0; ob < obj_n; ob += URR_LOCAL_MAX_OBJ) {
+    const int no = min(URR_LOCAL_MAX_OBJ, obj_n - ob);
+    // with a per-object r1 (r1_obj_stride != 0) only one object per pass can share the tile
+    const int npass = r1_obj_stride ? 1 : no;
+    for (int sub = 0; sub < no; sub += npass) {
+      const float* rp = r1 + (int64_t)(ob + sub) * r1_obj_stride + (int64_t)ch * plane;
+      const float* sp = seg + (int64_t)(ob + sub) * plane;
+      __syncthreads();
+#pragma unroll 4
+      for (int i = threadIdx.x; i < UHH * UW; i += URR_LOCAL_THREADS) {
+        const int ly = i / UW, lx = i - ly * UW;
+        const int yy = y0 + ly - UHALO, xx = x0 + lx - UHALO;
+        const bool in = (yy >= 0 && yy < h && xx >= 0 && xx < w);
         const int64_t off = (int64_t)yy * w + xx;
-        out_raw[off] = rp[off];
-        out_loc[off] = (s / 49.f) / (avg[(int64_t)o * h * w + off] + 1e-8f);   // AFB_URR.py:227-228
+        const float v = in ? __ldg(rp + off) : 0.f;
+        const float s0 = in ? __ldg(sp + off) : 0.f;
+        const float s1 = (in && npass > 1) ? __ldg(sp + plane + off) : 0.f;
+        sr1[ly][lx] = v;
+        prod[0][ly][lx] = v * s0;                         // r1 * rough_seg                   AFB_URR.py:226
+        prod[1][ly][lx] = v * s1;
+      }
+      __syncthreads();
+      // one thread per (column, object): horizontal 7-tap from shared memory, vertical 7-tap from a register ring
+      const int lx = threadIdx.x & (UT_W - 1), k = threadIdx.x >> 7, xx = x0 + lx;
+      if (xx < w && k < npass) {
+        const int o = ob + sub + k;
+        float* out_raw = lm + ((int64_t)o * 2 * c_n + ch) * plane;
+        float* out_loc = lm + ((int64_t)o * 2 * c_n + c_n + ch) * plane;
+        const float* av = avg + (int64_t)o * plane;
+        float ring[7];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          float s = 0.f;
+#pragma unroll
+          for (int t = 0; t < 7; ++t) s += prod[k][r][lx + t];
+          ring[r] = s;
+        }
+        float avv[UT_H];
+#pragma unroll
+        for (int ly = 0; ly < UT_H; ++ly) avv[ly] = (y0 + ly < h) ? __ldg(av + (int64_t)(y0 + ly) * w + xx) : 1.f;
+#pragma unroll
+        for (int ly = 0; ly < UT_H; ++ly) {
+          float s = 0.f;
+#pragma unroll
+          for (int t = 0; t < 7; ++t) s += prod[k][ly + 6][lx + t];
+          ring[(ly + 6) % 7] = s;
+          const int yy = y0 + ly;
+          if (yy < h) {
+            float tot = 0.f;
+#pragma unroll
+            for (int r = 0; r < 7; ++r) tot += ring[(ly + r) % 7];       // rows ly .. ly+6 of the tile, top to bottom
+            const int64_t off = (int64_t)yy * w + xx;
+            out_raw[off] = sr1[ly + UHALO][lx + UHALO];
+            out_loc[off] = (tot / 49.f) / (avv[ly] + 1e-8f);             // AFB_URR.py:227-228
+          }
+        }
       }
     }
-    __syncthreads();
   }
 }
 
@@ -183,15 +206,15 @@ int vfn_urr_pre(const float* d_p, const float* d_r1, int64_t r1_obj_stride, int3
   VFN_CHECK_ARG(d_p && d_r1 && d_p_up && d_seg && d_unc && d_conf && d_avg && d_local_match, "urr_pre: NULL argument");
   VFN_CHECK_ARG(obj_n >= 1 && obj_n <= URR_MAX_OBJ, "urr_pre: obj_n=%d out of range", obj_n);
   VFN_CHECK_ARG(h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "urr_pre: h,w must be even");
-  VFN_CHECK_ARG(c > 0 && c % CH_PER_CTA == 0, "urr_pre: channels must be a multiple of %d", CH_PER_CTA);
+  VFN_CHECK_ARG(c > 0, "urr_pre: channels must be positive");
   cudaStream_t st = as_stream(stream);
   dim3 g1((unsigned)cdiv(w, 128), h);
   urr_seg_kernel<<<g1, 128, 0, st>>>(d_p, obj_n, h, w, d_p_up, d_seg, d_unc);
   dim3 g2((unsigned)cdiv(w, 128), h, obj_n);
   urr_window_kernel<<<g2, 128, 0, st>>>(d_seg, obj_n, h, w, d_conf, d_avg);
-  dim3 g3((unsigned)cdiv(w, UT), (unsigned)cdiv(h, UT), obj_n * (c / CH_PER_CTA));
+  dim3 g3((unsigned)cdiv(w, UT_W), (unsigned)cdiv(h, UT_H), c);
   prof_begin(PROF_URR, st);
-  urr_local_kernel<<<g3, 256, 0, st>>>(d_r1, r1_obj_stride, c, h, w, d_seg, d_avg, d_local_match);
+  urr_local_kernel<<<g3, URR_LOCAL_THREADS, 0, st>>>(d_r1, r1_obj_stride, c, obj_n, h, w, d_seg, d_avg, d_local_match);
   // algorithmic bytes: read r1 once, write [r1 ; r1_local] per object, + small planes
   prof_end(PROF_URR, st, 4.0 * (double)h * w * ((r1_obj_stride ? obj_n : 1) * (double)c + obj_n * (2.0 * c + 8.0)));
   VFN_LAUNCH_OK();
