@@ -232,8 +232,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// remote arrive with the default (.release.cta) semantics, as CUTLASS' umma_arrive_2x1SM_sm0: the data handed over
+// lives in TMEM and is ordered by the tcgen05 fences; a .release.cluster arrive costs a MEMBAR.ALL.GPU per call
+// (31 % of all stall samples in profiles/r1e)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into this CTA's smem whose completion bytes are counted on a barrier of the pair's leader CTA
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t mbar_cluster_addr, int c0,
@@ -569,21 +572,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const __grid_con
 constexpr int B_TILE = 64;
 constexpr int B_KSTAGE_BYTES = B_TILE * DK * 2 * 2;                 // 32 KB
 constexpr int B_VSTAGE_BYTES = B_TILE * 256 * (2 + 1 + 1);          // 64 KB
-constexpr int B_SMEM = 2 * B_KSTAGE_BYTES + 2 * B_VSTAGE_BYTES + 1024 + 1024;
+constexpr int B_SMEM = 2 * B_KSTAGE_BYTES + 2 * B_VSTAGE_BYTES + 1024 + 256 + 96 * 64 * 4;   // + alignment, barriers, item counts
 constexpr uint32_t TM_O = 0, TM_QH = 256, TM_QL = 320, TM_S = 384;
 constexpr float P_SCALE_LOG2 = 8.f, P_SCALE = 256.f;
 
-// 16 logits -> P' = 2^(s - lse2 + 8); returns packed fp16 hi (8 regs), e4m3 residual (4), e4m3 P' (4), threshold bits
+// 16 logits -> P' = 2^(s - lse2 + 8): packed fp16 hi (8 regs), e4m3 residual (4), e4m3 P' (4).
+// MASK: slots >= lim are zeroed (only the last tile of an object needs it).  COUNT: returns the threshold bits,
+// bit (15 - i) set iff P'_i > thres_s (sign bit of thres_s - P' shifted in: one FADD + one SHF per element).
+template <bool MASK, bool COUNT>
 __device__ __forceinline__ uint32_t softmax_chunk16(const uint32_t (&s)[16], float lse2m, float thres_s, int lim,
                                                     uint32_t (&hi)[8], uint32_t (&lo)[4], uint32_t (&p8)[4]) {
   uint32_t bits = 0u;
 #pragma unroll
   for (int i = 0; i < 16; i += 2) {
     float p0 = ex2(__uint_as_float(s[i]) - lse2m), p1 = ex2(__uint_as_float(s[i + 1]) - lse2m);
-    p0 = (i < lim) ? p0 : 0.f;
-    p1 = (i + 1 < lim) ? p1 : 0.f;
-    bits |= (uint32_t)(p0 > thres_s) << i;
-    bits |= (uint32_t)(p1 > thres_s) << (i + 1);
+    if (MASK) {
+      p0 = (i < lim) ? p0 : 0.f;
+      p1 = (i + 1 < lim) ? p1 : 0.f;
+    }
+    if (COUNT) {
+      bits = __funnelshift_l(__float_as_uint(thres_s - p0), bits, 1);
+      bits = __funnelshift_l(__float_as_uint(thres_s - p1), bits, 1);
+    }
     const uint32_t h = f16x2_rn(p0, p1);
     const float2 hf = f16x2_to_f32(h);
     hi[i >> 1] = h;
@@ -593,6 +603,11 @@ __device__ __forceinline__ uint32_t softmax_chunk16(const uint32_t (&s)[16], flo
   }
   return bits;
 }
+
+// usage counts of one item are accumulated in shared memory (CNT_TILES tiles x 64 slots) and flushed to the bank's
+// counters with global atomics once per chunk of CNT_TILES tiles, not once per tile
+constexpr int CNT_TILES = 96;
+constexpr int CNT_BYTES = CNT_TILES * B_TILE * 4;
 
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_constant__ TcMaps maps, TcArgs args,
                                                                    const float* __restrict__ lse, float thres,
@@ -610,7 +625,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
   uint64_t* p_full = bars + 10;       // [2]
   uint64_t* o_full = bars + 12;       // [1]
   uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(bars + 13);
-  int* cnt_s = reinterpret_cast<int*>(bars + 16);   // [4 groups][32]
+  int* cnt_item = reinterpret_cast<int*>(bars + 32);   // [CNT_TILES][64] usage counts of the current item
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -622,7 +637,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
-  if (threadIdx.x < 128) cnt_s[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < CNT_TILES * B_TILE; i += TC_THREADS) cnt_item[i] = 0;
   if (warp == 2) tmem_alloc(tmem_base_p, 512);
   tc_fence_before();
   __syncthreads();
@@ -746,13 +761,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
       const int quarter = warp & 3, sg = (warp - 4) >> 2;
       const int hsel = sg >> 1, sub = sg & 1;
       const int row = (quarter << 5) + lane;
-      const int gtid = row;                                      // 0..127 within the slot group
+      const int et = threadIdx.x - 128;                          // 0..511
       const uint32_t tlane = tmem + (((uint32_t)quarter * 32u) << 16);
       const int j = qt * QT + row;
       const float lse2m = (j < args.hw) ? (lse[(size_t)obj * args.hw + j] * LOG2E - P_SCALE_LOG2) : INFINITY;
       const float thres_s = thres * P_SCALE;
-      int* mycnt = cnt_s + sg * 16;
       const bool counting = do_count && (half == 0);
+      auto flush_counts = [&](int tile_first, int n_tiles) {
+        named_bar_sync(9, EPI_THREADS);
+        for (int idx = et; idx < n_tiles * B_TILE; idx += EPI_THREADS) {
+          const int c = cnt_item[idx];
+          if (c) {
+            atomicAdd(&args.cnt[obj][(size_t)(t0 + tile_first) * B_TILE + idx], c);
+            cnt_item[idx] = 0;
+          }
+        }
+        named_bar_sync(9, EPI_THREADS);
+      };
+      int chunk0 = 0;                                            // first tile of the current count chunk
       for (int t = 0; t < ntile; ++t) {
         const int b = t & 1;
         mbar_wait(&s_full[b], buf_it[b] & 1);
@@ -773,7 +799,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
         named_bar_sync(5 + quarter, 128);
         tc_fence_after();
         uint32_t hi[8], lo[4], p8[4];
-        uint32_t bits = softmax_chunk16(sv, lse2m, thres_s, n_obj - slot0, hi, lo, p8);
+        uint32_t bits;
+        const int lim = n_obj - slot0;
+        if (lim >= 16) {
+          bits = counting ? softmax_chunk16<false, true>(sv, lse2m, thres_s, lim, hi, lo, p8)
+                          : softmax_chunk16<false, false>(sv, lse2m, thres_s, lim, hi, lo, p8);
+        } else {
+          bits = softmax_chunk16<true, true>(sv, lse2m, thres_s, lim, hi, lo, p8);
+        }
         tmem_st8(pb + (uint32_t)sub * 8, hi);
         tmem_st4(pb + 16 + (uint32_t)sub * 4, lo);
         tmem_st4(pb + 24 + (uint32_t)sub * 4, p8);
@@ -782,34 +815,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[b]);
         if (counting) {
-          if (j >= args.hw) bits = 0u;
-          const int dense = __any_sync(0xffffffffu, __popc(bits) > 2);
-          if (dense) {
+          // bit (15 - i) <-> slot slot0 + i of this row; rows beyond hw have lse = +inf, P = 0: no bits
+          int* cdst = cnt_item + (t - chunk0) * B_TILE + sg * 16;
+          if (__any_sync(0xffffffffu, __popc(bits) > 2)) {
             int c_mine = 0;
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
               const unsigned bal = __ballot_sync(0xffffffffu, (bits >> c) & 1u);
               if (lane == c) c_mine = __popc(bal);
             }
-            if (c_mine) atomicAdd(&mycnt[lane], c_mine);
+            if (c_mine) atomicAdd(&cdst[15 - lane], c_mine);
           } else {
             while (bits) {
-              const int c = __ffs((int)bits) - 1;
-              bits &= bits - 1;
-              atomicAdd(&mycnt[c], 1);
+              const int c = 31 - __clz((int)bits);
+              bits &= ~(1u << c);
+              atomicAdd(&cdst[15 - c], 1);
             }
           }
-          named_bar_sync(1 + sg, 128);
-          if (gtid < 16) {
-            const int c = mycnt[gtid];
-            if (c) {
-              atomicAdd(&args.cnt[obj][slot0 + gtid], c);
-              mycnt[gtid] = 0;
-            }
+          if (t - chunk0 + 1 == CNT_TILES && t + 1 < ntile) {
+            flush_counts(chunk0, CNT_TILES);
+            chunk0 = t + 1;
           }
-          named_bar_sync(1 + sg, 128);
         }
       }
+      if (counting && ntile > chunk0) flush_counts(chunk0, ntile - chunk0);
       // epilogue: O^T (128 queries x 256 channels) * 2^-8 -> partial buffer; group g takes channels [64 g, 64 g + 64)
       mbar_wait(o_full, seg_it & 1);
       tc_fence_after();
@@ -849,7 +878,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
 constexpr int P_STAGES = 4;
 constexpr int P_KSTAGE_BYTES = 32 * DK * 2 * 2;                 // this CTA's 32 slots, hi + lo: 16 KB
 constexpr int P_VSTAGE_BYTES = B_TILE * 128 * (2 + 1 + 1);      // 64 slots x this CTA's 128 channels: 32 KB
-constexpr int P_SMEM = P_STAGES * (P_KSTAGE_BYTES + P_VSTAGE_BYTES) + 1024 + 1024;
+constexpr int P_SMEM = P_STAGES * (P_KSTAGE_BYTES + P_VSTAGE_BYTES) + 1024 + 256 + 96 * 64 * 4;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     tc_phase_b_pair_kernel(const __grid_constant__ TcMaps maps, TcArgs args, const float* __restrict__ lse, float thres,
@@ -867,7 +896,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   uint64_t* p_full = bars + 18;        // [2]  (used on the leader: 8 local + 8 remote warps)
   uint64_t* o_full = bars + 20;        // [1]
   uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(bars + 21);
-  int* cnt_s = reinterpret_cast<int*>(bars + 24);   // [4 groups][32]
+  int* cnt_item = reinterpret_cast<int*>(bars + 32);   // [CNT_TILES][64] usage counts of the current item
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -881,7 +910,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
-  if (threadIdx.x < 128) cnt_s[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < CNT_TILES * B_TILE; i += TC_THREADS) cnt_item[i] = 0;
   if (warp == 2) tmem_alloc_pair(tmem_base_p, 512);
   tc_fence_before();
   cluster_sync_all();
@@ -1008,17 +1037,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       const int quarter = warp & 3, sg = (warp - 4) >> 2;
       const int hsel = sg >> 1, sub = sg & 1;
       const int row = (quarter << 5) + lane;
-      const int gtid = row;                                      // 0..127 within the slot group
+      const int et = threadIdx.x - 128;                          // 0..511
       const uint32_t tlane = tmem + (((uint32_t)quarter * 32u) << 16);
       const int j = qt * QT + row;
       const float lse2m = (j < args.hw) ? (lse[(size_t)obj * args.hw + j] * LOG2E - P_SCALE_LOG2) : INFINITY;
       const float thres_s = thres * P_SCALE;
-      int* mycnt = cnt_s + sg * 16;
       const bool counting = do_count && (half == 0);
       const uint32_t pf_leader0 = mapa_u32(smem_u32(&p_full[0]), 0), pf_leader1 = mapa_u32(smem_u32(&p_full[1]), 0);
+      auto flush_counts = [&](int tile_first, int n_tiles) {
+        named_bar_sync(9, EPI_THREADS);
+        for (int idx = et; idx < n_tiles * B_TILE; idx += EPI_THREADS) {
+          const int c = cnt_item[idx];
+          if (c) {
+            atomicAdd(&args.cnt[obj][(size_t)(t0 + tile_first) * B_TILE + idx], c);
+            cnt_item[idx] = 0;
+          }
+        }
+        named_bar_sync(9, EPI_THREADS);
+      };
+      int chunk0 = 0;                                            // first tile of the current count chunk
       for (int t = 0; t < ntile; ++t) {
         const int b = t & 1;
-        const uint32_t pf_leader = b ? pf_leader1 : pf_leader0;
         mbar_wait(&s_full[b], buf_it[b] & 1);
         ++buf_it[b];
         tc_fence_after();
@@ -1037,43 +1076,46 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         named_bar_sync(5 + quarter, 128);
         tc_fence_after();
         uint32_t hi[8], lo[4], p8[4];
-        uint32_t bits = softmax_chunk16(sv, lse2m, thres_s, n_obj - slot0, hi, lo, p8);
+        uint32_t bits;
+        const int lim = n_obj - slot0;
+        if (lim >= 16) {
+          bits = counting ? softmax_chunk16<false, true>(sv, lse2m, thres_s, lim, hi, lo, p8)
+                          : softmax_chunk16<false, false>(sv, lse2m, thres_s, lim, hi, lo, p8);
+        } else {
+          bits = softmax_chunk16<true, true>(sv, lse2m, thres_s, lim, hi, lo, p8);
+        }
         tmem_st8(pb + (uint32_t)sub * 8, hi);
         tmem_st4(pb + 16 + (uint32_t)sub * 4, lo);
         tmem_st4(pb + 24 + (uint32_t)sub * 4, p8);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(pf_leader);
+        if (lane == 0) mbar_arrive_cluster(b ? pf_leader1 : pf_leader0);
         if (counting) {
-          if (j >= args.hw) bits = 0u;
-          const int dense = __any_sync(0xffffffffu, __popc(bits) > 2);
-          if (dense) {
+          // bit (15 - i) <-> slot slot0 + i of this row; rows beyond hw have lse = +inf, P = 0: no bits
+          int* cdst = cnt_item + (t - chunk0) * B_TILE + sg * 16;
+          if (__any_sync(0xffffffffu, __popc(bits) > 2)) {
             int c_mine = 0;
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
               const unsigned bal = __ballot_sync(0xffffffffu, (bits >> c) & 1u);
               if (lane == c) c_mine = __popc(bal);
             }
-            if (c_mine) atomicAdd(&mycnt[lane], c_mine);
+            if (c_mine) atomicAdd(&cdst[15 - lane], c_mine);
           } else {
             while (bits) {
-              const int c = __ffs((int)bits) - 1;
-              bits &= bits - 1;
-              atomicAdd(&mycnt[c], 1);
+              const int c = 31 - __clz((int)bits);
+              bits &= ~(1u << c);
+              atomicAdd(&cdst[15 - c], 1);
             }
           }
-          named_bar_sync(1 + sg, 128);
-          if (gtid < 16) {
-            const int c = mycnt[gtid];
-            if (c) {
-              atomicAdd(&args.cnt[obj][slot0 + gtid], c);
-              mycnt[gtid] = 0;
-            }
+          if (t - chunk0 + 1 == CNT_TILES && t + 1 < ntile) {
+            flush_counts(chunk0, CNT_TILES);
+            chunk0 = t + 1;
           }
-          named_bar_sync(1 + sg, 128);
         }
       }
+      if (counting && ntile > chunk0) flush_counts(chunk0, ntile - chunk0);
       mbar_wait(o_full, seg_it & 1);
       tc_fence_after();
       if (ntile > 0) {
