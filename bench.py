@@ -171,7 +171,9 @@ class ClockSampler(threading.Thread):
                         self.samples.append([x.strip() for x in o.split(',')])
             except Exception:
                 pass
-            time.sleep(0.05 if self.nvml is not None else 0.5)
+            # sparse on purpose: NVML queries contend with kernel launches for a driver lock (profiles/r1h: a 20 Hz
+            # sampler on rank 0 tripled the step time of a 2-GPU run; nvidia-smi forks cost 25 % at 10 Hz on one GPU)
+            time.sleep(0.3 if self.nvml is not None else 0.6)
 
     def summary(self):
         if not self.samples:
@@ -304,7 +306,11 @@ def main_ours(args, rank, world, local_rank):
     ms_e2e = t0.elapsed_time(t1)
 
     t_ms = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    per_rank = [[ms, ms_e2e]]
     if dist is not None:
+        allt = [torch.empty_like(t_ms) for _ in range(world)]
+        dist.all_gather(allt, t_ms)
+        per_rank = [t.tolist() for t in allt]
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t_ms.tolist()
     if rank != 0:
@@ -360,7 +366,8 @@ def main_ours(args, rank, world, local_rank):
                        'final_bank_slots': final_n, 'l2_policy': 'inputs_exceed_l2 (bank operands 0.5-1.1 GB >> 126 MB)',
                        'read_impl': args.read_impl},
             'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
-            'gpu_launches': int(launches), 'roofline': roofline, 'kernels': extra, 'clocks': sampler.summary()}
+            'gpu_launches': int(launches), 'roofline': roofline, 'kernels': extra, 'clocks': sampler.summary(),
+            'ms_per_rank': [[round(a / args.steps, 2), round(b / args.steps, 2)] for a, b in per_rank]}
     if not args.no_cpu_baseline and world == 1:
         fps, desc, secs = cpu_sample(args.frac_merge)
         line['cpu_baseline'] = {'value': fps, 'unit': 'frames/s', 'cores': os.cpu_count(), 'kind': 'port',
