@@ -166,13 +166,22 @@ typedef struct vfn_update_io {
   int32_t kept, n_iter;
   int32_t thresholds[64];        /* T sequence of remove() */
   int64_t n_before;              /* bank size before this update */
+  int32_t deferred;              /* 1: counts not read back yet - call vfn_bank_update_finish() after the event */
+  int32_t reserved;
 } vfn_update_io;
 
 size_t vfn_bank_update_workspace_bytes(int32_t obj_n, int64_t n_max, int64_t hw, int32_t d_key, int32_t d_val);
-/* h_pinned: obj_n * 80 int32 of pinned host memory (counts + eviction plans land there). */
+/* h_pinned: obj_n * 80 int32 of pinned host memory (counts + eviction plans land there).
+ * defer_event: NULL, or a cudaEvent_t.  With an event, an update in which no object can reach its budget
+ * (n + hw <= class_budget for all objects, so FeatureBank.py:102 cannot fire) does NOT synchronise the stream: the
+ * event is recorded once the counts are on their way to h_pinned, io[c].deferred is set, banks[c].n is left unchanged,
+ * and the caller completes the update with vfn_bank_update_finish() after cudaEventSynchronize(defer_event), before
+ * anything else touches the banks or h_pinned.  Updates that may evict keep the reference's synchronous behaviour. */
 int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_io* io, int64_t hw, float frame_idx,
                     float update_rate, float thres_close, double class_budget, void* d_ws, size_t ws_bytes,
-                    int32_t* h_pinned, int32_t impl, void* stream);
+                    int32_t* h_pinned, int32_t impl, void* defer_event, void* stream);
+/* host-only: reads |merge|, |runs|, |append| of a deferred update from h_pinned, fills io and advances banks[c].n */
+int vfn_bank_update_finish(vfn_bank* banks, int32_t obj_n, vfn_update_io* io, const int32_t* h_pinned);
 
 /* ---- URR: non-convolution parts of Decoder.forward (AFB_URR.py:214-237, myutils/data.py:42-48) -----
  * pre:  p (obj_n,2,h/2,w/2) coarse logits from pred2, r1 (obj_n or 1, c, h, w)  ->
@@ -201,8 +210,11 @@ int64_t vfn_launch_count(void);
 /* ---- self-test hooks for the tcgen05/TMA building blocks (used by tests/, not by the product path) ---- */
 /* d_ptr != NULL: the next tcgen05 read launches dump the first S^T tile of CTA 0 (128 x tile floats) there. */
 int vfn_debug_set_dump(float* d_ptr);
-/* 1 (default): CTA-pair (cta_group::2) tcgen05 kernels; 0: the single-CTA kernels (cross-check in tests/) */
-int vfn_debug_set_pair(int32_t on);
+/* bit mask, default 3: bit 0 = CTA-pair (cta_group::2) phase B, bit 1 = CTA-pair score scan (phase A, match);
+ * 0 selects the single-CTA kernels (cross-check in tests/) */
+int vfn_debug_set_pair(int32_t mask);
+/* 1 (default): streaming (warp-shuffle, register-ring) URR local kernel when w % 4 == 0; 0: tiled shared-memory kernel */
+int vfn_debug_set_urr_stream(int32_t on);
 
 #ifdef __cplusplus
 }

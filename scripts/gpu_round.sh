@@ -13,6 +13,6 @@ timeout 600 python bench.py --impl reference --steps 1 --warmup 1 > $out/bench_r
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $out/launches.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $out/bench_under_ncu.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on \
-    -k regex:'tc_phase_a|tc_phase_b|tc_match|compact_move|merge_runs|urr_local|match_rescore' -s 7 -c 8 -f -o $out/prof \
+    -k regex:'tc_scan|tc_phase_b|urr_local' -s 4 -c 4 -f -o $out/prof \
     python tests/profile_kernels.py 100000 1620 1 > $out/ncu_full.log 2>&1
 tail -3 $out/pytest_gpu.log; tail -2 $out/smoke.log; cat $out/profile_kernels.log; cat $out/bench.json; cat $out/bench_ref.json

@@ -25,6 +25,8 @@ dev = torch.device('cuda', 0)
 q_in, q_out = q_in.to(dev), q_out.to(dev)
 pk, pv = [k.to(dev) for k in pk], [v.to(dev) for v in pv]
 m = vfn.Matcher(update_bank=True)
+urr_p, urr_r1, _ = [t.to(dev) for t in synth.gen_urr_inputs(g, 2, 240, 432)]
+urr_r1 = urr_r1.expand(2, -1, -1, -1)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
@@ -36,6 +38,7 @@ def fresh():
 
 fb = fresh()
 m(fb, q_in, q_out)
+vfn.urr_pre(urr_p, urr_r1, (1, 2, 240, 432))
 fb.update(pk, pv, 51)
 torch.cuda.synchronize()
 lib.vfn_profile_enable(1)
@@ -43,6 +46,8 @@ for _ in range(reps):
     fb = fresh()
     flush.zero_()
     m(fb, q_in, q_out)
+    flush.zero_()
+    vfn.urr_pre(urr_p, urr_r1, (1, 2, 240, 432))
     flush.zero_()
     fb.update(pk, pv, 51)
 torch.cuda.synchronize()

@@ -40,9 +40,10 @@ def test_struct_layout_matches_header():
     # 2 x int32, 2 x int64, 12 pointers
     assert ctypes.sizeof(VfnBank) == 8 + 16 + 12 * 8
     assert VfnBank.keys.offset == 24 and VfnBank.cnt.offset == 24 + 11 * 8
-    # 8 pointers, 8 + 64 int32, 1 int64
-    assert ctypes.sizeof(VfnUpdateIO) == 8 * 8 + 72 * 4 + 8
+    # 8 pointers, 8 + 64 int32, 1 int64, 2 int32
+    assert ctypes.sizeof(VfnUpdateIO) == 8 * 8 + 72 * 4 + 8 + 8
     assert VfnUpdateIO.thresholds.offset == 8 * 8 + 8 * 4 and VfnUpdateIO.n_before.offset == 8 * 8 + 72 * 4
+    assert VfnUpdateIO.deferred.offset == 8 * 8 + 72 * 4 + 8
 
 
 def test_argument_errors_are_reported_not_fatal():

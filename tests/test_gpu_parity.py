@@ -255,6 +255,42 @@ def test_append_api(vfn, golden_dir):
 
 
 # ---------------------------------------------------------------------------------------------------
+# deferred completion of update(): no stream drain per frame, same bank
+# ---------------------------------------------------------------------------------------------------
+def test_deferred_update_equals_synchronous(vfn):
+    """a clip run with deferred update completion (counts read back lazily, append sized on the device) must leave
+    the bank bit-identical to the synchronous run - including frames where the budget forces the synchronous path."""
+    from vfloodnet_b200 import synth
+    hw, frames = 400, 9
+    gen = synth.ClipGenerator(seed=5, obj_n=2, hw=hw, frac_merge=0.3)
+    keys0, vals0 = gen.init()
+    clip = [gen.frame() for _ in range(frames)]
+    res = []
+    for defer in (False, True):
+        fb = vfn.FeatureBank(2, 5500, 'cuda')        # class_budget 2200: frames 1..4 defer, later ones may evict
+        fb.defer = defer
+        m = vfn.Matcher(update_bank=True)
+        fb.init_bank([k.cuda() for k in keys0], [v.cuda() for v in vals0])
+        outs, sizes = [], []
+        for t, (q_in, q_out, pk, pv) in enumerate(clip):
+            outs.append(m(fb, q_in.cuda(), q_out.cuda()))
+            fb.update([k.cuda() for k in pk], [v.cuda() for v in pv], t + 1)
+            if defer and t < 3:
+                assert fb._pending is not None           # really deferred while the budget is far away
+            sizes.append([fb.bank_n(c) for c in range(2)])
+        res.append((fb, outs, sizes))
+    (fa, oa, sa), (fb_, ob, sb) = res
+    assert sa == sb
+    assert any(d['evicted'] for d in fa.last_decisions) or fa.replace_n.sum() > 0
+    for a, b in zip(oa, ob):
+        assert torch.equal(a, b)
+    for c in range(2):
+        assert torch.equal(fa.keys[c], fb_.keys[c]) and torch.equal(fa.values[c], fb_.values[c])
+        assert torch.equal(fa.info[c], fb_.info[c])
+    assert np.array_equal(fa.peak_n, fb_.peak_n) and np.array_equal(fa.replace_n, fb_.replace_n)
+
+
+# ---------------------------------------------------------------------------------------------------
 # URR
 # ---------------------------------------------------------------------------------------------------
 def test_urr_golden(vfn, golden_dir):
@@ -285,6 +321,28 @@ def test_urr_vs_oracle_480p(vfn):
     a, b = out.cpu()[1] > 0.5, out_o[1] > 0.5
     iou = (a & b).sum().item() / max((a | b).sum().item(), 1)
     assert iou >= 0.999
+
+
+@pytest.mark.parametrize('obj_n,c,h,w,shared', [(2, 64, 240, 432, True), (3, 8, 30, 52, True), (2, 5, 46, 488, False),
+                                                (1, 4, 8, 8, True), (4, 3, 64, 1000, True)])
+def test_urr_local_streaming_equals_tiled(vfn, obj_n, c, h, w, shared):
+    """the warp-shuffle / register-ring URR kernel keeps the summation order of the tiled shared-memory kernel: the two
+    must agree bit for bit on every shape (several x tiles, ragged bands, 1..4 objects, shared or per-object r1)."""
+    from vfloodnet_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(100 + h + w)
+    p = torch.randn((obj_n, 2, h // 2, w // 2), generator=g).cuda()
+    r1 = torch.randn((1 if shared else obj_n, c, h, w), generator=g).cuda()
+    r1 = r1.expand(obj_n, -1, -1, -1) if shared else r1
+    try:
+        lib.vfn_debug_set_urr_stream(0)
+        ref = vfn.urr_pre(p, r1, (1, obj_n, h, w))[3].clone()
+        lib.vfn_debug_set_urr_stream(1)
+        got = vfn.urr_pre(p, r1, (1, obj_n, h, w))[3]
+        torch.cuda.synchronize()
+    finally:
+        lib.vfn_debug_set_urr_stream(1)
+    assert torch.equal(ref, got), (ref - got).abs().max().item()
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -356,7 +414,7 @@ def test_read_pair_and_single_cta_kernels(vfn, n, hw):
     rr, _ = _oracle_read(list(keys), list(vals), info, q_in, q_out)
     outs, infos = [], []
     try:
-        for pair in (1, 0):
+        for pair in (3, 0, 1):                     # bit 0: pair phase B, bit 1: pair score scan (phase A)
             lib.vfn_debug_set_pair(pair)
             fb = vfn.FeatureBank(2, 10 ** 6, 'cuda', impl=2)
             fb.load_state(list(keys), list(vals), info)
@@ -366,8 +424,36 @@ def test_read_pair_and_single_cta_kernels(vfn, n, hw):
             outs.append(out.cpu())
             infos.append([fb.info[c].cpu().clone() for c in range(2)])
     finally:
-        lib.vfn_debug_set_pair(1)
-    assert (outs[0] - outs[1]).abs().max().item() <= 2e-4
+        lib.vfn_debug_set_pair(3)
+    for k in (1, 2):
+        assert (outs[0] - outs[k]).abs().max().item() <= 2e-4
+        for c in range(2):
+            # same logits and LSE in all kernels: identical usage counts up to threshold-band flips
+            assert (infos[0][c] - infos[k][c]).abs().gt(1e-5).sum().item() <= 2
+
+
+@pytest.mark.parametrize('n,hw', [(5000, 1620), (20011, 300), (100, 129)])
+def test_match_pair_and_single_cta_kernels(vfn, n, hw):
+    """the CTA-pair score scan and the single-CTA one feed the same exact fp32 re-score: identical j*, c* and banks"""
+    from vfloodnet_b200 import synth, _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(21)
+    ns = [n, max(n - 129, 1)]
+    keys, vals = zip(*[synth.gen_bank(g, k) for k in ns])
+    info = [synth.gen_info(g, k, 10) for k in ns]
+    pk, pv = zip(*[synth.gen_candidates(g, keys[c], vals[c], hw, 0.5) for c in range(2)])
+    res = []
+    try:
+        for pair in (3, 0):
+            lib.vfn_debug_set_pair(pair)
+            fb = vfn.FeatureBank(2, 10 ** 6, 'cuda', impl=2)
+            fb.load_state(list(keys), list(vals), info)
+            fb.update([k.cuda() for k in pk], [v.cuda() for v in pv], 11)
+            d = fb.last_decisions
+            res.append(([d[c]['match_idx'].clone() for c in range(2)], [d[c]['match_corr'].clone() for c in range(2)],
+                        [fb.keys[c].clone() for c in range(2)]))
+    finally:
+        lib.vfn_debug_set_pair(3)
     for c in range(2):
-        # same logits and LSE in both kernels: identical usage counts up to threshold-band flips
-        assert (infos[0][c] - infos[1][c]).abs().gt(1e-5).sum().item() <= 2
+        assert torch.equal(res[0][0][c], res[1][0][c]) and torch.equal(res[0][1][c], res[1][1][c])
+        assert torch.equal(res[0][2][c], res[1][2][c])

@@ -24,7 +24,7 @@ class VfnUpdateIO(C.Structure):
                 ('d_merge_q', c_vp), ('d_merge_slot', c_vp), ('d_run_off', c_vp), ('d_append_q', c_vp),
                 ('n_merge', c_i32), ('n_runs', c_i32), ('n_append', c_i32), ('evicted', c_i32), ('swapped', c_i32),
                 ('evict_status', c_i32), ('kept', c_i32), ('n_iter', c_i32), ('thresholds', c_i32 * 64),
-                ('n_before', c_i64)]
+                ('n_before', c_i64), ('deferred', c_i32), ('reserved', c_i32)]
 
 
 BANK_P = C.POINTER(VfnBank)
@@ -54,7 +54,8 @@ SIGNATURES = {
     'vfn_bank_clamp_info': (c_i32, [BANK_P, c_i64, c_vp]),
     'vfn_bank_update_workspace_bytes': (c_sz, [c_i32, c_i64, c_i64, c_i32, c_i32]),
     'vfn_bank_update': (c_i32, [BANK_P, BANK_P, c_i32, IO_P, c_i64, c_f32, c_f32, c_f32, c_f64, c_vp, c_sz, c_vp,
-                                c_i32, c_vp]),
+                                c_i32, c_vp, c_vp]),
+    'vfn_bank_update_finish': (c_i32, [BANK_P, c_i32, IO_P, c_vp]),
     'vfn_urr_pre': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vfn_urr_post': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     'vfn_profile_enable': (c_i32, [c_i32]),
@@ -63,6 +64,7 @@ SIGNATURES = {
     'vfn_launch_count': (c_i64, []),
     'vfn_debug_set_dump': (c_i32, [c_vp]),
     'vfn_debug_set_pair': (c_i32, [c_i32]),
+    'vfn_debug_set_urr_stream': (c_i32, [c_i32]),
 }
 
 _lib = None

@@ -641,7 +641,7 @@ int launch_append(const UpdObj* o, int n_obj, float info0, float info1, cudaStre
     }
     set.o[c] = AppendObj{o[c].bank, o[c].ck, o[c].cv, o[c].nck, o[c].sel, o[c].n_sel_dev, o[c].n_sel};
     if (o[c].n_sel > n_max) n_max = o[c].n_sel;
-    bytes += 2.0 * 4.0 * (o[c].bank.d_key + o[c].bank.d_val + 2) * (double)o[c].n_sel;
+    if (!o[c].n_sel_dev) bytes += 2.0 * 4.0 * (o[c].bank.d_key + o[c].bank.d_val + 2) * (double)o[c].n_sel;
   }
   if (n_max == 0) return VFN_OK;
   dim3 grid((unsigned)(n_max < 148 * 16 ? n_max : 148 * 16), n_obj);

@@ -560,6 +560,224 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------
+// score scan on CTA pairs (cta_group::2, M = 256): the two CTAs of a cluster take adjacent query tiles of the same
+// (object, slot split) and SHARE every 128-slot B tile - each CTA TMA-loads 64 of its slots, the pair's tensor cores
+// read both halves.  The single-CTA kernel pulls 64 KB per 1536-clk tile from L2 (43 B/clk/SM x 148 SMs = the whole
+// L2 slice throughput, B300_MICROARCH.md "LTS throughput cap"); the pair halves that and leaves room for six stages.
+// Everything per CTA (TMEM layout, epilogue) is as in tc_scan_kernel; only the leader issues MMAs, its "full" barriers
+// count both CTAs' bytes, commits are multicast, the peer's epilogue warps free S buffers with remote arrives.
+// ------------------------------------------------------------------------------------------------
+constexpr int SP_STAGES = 6;
+constexpr int SP_STAGE_BYTES = 64 * DK * 2 * 2;        // this CTA's 64 slots, hi + lo: 32 KB
+constexpr int SP_SMEM = SP_STAGES * SP_STAGE_BYTES + 1024 + 256 + SC_AUX_BYTES;
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+    tc_scan_pair_kernel(const __grid_constant__ TcMaps maps, TcArgs args, float2* __restrict__ part) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* kst = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SP_STAGES * SP_STAGE_BYTES);
+  uint64_t* k_full = bars;                       // [SP_STAGES]  (used on the leader: bytes of both CTAs' loads)
+  uint64_t* k_empty = bars + SP_STAGES;          // [SP_STAGES]
+  uint64_t* s_full = bars + 2 * SP_STAGES;       // [3]
+  uint64_t* s_empty = bars + 2 * SP_STAGES + 3;  // [3]  (used on the leader: 16 local + 16 remote warps)
+  uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(bars + 2 * SP_STAGES + 6);
+  float2* aux = reinterpret_cast<float2*>(smem + SP_STAGES * SP_STAGE_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SP_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 2 * EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair(tmem_base_p, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_base_p;
+
+  // work items = (split, object, query-tile pair), dealt round-robin to the persistent clusters
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int qpairs = (args.q_tiles + 1) >> 1;
+  const int n_combos = args.obj_n * qpairs;
+  const int n_items = n_combos * args.pieces;
+  uint32_t tile_ctr = 0;        // tiles streamed so far by this cluster (all roles agree)
+  for (int item = cluster_id; item < n_items; item += n_clusters) {
+    const int piece = item / n_combos;
+    const int combo = item - piece * n_combos;
+    const int obj = combo / qpairs;
+    const int qt = (combo - obj * qpairs) * 2 + (int)rank;
+    const int tiles_o = args.tiles[obj];
+    const int t0 = (int)((long long)tiles_o * piece / args.pieces);
+    const int t1 = (int)((long long)tiles_o * (piece + 1) / args.pieces);
+    const int n_obj = args.n[obj];
+    const int ntile = t1 - t0;
+    const bool first_item = (item == cluster_id);
+
+    if (warp >= 4) load_a_operand(args, obj, qt, tmem, TS_AH, TS_AL, warp, lane);
+    tc_fence_before();
+    cluster_sync_all();      // both CTAs' A tiles are in TMEM, both epilogues of the previous item are done
+    tc_fence_after();
+
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int t = 0; t < ntile; ++t) {
+          const uint32_t c = tile_ctr + t, st = c % SP_STAGES, ph = (c / SP_STAGES) & 1;
+          mbar_wait(&k_empty[st], ph ^ 1);
+          if (leader) mbar_arrive_expect_tx(&k_full[st], 2 * SP_STAGE_BYTES);
+          const uint32_t kf = mapa_u32(smem_u32(&k_full[st]), 0);
+          uint8_t* dst = kst + st * SP_STAGE_BYTES;
+          const int row0 = (t0 + t) * SC_TILE + (int)rank * 64;     // this CTA's 64 of the tile's 128 slots
+          tma_load_2d_pair(dst, &maps.kh[obj], kf, 0, row0);
+          tma_load_2d_pair(dst + 8192, &maps.kh[obj], kf, 64, row0);
+          tma_load_2d_pair(dst + 16384, &maps.kl[obj], kf, 0, row0);
+          tma_load_2d_pair(dst + 24576, &maps.kl[obj], kf, 64, row0);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (leader) {
+        constexpr uint32_t idesc = make_idesc(256, SC_TILE, FMT_F16, FMT_F16, 0, 0);
+        for (int t = 0; t < ntile; ++t) {
+          const uint32_t c = tile_ctr + t, st = c % SP_STAGES, ph = (c / SP_STAGES) & 1;
+          const uint32_t sb = c % SC_BUFS, phs = (c / SC_BUFS) & 1;
+          mbar_wait(&s_empty[sb], phs ^ 1);
+          mbar_wait(&k_full[st], ph);
+          tc_fence_after();
+          const uint32_t kbase = smem_u32(kst + st * SP_STAGE_BYTES);
+          const uint32_t d_t = tmem + TS_S + sb * SC_TILE;
+          if (elect_one()) {
+            // passes: (Ah,Bh) (Al,Bh) (Ah,Bl); each CTA's smem holds its 64 slots of the 128-slot B tile
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint32_t a_col = (pass == 1) ? TS_AL : TS_AH;
+              const uint32_t kb = kbase + ((pass == 2) ? 16384u : 0u);
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                const uint64_t bd = make_sdesc(kb + (ks >> 2) * 8192u + (ks & 3) * 32u, 16, 1024);
+                mma_ts_pair(d_t, tmem + a_col + ks * 8, bd, idesc, (pass | ks) ? 1u : 0u);
+              }
+            }
+            tc_commit_pair(&k_empty[st]);
+            tc_commit_pair(&s_full[sb]);
+          }
+          __syncwarp();
+        }
+      }
+    } else if (warp >= 4) {
+      const int quarter = warp & 3, cg = (warp - 4) >> 2;
+      const int row = (quarter << 5) + lane;
+      const int et = threadIdx.x - 128;                       // 0..511
+      const uint32_t tlane = tmem + (((uint32_t)quarter * 32u) << 16) + TS_S + (uint32_t)cg * 32u;
+      float m_run = -INFINITY, l_run = 0.f;
+      int cnt = 0;
+      float2* ring = aux + et * MATCH_RING;
+      for (int t = 0; t < ntile; ++t) {
+        const uint32_t c = tile_ctr + t, st = c % SC_BUFS, ph = (c / SC_BUFS) & 1;
+        mbar_wait(&s_full[st], ph);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(tlane + st * SC_TILE, v);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&s_empty[st]), 0));   // values are in registers: free the buffer (leader's barrier)
+        if (args.dbg && blockIdx.x == 0 && first_item && t == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) args.dbg[row * SC_TILE + cg * 32 + i] = __uint_as_float(v[i]);
+        }
+        const int slot0 = (t0 + t) * SC_TILE + cg * 32;
+        const int lim = n_obj - slot0;                        // valid slots in this thread's 32 columns
+        if (lim <= 0) continue;
+        if (lim < 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i >= lim) v[i] = __float_as_uint(-INFINITY);
+        }
+        float cm = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) cm = fmax3(cm, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+        if (MODE == MODE_LSE) {
+          const float m_new = fmaxf(m_run, cm);
+          if (m_new > -INFINITY) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              a0 += ex2(__uint_as_float(v[i]) - m_new);
+              a1 += ex2(__uint_as_float(v[i + 1]) - m_new);
+            }
+            l_run = l_run * ex2(m_run - m_new) + (a0 + a1);
+            m_run = m_new;
+          }
+        } else {
+          // candidates = every slot whose score is within `band` of the running maximum at its time; a jump of the
+          // maximum by more than the band invalidates everything before it
+          if (cm > m_run + args.band) cnt = 0;
+          const float m_new = fmaxf(m_run, cm);
+          const float thr = m_new - args.band;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float sv = __uint_as_float(v[i]);
+            if (sv >= thr) {
+              ring[cnt & (MATCH_RING - 1)] = make_float2(sv, __int_as_float(slot0 + i));
+              ++cnt;
+            }
+          }
+          m_run = m_new;
+        }
+      }
+      const int j = qt * QT + row;
+      if (MODE == MODE_LSE) {
+        // combine the four column groups' statistics and publish the piece
+        aux[cg * QT + row] = make_float2(m_run, l_run);
+        named_bar_sync(1, EPI_THREADS);
+        if (cg == 0) {
+          float m = m_run;
+#pragma unroll
+          for (int g = 1; g < 4; ++g) m = fmaxf(m, aux[g * QT + row].x);
+          float l = 0.f;
+          if (m > -INFINITY) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float2 o = aux[g * QT + row];
+              if (o.x > -INFINITY) l += o.y * ex2(o.x - m);
+            }
+          }
+          if (j < args.hw) part[((size_t)obj * args.pieces + piece) * args.hw + j] = make_float2(m * LN2, l);
+        }
+        named_bar_sync(1, EPI_THREADS);                      // aux is reused by the next item
+      } else {
+        if (j < args.hw) {
+          float2 e[MATCH_RING];
+          const float thr = m_run - args.band;
+#pragma unroll
+          for (int r = 0; r < MATCH_RING; ++r) {
+            const float2 x = ring[r];
+            e[r] = (r < cnt && x.x >= thr) ? x : make_float2(-INFINITY, __int_as_float(0x7fffffff));
+          }
+          if (cnt > MATCH_RING) e[0] = make_float2(m_run, __int_as_float(-1));     // overflow: exact scan needed
+          float4* dst = reinterpret_cast<float4*>(
+              part + (((size_t)obj * args.pieces + piece) * args.hw + j) * MATCH_CAND + cg * MATCH_RING);
+          dst[0] = make_float4(e[0].x, e[0].y, e[1].x, e[1].y);
+          dst[1] = make_float4(e[2].x, e[2].y, e[3].x, e[3].y);
+        }
+      }
+    }
+    tile_ctr += ntile;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_pair(tmem, 512);
+}
+
+
+// ------------------------------------------------------------------------------------------------
 // phase B
 //   TMEM: O^T accumulator [0,256) | Q hi [256,320) | Q lo [320,384) | two S/P buffers of 64 columns at 384 + 64 b
 //   smem: K stages 32 KB [kh: 2 boxes of 64 d | kl: 2 boxes], V stages 64 KB [vh: 4 boxes of 64 ch | v8: 2 boxes of
@@ -1278,7 +1496,7 @@ static int num_sms() {
 }
 
 static float* g_dbg = nullptr;
-static int g_pair = 1;    // CTA-pair (cta_group::2) kernels where available; vfn_debug_set_pair(0) selects the single-CTA ones
+static int g_pair = 3;    // bit 0: CTA-pair (cta_group::2) phase B, bit 1: CTA-pair scan (phase A, match); vfn_debug_set_pair()
 
 bool tc_shapes_ok(int d_key, int d_val) { return d_key == DK && d_val == DV; }
 
@@ -1318,6 +1536,8 @@ static int set_attrs() {
   if (!attr) {
     VFN_CUDA_OK(cudaFuncSetAttribute(tc_scan_kernel<MODE_LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
     VFN_CUDA_OK(cudaFuncSetAttribute(tc_scan_kernel<MODE_MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
+    VFN_CUDA_OK(cudaFuncSetAttribute(tc_scan_pair_kernel<MODE_LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
+    VFN_CUDA_OK(cudaFuncSetAttribute(tc_scan_pair_kernel<MODE_MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
     VFN_CUDA_OK(cudaFuncSetAttribute(tc_phase_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
     VFN_CUDA_OK(cudaFuncSetAttribute(tc_phase_b_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
     attr = true;
@@ -1363,10 +1583,12 @@ int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t h
     tmin = t < tmin ? t : tmin;
     tmax = t > tmax ? t : tmax;
   }
-  const int pieces = best_split(obj_n * (int)cdiv(hw, QT), tmin, tmax, 2);
+  const bool pair = (g_pair & 2) && (num_sms() % 2 == 0);
+  const int pieces = pair ? best_split(obj_n * (int)cdiv(hw, 2 * QT), tmin, tmax, 2, num_sms() / 2)
+                          : best_split(obj_n * (int)cdiv(hw, QT), tmin, tmax, 2);
   if (pieces > split_a) { set_error("phase A: split %d exceeds workspace bound %d", pieces, split_a); return VFN_E_CAPACITY; }
   *pieces_out = pieces;
-  if (int rc = fill_args(banks, obj_n, hw, pieces, SC_TILE, ws_tc, &maps, &a, false)) return rc;
+  if (int rc = fill_args(banks, obj_n, hw, pieces, SC_TILE, ws_tc, &maps, &a, false, pair ? 64 : SC_TILE)) return rc;
   // Q hi/lo of q * log2(e)/sqrt(d): logits land in the log2 domain; pad rows zeroed
   VFN_CUDA_OK(cudaMemsetAsync(ws_tc, 0, 2 * a_operand_bytes(hw), st));
   const float scale = LOG2E / sqrtf((float)DK);
@@ -1376,7 +1598,10 @@ int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t h
   double work = 0;
   for (int o = 0; o < obj_n; ++o) work += 2.0 * DK * (double)banks[o].n * (double)hw;
   prof_begin(PROF_READ_A, st);
-  tc_scan_kernel<MODE_LSE><<<num_sms(), TC_THREADS, SC_SMEM, st>>>(maps, a, part);
+  if (pair)
+    tc_scan_pair_kernel<MODE_LSE><<<num_sms(), TC_THREADS, SP_SMEM, st>>>(maps, a, part);
+  else
+    tc_scan_kernel<MODE_LSE><<<num_sms(), TC_THREADS, SC_SMEM, st>>>(maps, a, part);
   prof_end(PROF_READ_A, st, work);
   VFN_LAUNCH_OK();
   count_launches(2);
@@ -1394,7 +1619,7 @@ int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const 
     tmin = t < tmin ? t : tmin;
     tmax = t > tmax ? t : tmax;
   }
-  const bool pair = g_pair && (num_sms() % 2 == 0);
+  const bool pair = (g_pair & 1) && (num_sms() % 2 == 0);
   const int combos = pair ? obj_n * 2 * (int)cdiv(hw, 2 * QT) : obj_n * 2 * (int)cdiv(hw, QT);
   const int pieces = best_split(combos, tmin, tmax, 4, pair ? num_sms() / 2 : num_sms());
   if (pieces > split_b) { set_error("phase B: split %d exceeds workspace bound %d", pieces, split_b); return VFN_E_CAPACITY; }
@@ -1447,18 +1672,20 @@ int tc_match(const vfn_bank* banks, int obj_n, const float* const* nck_em, int64
   RescoreArgs r;
   int64_t tmin = INT64_MAX, tmax = 0;
   double work = 0;
+  const bool pair = (g_pair & 2) && (num_sms() % 2 == 0);
   for (int o = 0; o < obj_n; ++o) {
     VFN_CHECK_ARG(banks[o].d_key == DK && banks[o].n < (1ll << 31) && banks[o].nkh, "tcgen05 match needs d_key = 128");
     const int64_t t = cdiv(banks[o].n, SC_TILE);
     tmin = t < tmin ? t : tmin;
     tmax = t > tmax ? t : tmax;
-    if (int rc = make_map(&maps.kh[o], banks[o].nkh, banks[o].n, DK, SC_TILE, 2)) return rc;
-    if (int rc = make_map(&maps.kl[o], banks[o].nkl, banks[o].n, DK, SC_TILE, 2)) return rc;
+    if (int rc = make_map(&maps.kh[o], banks[o].nkh, banks[o].n, DK, pair ? 64 : SC_TILE, 2)) return rc;
+    if (int rc = make_map(&maps.kl[o], banks[o].nkl, banks[o].n, DK, pair ? 64 : SC_TILE, 2)) return rc;
     a.n[o] = (int)banks[o].n; a.tiles[o] = (int)t; a.cnt[o] = nullptr;
     r.n[o] = (int)banks[o].n; r.nk[o] = banks[o].nk; r.nck[o] = nck_em[o]; r.idx_out[o] = idx_out[o]; r.corr_out[o] = corr_out[o];
     work += 2.0 * DK * (double)banks[o].n * (double)hw;
   }
-  const int pieces = best_split(obj_n * (int)cdiv(hw, QT), tmin, tmax, 2);
+  const int pieces = pair ? best_split(obj_n * (int)cdiv(hw, 2 * QT), tmin, tmax, 2, num_sms() / 2)
+                          : best_split(obj_n * (int)cdiv(hw, QT), tmin, tmax, 2);
   a.obj_n = obj_n; a.hw = (int)hw; a.q_tiles = (int)cdiv(hw, QT); a.pieces = pieces;
   a.qh = tc_match_cand_hi(ws, obj_n, hw, 0);
   a.ql = tc_match_cand_lo(ws, obj_n, hw, 0);
@@ -1476,7 +1703,10 @@ int tc_match(const vfn_bank* banks, int obj_n, const float* const* nck_em, int64
   }
   float2* part = reinterpret_cast<float2*>(ws);
   prof_begin(PROF_MATCH, st);
-  tc_scan_kernel<MODE_MATCH><<<num_sms(), TC_THREADS, SC_SMEM, st>>>(maps, a, part);
+  if (pair)
+    tc_scan_pair_kernel<MODE_MATCH><<<num_sms(), TC_THREADS, SP_SMEM, st>>>(maps, a, part);
+  else
+    tc_scan_kernel<MODE_MATCH><<<num_sms(), TC_THREADS, SC_SMEM, st>>>(maps, a, part);
   prof_end(PROF_MATCH, st, work);
   r.obj_n = obj_n; r.pieces = pieces; r.hw = (int)hw; r.band = a.band;
   dim3 grid((unsigned)cdiv(hw, 8), obj_n);
@@ -1488,8 +1718,8 @@ int tc_match(const vfn_bank* banks, int obj_n, const float* const* nck_em, int64
 
 }  // namespace vfn
 
-extern "C" int vfn_debug_set_pair(int32_t on) {
-  vfn::g_pair = on ? 1 : 0;
+extern "C" int vfn_debug_set_pair(int32_t mask) {
+  vfn::g_pair = mask & 3;
   return VFN_OK;
 }
 

@@ -52,7 +52,7 @@ size_t vfn_bank_update_workspace_bytes(int32_t obj_n, int64_t n_max, int64_t hw,
 
 int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_io* io, int64_t hw, float frame_idx,
                     float update_rate, float thres_close, double class_budget, void* d_ws, size_t ws_bytes,
-                    int32_t* h_pinned, int32_t impl, void* stream) {
+                    int32_t* h_pinned, int32_t impl, void* defer_event, void* stream) {
   VFN_CHECK_ARG(banks && alts && io && d_ws && h_pinned && obj_n >= 1 && obj_n <= 4 && hw >= 1, "bank_update: bad args");
   const int d_key = banks[0].d_key, d_val = banks[0].d_val;
   int64_t n_max = 0;
@@ -64,7 +64,7 @@ int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_i
                   "bank_update: io[%d] has NULL buffers", c);
     if (banks[c].n > n_max) n_max = banks[c].n;
     io[c].n_before = banks[c].n;
-    io[c].evicted = io[c].swapped = io[c].evict_status = io[c].kept = io[c].n_iter = 0;
+    io[c].evicted = io[c].swapped = io[c].evict_status = io[c].kept = io[c].n_iter = io[c].deferred = 0;
   }
   const UpdLayout L = upd_layout(obj_n, n_max, hw, d_key, d_val);
   if (ws_bytes < L.total) { set_error("bank_update: workspace %zu < %zu", ws_bytes, L.total); return VFN_E_CAPACITY; }
@@ -117,6 +117,29 @@ int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_i
     uo[c].plan_ws = ws + L.pws + c * L.s_pws;
   }
   if (int rc = launch_plan(uo, obj_n, hw, thres_close, st)) return rc;
+  // Deferred completion: when no object can reach its budget whatever |A| turns out to be (n + hw <= class_budget,
+  // FeatureBank.py:102 cannot fire), nothing on the host depends on the counts: append and clamp take |A| from device
+  // memory, the counts land in h_pinned when the plan kernel retires, and the caller learns the new bank sizes from
+  // vfn_bank_update_finish() after waiting on `defer_event` - the stream is never drained.
+  bool can_defer = defer_event != nullptr;
+  for (int c = 0; c < obj_n; ++c) can_defer = can_defer && !(class_budget < (double)(banks[c].n + hw));
+  if (can_defer) {
+    VFN_CUDA_OK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(defer_event), st));
+    if (int rc = launch_merge(uo, obj_n, hw, update_rate, st)) return rc;
+    UpdObj ao[4];
+    vfn_bank cb[4];
+    for (int c = 0; c < obj_n; ++c) {
+      ao[c] = uo[c];
+      ao[c].sel = io[c].d_append_q; ao[c].n_sel_dev = counts + 4 * c + 2; ao[c].n_sel = hw;   // grid bound; rows = *n_sel_dev
+      cb[c] = banks[c];
+      cb[c].n = banks[c].n + hw;            // clamp over an upper bound: rows beyond the live count are dead storage
+      io[c].deferred = 1;
+      io[c].n_merge = io[c].n_runs = io[c].n_append = -1;
+    }
+    if (int rc = launch_append(ao, obj_n, frame_idx, 0.f, st)) return rc;
+    if (int rc = launch_clamp(cb, obj_n, st)) return rc;
+    return VFN_OK;
+  }
   if (int rc = launch_merge(uo, obj_n, hw, update_rate, st)) return rc;
   VFN_CUDA_OK(cudaStreamSynchronize(st));                 // |merge|, |runs|, |append| per object (nonzero/unique syncs)
   bool any_evict = false;
@@ -172,6 +195,23 @@ int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_i
     if (int rc = launch_append(ao, n_a, frame_idx, 0.f, st)) return rc;
   if (n_c > 0)
     if (int rc = launch_clamp(cb, n_c, st)) return rc;
+  return VFN_OK;
+}
+
+int vfn_bank_update_finish(vfn_bank* banks, int32_t obj_n, vfn_update_io* io, const int32_t* h_pinned) {
+  VFN_CHECK_ARG(banks && io && h_pinned && obj_n >= 1 && obj_n <= 4, "bank_update_finish: bad args");
+  for (int c = 0; c < obj_n; ++c) {
+    if (!io[c].deferred) continue;
+    io[c].n_merge = h_pinned[4 * c + 0];
+    io[c].n_runs = h_pinned[4 * c + 1];
+    io[c].n_append = h_pinned[4 * c + 2];
+    VFN_CHECK_ARG(io[c].n_append >= 0 && banks[c].n + io[c].n_append <= banks[c].cap,
+                  "bank_update_finish: counts of object %d are not valid (was the event waited on?)", c);
+    banks[c].n += io[c].n_append;
+    io[c].deferred = 0;
+    // algorithmic bytes of the deferred append (the launch could only account an upper bound: it recorded 0)
+    vfn_profile_add_work(PROF_APPEND, 2.0 * 4.0 * (banks[c].d_key + banks[c].d_val + 2) * (double)io[c].n_append);
+  }
   return VFN_OK;
 }
 

@@ -157,6 +157,104 @@ __global__ void __launch_bounds__(URR_LOCAL_THREADS) urr_local_kernel(const floa
   }
 }
 
+// stage 3, streaming form (w % 4 == 0): same arithmetic as urr_local_kernel, organised for HBM bandwidth.
+// A warp owns 30 float4 columns (lanes 1..30; lanes 0 and 31 only carry the 3-pixel horizontal halo) of ONE channel and
+// streams down a band of rows: per input row it loads r1 and seg[o] as float4, forms r1*seg, gets the horizontal 7-tap
+// sums with six warp shuffles per object, and keeps the last seven row sums in a register ring for the vertical 7-tap.
+// No shared memory, no barriers; every global access is a 128-bit coalesced load/store; r1 is read once for all objects
+// of a pass (the reference's `expand`) and written once per object into [r1 ; r1_local].
+constexpr int UL_COLS = 30;          // float4 columns per warp
+constexpr int UL_WARPS = 4;
+template <int NO>
+__global__ void __launch_bounds__(UL_WARPS * 32) urr_local_stream_kernel(
+    const float* __restrict__ r1, int64_t r1_obj_stride, int c_n, int obj_n, int h, int w, int band,
+    const float* __restrict__ seg, const float* __restrict__ avg, float* __restrict__ lm) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int w4 = w >> 2;
+  const int x4 = (blockIdx.x * UL_WARPS + warp) * UL_COLS + lane - 1;
+  const bool col_ok = (x4 >= 0 && x4 < w4);
+  const bool out_lane = col_ok && lane >= 1 && lane <= UL_COLS;
+  const int ch = blockIdx.z % c_n, ob = (blockIdx.z / c_n) * NO;
+  const int no = min(NO, obj_n - ob);
+  const int y0 = blockIdx.y * band, y1 = min(h, y0 + band);
+  const int64_t plane4 = (int64_t)h * w4;
+  const float4* rp = reinterpret_cast<const float4*>(r1 + (int64_t)ob * r1_obj_stride) + (int64_t)ch * plane4 + x4;
+  const float4* sp = reinterpret_cast<const float4*>(seg) + (int64_t)ob * plane4 + x4;
+  const float4* ap = reinterpret_cast<const float4*>(avg) + (int64_t)ob * plane4 + x4;
+  float4* out = reinterpret_cast<float4*>(lm) + ((int64_t)ob * 2 * c_n + ch) * plane4 + x4;
+  const int64_t obj_out4 = (int64_t)2 * c_n * plane4, loc4 = (int64_t)c_n * plane4;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  float4 ring[NO][7];
+  float4 rring[4];                                  // r1 rows yin-3 .. yin
+#pragma unroll
+  for (int o = 0; o < NO; ++o)
+#pragma unroll
+    for (int r = 0; r < 7; ++r) ring[o][r] = z4;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) rring[r] = z4;
+
+  auto load_row = [&](int y, float4& rv, float4 (&sv)[NO]) {
+    const bool ok = col_ok && y >= 0 && y < h;
+    rv = ok ? __ldg(rp + (int64_t)y * w4) : z4;
+#pragma unroll
+    for (int o = 0; o < NO; ++o) sv[o] = (ok && o < no) ? __ldg(sp + (int64_t)o * plane4 + (int64_t)y * w4) : z4;
+  };
+  float4 rv, sv[NO];
+  load_row(y0 - UHALO, rv, sv);
+  for (int yin = y0 - UHALO; yin < y1 + UHALO; ++yin) {
+    float4 rn, sn[NO], av[NO];
+    load_row(yin + 1 < y1 + UHALO ? yin + 1 : -1, rn, sn);          // prefetch the next input row
+    const int yout = yin - UHALO;
+    const bool emit = out_lane && yout >= y0;
+#pragma unroll
+    for (int o = 0; o < NO; ++o) av[o] = (emit && o < no) ? __ldg(ap + (int64_t)o * plane4 + (int64_t)yout * w4) : z4;
+    rring[0] = rring[1]; rring[1] = rring[2]; rring[2] = rring[3]; rring[3] = rv;
+#pragma unroll
+    for (int o = 0; o < NO; ++o) {
+      // __fmul_rn: the products must round before the tap sums (no FMA contraction), as in the tiled kernel
+      const float4 c = make_float4(__fmul_rn(rv.x, sv[o].x), __fmul_rn(rv.y, sv[o].y), __fmul_rn(rv.z, sv[o].z),
+                                   __fmul_rn(rv.w, sv[o].w));   // AFB_URR.py:226
+      const float ly = __shfl_up_sync(0xffffffffu, c.y, 1), lz = __shfl_up_sync(0xffffffffu, c.z, 1),
+                  lw = __shfl_up_sync(0xffffffffu, c.w, 1);
+      const float rx = __shfl_down_sync(0xffffffffu, c.x, 1), ry = __shfl_down_sync(0xffffffffu, c.y, 1),
+                  rz = __shfl_down_sync(0xffffffffu, c.z, 1);
+      float4 hs;                                   // 7 taps, left to right (the order of urr_local_kernel)
+      hs.x = (((((ly + lz) + lw) + c.x) + c.y) + c.z) + c.w;
+      hs.y = (((((lz + lw) + c.x) + c.y) + c.z) + c.w) + rx;
+      hs.z = (((((lw + c.x) + c.y) + c.z) + c.w) + rx) + ry;
+      hs.w = (((((c.x + c.y) + c.z) + c.w) + rx) + ry) + rz;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) ring[o][r] = ring[o][r + 1];
+      ring[o][6] = hs;
+    }
+    if (emit) {
+      const float4 rc = rring[0];                  // r1 of the output row
+#pragma unroll
+      for (int o = 0; o < NO; ++o) {
+        if (o < no) {
+          float4 tot = ring[o][0];
+#pragma unroll
+          for (int r = 1; r < 7; ++r) {
+            tot.x += ring[o][r].x; tot.y += ring[o][r].y; tot.z += ring[o][r].z; tot.w += ring[o][r].w;
+          }
+          float4 res;                              // AFB_URR.py:227-228
+          res.x = (tot.x / 49.f) / (av[o].x + 1e-8f);
+          res.y = (tot.y / 49.f) / (av[o].y + 1e-8f);
+          res.z = (tot.z / 49.f) / (av[o].z + 1e-8f);
+          res.w = (tot.w / 49.f) / (av[o].w + 1e-8f);
+          float4* dst = out + (int64_t)o * obj_out4 + (int64_t)yout * w4;
+          __stcs(dst, rc);
+          __stcs(dst + loc4, res);
+        }
+      }
+    }
+    rv = rn;
+#pragma unroll
+    for (int o = 0; o < NO; ++o) sv[o] = sn[o];
+  }
+}
+
 // post: prob[o][Y][X] = softmax_c( bilinear_x2( p_up + unc * (conf * q_local) ) )[1]      AFB_URR.py:233-237
 __global__ void urr_post_kernel(const float* __restrict__ p_up, const float* __restrict__ unc,
                                 const float* __restrict__ conf, const float* __restrict__ ql, int obj_n, int h, int w,
@@ -198,7 +296,14 @@ __global__ void urr_post_kernel(const float* __restrict__ p_up, const float* __r
 
 using namespace vfn;
 
+static int g_urr_stream = 1;   // vfn_debug_set_urr_stream(0): tiled shared-memory kernel (cross-check in tests/)
+
 extern "C" {
+
+int vfn_debug_set_urr_stream(int32_t on) {
+  g_urr_stream = on ? 1 : 0;
+  return VFN_OK;
+}
 
 int vfn_urr_pre(const float* d_p, const float* d_r1, int64_t r1_obj_stride, int32_t obj_n, int32_t c, int32_t h,
                 int32_t w, float* d_p_up, float* d_seg, float* d_unc, float* d_conf, float* d_avg,
@@ -214,7 +319,29 @@ int vfn_urr_pre(const float* d_p, const float* d_r1, int64_t r1_obj_stride, int3
   urr_window_kernel<<<g2, 128, 0, st>>>(d_seg, obj_n, h, w, d_conf, d_avg);
   dim3 g3((unsigned)cdiv(w, UT_W), (unsigned)cdiv(h, UT_H), c);
   prof_begin(PROF_URR, st);
-  urr_local_kernel<<<g3, URR_LOCAL_THREADS, 0, st>>>(d_r1, r1_obj_stride, c, obj_n, h, w, d_seg, d_avg, d_local_match);
+  if (w % 4 == 0 && g_urr_stream) {
+    // streaming kernel: bands of rows sized so that the grid holds a few CTAs per SM; halo cost 6 / band input rows
+    // band height: one wave of CTAs (4 resident per SM at 119 registers) where that keeps bands >= 8 rows
+    const int no = (r1_obj_stride == 0 && obj_n >= 2) ? 2 : 1;
+    const int64_t per_band = cdiv(w / 4, UL_WARPS * UL_COLS) * c * cdiv(obj_n, no);
+    static int sms = 0;
+    if (sms == 0) {
+      int dev = 0;
+      VFN_CUDA_OK(cudaGetDevice(&dev));
+      VFN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    int64_t n_bands = (int64_t)sms * 4 / per_band;
+    if (n_bands < 1) n_bands = 1;
+    int band = (int)cdiv(h, n_bands);
+    if (band < 8) band = 8;
+    dim3 gs((unsigned)cdiv(w / 4, UL_WARPS * UL_COLS), (unsigned)cdiv(h, band), (unsigned)(c * cdiv(obj_n, no)));
+    if (no == 2)
+      urr_local_stream_kernel<2><<<gs, UL_WARPS * 32, 0, st>>>(d_r1, r1_obj_stride, c, obj_n, h, w, band, d_seg, d_avg, d_local_match);
+    else
+      urr_local_stream_kernel<1><<<gs, UL_WARPS * 32, 0, st>>>(d_r1, r1_obj_stride, c, obj_n, h, w, band, d_seg, d_avg, d_local_match);
+  } else {
+    urr_local_kernel<<<g3, URR_LOCAL_THREADS, 0, st>>>(d_r1, r1_obj_stride, c, obj_n, h, w, d_seg, d_avg, d_local_match);
+  }
   // algorithmic bytes: read r1 once, write [r1 ; r1_local] per object, + small planes
   prof_end(PROF_URR, st, 4.0 * (double)h * w * ((r1_obj_stride ? obj_n : 1) * (double)c + obj_n * (2.0 * c + 8.0)));
   VFN_LAUNCH_OK();

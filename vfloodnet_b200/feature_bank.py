@@ -72,6 +72,7 @@ class _ViewList:
             return [self[j] for j in range(*i.indices(len(self)))]
         if i < 0:
             i += len(self)
+        self._fb._resolve()
         s, n = self._fb._slabs[i], self._fb._n[i]
         if s is None:
             return None
@@ -100,7 +101,7 @@ class FeatureBank:
         if self.device.type != 'cuda':
             raise ValueError('vfloodnet_b200.FeatureBank lives in GPU memory; device must be a CUDA device '
                              '(there is no CPU fallback)')
-        self.peak_n = np.zeros(obj_n)
+        self._peak_n = np.zeros(obj_n)
         self.replace_n = np.zeros(obj_n)
         self.class_budget = memory_budget // obj_n              # FeatureBank.py:20
         if obj_n == 2:
@@ -113,8 +114,14 @@ class FeatureBank:
         self._scratch = {}
         self._h_plan = torch.zeros((obj_n, 72), dtype=torch.int32).pin_memory()
         self._h_pinned = torch.zeros((obj_n * 80,), dtype=torch.int32).pin_memory()
-        self.last_decisions = [None] * obj_n    # device tensors of the last update (tests / debugging)
+        self._last_decisions = [None] * obj_n   # device tensors of the last update (tests / debugging)
         self.launches = 0                       # kernels launched by this bank (bench accounting)
+        # deferred completion of update() (vfn.h: vfn_bank_update / vfn_bank_update_finish): the event is recorded when
+        # the counts of the update are on their way to pinned memory; _resolve() waits on it the next time a bank size
+        # is needed (normally the next frame's read), instead of draining the stream at the end of every update
+        self.defer = True
+        self._event = None
+        self._pending = None
 
     # ---- reference attribute surface -------------------------------------------------------------
     @property
@@ -129,11 +136,39 @@ class FeatureBank:
     def info(self):
         return _ViewList(self, 'info')
 
+    @property
+    def peak_n(self):
+        self._resolve()
+        return self._peak_n
+
+    @property
+    def last_decisions(self):
+        self._resolve()
+        return self._last_decisions
+
     def bank_n(self, class_idx: int) -> int:
+        self._resolve()
         return self._n[class_idx]
 
     def bank_struct(self, class_idx: int) -> VfnBank:
+        self._resolve()
         return self._slabs[class_idx].struct(self._n[class_idx])
+
+    def _resolve(self):
+        """complete a deferred update(): wait for its counts, advance the bank sizes (FeatureBank.py:105-113)"""
+        pend = self._pending
+        if pend is None:
+            return
+        self._pending = None
+        banks, io, dec = pend
+        self._event.synchronize()
+        check(self._lib.vfn_bank_update_finish(banks, self.obj_n, io, self._h_pinned.data_ptr()), 'bank_update_finish')
+        for c in range(self.obj_n):
+            r = io[c]
+            self._n[c] = int(banks[c].n)
+            self._peak_n[c] = max(self._peak_n[c], self._n[c])                       # FeatureBank.py:113
+            self._last_decisions[c] = dict(n_merge=int(r.n_merge), n_runs=int(r.n_runs), n_append=int(r.n_append),
+                                           evicted=False, **dec[c])
 
     def bank_array(self):
         arr = (VfnBank * self.obj_n)()
@@ -175,6 +210,7 @@ class FeatureBank:
 
     def _ingest(self, c: int, key_dm: torch.Tensor, val_dm: torch.Tensor, info0: float, info1: float):
         """append all columns of (d, n) tensors as new slots (init_bank / append)."""
+        self._resolve()
         lib, st = self._lib, stream_ptr()
         key_dm = key_dm.to(self.device, torch.float32).contiguous()
         val_dm = val_dm.to(self.device, torch.float32).contiguous()
@@ -190,11 +226,12 @@ class FeatureBank:
                                        float(info1), st), 'append_rows')
         self.launches += 3
         self._n[c] += n_new
-        self.peak_n[c] = max(self.peak_n[c], self._n[c])
+        self._peak_n[c] = max(self._peak_n[c], self._n[c])
 
     # ---- reference methods -----------------------------------------------------------------------
     def init_bank(self, keys, values, frame_idx=0):
         """FeatureBank.py:27-36.  keys[i]: (d_key, n), values[i]: (d_val, n); copied into the slabs."""
+        self._resolve()
         for c in range(self.obj_n):
             self._slabs[c], self._alt[c], self._n[c] = None, None, 0
             self._ingest(c, keys[c], values[c], frame_idx, 0.0)
@@ -212,6 +249,7 @@ class FeatureBank:
         into the library (vfn_bank_update orders the kernel launches in C++)."""
         if update_rate == -1:
             update_rate = self.update_rate
+        self._resolve()
         lib, st = self._lib, stream_ptr()
         obj_n = self.obj_n
         pk = [prev_key[c].to(self.device, torch.float32).contiguous() for c in range(obj_n)]
@@ -248,10 +286,19 @@ class FeatureBank:
         ws_bytes = lib.vfn_bank_update_workspace_bytes(obj_n, n_max, hw, d_key, d_val)
         ws = self._buf('upd_ws', (ws_bytes,), torch.uint8)
         l0 = lib.vfn_launch_count()
+        ev = None
+        if self.defer:
+            if self._event is None:
+                self._event = torch.cuda.Event()
+                self._event.record()                  # creates the underlying cudaEvent_t
+            ev = self._event.cuda_event
         check(lib.vfn_bank_update(banks, alts, obj_n, io, hw, float(frame_idx), float(update_rate),
                                   float(self.thres_close), float(self.class_budget), ptr(ws), ws.numel(),
-                                  self._h_pinned.data_ptr(), self.impl, st), 'bank_update')
+                                  self._h_pinned.data_ptr(), self.impl, ev, st), 'bank_update')
         self.launches += lib.vfn_launch_count() - l0
+        if io[0].deferred:
+            self._pending = (banks, io, dec)
+            return
         err = None
         for c in range(obj_n):
             r = io[c]
@@ -268,13 +315,14 @@ class FeatureBank:
                 self._slabs[c], self._alt[c] = self._alt[c], self._slabs[c]
                 self.replace_n[c] += r.n_before - r.kept                         # FeatureBank.py:140-141
             self._n[c] = int(banks[c].n)
-            self.peak_n[c] = max(self.peak_n[c], self._n[c])                       # FeatureBank.py:113
-            self.last_decisions[c] = dict(n_merge=int(r.n_merge), n_runs=int(r.n_runs), n_append=int(r.n_append),
-                                          evicted=bool(r.evicted), **dec[c])
+            self._peak_n[c] = max(self._peak_n[c], self._n[c])                       # FeatureBank.py:113
+            self._last_decisions[c] = dict(n_merge=int(r.n_merge), n_runs=int(r.n_runs), n_append=int(r.n_append),
+                                           evicted=bool(r.evicted), **dec[c])
         if err is not None:
             raise err
 
     def _launch_evict_plan(self, c: int, request_n: int, frame_idx):
+        self._resolve()
         lib, st = self._lib, stream_ptr()
         s, n = self._slabs[c], self._n[c]
         lfu = self._buf(f'lfu{c}', (max(n, 1),), torch.float32)
@@ -327,6 +375,7 @@ class FeatureBank:
     # ---- test / parity helpers (not in the reference) ---------------------------------------------
     def load_state(self, keys, values, info):
         """Teacher forcing: overwrite the bank with (d,N) keys/values and (N,2) info tensors."""
+        self._resolve()
         for c in range(self.obj_n):
             self._slabs[c], self._alt[c], self._n[c] = None, None, 0
             self._ingest(c, keys[c], values[c], 0.0, 0.0)
