@@ -5,7 +5,7 @@ tag=${1:-r1}
 out=gpurun_out/$tag
 mkdir -p $out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/smi.txt 2>&1
-timeout 600 python -m pytest tests -m gpu -x -q > $out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $out/pytest_gpu.log
+timeout 600 python -m pytest tests -m gpu -q > $out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $out/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $out/smoke.log
 for n in 1620 25000 100000; do timeout 300 python tests/profile_kernels.py $n 1620 5; done > $out/profile_kernels.log 2>&1
 timeout 600 python bench.py > $out/bench.json 2> $out/bench.err; echo "bench rc=$?"

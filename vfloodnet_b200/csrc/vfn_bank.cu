@@ -50,6 +50,7 @@ void count_launches(int n) { g_launches += n; }
 // hi/lo receive the split of raw*scale, or of normalised*scale when `split_normed` is set.
 // ------------------------------------------------------------------------------------------------
 constexpr int PREP_MAX_JOBS = 16;
+constexpr int PREP_CHUNK = 128;
 struct PrepJobs { PrepJob j[PREP_MAX_JOBS]; };
 
 __global__ void __launch_bounds__(256) prep_rows_kernel(const __grid_constant__ PrepJobs jobs) {
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const __grid_constant__ 
   const int64_t n = jb.n;
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int64_t q0 = (int64_t)blockIdx.x * 32;
-  if (q0 >= n) return;
+  if (q0 >= n || (int)blockIdx.z * PREP_CHUNK >= d) return;
   const int64_t q = q0 + tx;
   if (jb.normed || jb.split_normed) {
     float ss = 0.f;
@@ -81,7 +82,10 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const __grid_constant__ 
     }
     __syncthreads();
   }
-  for (int k0 = 0; k0 < d; k0 += 32) {
+  // blockIdx.z takes PREP_CHUNK of the d rows (the norm above is over all of them: cheap re-reads from L2), so that a
+  // 512-channel job spreads over four times as many CTAs as a 128-channel one
+  const int k_end = min(d, (int)(blockIdx.z + 1) * PREP_CHUNK);
+  for (int k0 = blockIdx.z * PREP_CHUNK; k0 < k_end; k0 += 32) {
     for (int r = ty; r < 32; r += 8) {
       int k = k0 + r;
       tile[r][tx] = (k < d && q < n) ? src[(int64_t)k * n + q] : 0.f;
@@ -113,9 +117,14 @@ int launch_prep(const PrepJob* jobs, int n_jobs, cudaStream_t st) {
   VFN_CHECK_ARG(n_jobs >= 1 && n_jobs <= PREP_MAX_JOBS, "prep: too many jobs");
   PrepJobs pj;
   int64_t n_max = 0;
-  for (int i = 0; i < n_jobs; ++i) { pj.j[i] = jobs[i]; if (jobs[i].n > n_max) n_max = jobs[i].n; }
+  int d_max = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    pj.j[i] = jobs[i];
+    if (jobs[i].n > n_max) n_max = jobs[i].n;
+    if (jobs[i].d > d_max) d_max = jobs[i].d;
+  }
   if (n_max == 0) return VFN_OK;
-  dim3 block(32, 8), grid((unsigned)cdiv(n_max, 32), n_jobs);
+  dim3 block(32, 8), grid((unsigned)cdiv(n_max, 32), n_jobs, (unsigned)cdiv(d_max, PREP_CHUNK));
   prep_rows_kernel<<<grid, block, 0, st>>>(pj);
   VFN_LAUNCH_OK();
   count_launches(1);

@@ -459,6 +459,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const __grid_con
       float m_run = -INFINITY, l_run = 0.f;
       int cnt = 0;
       float2* ring = aux + et * MATCH_RING;
+      const bool row_live = qt * QT + row < args.hw;
       for (int t = 0; t < ntile; ++t) {
         const uint32_t c = tile_ctr + t, st = c % SC_BUFS, ph = (c / SC_BUFS) & 1;
         mbar_wait(&s_full[st], ph);
@@ -499,9 +500,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const __grid_con
         } else {
           // candidates = every slot whose score is within `band` of the running maximum at its time; a jump of the
           // maximum by more than the band invalidates everything before it
+          // (rows beyond hw are zero A rows: every slot ties at score 0 and would take the slow path for nothing)
           if (cm > m_run + args.band) cnt = 0;
           const float m_new = fmaxf(m_run, cm);
-          const float thr = m_new - args.band;
+          const float thr = row_live ? m_new - args.band : INFINITY;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float sv = __uint_as_float(v[i]);
@@ -675,6 +677,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       float m_run = -INFINITY, l_run = 0.f;
       int cnt = 0;
       float2* ring = aux + et * MATCH_RING;
+      const bool row_live = qt * QT + row < args.hw;
       for (int t = 0; t < ntile; ++t) {
         const uint32_t c = tile_ctr + t, st = c % SC_BUFS, ph = (c / SC_BUFS) & 1;
         mbar_wait(&s_full[st], ph);
@@ -715,9 +718,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         } else {
           // candidates = every slot whose score is within `band` of the running maximum at its time; a jump of the
           // maximum by more than the band invalidates everything before it
+          // (rows beyond hw are zero A rows: every slot ties at score 0 and would take the slow path for nothing)
           if (cm > m_run + args.band) cnt = 0;
           const float m_new = fmaxf(m_run, cm);
-          const float thr = m_new - args.band;
+          const float thr = row_live ? m_new - args.band : INFINITY;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float sv = __uint_as_float(v[i]);

@@ -169,12 +169,16 @@ template <int NO>
 __global__ void __launch_bounds__(UL_WARPS * 32) urr_local_stream_kernel(
     const float* __restrict__ r1, int64_t r1_obj_stride, int c_n, int obj_n, int h, int w, int band,
     const float* __restrict__ seg, const float* __restrict__ avg, float* __restrict__ lm) {
+  // the warps of a CTA take DIFFERENT channels of the same (band, column range): their seg / avg loads coincide and are
+  // served by L1 after the first warp's miss (seg and avg are re-read by every channel: 4 planes x 64 channels)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int w4 = w >> 2;
-  const int x4 = (blockIdx.x * UL_WARPS + warp) * UL_COLS + lane - 1;
+  const int x4 = blockIdx.x * UL_COLS + lane - 1;
   const bool col_ok = (x4 >= 0 && x4 < w4);
   const bool out_lane = col_ok && lane >= 1 && lane <= UL_COLS;
-  const int ch = blockIdx.z % c_n, ob = (blockIdx.z / c_n) * NO;
+  const int cgroups = (c_n + UL_WARPS - 1) / UL_WARPS;
+  const int ch = (blockIdx.z % cgroups) * UL_WARPS + warp, ob = (blockIdx.z / cgroups) * NO;
+  if (ch >= c_n) return;
   const int no = min(NO, obj_n - ob);
   const int y0 = blockIdx.y * band, y1 = min(h, y0 + band);
   const int64_t plane4 = (int64_t)h * w4;
@@ -323,7 +327,7 @@ int vfn_urr_pre(const float* d_p, const float* d_r1, int64_t r1_obj_stride, int3
     // streaming kernel: bands of rows sized so that the grid holds a few CTAs per SM; halo cost 6 / band input rows
     // band height: one wave of CTAs (4 resident per SM at 119 registers) where that keeps bands >= 8 rows
     const int no = (r1_obj_stride == 0 && obj_n >= 2) ? 2 : 1;
-    const int64_t per_band = cdiv(w / 4, UL_WARPS * UL_COLS) * c * cdiv(obj_n, no);
+    const int64_t per_band = cdiv(w / 4, UL_COLS) * cdiv(c, UL_WARPS) * cdiv(obj_n, no);
     static int sms = 0;
     if (sms == 0) {
       int dev = 0;
@@ -334,7 +338,7 @@ int vfn_urr_pre(const float* d_p, const float* d_r1, int64_t r1_obj_stride, int3
     if (n_bands < 1) n_bands = 1;
     int band = (int)cdiv(h, n_bands);
     if (band < 8) band = 8;
-    dim3 gs((unsigned)cdiv(w / 4, UL_WARPS * UL_COLS), (unsigned)cdiv(h, band), (unsigned)(c * cdiv(obj_n, no)));
+    dim3 gs((unsigned)cdiv(w / 4, UL_COLS), (unsigned)cdiv(h, band), (unsigned)(cdiv(c, UL_WARPS) * cdiv(obj_n, no)));
     if (no == 2)
       urr_local_stream_kernel<2><<<gs, UL_WARPS * 32, 0, st>>>(d_r1, r1_obj_stride, c, obj_n, h, w, band, d_seg, d_avg, d_local_match);
     else

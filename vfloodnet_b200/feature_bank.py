@@ -116,6 +116,8 @@ class FeatureBank:
         self._h_pinned = torch.zeros((obj_n * 80,), dtype=torch.int32).pin_memory()
         self._last_decisions = [None] * obj_n   # device tensors of the last update (tests / debugging)
         self.launches = 0                       # kernels launched by this bank (bench accounting)
+        self.last_thresholds = []               # T sequence of the last remove() (tests / debugging)
+        self.last_thresholds_obj = [None] * obj_n
         # deferred completion of update() (vfn.h: vfn_bank_update / vfn_bank_update_finish): the event is recorded when
         # the counts of the update are on their way to pinned memory; _resolve() waits on it the next time a bank size
         # is needed (normally the next frame's read), instead of draining the stream at the end of every update
@@ -304,6 +306,7 @@ class FeatureBank:
             r = io[c]
             if r.evicted:
                 self.last_thresholds = [int(r.thresholds[k]) for k in range(r.n_iter)]
+                self.last_thresholds_obj[c] = list(self.last_thresholds)
                 if r.evict_status == 1:
                     err = err or RuntimeError('FeatureBank.remove: every entry was evicted and the budget is still '
                                               'exceeded (the reference raises on LFU.min() of an empty tensor, '
