@@ -42,7 +42,10 @@ def test_constant_values_read_back_at_full_size(vfn, hw, n):
     dev = torch.device('cuda')
     g = torch.Generator().manual_seed(hw)
     keys, vals, info = [], [], []
-    consts = torch.linspace(-3.0, 3.0, 512)
+    # per-channel constants at the scale of real value features (regime B value norm ~27): object 1's
+    # columns have norm 31.  Constant columns are the worst case for the split-operand readout: every slot carries the
+    # SAME fp16/fp8 rounding residue and the tensor core's truncating accumulation has one sign, nothing averages out.
+    consts = torch.linspace(-1.2, 1.2, 512)
     for c in range(2):
         k, _ = _bank(g, n - 17 * c, dev)
         keys.append(k)

@@ -1505,14 +1505,17 @@ static int g_pair = 3;    // bit 0: CTA-pair (cta_group::2) phase B, bit 1: CTA-
 bool tc_shapes_ok(int d_key, int d_val) { return d_key == DK && d_val == DV; }
 
 constexpr int TC_MAX_SPLIT = 24;
+constexpr int B_CHAIN_MAX = 8192;      // slots accumulated into one TMEM readout accumulator (see tc_phase_b)
 
 // number of slot splits per (object, query tile[, half]) combo: minimise rounds x (tiles per item + fixed per-item
 // overhead) for `combos` combos dealt round-robin to G persistent CTAs; every item keeps at least one tile.
-static int best_split(int combos, int64_t tiles_min, int64_t tiles_max, int overhead_tiles, int G = 0) {
+static int best_split(int combos, int64_t tiles_min, int64_t tiles_max, int overhead_tiles, int G = 0, int s_min = 1) {
   if (G <= 0) G = num_sms();
-  int best = 1;
+  if (s_min > TC_MAX_SPLIT) s_min = TC_MAX_SPLIT;
+  if (s_min > tiles_min) s_min = (int)(tiles_min > 1 ? tiles_min : 1);
+  int best = s_min;
   double best_cost = 1e30;
-  for (int s = 1; s <= TC_MAX_SPLIT && s <= tiles_min; ++s) {
+  for (int s = s_min; s <= TC_MAX_SPLIT && s <= tiles_min; ++s) {
     const int64_t rounds = cdiv((int64_t)combos * s, G);
     const double cost = (double)rounds * (double)(cdiv(tiles_max, s) + overhead_tiles);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
@@ -1625,7 +1628,12 @@ int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const 
   }
   const bool pair = (g_pair & 1) && (num_sms() % 2 == 0);
   const int combos = pair ? obj_n * 2 * (int)cdiv(hw, 2 * QT) : obj_n * 2 * (int)cdiv(hw, QT);
-  const int pieces = best_split(combos, tmin, tmax, 4, pair ? num_sms() / 2 : num_sms());
+  // The tensor core accumulates with truncation (a systematic -2^-25 relative per accumulation step, measured through
+  // the match scores and through constant-value banks in tests/test_gpu_fullsize.py): one TMEM accumulator must not
+  // run over more than B_CHAIN_MAX slots (512 + 256 accumulation steps -> bias < 5e-5 relative); longer banks are cut
+  // into at least that many pieces, whose partials are added in fp32 round-to-nearest by combine_out_kernel.
+  const int s_min = (int)cdiv(tmax * B_TILE, B_CHAIN_MAX);
+  const int pieces = best_split(combos, tmin, tmax, 4, pair ? num_sms() / 2 : num_sms(), s_min);
   if (pieces > split_b) { set_error("phase B: split %d exceeds workspace bound %d", pieces, split_b); return VFN_E_CAPACITY; }
   *pieces_out = pieces;
   if (int rc = fill_args(banks, obj_n, hw, pieces, B_TILE, ws_tc, &maps, &a, true, pair ? 32 : B_TILE)) return rc;
