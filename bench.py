@@ -26,6 +26,12 @@ HW_H, HW_W = 30, 54          # r4 grid of a 480x864 padded frame  (HW 
 R1_H, R1_W = 240, 432
 D_KEY, D_VAL = 128, 512
 BUDGET = 250000               # test_video_seg.py:24  -> class_budget 100000.0
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE tc_phase_b_pair_kernel launch, from the committed `ncu --set full`
+# capture (profiles/r1h_ncu_summary.md): N = 100000 slots/object, 2 objects, HW = 1620.  The operand arrays that launch
+# has to stream once are 2560 B/slot (kh, kl, vh, v8, vl) = 512 MB; its algorithmic work is 3.32e11 flop.
+NCU_PHASE_B_TRAFFIC = {'bytes': 600.24e6 + 86.58e6,
+                       'note': 'per launch at N=100000 slots/object (ncu capture profiles/r1h_ncu_summary.md); operand '
+                               'bytes streamed once = 512 MB; the bench launches average fewer slots'}
 METRIC = '480p frames/sec (1/2/4/8 B200); mem-read tensor util; bank-update HBM GB/s'
 
 
@@ -70,11 +76,13 @@ def to_device(clip, dev):
                 urr=tuple(D(t) for t in clip['urr']))
 
 
-def run_clip_gpu(vfn, clip, dev, read_impl, host_inputs=False, out_host=None):
+def run_clip_gpu(vfn, clip, dev, read_impl, host_inputs=False, out_host=None, exact_sizes=False):
     """one step: the whole clip through the drop-in API.  Returns (bank, last readout, last refined mask).
     host_inputs: every frame's tensors start in pinned HOST memory; their H2D copies are issued on a side stream one
     frame ahead (double buffering) and the refined mask is copied back to the host every frame."""
     fb = vfn.FeatureBank(2, BUDGET, dev, impl=read_impl)
+    if exact_sizes:
+        fb.defer = False
     m = vfn.Matcher(update_bank=True)
     cur = torch.cuda.current_stream(dev)
     if host_inputs:
@@ -276,7 +284,8 @@ def main_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    lib.vfn_profile_enable(1)
+    # timed region: K clips, no per-kernel events (bracketing every kernel with timing events serialises the stream:
+    # profiles/r1h measured 1.48 ms/frame with them against 1.16 ms without)
     l0 = lib.vfn_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -287,11 +296,21 @@ def main_ours(args, rank, world, local_rank):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = lib.vfn_launch_count() - l0
+    final_n = [fb.bank_n(c) for c in range(2)]
+    # roofline pass: the same K clips again with the library's CUDA events around each dominant kernel (recorded on the
+    # launching stream), bank sizes read back every frame so that the algorithmic work per launch is exact
+    lib.vfn_profile_enable(1)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(args.steps):
+        run_clip_gpu(vfn, dev_clip, dev, args.read_impl, exact_sizes=True)
+    p1.record()
+    torch.cuda.synchronize()
+    ms_prof = p0.elapsed_time(p1)
     prof = (ctypes.c_double * 24)()
     _lib.check(lib.vfn_profile_collect(prof, 8), 'profile_collect')
     lib.vfn_profile_enable(0)
     sampler.stop_flag = True
-    final_n = [fb.bank_n(c) for c in range(2)]
 
     # e2e: host inputs, copies inside the timed region
     for _ in range(1):
@@ -340,7 +359,11 @@ def main_ours(args, rank, world, local_rank):
     ach = (wb / (msb * 1e-3) / 1e12) if msb > 0 else 0.0
     roofline = {'bound': 'tensor', 'kernel': 'tc_phase_b_kernel (read phase B: P=softmax, O+=P.V, usage counts)',
                 'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': ach / tf_peak if tf_peak else None,
-                'traffic': None, 'peak_source': peak_src, 'launches': int(nb), 'avg_ms': msb / nb if nb else None,
+                'traffic': NCU_PHASE_B_TRAFFIC['bytes'], 'traffic_note': NCU_PHASE_B_TRAFFIC['note'],
+                'peak_source': peak_src, 'launches': int(nb), 'avg_ms': msb / nb if nb else None,
+                'timing': 'CUDA events around each launch, in a second pass over the same K clips (ms_per_step_profiled); '
+                          'the timed region itself carries no per-kernel events',
+                'ms_per_step_profiled': ms_prof / args.steps,
                 'algorithmic_flop_per_launch': wb / nb if nb else None,
                 'read_total': {'achieved': ((wa + wb) / ((msa + msb) * 1e-3) / 1e12) if msa + msb > 0 else 0.0,
                                'phase_a_avg_ms': msa / na if na else None, 'unit': 'TFLOP/s'}}
