@@ -51,6 +51,15 @@ typedef struct vfn_bank {
   uint8_t* v8;     /* (cap, d_val)  e4m3(value)        - partner of the P-residual pass */
   uint8_t* vl;     /* (cap, d_val)  e5m2(value - vh)   - partner of the e4m3(P) pass */
   int32_t* cnt;    /* (cap)         usage-count scratch, all zero between reads */
+  /* Device-resident live count (optional; NULL = `n` is exact and the kernels use it).  n_live[0] = live slots,
+   * n_live[1] = count staged by the update in flight.  When non-NULL the kernels take the live count from n_live[0]
+   * and the host fields become bounds: n_min <= n_live[0] <= n.  `n` sizes grids and workspaces, `n_min` bounds the
+   * work partition.  This lets a caller queue read(t+1) behind update(t) without reading |A| back first
+   * (the reference's nonzero() sync, FeatureBank.py:100).  tcgen05 paths only (d_key=128, d_val=512, impl != 1).
+   * vfn_bank_update keeps n_live current on every path; after vfn_bank_append_rows / vfn_bank_compact called directly,
+   * call vfn_bank_set_live. */
+  int32_t* n_live;
+  int64_t n_min;
 } vfn_bank;
 
 int vfn_version(void);
@@ -74,6 +83,9 @@ int vfn_prep_rows(const float* d_src_dm, int32_t d, int64_t n, float* d_raw_em, 
 int vfn_bank_append_rows(const vfn_bank* bank, const float* d_ck_em, const float* d_cv_em, const float* d_nck_em,
                          const int32_t* d_sel, int64_t n_sel_upper, const int32_t* d_n_sel, float info0, float info1,
                          void* stream);
+
+/* n_live[0] = n_live[1] = n (one tiny kernel on `stream`); no-op when bank->n_live is NULL */
+int vfn_bank_set_live(const vfn_bank* bank, int64_t n, void* stream);
 
 /* Recompute derived arrays (nk, nkh/nkl, kh/kl, vh/v8/vl) of slots [first, first+count) from keys/values. */
 int vfn_bank_refresh(const vfn_bank* bank, int64_t first, int64_t count, void* stream);
@@ -109,7 +121,9 @@ int vfn_bank_match(const vfn_bank* bank, const float* d_nck_em, int64_t hw, int3
 
 /* plan: from (j*, c*) build   merge set S = {q : c*>thres} as (slot,q) pairs sorted by (slot, q),
  * run offsets of equal-slot runs (= unique touched slots, ascending), append set A = {q : c*<=thres} ascending.
- * d_counts[0..3] = {n_merge, n_runs, n_append, 0}; also copied to h_counts (pinned) if non-NULL.
+ * d_counts[0..3] = {n_merge, n_runs, n_append, n_next}; also copied to h_counts (pinned) if non-NULL.
+ * n_next = live count after the append = n_live[0] + n_append when the plan is run for a bank with a device-resident
+ * count (vfn_bank_update), else 0.
  * Replaces nonzero / unique / index plumbing of FeatureBank.py:71-73,100. */
 size_t vfn_bank_plan_workspace_bytes(int64_t hw);
 int vfn_bank_plan(const int32_t* d_match_idx, const float* d_match_corr, int64_t hw, float thres_close,
@@ -176,11 +190,16 @@ size_t vfn_bank_update_workspace_bytes(int32_t obj_n, int64_t n_max, int64_t hw,
  * (n + hw <= class_budget for all objects, so FeatureBank.py:102 cannot fire) does NOT synchronise the stream: the
  * event is recorded once the counts are on their way to h_pinned, io[c].deferred is set, banks[c].n is left unchanged,
  * and the caller completes the update with vfn_bank_update_finish() after cudaEventSynchronize(defer_event), before
- * anything else touches the banks or h_pinned.  Updates that may evict keep the reference's synchronous behaviour. */
+ * anything else touches the banks or h_pinned.  Updates that may evict keep the reference's synchronous behaviour.
+ * Banks with a device-resident count (n_live) may be passed with n = upper bound / n_min = lower bound: the deferral
+ * test uses the upper bound, every kernel of the update reads the live count on the device, and the caller may issue
+ * the next read and the next update (bounds advanced by hw) without finishing this one. */
 int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_io* io, int64_t hw, float frame_idx,
                     float update_rate, float thres_close, double class_budget, void* d_ws, size_t ws_bytes,
                     int32_t* h_pinned, int32_t impl, void* defer_event, void* stream);
-/* host-only: reads |merge|, |runs|, |append| of a deferred update from h_pinned, fills io and advances banks[c].n */
+/* host-only: reads |merge|, |runs|, |append| of a deferred update from h_pinned, fills io and advances banks[c].n
+ * (banks with n_live: sets n = n_min = the exact live count the plan kernel staged, so any number of deferred updates
+ * may be in flight and only the last one is finished). */
 int vfn_bank_update_finish(vfn_bank* banks, int32_t obj_n, vfn_update_io* io, const int32_t* h_pinned);
 
 /* ---- URR: non-convolution parts of Decoder.forward (AFB_URR.py:214-237, myutils/data.py:42-48) -----

@@ -37,13 +37,42 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     from vfloodnet_b200._lib import VfnBank, VfnUpdateIO
-    # 2 x int32, 2 x int64, 12 pointers
-    assert ctypes.sizeof(VfnBank) == 8 + 16 + 12 * 8
+    # 2 x int32, 2 x int64, 12 pointers, n_live pointer, n_min int64
+    assert ctypes.sizeof(VfnBank) == 8 + 16 + 12 * 8 + 16
     assert VfnBank.keys.offset == 24 and VfnBank.cnt.offset == 24 + 11 * 8
+    assert VfnBank.n_live.offset == 24 + 12 * 8 and VfnBank.n_min.offset == 24 + 13 * 8
     # 8 pointers, 8 + 64 int32, 1 int64, 2 int32
     assert ctypes.sizeof(VfnUpdateIO) == 8 * 8 + 72 * 4 + 8 + 8
     assert VfnUpdateIO.thresholds.offset == 8 * 8 + 8 * 4 and VfnUpdateIO.n_before.offset == 8 * 8 + 72 * 4
     assert VfnUpdateIO.deferred.offset == 8 * 8 + 72 * 4 + 8
+
+
+def test_struct_layout_against_the_c_compiler(tmp_path):
+    """sizeof / offsetof as gcc sees include/vfn.h == the ctypes mirror"""
+    import os
+    import shutil
+    import subprocess
+    from vfloodnet_b200._lib import VfnBank, VfnUpdateIO
+    if shutil.which('gcc') is None:
+        import pytest
+        pytest.skip('gcc not available')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fields_b = [f[0] for f in VfnBank._fields_]
+    fields_u = [f[0] for f in VfnUpdateIO._fields_]
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "vfn.h"\nint main(void){\n'
+    src += 'printf("%zu\\n", sizeof(vfn_bank));\n'
+    src += ''.join(f'printf("%zu\\n", offsetof(vfn_bank, {f}));\n' for f in fields_b)
+    src += 'printf("%zu\\n", sizeof(vfn_update_io));\n'
+    src += ''.join(f'printf("%zu\\n", offsetof(vfn_update_io, {f}));\n' for f in fields_u)
+    src += 'return 0;}\n'
+    c = tmp_path / 'layout.c'
+    c.write_text(src)
+    exe = tmp_path / 'layout'
+    subprocess.check_call(['gcc', '-I', os.path.join(root, 'include'), str(c), '-o', str(exe)])
+    vals = [int(v) for v in subprocess.check_output([str(exe)], text=True).split()]
+    want = [ctypes.sizeof(VfnBank)] + [getattr(VfnBank, f).offset for f in fields_b]
+    want += [ctypes.sizeof(VfnUpdateIO)] + [getattr(VfnUpdateIO, f).offset for f in fields_u]
+    assert vals == want
 
 
 def test_argument_errors_are_reported_not_fatal():

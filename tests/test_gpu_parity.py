@@ -276,7 +276,7 @@ def test_deferred_update_equals_synchronous(vfn):
             outs.append(m(fb, q_in.cuda(), q_out.cuda()))
             fb.update([k.cuda() for k in pk], [v.cuda() for v in pv], t + 1)
             if defer and t < 3:
-                assert fb._pending is not None           # really deferred while the budget is far away
+                assert len(fb._pending) > 0              # really deferred while the budget is far away
             sizes.append([fb.bank_n(c) for c in range(2)])
         res.append((fb, outs, sizes))
     (fa, oa, sa), (fb_, ob, sb) = res
@@ -288,6 +288,43 @@ def test_deferred_update_equals_synchronous(vfn):
         assert torch.equal(fa.keys[c], fb_.keys[c]) and torch.equal(fa.values[c], fb_.values[c])
         assert torch.equal(fa.info[c], fb_.info[c])
     assert np.array_equal(fa.peak_n, fb_.peak_n) and np.array_equal(fa.replace_n, fb_.replace_n)
+
+
+@pytest.mark.parametrize('hw', [400, 1620])
+def test_run_ahead_equals_synchronous(vfn, hw):
+    """Reads and updates queued against the device-resident live counts (no size read-back for up to `run_ahead` frames:
+    vfn_bank::n_live, work split chosen on the device) must be bit-identical to the synchronous frame loop - outputs of
+    every read, the final bank, peak_n and replace_n - across frames that defer, frames that fall back because the
+    budget is near, and an eviction."""
+    from vfloodnet_b200 import synth
+    frames = 14
+    gen = synth.ClipGenerator(seed=11, obj_n=2, hw=hw, frac_merge=0.3)
+    keys0, vals0 = gen.init()
+    clip = [gen.frame() for _ in range(frames)]
+    budget = int(2.5 * 9 * hw)                       # class_budget = 9 hw: ~10 frames of run-ahead, then eviction
+    res = []
+    for defer, depth in ((False, 0), (True, 1), (True, 3)):
+        fb = vfn.FeatureBank(2, budget, 'cuda')
+        fb.defer, fb.run_ahead = defer, max(depth, 1)
+        m = vfn.Matcher(update_bank=True)
+        fb.init_bank([k.cuda() for k in keys0], [v.cuda() for v in vals0])
+        outs, max_pending = [], 0
+        for t, (q_in, q_out, pk, pv) in enumerate(clip):
+            outs.append(m(fb, q_in.cuda(), q_out.cuda()))
+            fb.update([k.cuda() for k in pk], [v.cuda() for v in pv], t + 1)
+            max_pending = max(max_pending, len(fb._pending))
+        assert max_pending == depth, (max_pending, depth)
+        res.append((fb, outs))
+    fa, oa = res[0]
+    assert fa.replace_n.sum() > 0                    # the clip did evict
+    for fb_, ob in res[1:]:
+        for t, (a, b) in enumerate(zip(oa, ob)):
+            assert torch.equal(a, b), f'read of frame {t} differs'
+        assert [fa.bank_n(c) for c in range(2)] == [fb_.bank_n(c) for c in range(2)]
+        for c in range(2):
+            assert torch.equal(fa.keys[c], fb_.keys[c]) and torch.equal(fa.values[c], fb_.values[c])
+            assert torch.equal(fa.info[c], fb_.info[c])
+        assert np.array_equal(fa.peak_n, fb_.peak_n) and np.array_equal(fa.replace_n, fb_.replace_n)
 
 
 # ---------------------------------------------------------------------------------------------------

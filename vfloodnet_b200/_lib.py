@@ -15,7 +15,8 @@ class VfnBank(C.Structure):
     """struct vfn_bank (include/vfn.h)"""
     _fields_ = [('d_key', c_i32), ('d_val', c_i32), ('cap', c_i64), ('n', c_i64),
                 ('keys', c_vp), ('values', c_vp), ('info', c_vp), ('nk', c_vp), ('nkh', c_vp), ('nkl', c_vp),
-                ('kh', c_vp), ('kl', c_vp), ('vh', c_vp), ('v8', c_vp), ('vl', c_vp), ('cnt', c_vp)]
+                ('kh', c_vp), ('kl', c_vp), ('vh', c_vp), ('v8', c_vp), ('vl', c_vp), ('cnt', c_vp),
+                ('n_live', c_vp), ('n_min', c_i64)]
 
 
 class VfnUpdateIO(C.Structure):
@@ -37,6 +38,7 @@ SIGNATURES = {
     'vfn_device_is_sm100': (c_i32, []),
     'vfn_prep_rows': (c_i32, [c_vp, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp]),
     'vfn_bank_append_rows': (c_i32, [BANK_P, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_f32, c_f32, c_vp]),
+    'vfn_bank_set_live': (c_i32, [BANK_P, c_i64, c_vp]),
     'vfn_bank_refresh': (c_i32, [BANK_P, c_i64, c_i64, c_vp]),
     'vfn_memread_workspace_bytes': (c_sz, [c_i32, c_i64, c_i64, c_i32, c_i32]),
     'vfn_memread': (c_i32, [BANK_P, c_i32, c_vp, c_vp, c_i64, c_f32, c_i32, c_vp, c_vp, c_vp, c_sz, c_i32, c_vp]),

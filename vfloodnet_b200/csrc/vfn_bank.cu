@@ -152,10 +152,11 @@ __global__ void __launch_bounds__(128) append_rows_kernel(const __grid_constant_
   const int32_t* __restrict__ n_sel_dev = ao.n_sel_dev;
   const int64_t n_sel_upper = ao.n_sel_upper;
   const int64_t n_sel = n_sel_dev ? (int64_t)*n_sel_dev : n_sel_upper;
+  const int64_t n_base = live_n(bank);          // the live count is only advanced by the clamp kernel that follows
   const int dk4 = bank.d_key >> 2, dv4 = bank.d_val >> 2;
   for (int64_t i = blockIdx.x; i < n_sel; i += gridDim.x) {
     const int64_t s = sel ? (int64_t)sel[i] : i;
-    const int64_t dst = bank.n + i;
+    const int64_t dst = n_base + i;
     const float4* ks = reinterpret_cast<const float4*>(ck + s * bank.d_key);
     const float4* vs = reinterpret_cast<const float4*>(cv + s * bank.d_val);
     float ss = 0.f;
@@ -253,7 +254,8 @@ __device__ __forceinline__ void plan_body(const int32_t* __restrict__ match_idx,
                                           int hw, float thres, int32_t* __restrict__ merge_q,
                                           int32_t* __restrict__ merge_slot, int32_t* __restrict__ run_off,
                                           int32_t* __restrict__ append_q, int32_t* __restrict__ counts,
-                                          int32_t* __restrict__ h_counts, unsigned long long* __restrict__ gkeys) {
+                                          int32_t* __restrict__ h_counts, unsigned long long* __restrict__ gkeys,
+                                          int32_t* __restrict__ n_live) {
   __shared__ unsigned long long skeys[PLAN_SMEM_KEYS];
   __shared__ int wt[33];
   const int tid = threadIdx.x;
@@ -321,12 +323,15 @@ __device__ __forceinline__ void plan_body(const int32_t* __restrict__ match_idx,
     counts[0] = n_merge;
     counts[1] = off_r;
     counts[2] = off_a;
-    counts[3] = 0;
+    // live count after the append that follows (the clamp kernel at the end of the update commits it to n_live[0])
+    const int n_next = n_live ? n_live[0] + off_a : 0;
+    if (n_live) n_live[1] = n_next;
+    counts[3] = n_next;
     if (h_counts) {
       h_counts[0] = n_merge;
       h_counts[1] = off_r;
       h_counts[2] = off_a;
-      h_counts[3] = 0;
+      h_counts[3] = n_next;
     }
   }
 }
@@ -334,13 +339,14 @@ __device__ __forceinline__ void plan_body(const int32_t* __restrict__ match_idx,
 struct PlanObj {
   const int32_t* match_idx; const float* match_corr; int32_t *merge_q, *merge_slot, *run_off, *append_q, *counts, *h_counts;
   unsigned long long* gkeys;
+  int32_t* n_live;
 };
 struct PlanSet { PlanObj o[4]; };
 // one CTA per object (blockIdx.x)
 __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(const __grid_constant__ PlanSet set, int hw, float thres) {
   const PlanObj& p = set.o[blockIdx.x];
   plan_body(p.match_idx, p.match_corr, hw, thres, p.merge_q, p.merge_slot, p.run_off, p.append_q, p.counts, p.h_counts,
-            p.gkeys);
+            p.gkeys, p.n_live);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -570,18 +576,27 @@ __global__ void __launch_bounds__(CP_THREADS) compact_move_kernel(vfn_bank src, 
   }
 }
 
-struct ClampSet { float* info[4]; int64_t n[4]; };
-// grid (rows / 256, objects)
+struct ClampSet { float* info[4]; int64_t n[4]; int32_t* n_live[4]; int64_t commit[4]; };
+// grid (rows / 256, objects).  Last kernel of an update: also commits the bank's device-resident live count (nothing in
+// this kernel reads it; rows are bounded by the host-side upper bound).
 __global__ void clamp_info_kernel(const __grid_constant__ ClampSet set) {
   float* __restrict__ info = set.info[blockIdx.y];
   const int64_t n = set.n[blockIdx.y];
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && set.n_live[blockIdx.y]) {
+    int32_t* nl = set.n_live[blockIdx.y];
+    const int32_t v = set.commit[blockIdx.y] >= 0 ? (int32_t)set.commit[blockIdx.y] : nl[1];
+    nl[0] = v;
+    nl[1] = v;
+  }
   if (i < n) {
     float v = info[2 * i + 1];
     v = v < 0.f ? 0.f : (v > 1e5f ? 1e5f : v);   // torch.clamp(.,0,1e5), NaN preserved (FeatureBank.py:115)
     info[2 * i + 1] = v;
   }
 }
+
+__global__ void set_live_kernel(int32_t* n_live, int32_t n) { n_live[0] = n; n_live[1] = n; }
 
 static int check_bank(const vfn_bank* b) {
   VFN_CHECK_ARG(b != nullptr, "bank is NULL");
@@ -604,7 +619,7 @@ int launch_plan(const UpdObj* o, int n_obj, int64_t hw, float thres_close, cudaS
     VFN_CHECK_ARG(o[c].match_idx && o[c].match_corr && o[c].merge_q && o[c].merge_slot && o[c].run_off && o[c].append_q &&
                       o[c].counts && o[c].plan_ws, "plan: NULL argument");
     set.o[c] = PlanObj{o[c].match_idx, o[c].match_corr, o[c].merge_q, o[c].merge_slot, o[c].run_off, o[c].append_q,
-                       o[c].counts, o[c].h_counts, reinterpret_cast<unsigned long long*>(o[c].plan_ws)};
+                       o[c].counts, o[c].h_counts, reinterpret_cast<unsigned long long*>(o[c].plan_ws), o[c].n_live};
   }
   plan_kernel<<<n_obj, PLAN_THREADS, 0, st>>>(set, (int)hw, thres_close);
   VFN_LAUNCH_OK();
@@ -663,15 +678,20 @@ int launch_append(const UpdObj* o, int n_obj, float info0, float info1, cudaStre
   return VFN_OK;
 }
 
-int launch_clamp(const vfn_bank* banks, int n_obj, cudaStream_t st) {
+int launch_clamp(const vfn_bank* banks, int n_obj, cudaStream_t st, const int64_t* commit) {
   VFN_CHECK_ARG(n_obj >= 1 && n_obj <= 4, "clamp: 1..4 objects per launch");
   ClampSet set;
   int64_t n_max = 0;
+  bool any_live = false;
   for (int c = 0; c < n_obj; ++c) {
     set.info[c] = banks[c].info;
     set.n[c] = banks[c].n;
+    set.n_live[c] = banks[c].n_live;
+    set.commit[c] = commit ? commit[c] : -1;
+    any_live = any_live || banks[c].n_live != nullptr;
     if (banks[c].n > n_max) n_max = banks[c].n;
   }
+  if (n_max == 0 && any_live) n_max = 1;          // the commit must still happen
   if (n_max == 0) return VFN_OK;
   dim3 grid((unsigned)cdiv(n_max, 256), n_obj);
   clamp_info_kernel<<<grid, 256, 0, st>>>(set);
@@ -688,6 +708,15 @@ extern "C" {
 
 int vfn_version(void) { return VFN_VERSION; }
 const char* vfn_last_error(void) { return g_err; }
+
+int vfn_bank_set_live(const vfn_bank* bank, int64_t n, void* stream) {
+  VFN_CHECK_ARG(bank != nullptr && n >= 0 && n <= bank->cap && n < (1ll << 31), "set_live: bad args");
+  if (!bank->n_live) return VFN_OK;
+  set_live_kernel<<<1, 1, 0, as_stream(stream)>>>(bank->n_live, (int32_t)n);
+  VFN_LAUNCH_OK();
+  count_launches(1);
+  return VFN_OK;
+}
 
 int vfn_profile_enable(int32_t on) {
   for (auto& r : g_prof) { g_ev_pool.push_back(r.a); g_ev_pool.push_back(r.b); }

@@ -35,12 +35,15 @@ struct UpdObj {
   const int32_t* match_idx; const float* match_corr;
   int32_t *merge_q, *merge_slot, *run_off, *append_q, *counts, *h_counts;
   void* plan_ws;
+  int32_t* n_live;                              // plan: stage n_live[1] = n_live[0] + |A| (NULL: no device count)
   const int32_t* sel; const int32_t* n_sel_dev; int64_t n_sel;   // append: rows to ingest
 };
 int launch_plan(const UpdObj* o, int n_obj, int64_t hw, float thres_close, cudaStream_t st);
 int launch_merge(const UpdObj* o, int n_obj, int64_t hw, float update_rate, cudaStream_t st);
 int launch_append(const UpdObj* o, int n_obj, float info0, float info1, cudaStream_t st);
-int launch_clamp(const vfn_bank* banks, int n_obj, cudaStream_t st);
+// clamp over rows [0, banks[c].n); banks with n_live also commit their live count: n_live[0] = commit[c] when
+// commit && commit[c] >= 0, else the count staged by the plan kernel (n_live[1])
+int launch_clamp(const vfn_bank* banks, int n_obj, cudaStream_t st, const int64_t* commit = nullptr);
 
 #define VFN_CHECK_ARG(cond, ...)              \
   do {                                        \
@@ -112,6 +115,11 @@ __device__ __forceinline__ void store_val_ops4(uint16_t* vh, uint8_t* v8, uint8_
 __device__ __forceinline__ void store_nk4(float* nk, uint16_t* nkh, uint16_t* nkl, int64_t off, float4 v) {
   *reinterpret_cast<float4*>(nk + off) = v;
   if (nkh) store_key_ops4(nkh, nkl, off, make_float4(v.x * NK_SCALE, v.y * NK_SCALE, v.z * NK_SCALE, v.w * NK_SCALE));
+}
+
+// live slot count of a bank: device-resident when the bank carries n_live (vfn.h), else the host-tracked n
+__device__ __forceinline__ int64_t live_n(const vfn_bank& b) {
+  return b.n_live ? (int64_t)*reinterpret_cast<const volatile int32_t*>(b.n_live) : b.n;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

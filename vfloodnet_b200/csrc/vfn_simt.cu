@@ -191,10 +191,12 @@ __global__ void __launch_bounds__(ST_THREADS) simt_score_kernel(BankSet banks, c
 
 // (m, l) partials -> natural-log LSE = M + log(sum_s l_s * exp(m_s - M)).  rows = obj_n*hw; parts strided by `rows`
 // for every object: part index ((obj*n_split + s)*hw + j).
-__global__ void lse_combine_kernel(const float2* __restrict__ part, int n_split, int64_t hw, int obj_n,
-                                   float* __restrict__ lse, float* __restrict__ lse_copy) {
+// n_split_dev (optional): the split chosen on the device (banks with live counts, vfn_tc.cu split_plan_kernel)
+__global__ void lse_combine_kernel(const float2* __restrict__ part, int n_split, const int32_t* __restrict__ n_split_dev,
+                                   int64_t hw, int obj_n, float* __restrict__ lse, float* __restrict__ lse_copy) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= hw * obj_n) return;
+  if (n_split_dev) n_split = *n_split_dev;
   const int64_t obj = idx / hw, j = idx % hw;
   float M = -INFINITY;
   for (int s = 0; s < n_split; ++s) M = fmaxf(M, part[((int64_t)obj * n_split + s) * hw + j].x);
@@ -225,10 +227,12 @@ __global__ void lse_combine_flat_kernel(const float2* __restrict__ part, int n_p
   lse[idx] = (M > -INFINITY) ? M + logf(L) : -INFINITY;
 }
 
-__global__ void ml_merge_kernel(const float2* __restrict__ part, int n_split, int64_t hw, int obj_n,
+__global__ void ml_merge_kernel(const float2* __restrict__ part, int n_split, const int32_t* __restrict__ n_split_dev,
+                                int64_t hw, int obj_n,
                                 float2* __restrict__ ml) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= hw * obj_n) return;
+  if (n_split_dev) n_split = *n_split_dev;
   const int64_t obj = idx / hw, j = idx % hw;
   float M = -INFINITY;
   for (int s = 0; s < n_split; ++s) M = fmaxf(M, part[((int64_t)obj * n_split + s) * hw + j].x);
@@ -363,11 +367,13 @@ __global__ void __launch_bounds__(ST_THREADS) simt_readout_kernel(BankSet banks,
 }
 
 // out[obj][c][j] = sum_s po[obj][s][c][j] (c < dv) ; out[obj][dv + c][j] = q_out[c][j]     (AFB_URR.py:159,176)
-__global__ void combine_out_kernel(const float* __restrict__ po, int n_split, int64_t plane /* dv*hw */, int obj_n,
-                                   const float* __restrict__ q_out, float* __restrict__ out, int with_qout) {
+__global__ void combine_out_kernel(const float* __restrict__ po, int n_split, const int32_t* __restrict__ n_split_dev,
+                                   int64_t plane /* dv*hw */, int obj_n, const float* __restrict__ q_out,
+                                   float* __restrict__ out, int with_qout) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = plane * obj_n;
   if (idx >= total) return;
+  if (n_split_dev) n_split = *n_split_dev;
   const int64_t obj = idx / plane, r = idx % plane;
   float s = 0.f;
   for (int k = 0; k < n_split; ++k) s += po[((int64_t)obj * n_split + k) * plane + r];
@@ -384,7 +390,7 @@ __global__ void finalize_counts_kernel(BankSet banks, int obj_n) {
   const int obj = blockIdx.y;
   const vfn_bank bk = banks.b[obj];
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= bk.n) return;
+  if (i >= live_n(bk)) return;
   const int c = bk.cnt[i];
   bk.cnt[i] = 0;
   // bank_cnt + 1 is exact in fp32; log evaluated in double and rounded once
@@ -400,6 +406,7 @@ struct ReadPlan {
   int d_key, d_val;
   int q_tiles, split_a, split_b, n_chunk;
   bool tc;
+  const int32_t *dev_a, *dev_b;      // splits chosen on the device (banks with live counts), else NULL
   size_t off_q, off_part, off_lse, off_po, off_tc, total;
 };
 
@@ -450,7 +457,10 @@ static int check_banks(const vfn_bank* banks, int obj_n, int64_t* n_max, BankSet
 static int run_phase_a(const BankSet& set, ReadPlan& p, const float* q_in_dm, char* ws, cudaStream_t st) {
   float* Q = reinterpret_cast<float*>(ws + p.off_q);
   float2* part = reinterpret_cast<float2*>(ws + p.off_part);
-  if (p.tc) return tc_phase_a(set.b, p.obj_n, q_in_dm, p.hw, p.split_a, part, ws + p.off_tc, st, &p.split_a);
+  if (p.tc) return tc_phase_a(set.b, p.obj_n, q_in_dm, p.hw, p.split_a, part, ws + p.off_tc, st, &p.split_a, &p.dev_a);
+  for (int o = 0; o < p.obj_n; ++o)
+    VFN_CHECK_ARG(!set.b[o].n_live || set.b[o].n_min == set.b[o].n,
+                  "the fp32 SIMT read needs exact bank sizes (bank %d was passed with bounds)", o);
   if (int rc = vfn_prep_rows(q_in_dm, p.d_key, p.hw, Q, nullptr, nullptr, nullptr, 1.f, st)) return rc;
   dim3 grid(p.q_tiles, p.split_a, p.obj_n);
   double work = 0;
@@ -468,7 +478,10 @@ static int run_phase_b(const BankSet& set, ReadPlan& p, const float* lse, float 
   float* Q = reinterpret_cast<float*>(ws + p.off_q);
   float* po = reinterpret_cast<float*>(ws + p.off_po);
   if (p.tc) return tc_phase_b(set.b, p.obj_n, p.hw, p.split_b, lse, thres_valid, update_bank, po, ws + p.off_tc, st,
-                              &p.split_b);
+                              &p.split_b, &p.dev_b);
+  for (int o = 0; o < p.obj_n; ++o)
+    VFN_CHECK_ARG(!set.b[o].n_live || set.b[o].n_min == set.b[o].n,
+                  "the fp32 SIMT read needs exact bank sizes (bank %d was passed with bounds)", o);
   static bool attr_set = false;
   if (!attr_set) {
     VFN_CUDA_OK(cudaFuncSetAttribute(simt_readout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -517,8 +530,8 @@ int vfn_memread_phase_a(const vfn_bank* banks, int32_t obj_n, const float* d_q_i
   char* ws = reinterpret_cast<char*>(d_ws);
   if (int rc = run_phase_a(set, p, d_q_in_dm, ws, st)) return rc;
   const int64_t rows = hw * obj_n;
-  ml_merge_kernel<<<(unsigned)cdiv(rows, 256), 256, 0, st>>>(reinterpret_cast<float2*>(ws + p.off_part), p.split_a, hw,
-                                                             obj_n, reinterpret_cast<float2*>(d_ml));
+  ml_merge_kernel<<<(unsigned)cdiv(rows, 256), 256, 0, st>>>(reinterpret_cast<float2*>(ws + p.off_part), p.split_a,
+                                                             p.dev_a, hw, obj_n, reinterpret_cast<float2*>(d_ml));
   VFN_LAUNCH_OK();
   return VFN_OK;
 }
@@ -546,7 +559,7 @@ int vfn_memread_phase_b(const vfn_bank* banks, int32_t obj_n, const float* d_q_i
   if (int rc = run_phase_b(set, p, d_lse, thres_valid, update_bank, ws, st)) return rc;
   const int64_t plane = (int64_t)set.b[0].d_val * hw;
   combine_out_kernel<<<(unsigned)cdiv(plane * obj_n, 256), 256, 0, st>>>(reinterpret_cast<float*>(ws + p.off_po),
-                                                                        p.split_b, plane, obj_n, nullptr,
+                                                                        p.split_b, p.dev_b, plane, obj_n, nullptr,
                                                                         d_partial_out, 0);
   if (update_bank) {
     dim3 g((unsigned)cdiv(n_max, 256), obj_n);
@@ -575,12 +588,13 @@ int vfn_memread(const vfn_bank* banks, int32_t obj_n, const float* d_q_in_dm, co
   float* lse = reinterpret_cast<float*>(ws + p.off_lse);
   const int64_t rows = hw * obj_n;
   lse_combine_kernel<<<(unsigned)cdiv(rows, 256), 256, 0, st>>>(reinterpret_cast<float2*>(ws + p.off_part), p.split_a,
-                                                                hw, obj_n, lse, d_lse);
+                                                                p.dev_a, hw, obj_n, lse, d_lse);
   VFN_LAUNCH_OK();
   if (int rc = run_phase_b(set, p, lse, thres_valid, update_bank, ws, st)) return rc;
   const int64_t plane = (int64_t)set.b[0].d_val * hw;
   combine_out_kernel<<<(unsigned)cdiv(plane * obj_n, 256), 256, 0, st>>>(reinterpret_cast<float*>(ws + p.off_po),
-                                                                        p.split_b, plane, obj_n, d_q_out_dm, d_out, 1);
+                                                                        p.split_b, p.dev_b, plane, obj_n, d_q_out_dm,
+                                                                        d_out, 1);
   if (update_bank) {
     dim3 g((unsigned)cdiv(n_max, 256), obj_n);
     finalize_counts_kernel<<<g, 256, 0, st>>>(set, obj_n);

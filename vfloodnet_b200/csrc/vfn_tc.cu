@@ -313,8 +313,10 @@ struct TcMaps {
 };
 struct TcArgs {
   int obj_n, hw, q_tiles, pieces;       // pieces = partial slots per combo
-  int n[TC_MAX_OBJ];                    // live slots per object
-  int tiles[TC_MAX_OBJ];                // slot tiles per object for this phase
+  int n[TC_MAX_OBJ];                    // live slots per object (an upper bound when n_live[obj] is set)
+  int tiles[TC_MAX_OBJ];                // slot tiles per object for this phase (same)
+  const int32_t* n_live[TC_MAX_OBJ];    // device-resident live count (vfn_bank::n_live) or NULL
+  const int32_t* pieces_dev;            // with live counts: `pieces` chosen on the device by split_plan_kernel, else NULL
   const uint16_t* qh;                   // (rows, 128) fp16 hi of the A operand (q * log2e/sqrt(d), or 16 * normalised candidate)
   const uint16_t* ql;
   long long a_obj_stride;               // elements between objects in qh/ql (0: one query set for all objects)
@@ -390,17 +392,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const __grid_con
   // work items = (split, object, query tile), dealt round-robin to the persistent CTAs: in any round all CTAs
   // stream the same few slot ranges, so the tiles are served from L2 (profiles/r1a_summary.md).
   const int n_combos = args.obj_n * args.q_tiles;
-  const int n_items = n_combos * args.pieces;
+  const int pieces = args.pieces_dev ? *reinterpret_cast<const volatile int32_t*>(args.pieces_dev) : args.pieces;
+  const int n_items = n_combos * pieces;
   uint32_t tile_ctr = 0;        // tiles streamed so far by this CTA (all roles agree)
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int piece = item / n_combos;
     const int combo = item - piece * n_combos;
     const int obj = combo / args.q_tiles;
     const int qt = combo - obj * args.q_tiles;
-    const int tiles_o = args.tiles[obj];
-    const int t0 = (int)((long long)tiles_o * piece / args.pieces);
-    const int t1 = (int)((long long)tiles_o * (piece + 1) / args.pieces);
-    const int n_obj = args.n[obj];
+    const int n_obj = args.n_live[obj] ? *reinterpret_cast<const volatile int32_t*>(args.n_live[obj]) : args.n[obj];
+    const int tiles_o = args.n_live[obj] ? (n_obj + SC_TILE - 1) / SC_TILE : args.tiles[obj];
+    const int t0 = (int)((long long)tiles_o * piece / pieces);
+    const int t1 = (int)((long long)tiles_o * (piece + 1) / pieces);
     const int ntile = t1 - t0;
     const bool first_item = (item == (int)blockIdx.x);
 
@@ -532,7 +535,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const __grid_con
               if (o.x > -INFINITY) l += o.y * ex2(o.x - m);
             }
           }
-          if (j < args.hw) part[((size_t)obj * args.pieces + piece) * args.hw + j] = make_float2(m * LN2, l);
+          if (j < args.hw) part[((size_t)obj * pieces + piece) * args.hw + j] = make_float2(m * LN2, l);
         }
         named_bar_sync(1, EPI_THREADS);                      // aux is reused by the next item
       } else {
@@ -546,7 +549,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const __grid_con
           }
           if (cnt > MATCH_RING) e[0] = make_float2(m_run, __int_as_float(-1));     // overflow: exact scan needed
           float4* dst = reinterpret_cast<float4*>(
-              part + (((size_t)obj * args.pieces + piece) * args.hw + j) * MATCH_CAND + cg * MATCH_RING);
+              part + (((size_t)obj * pieces + piece) * args.hw + j) * MATCH_CAND + cg * MATCH_RING);
           dst[0] = make_float4(e[0].x, e[0].y, e[1].x, e[1].y);
           dst[1] = make_float4(e[2].x, e[2].y, e[3].x, e[3].y);
         }
@@ -605,17 +608,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   const int qpairs = (args.q_tiles + 1) >> 1;
   const int n_combos = args.obj_n * qpairs;
-  const int n_items = n_combos * args.pieces;
+  const int pieces = args.pieces_dev ? *reinterpret_cast<const volatile int32_t*>(args.pieces_dev) : args.pieces;
+  const int n_items = n_combos * pieces;
   uint32_t tile_ctr = 0;        // tiles streamed so far by this cluster (all roles agree)
   for (int item = cluster_id; item < n_items; item += n_clusters) {
     const int piece = item / n_combos;
     const int combo = item - piece * n_combos;
     const int obj = combo / qpairs;
     const int qt = (combo - obj * qpairs) * 2 + (int)rank;
-    const int tiles_o = args.tiles[obj];
-    const int t0 = (int)((long long)tiles_o * piece / args.pieces);
-    const int t1 = (int)((long long)tiles_o * (piece + 1) / args.pieces);
-    const int n_obj = args.n[obj];
+    const int n_obj = args.n_live[obj] ? *reinterpret_cast<const volatile int32_t*>(args.n_live[obj]) : args.n[obj];
+    const int tiles_o = args.n_live[obj] ? (n_obj + SC_TILE - 1) / SC_TILE : args.tiles[obj];
+    const int t0 = (int)((long long)tiles_o * piece / pieces);
+    const int t1 = (int)((long long)tiles_o * (piece + 1) / pieces);
     const int ntile = t1 - t0;
     const bool first_item = (item == cluster_id);
 
@@ -750,7 +754,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
               if (o.x > -INFINITY) l += o.y * ex2(o.x - m);
             }
           }
-          if (j < args.hw) part[((size_t)obj * args.pieces + piece) * args.hw + j] = make_float2(m * LN2, l);
+          if (j < args.hw) part[((size_t)obj * pieces + piece) * args.hw + j] = make_float2(m * LN2, l);
         }
         named_bar_sync(1, EPI_THREADS);                      // aux is reused by the next item
       } else {
@@ -764,7 +768,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           }
           if (cnt > MATCH_RING) e[0] = make_float2(m_run, __int_as_float(-1));     // overflow: exact scan needed
           float4* dst = reinterpret_cast<float4*>(
-              part + (((size_t)obj * args.pieces + piece) * args.hw + j) * MATCH_CAND + cg * MATCH_RING);
+              part + (((size_t)obj * pieces + piece) * args.hw + j) * MATCH_CAND + cg * MATCH_RING);
           dst[0] = make_float4(e[0].x, e[0].y, e[1].x, e[1].y);
           dst[1] = make_float4(e[2].x, e[2].y, e[3].x, e[3].y);
         }
@@ -869,7 +873,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
   // work items = (split, object, query tile, channel half), round-robin over the persistent CTAs
   const int cpo = args.q_tiles * 2;
   const int n_combos = args.obj_n * cpo;
-  const int n_items = n_combos * args.pieces;
+  const int pieces = args.pieces_dev ? *reinterpret_cast<const volatile int32_t*>(args.pieces_dev) : args.pieces;
+  const int n_items = n_combos * pieces;
   uint32_t k_it = 0;            // tiles streamed so far (K/V stage = k_it & 1)
   uint32_t buf_it[2] = {0, 0};  // uses of each S/P buffer so far
   uint32_t seg_it = 0;          // items finished (o_full phase)
@@ -879,10 +884,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
     const int obj = combo / cpo;
     const int cidx = combo - obj * cpo;                // qt * 2 + half
     const int qt = cidx >> 1, half = cidx & 1;
-    const int tiles_o = args.tiles[obj];
-    const int t0 = (int)((long long)tiles_o * piece / args.pieces);
-    const int t1 = (int)((long long)tiles_o * (piece + 1) / args.pieces);
-    const int n_obj = args.n[obj];
+    const int n_obj = args.n_live[obj] ? *reinterpret_cast<const volatile int32_t*>(args.n_live[obj]) : args.n[obj];
+    const int tiles_o = args.n_live[obj] ? (n_obj + B_TILE - 1) / B_TILE : args.tiles[obj];
+    const int t0 = (int)((long long)tiles_o * piece / pieces);
+    const int t1 = (int)((long long)tiles_o * (piece + 1) / pieces);
     const int ntile = t1 - t0;
     const bool first_item = (item == (int)blockIdx.x);
 
@@ -1065,7 +1070,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
       mbar_wait(o_full, seg_it & 1);
       tc_fence_after();
       if (ntile > 0) {
-        float* dst = po + (((size_t)obj * args.pieces + piece) * DV + half * 256 + sg * 64) * (size_t)args.hw;
+        float* dst = po + (((size_t)obj * pieces + piece) * DV + half * 256 + sg * 64) * (size_t)args.hw;
 #pragma unroll 1
         for (int ch = 0; ch < 2; ++ch) {
           uint32_t v[32];
@@ -1144,7 +1149,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   const int qpairs = (args.q_tiles + 1) >> 1;
   const int cpo = qpairs * 2;
   const int n_combos = args.obj_n * cpo;
-  const int n_items = n_combos * args.pieces;
+  const int pieces = args.pieces_dev ? *reinterpret_cast<const volatile int32_t*>(args.pieces_dev) : args.pieces;
+  const int n_items = n_combos * pieces;
   uint32_t k_it = 0;            // tiles streamed so far (stage = k_it & 3)
   uint32_t buf_it[2] = {0, 0};  // uses of each S/P buffer so far
   uint32_t seg_it = 0;          // items finished (o_full phase)
@@ -1154,10 +1160,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     const int obj = combo / cpo;
     const int cidx = combo - obj * cpo;                // qp * 2 + half
     const int qt = (cidx >> 1) * 2 + (int)rank, half = cidx & 1;
-    const int tiles_o = args.tiles[obj];
-    const int t0 = (int)((long long)tiles_o * piece / args.pieces);
-    const int t1 = (int)((long long)tiles_o * (piece + 1) / args.pieces);
-    const int n_obj = args.n[obj];
+    const int n_obj = args.n_live[obj] ? *reinterpret_cast<const volatile int32_t*>(args.n_live[obj]) : args.n[obj];
+    const int tiles_o = args.n_live[obj] ? (n_obj + B_TILE - 1) / B_TILE : args.tiles[obj];
+    const int t0 = (int)((long long)tiles_o * piece / pieces);
+    const int t1 = (int)((long long)tiles_o * (piece + 1) / pieces);
     const int ntile = t1 - t0;
     const bool first_item = (item == cluster_id);
 
@@ -1341,7 +1347,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       mbar_wait(o_full, seg_it & 1);
       tc_fence_after();
       if (ntile > 0) {
-        float* dst = po + (((size_t)obj * args.pieces + piece) * DV + half * 256 + sg * 64) * (size_t)args.hw;
+        float* dst = po + (((size_t)obj * pieces + piece) * DV + half * 256 + sg * 64) * (size_t)args.hw;
 #pragma unroll 1
         for (int ch = 0; ch < 2; ++ch) {
           uint32_t v[32];
@@ -1391,7 +1397,9 @@ __device__ __forceinline__ float exact_dot128(const float* __restrict__ nk, cons
 
 struct RescoreArgs {
   int obj_n, pieces, hw;
+  const int32_t* pieces_dev;
   int n[TC_MAX_OBJ];
+  const int32_t* n_live[TC_MAX_OBJ];
   const float* nk[TC_MAX_OBJ];
   const float* nck[TC_MAX_OBJ];
   int32_t* idx_out[TC_MAX_OBJ];
@@ -1404,13 +1412,14 @@ __global__ void __launch_bounds__(256) match_rescore_kernel(const float2* __rest
   const int obj = blockIdx.y;
   const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (j >= a.hw) return;
-  const int n = a.n[obj];
+  const int n = a.n_live[obj] ? *reinterpret_cast<const volatile int32_t*>(a.n_live[obj]) : a.n[obj];
   const float* nk = a.nk[obj];
-  const int n_cand = a.pieces * MATCH_CAND;
+  const int pieces = a.pieces_dev ? *reinterpret_cast<const volatile int32_t*>(a.pieces_dev) : a.pieces;
+  const int n_cand = pieces * MATCH_CAND;
   const float* q = a.nck[obj] + (size_t)j * DK;
   auto entry = [&](int c) {
     const int pc = c / MATCH_CAND, r = c - pc * MATCH_CAND;
-    return part[(((size_t)obj * a.pieces + pc) * a.hw + j) * MATCH_CAND + r];
+    return part[(((size_t)obj * pieces + pc) * a.hw + j) * MATCH_CAND + r];
   };
   // approximate maximum over all pieces (overflow markers carry their group's maximum)
   float amax = -INFINITY;
@@ -1504,6 +1513,12 @@ static int g_pair = 3;    // bit 0: CTA-pair (cta_group::2) phase B, bit 1: CTA-
 
 bool tc_shapes_ok(int d_key, int d_val) { return d_key == DK && d_val == DV; }
 
+// Banks with a device-resident live count (vfn_bank::n_live): `n` is an upper bound, `n_min` a lower bound; the tensor
+// maps then span the whole slab (rows in [live, cap) hold finite stale operands, masked by the kernels) and the work
+// partition is chosen so that every piece keeps a tile even at the lower bound.
+static int64_t map_rows(const vfn_bank& b) { return b.n_live ? b.cap : b.n; }
+static int64_t n_low(const vfn_bank& b) { return b.n_live ? b.n_min : b.n; }
+
 constexpr int TC_MAX_SPLIT = 24;
 constexpr int B_CHAIN_MAX = 8192;      // slots accumulated into one TMEM readout accumulator (see tc_phase_b)
 
@@ -1523,6 +1538,64 @@ static int best_split(int combos, int64_t tiles_min, int64_t tiles_max, int over
   return best;
 }
 
+// best_split evaluated on the device from the live counts (banks with vfn_bank::n_live): the same choice the host makes
+// from exact sizes, so a read / match issued against bounds is bit-identical to one issued after reading the sizes back.
+// One warp: lane s-1 evaluates split s; integer costs, ties -> smallest s (the host loop keeps the first minimum).
+struct SplitPlanArgs {
+  int obj_n, tile, combos, overhead, G, chain_max;     // chain_max > 0: s_min = cdiv(tiles_max * tile, chain_max)
+  const int32_t* n_live[TC_MAX_OBJ];
+  int32_t* out;
+};
+__global__ void split_plan_kernel(SplitPlanArgs a) {
+  const int lane = threadIdx.x;
+  long long tmin = 0x7fffffffffffffffll, tmax = 0;
+  for (int o = 0; o < a.obj_n; ++o) {
+    const long long n = *reinterpret_cast<const volatile int32_t*>(a.n_live[o]);
+    const long long t = (n + a.tile - 1) / a.tile;
+    tmin = t < tmin ? t : tmin;
+    tmax = t > tmax ? t : tmax;
+  }
+  int s_min = 1;
+  if (a.chain_max > 0) s_min = (int)((tmax * a.tile + a.chain_max - 1) / a.chain_max);
+  if (s_min < 1) s_min = 1;
+  if (s_min > TC_MAX_SPLIT) s_min = TC_MAX_SPLIT;
+  if (s_min > tmin) s_min = (int)(tmin > 1 ? tmin : 1);
+  const int sp = lane + 1;
+  long long cost = 0x7fffffffffffffffll;
+  if (sp >= s_min && sp <= TC_MAX_SPLIT && sp <= tmin) {
+    const long long rounds = ((long long)a.combos * sp + a.G - 1) / a.G;
+    cost = rounds * ((tmax + sp - 1) / sp + a.overhead);
+  }
+  int best = sp;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const long long oc = __shfl_xor_sync(0xffffffffu, cost, o);
+    const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+    if (oc < cost || (oc == cost && ob < best)) { cost = oc; best = ob; }
+  }
+  if (lane == 0) *a.out = (cost == 0x7fffffffffffffffll) ? s_min : best;
+}
+
+// all banks of a call carry a live count, or none does
+static int live_mode(const vfn_bank* banks, int obj_n, bool* live) {
+  *live = banks[0].n_live != nullptr;
+  for (int o = 1; o < obj_n; ++o)
+    VFN_CHECK_ARG((banks[o].n_live != nullptr) == *live, "banks mix device-resident and host-tracked sizes");
+  return VFN_OK;
+}
+
+static int launch_split_plan(const vfn_bank* banks, int obj_n, int tile, int combos, int overhead, int G, int chain_max,
+                             int32_t* out, cudaStream_t st) {
+  SplitPlanArgs sp{};
+  sp.obj_n = obj_n; sp.tile = tile; sp.combos = combos; sp.overhead = overhead; sp.G = G; sp.chain_max = chain_max;
+  for (int o = 0; o < obj_n; ++o) sp.n_live[o] = banks[o].n_live;
+  sp.out = out;
+  split_plan_kernel<<<1, 32, 0, st>>>(sp);
+  VFN_LAUNCH_OK();
+  count_launches(1);
+  return VFN_OK;
+}
+
 void tc_pick_splits(int obj_n, int64_t n_max, int64_t hw, int* split_a, int* split_b) {
   // upper bounds used to size the workspace; the per-launch choice (<= these) is made in tc_phase_a / tc_phase_b
   (void)obj_n; (void)n_max; (void)hw;
@@ -1533,10 +1606,12 @@ void tc_pick_splits(int obj_n, int64_t n_max, int64_t hw, int* split_a, int* spl
 // rows padded to a whole number of query-tile PAIRS (the pair kernels read two adjacent tiles)
 static size_t a_operand_bytes(int64_t hw) { return align_up((size_t)cdiv(hw, 2 * QT) * 2 * QT * DK * sizeof(uint16_t), 256); }
 
+// [Q hi | Q lo | 256 B: device-chosen splits {phase A, phase B}]
 size_t tc_workspace_bytes(int obj_n, int64_t hw) {
   (void)obj_n;
-  return 2 * a_operand_bytes(hw);
+  return 2 * a_operand_bytes(hw) + 256;
 }
+static int32_t* tc_plan_cell(char* ws_tc, int64_t hw) { return reinterpret_cast<int32_t*>(ws_tc + 2 * a_operand_bytes(hw)); }
 
 static int set_attrs() {
   static bool attr = false;
@@ -1560,34 +1635,41 @@ static int fill_args(const vfn_bank* banks, int obj_n, int64_t hw, int pieces, i
   a->qh = reinterpret_cast<const uint16_t*>(ws_tc);
   a->ql = reinterpret_cast<const uint16_t*>(ws_tc + a_operand_bytes(hw));
   a->a_obj_stride = 0;
+  a->pieces_dev = nullptr;
   a->band = 0.f;
   a->dbg = g_dbg;
   for (int o = 0; o < obj_n; ++o) {
     VFN_CHECK_ARG(banks[o].kh && banks[o].vh, "bank %d has no tensor-core operand arrays", o);
     VFN_CHECK_ARG(banks[o].n < (1ll << 31), "bank too large");
+    VFN_CHECK_ARG(!banks[o].n_live || (banks[o].n_min >= 1 && banks[o].n_min <= banks[o].n), "bank %d: bad n_min", o);
     a->n[o] = (int)banks[o].n;
     a->tiles[o] = (int)cdiv(banks[o].n, tile);
+    a->n_live[o] = banks[o].n_live;
     a->cnt[o] = banks[o].cnt;
-    if (int rc = make_map(&maps->kh[o], banks[o].kh, banks[o].n, DK, k_box_rows, 2)) return rc;
-    if (int rc = make_map(&maps->kl[o], banks[o].kl, banks[o].n, DK, k_box_rows, 2)) return rc;
+    const int64_t rows = map_rows(banks[o]);
+    if (int rc = make_map(&maps->kh[o], banks[o].kh, rows, DK, k_box_rows, 2)) return rc;
+    if (int rc = make_map(&maps->kl[o], banks[o].kl, rows, DK, k_box_rows, 2)) return rc;
     if (need_v) {
-      if (int rc = make_map(&maps->vh[o], banks[o].vh, banks[o].n, DV, tile, 2)) return rc;
-      if (int rc = make_map(&maps->v8[o], banks[o].v8, banks[o].n, DV, tile, 1)) return rc;
-      if (int rc = make_map(&maps->vl[o], banks[o].vl, banks[o].n, DV, tile, 1)) return rc;
+      if (int rc = make_map(&maps->vh[o], banks[o].vh, rows, DV, tile, 2)) return rc;
+      if (int rc = make_map(&maps->v8[o], banks[o].v8, rows, DV, tile, 1)) return rc;
+      if (int rc = make_map(&maps->vl[o], banks[o].vl, rows, DV, tile, 1)) return rc;
     }
   }
+  for (int o = obj_n; o < TC_MAX_OBJ; ++o) a->n_live[o] = nullptr;
   return VFN_OK;
 }
 
 int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t hw, int split_a, float2* part,
-               char* ws_tc, cudaStream_t st, int* pieces_out) {
+               char* ws_tc, cudaStream_t st, int* pieces_out, const int32_t** pieces_dev_out) {
   if (int rc = set_attrs()) return rc;
+  bool live;
+  if (int rc = live_mode(banks, obj_n, &live)) return rc;
   TcMaps maps;
   TcArgs a;
   int64_t tmin = INT64_MAX, tmax = 0;
   for (int o = 0; o < obj_n; ++o) {
-    const int64_t t = cdiv(banks[o].n, SC_TILE);
-    tmin = t < tmin ? t : tmin;
+    const int64_t t = cdiv(banks[o].n, SC_TILE), tl = cdiv(n_low(banks[o]), SC_TILE);
+    tmin = tl < tmin ? tl : tmin;
     tmax = t > tmax ? t : tmax;
   }
   const bool pair = (g_pair & 2) && (num_sms() % 2 == 0);
@@ -1596,6 +1678,15 @@ int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t h
   if (pieces > split_a) { set_error("phase A: split %d exceeds workspace bound %d", pieces, split_a); return VFN_E_CAPACITY; }
   *pieces_out = pieces;
   if (int rc = fill_args(banks, obj_n, hw, pieces, SC_TILE, ws_tc, &maps, &a, false, pair ? 64 : SC_TILE)) return rc;
+  *pieces_dev_out = nullptr;
+  if (live) {
+    int32_t* cell = tc_plan_cell(ws_tc, hw);
+    if (int rc = launch_split_plan(banks, obj_n, SC_TILE, obj_n * (int)cdiv(hw, pair ? 2 * QT : QT), 2,
+                                   pair ? num_sms() / 2 : num_sms(), 0, cell, st))
+      return rc;
+    a.pieces_dev = cell;
+    *pieces_dev_out = cell;
+  }
   // Q hi/lo of q * log2(e)/sqrt(d): logits land in the log2 domain; pad rows zeroed
   VFN_CUDA_OK(cudaMemsetAsync(ws_tc, 0, 2 * a_operand_bytes(hw), st));
   const float scale = LOG2E / sqrtf((float)DK);
@@ -1616,14 +1707,17 @@ int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t h
 }
 
 int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const float* lse, float thres_valid,
-               int update_bank, float* po, char* ws_tc, cudaStream_t st, int* pieces_out) {
+               int update_bank, float* po, char* ws_tc, cudaStream_t st, int* pieces_out,
+               const int32_t** pieces_dev_out) {
   if (int rc = set_attrs()) return rc;
+  bool live;
+  if (int rc = live_mode(banks, obj_n, &live)) return rc;
   TcMaps maps;
   TcArgs a;
   int64_t tmin = INT64_MAX, tmax = 0;
   for (int o = 0; o < obj_n; ++o) {
-    const int64_t t = cdiv(banks[o].n, B_TILE);
-    tmin = t < tmin ? t : tmin;
+    const int64_t t = cdiv(banks[o].n, B_TILE), tl = cdiv(n_low(banks[o]), B_TILE);
+    tmin = tl < tmin ? tl : tmin;
     tmax = t > tmax ? t : tmax;
   }
   const bool pair = (g_pair & 1) && (num_sms() % 2 == 0);
@@ -1637,6 +1731,14 @@ int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const 
   if (pieces > split_b) { set_error("phase B: split %d exceeds workspace bound %d", pieces, split_b); return VFN_E_CAPACITY; }
   *pieces_out = pieces;
   if (int rc = fill_args(banks, obj_n, hw, pieces, B_TILE, ws_tc, &maps, &a, true, pair ? 32 : B_TILE)) return rc;
+  *pieces_dev_out = nullptr;
+  if (live) {
+    int32_t* cell = tc_plan_cell(ws_tc, hw) + 1;
+    if (int rc = launch_split_plan(banks, obj_n, B_TILE, combos, 4, pair ? num_sms() / 2 : num_sms(), B_CHAIN_MAX, cell, st))
+      return rc;
+    a.pieces_dev = cell;
+    *pieces_dev_out = cell;
+  }
   double work = 0;
   for (int o = 0; o < obj_n; ++o) work += 2.0 * DV * (double)banks[o].n * (double)hw;
   prof_begin(PROF_READ_B, st);
@@ -1650,8 +1752,9 @@ int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const 
   return VFN_OK;
 }
 
+// [candidate partials | per object: cand hi, cand lo | 256 B: device-chosen split]
 size_t tc_match_workspace_bytes(int obj_n, int64_t hw) {
-  return align_up((size_t)obj_n * TC_MAX_SPLIT * hw * MATCH_CAND * sizeof(float2), 256) + 2 * (size_t)obj_n * a_operand_bytes(hw);
+  return align_up((size_t)obj_n * TC_MAX_SPLIT * hw * MATCH_CAND * sizeof(float2), 256) + 2 * (size_t)obj_n * a_operand_bytes(hw) + 256;
 }
 
 // fp32 (hw, 128) entry-major normalised candidates -> fp16 hi/lo of 16x (single-object API path)
@@ -1687,18 +1790,31 @@ int tc_match(const vfn_bank* banks, int obj_n, const float* const* nck_em, int64
   const bool pair = (g_pair & 2) && (num_sms() % 2 == 0);
   for (int o = 0; o < obj_n; ++o) {
     VFN_CHECK_ARG(banks[o].d_key == DK && banks[o].n < (1ll << 31) && banks[o].nkh, "tcgen05 match needs d_key = 128");
-    const int64_t t = cdiv(banks[o].n, SC_TILE);
-    tmin = t < tmin ? t : tmin;
+    VFN_CHECK_ARG(!banks[o].n_live || (banks[o].n_min >= 1 && banks[o].n_min <= banks[o].n), "bank %d: bad n_min", o);
+    const int64_t t = cdiv(banks[o].n, SC_TILE), tl = cdiv(n_low(banks[o]), SC_TILE);
+    tmin = tl < tmin ? tl : tmin;
     tmax = t > tmax ? t : tmax;
-    if (int rc = make_map(&maps.kh[o], banks[o].nkh, banks[o].n, DK, pair ? 64 : SC_TILE, 2)) return rc;
-    if (int rc = make_map(&maps.kl[o], banks[o].nkl, banks[o].n, DK, pair ? 64 : SC_TILE, 2)) return rc;
-    a.n[o] = (int)banks[o].n; a.tiles[o] = (int)t; a.cnt[o] = nullptr;
+    if (int rc = make_map(&maps.kh[o], banks[o].nkh, map_rows(banks[o]), DK, pair ? 64 : SC_TILE, 2)) return rc;
+    if (int rc = make_map(&maps.kl[o], banks[o].nkl, map_rows(banks[o]), DK, pair ? 64 : SC_TILE, 2)) return rc;
+    a.n[o] = (int)banks[o].n; a.tiles[o] = (int)t; a.cnt[o] = nullptr; a.n_live[o] = banks[o].n_live;
+    r.n_live[o] = banks[o].n_live;
     r.n[o] = (int)banks[o].n; r.nk[o] = banks[o].nk; r.nck[o] = nck_em[o]; r.idx_out[o] = idx_out[o]; r.corr_out[o] = corr_out[o];
     work += 2.0 * DK * (double)banks[o].n * (double)hw;
   }
+  for (int o = obj_n; o < TC_MAX_OBJ; ++o) { a.n_live[o] = nullptr; r.n_live[o] = nullptr; }
   const int pieces = pair ? best_split(obj_n * (int)cdiv(hw, 2 * QT), tmin, tmax, 2, num_sms() / 2)
                           : best_split(obj_n * (int)cdiv(hw, QT), tmin, tmax, 2);
+  bool live;
+  if (int rc = live_mode(banks, obj_n, &live)) return rc;
   a.obj_n = obj_n; a.hw = (int)hw; a.q_tiles = (int)cdiv(hw, QT); a.pieces = pieces;
+  a.pieces_dev = r.pieces_dev = nullptr;
+  if (live) {
+    int32_t* cell = reinterpret_cast<int32_t*>(ws + tc_match_workspace_bytes(obj_n, hw) - 256);
+    if (int rc = launch_split_plan(banks, obj_n, SC_TILE, obj_n * (int)cdiv(hw, pair ? 2 * QT : QT), 2,
+                                   pair ? num_sms() / 2 : num_sms(), 0, cell, st))
+      return rc;
+    a.pieces_dev = r.pieces_dev = cell;
+  }
   a.qh = tc_match_cand_hi(ws, obj_n, hw, 0);
   a.ql = tc_match_cand_lo(ws, obj_n, hw, 0);
   a.a_obj_stride = (long long)(a_operand_bytes(hw) / sizeof(uint16_t));

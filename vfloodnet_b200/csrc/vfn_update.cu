@@ -62,6 +62,9 @@ int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_i
     VFN_CHECK_ARG(io[c].d_prev_key_dm && io[c].d_prev_value_dm && io[c].d_match_idx && io[c].d_match_corr &&
                       io[c].d_merge_q && io[c].d_merge_slot && io[c].d_run_off && io[c].d_append_q,
                   "bank_update: io[%d] has NULL buffers", c);
+    VFN_CHECK_ARG(!banks[c].n_live || (banks[c].n_min >= 1 && banks[c].n_min <= banks[c].n),
+                  "bank_update: bank %d has n_live but n_min=%lld is not a lower bound of n=%lld", c,
+                  (long long)banks[c].n_min, (long long)banks[c].n);
     if (banks[c].n > n_max) n_max = banks[c].n;
     io[c].n_before = banks[c].n;
     io[c].evicted = io[c].swapped = io[c].evict_status = io[c].kept = io[c].n_iter = io[c].deferred = 0;
@@ -82,6 +85,10 @@ int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_i
 
   const bool tc = (impl != 1) && d_key == 128 && banks[0].nkh != nullptr && vfn_device_is_sm100();
   if (impl == 2 && !tc) { set_error("tcgen05 match needs d_key = 128 operands on an sm_100 device"); return VFN_E_UNSUPPORTED; }
+  if (!tc)
+    for (int c = 0; c < obj_n; ++c)
+      VFN_CHECK_ARG(!banks[c].n_live || banks[c].n_min == banks[c].n,
+                    "bank_update: the fp32 SIMT kernels need exact bank sizes (bank %d was passed with bounds)", c);
 
   // (1) candidates: (d, hw) -> entry-major raw + normalised (FeatureBank.py:64,88), + fp16 split of 16 * normalised keys
   PrepJob jobs[8];
@@ -115,6 +122,7 @@ int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_i
     uo[c].merge_q = io[c].d_merge_q; uo[c].merge_slot = io[c].d_merge_slot; uo[c].run_off = io[c].d_run_off;
     uo[c].append_q = io[c].d_append_q; uo[c].counts = counts + 4 * c; uo[c].h_counts = h_counts + 4 * c;
     uo[c].plan_ws = ws + L.pws + c * L.s_pws;
+    uo[c].n_live = banks[c].n_live;
   }
   if (int rc = launch_plan(uo, obj_n, hw, thres_close, st)) return rc;
   // Deferred completion: when no object can reach its budget whatever |A| turns out to be (n + hw <= class_budget,
@@ -140,6 +148,11 @@ int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_i
     if (int rc = launch_clamp(cb, obj_n, st)) return rc;
     return VFN_OK;
   }
+  // synchronous path: the host needs exact bank sizes from here on
+  for (int c = 0; c < obj_n; ++c)
+    VFN_CHECK_ARG(!banks[c].n_live || banks[c].n_min == banks[c].n,
+                  "bank_update: bank %d was passed with bounds (n_min < n) but this update may evict: finish the "
+                  "deferred updates first", c);
   if (int rc = launch_merge(uo, obj_n, hw, update_rate, st)) return rc;
   VFN_CUDA_OK(cudaStreamSynchronize(st));                 // |merge|, |runs|, |append| per object (nonzero/unique syncs)
   bool any_evict = false;
@@ -170,7 +183,9 @@ int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_i
         return rc;
       // algorithmic bytes of the compaction: evicted rows read once, kept rows read + written
       vfn_profile_add_work(PROF_COMPACT, 4.0 * (d_key + d_val + 2) * ((double)(banks[c].n - hp[1]) + 2.0 * hp[1]));
+      int32_t* nl = banks[c].n_live;                        // the live count belongs to the bank, not to a slab
       vfn_bank tmp = banks[c]; banks[c] = alts[c]; alts[c] = tmp;
+      banks[c].n_live = nl; alts[c].n_live = nullptr;
       banks[c].n = hp[1];
       io[c].swapped = 1;
     }
@@ -178,23 +193,30 @@ int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_i
   // (4) append + clamp (FeatureBank.py:105-115), one launch each
   UpdObj ao[4];
   vfn_bank cb[4];
+  int64_t commit[4];
   int n_a = 0, n_c = 0;
   for (int c = 0; c < obj_n; ++c) {
-    if (io[c].evict_status != 0) continue;
+    if (io[c].evict_status != 0) {            // the caller raises; keep the device count equal to the host's
+      if (int rc = vfn_bank_set_live(&banks[c], banks[c].n, stream)) return rc;
+      continue;
+    }
     const int64_t n_app = io[c].n_append;
     if (n_app > 0) {
       ao[n_a] = uo[c];
       ao[n_a].bank = banks[c];                // after a possible ping-pong swap
+      ao[n_a].bank.n_live = nullptr;          // the host count is exact here (and an eviction changed it)
       ao[n_a].sel = io[c].d_append_q; ao[n_a].n_sel_dev = nullptr; ao[n_a].n_sel = n_app;
       ++n_a;
     }
     banks[c].n += n_app;
+    banks[c].n_min = banks[c].n;
+    commit[n_c] = banks[c].n;                 // device-resident count := exact host count
     cb[n_c++] = banks[c];
   }
   if (n_a > 0)
     if (int rc = launch_append(ao, n_a, frame_idx, 0.f, st)) return rc;
   if (n_c > 0)
-    if (int rc = launch_clamp(cb, n_c, st)) return rc;
+    if (int rc = launch_clamp(cb, n_c, st, commit)) return rc;
   return VFN_OK;
 }
 
@@ -205,9 +227,18 @@ int vfn_bank_update_finish(vfn_bank* banks, int32_t obj_n, vfn_update_io* io, co
     io[c].n_merge = h_pinned[4 * c + 0];
     io[c].n_runs = h_pinned[4 * c + 1];
     io[c].n_append = h_pinned[4 * c + 2];
-    VFN_CHECK_ARG(io[c].n_append >= 0 && banks[c].n + io[c].n_append <= banks[c].cap,
-                  "bank_update_finish: counts of object %d are not valid (was the event waited on?)", c);
-    banks[c].n += io[c].n_append;
+    if (banks[c].n_live) {
+      // device-resident count: the plan kernel staged the exact live count after this update's append
+      const int64_t n_next = h_pinned[4 * c + 3];
+      VFN_CHECK_ARG(io[c].n_append >= 0 && n_next >= banks[c].n_min && n_next <= banks[c].n + io[c].n_append &&
+                        n_next <= banks[c].cap,
+                    "bank_update_finish: counts of object %d are not valid (was the event waited on?)", c);
+      banks[c].n = banks[c].n_min = n_next;
+    } else {
+      VFN_CHECK_ARG(io[c].n_append >= 0 && banks[c].n + io[c].n_append <= banks[c].cap,
+                    "bank_update_finish: counts of object %d are not valid (was the event waited on?)", c);
+      banks[c].n += io[c].n_append;
+    }
     io[c].deferred = 0;
     // algorithmic bytes of the deferred append (the launch could only account an upper bound: it recorded 0)
     vfn_profile_add_work(PROF_APPEND, 2.0 * 4.0 * (banks[c].d_key + banks[c].d_val + 2) * (double)io[c].n_append);

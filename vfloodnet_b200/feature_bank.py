@@ -8,6 +8,7 @@ All arithmetic runs in libvfn_sm100a.so; there is no CPU / PyTorch fallback.
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import math
 from typing import List, Optional
@@ -46,10 +47,12 @@ class _Slab:
 
     _ARRAYS = ('keys', 'values', 'info', 'nk', 'nkh', 'nkl', 'kh', 'kl', 'vh', 'v8', 'vl', 'cnt')
 
-    def struct(self, n: int) -> VfnBank:
+    def struct(self, n: int, n_live=None, n_min: Optional[int] = None) -> VfnBank:
+        """n_live: device int32[2] live-count cell of the bank (vfn.h); then n / n_min are upper / lower bounds"""
         return VfnBank(self.d_key, self.d_val, self.cap, n, ptr(self.keys), ptr(self.values), ptr(self.info),
                        ptr(self.nk), ptr(self.nkh), ptr(self.nkl), ptr(self.kh), ptr(self.kl), ptr(self.vh),
-                       ptr(self.v8), ptr(self.vl), ptr(self.cnt))
+                       ptr(self.v8), ptr(self.vl), ptr(self.cnt), ptr(n_live) if self.kh is not None else None,
+                       n if n_min is None else n_min)
 
     def copy_rows_from(self, other: '_Slab', n: int):
         for name in self._ARRAYS:
@@ -113,17 +116,26 @@ class FeatureBank:
         self._n = [0] * obj_n
         self._scratch = {}
         self._h_plan = torch.zeros((obj_n, 72), dtype=torch.int32).pin_memory()
-        self._h_pinned = torch.zeros((obj_n * 80,), dtype=torch.int32).pin_memory()
         self._last_decisions = [None] * obj_n   # device tensors of the last update (tests / debugging)
         self.launches = 0                       # kernels launched by this bank (bench accounting)
         self.last_thresholds = []               # T sequence of the last remove() (tests / debugging)
         self.last_thresholds_obj = [None] * obj_n
-        # deferred completion of update() (vfn.h: vfn_bank_update / vfn_bank_update_finish): the event is recorded when
-        # the counts of the update are on their way to pinned memory; _resolve() waits on it the next time a bank size
-        # is needed (normally the next frame's read), instead of draining the stream at the end of every update
+        # Deferred completion of update() (vfn.h: vfn_bank_update / vfn_bank_update_finish) with a device-resident live
+        # count per object (vfn_bank::n_live): an update that cannot evict does not read |A| back.  Its counts travel to a
+        # pinned slot, the kernels of the following read / update take the live count from device memory, and the host
+        # only keeps bounds (n_min <= live <= n).  Up to `run_ahead` updates stay unfinished; update t waits for the
+        # counts of update t - run_ahead (normally long there), which refreshes the exact size and bounds the host's
+        # lead over the GPU.  Anything that needs an exact size (keys/values/info views, bank_n, an update that may evict,
+        # capacity growth) finishes everything first (_resolve).
         self.defer = True
-        self._event = None
-        self._pending = None
+        self.run_ahead = 3
+        self._ring = 4                          # pinned count slots / events; > run_ahead
+        self._h_pinned = torch.zeros((self._ring, obj_n * 80), dtype=torch.int32).pin_memory()
+        self._events = [None] * self._ring
+        self._seq = 0
+        self._pending = collections.deque()     # unfinished updates, oldest first
+        self._n_hi = [0] * obj_n                # upper bound of the live count (== _n when nothing is pending)
+        self._n_live = torch.zeros((obj_n, 2), dtype=torch.int32, device=self.device)
 
     # ---- reference attribute surface -------------------------------------------------------------
     @property
@@ -153,29 +165,58 @@ class FeatureBank:
         return self._n[class_idx]
 
     def bank_struct(self, class_idx: int) -> VfnBank:
+        """exact view of one object's bank (finishes deferred updates first)"""
         self._resolve()
-        return self._slabs[class_idx].struct(self._n[class_idx])
+        return self._slabs[class_idx].struct(self._n[class_idx], self._n_live[class_idx])
 
-    def _resolve(self):
-        """complete a deferred update(): wait for its counts, advance the bank sizes (FeatureBank.py:105-113)"""
-        pend = self._pending
-        if pend is None:
-            return
-        self._pending = None
-        banks, io, dec = pend
-        self._event.synchronize()
-        check(self._lib.vfn_bank_update_finish(banks, self.obj_n, io, self._h_pinned.data_ptr()), 'bank_update_finish')
+    def _struct_bounds(self, c: int) -> VfnBank:
+        """view with bounds: n = upper bound, n_min = last exact size; the kernels read the live count on the device"""
+        return self._slabs[c].struct(self._n_hi[c], self._n_live[c], self._n[c])
+
+    def _finish_oldest(self):
+        """complete the oldest deferred update(): wait for its counts, advance the exact sizes (FeatureBank.py:105-113)"""
+        pend = self._pending.popleft()
+        slot, banks, io, dec, hw = pend
+        self._events[slot].synchronize()
+        check(self._lib.vfn_bank_update_finish(banks, self.obj_n, io, self._h_pinned[slot].data_ptr()),
+              'bank_update_finish')
+        later = sum(p[4] for p in self._pending)
         for c in range(self.obj_n):
             r = io[c]
             self._n[c] = int(banks[c].n)
+            self._n_hi[c] = self._n[c] + later
             self._peak_n[c] = max(self._peak_n[c], self._n[c])                       # FeatureBank.py:113
             self._last_decisions[c] = dict(n_merge=int(r.n_merge), n_runs=int(r.n_runs), n_append=int(r.n_append),
                                            evicted=False, **dec[c])
 
-    def bank_array(self):
+    def _drain(self, keep: int):
+        while len(self._pending) > keep:
+            self._finish_oldest()
+
+    def _resolve(self):
+        """finish every deferred update: bank sizes are exact afterwards"""
+        self._drain(0)
+
+    def _set_live(self, c: int):
+        """device-resident live count := exact host count (after ingest / remove, which bypass vfn_bank_update)"""
+        s = self._slabs[c]
+        if s is not None and s.kh is not None:
+            bank = s.struct(self._n[c], self._n_live[c])
+            check(self._lib.vfn_bank_set_live(C.byref(bank), self._n[c], stream_ptr()), 'bank_set_live')
+            self.launches += 1
+        self._n_hi[c] = self._n[c]
+
+    def can_use_bounds(self, impl: int) -> bool:
+        """True when a read may run against the live count without finishing the pending updates"""
+        return bool(self._pending) and impl != 1 and all(s is not None and s.kh is not None for s in self._slabs)
+
+    def bank_array(self, bounds_ok: bool = False, impl: int = 0):
+        """struct vfn_bank[obj_n].  bounds_ok: the caller's kernels accept a device-resident live count (tcgen05 read),
+        so pending updates need not be finished"""
         arr = (VfnBank * self.obj_n)()
+        use_bounds = bounds_ok and self.can_use_bounds(impl)
         for c in range(self.obj_n):
-            arr[c] = self.bank_struct(c)
+            arr[c] = self._struct_bounds(c) if use_bounds else self.bank_struct(c)
         return arr
 
     # ---- internals -------------------------------------------------------------------------------
@@ -223,11 +264,12 @@ class FeatureBank:
         cv = self._buf(f'ing_cv{c}', (n_new, d_val), torch.float32)
         check(lib.vfn_prep_rows(ptr(key_dm), d_key, n_new, ptr(ck), None, None, None, 1.0, st), 'prep_rows')
         check(lib.vfn_prep_rows(ptr(val_dm), d_val, n_new, ptr(cv), None, None, None, 1.0, st), 'prep_rows')
-        bank = self.bank_struct(c)
+        bank = self._slabs[c].struct(self._n[c])      # exact host count; the device-resident count is set below
         check(lib.vfn_bank_append_rows(C.byref(bank), ptr(ck), ptr(cv), None, None, n_new, None, float(info0),
                                        float(info1), st), 'append_rows')
         self.launches += 3
         self._n[c] += n_new
+        self._set_live(c)
         self._peak_n[c] = max(self._peak_n[c], self._n[c])
 
     # ---- reference methods -----------------------------------------------------------------------
@@ -251,27 +293,39 @@ class FeatureBank:
         into the library (vfn_bank_update orders the kernel launches in C++)."""
         if update_rate == -1:
             update_rate = self.update_rate
-        self._resolve()
         lib, st = self._lib, stream_ptr()
         obj_n = self.obj_n
         pk = [prev_key[c].to(self.device, torch.float32).contiguous() for c in range(obj_n)]
         pv = [prev_value[c].to(self.device, torch.float32).contiguous() for c in range(obj_n)]
         d_key, hw = pk[0].shape
         d_val = pv[0].shape[0]
+        for c in range(obj_n):
+            s = self._slabs[c]
+            if pk[c].shape != (s.d_key, hw) or pv[c].shape != (s.d_val, hw):
+                raise ValueError('candidate dims do not match the bank')
+        # run ahead of the GPU only while no object can reach its budget or its slab's capacity even at the upper bound
+        # of its size (then FeatureBank.py:102 cannot fire and nothing on the host depends on |A|)
+        self._drain(max(self.run_ahead - 1, 0) if self.defer else 0)
+        bounds = (self.defer and self.run_ahead > 0 and self.impl != 1 and
+                  all(s.kh is not None and self._n_hi[c] + hw <= self.class_budget and self._n_hi[c] + hw <= s.cap
+                      for c, s in enumerate(self._slabs)))
+        if not bounds:
+            self._resolve()
         banks, alts = (VfnBank * obj_n)(), (VfnBank * obj_n)()
         io = (VfnUpdateIO * obj_n)()
         dec = []
         for c in range(obj_n):
             s = self._slabs[c]
-            if pk[c].shape != (s.d_key, hw) or pv[c].shape != (s.d_val, hw):
-                raise ValueError('candidate dims do not match the bank')
-            self._ensure_capacity(c, self._n[c] + hw, s.d_key, s.d_val, slack=hw)
-            s = self._slabs[c]
-            if self.class_budget < self._n[c] + hw:           # remove() may run: keep the ping-pong slab ready
-                alt = self._alt[c]
-                if alt is None or alt.cap < s.cap:
-                    self._alt[c] = _Slab(s.d_key, s.d_val, s.cap, self.device, s.kh is not None)
-            banks[c] = s.struct(self._n[c])
+            if not bounds:
+                self._ensure_capacity(c, self._n[c] + hw, s.d_key, s.d_val, slack=hw)
+                s = self._slabs[c]
+                if self.class_budget < self._n[c] + hw:           # remove() may run: keep the ping-pong slab ready
+                    alt = self._alt[c]
+                    if alt is None or alt.cap < s.cap:
+                        self._alt[c] = _Slab(s.d_key, s.d_val, s.cap, self.device, s.kh is not None)
+                banks[c] = s.struct(self._n[c], self._n_live[c])
+            else:
+                banks[c] = self._struct_bounds(c)
             alts[c] = self._alt[c].struct(0) if self._alt[c] is not None else VfnBank()
             d = dict(match_idx=self._buf(f'midx{c}', (hw,), torch.int32),
                      match_corr=self._buf(f'mcorr{c}', (hw,), torch.float32),
@@ -284,22 +338,27 @@ class FeatureBank:
             io[c].d_match_idx, io[c].d_match_corr = ptr(d['match_idx']), ptr(d['match_corr'])
             io[c].d_merge_q, io[c].d_merge_slot = ptr(d['merge_q']), ptr(d['merge_slot'])
             io[c].d_run_off, io[c].d_append_q = ptr(d['run_off']), ptr(d['append_q'])
-        n_max = max(self._n)
+        n_max = max(int(banks[c].n) for c in range(obj_n))
         ws_bytes = lib.vfn_bank_update_workspace_bytes(obj_n, n_max, hw, d_key, d_val)
         ws = self._buf('upd_ws', (ws_bytes,), torch.uint8)
         l0 = lib.vfn_launch_count()
-        ev = None
+        ev, slot = None, self._seq % self._ring
         if self.defer:
-            if self._event is None:
-                self._event = torch.cuda.Event()
-                self._event.record()                  # creates the underlying cudaEvent_t
-            ev = self._event.cuda_event
+            if self._events[slot] is None:
+                self._events[slot] = torch.cuda.Event()
+                self._events[slot].record()           # creates the underlying cudaEvent_t
+            ev = self._events[slot].cuda_event
         check(lib.vfn_bank_update(banks, alts, obj_n, io, hw, float(frame_idx), float(update_rate),
                                   float(self.thres_close), float(self.class_budget), ptr(ws), ws.numel(),
-                                  self._h_pinned.data_ptr(), self.impl, ev, st), 'bank_update')
+                                  self._h_pinned[slot].data_ptr(), self.impl, ev, st), 'bank_update')
         self.launches += lib.vfn_launch_count() - l0
         if io[0].deferred:
-            self._pending = (banks, io, dec)
+            self._seq += 1
+            self._pending.append((slot, banks, io, dec, hw))
+            for c in range(obj_n):
+                self._n_hi[c] = int(banks[c].n) + hw
+            if not any(s.kh is not None for s in self._slabs):
+                self._resolve()       # no device-resident count on this bank: the next call needs the exact size
             return
         err = None
         for c in range(obj_n):
@@ -317,7 +376,7 @@ class FeatureBank:
             if r.swapped:
                 self._slabs[c], self._alt[c] = self._alt[c], self._slabs[c]
                 self.replace_n[c] += r.n_before - r.kept                         # FeatureBank.py:140-141
-            self._n[c] = int(banks[c].n)
+            self._n[c] = self._n_hi[c] = int(banks[c].n)
             self._peak_n[c] = max(self._peak_n[c], self._n[c])                       # FeatureBank.py:113
             self._last_decisions[c] = dict(n_merge=int(r.n_merge), n_runs=int(r.n_runs), n_append=int(r.n_append),
                                            evicted=bool(r.evicted), **dec[c])
@@ -330,7 +389,7 @@ class FeatureBank:
         s, n = self._slabs[c], self._n[c]
         lfu = self._buf(f'lfu{c}', (max(n, 1),), torch.float32)
         plan = self._buf(f'plan{c}', (72,), torch.int32)
-        bank = s.struct(n)
+        bank = s.struct(n, self._n_live[c])
         check(lib.vfn_bank_evict_plan(C.byref(bank), float(frame_idx), float(self.class_budget), int(request_n),
                                       ptr(plan), self._h_plan[c].data_ptr(), ptr(lfu), st), 'evict_plan')
         self.launches += 1
@@ -361,6 +420,7 @@ class FeatureBank:
         self.launches += 3
         self._slabs[c], self._alt[c] = alt, s
         self._n[c] = kept
+        self._set_live(c)
         self.replace_n[c] += n - kept                                             # FeatureBank.py:140-141
         return (self.class_budget - kept) - request_n
 

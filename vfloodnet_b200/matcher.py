@@ -47,8 +47,9 @@ class Matcher(nn.Module):
         out = torch.empty((1, fb.obj_n, 2 * d_val, hw), dtype=torch.float32, device=fb.device)
         lse = torch.empty((fb.obj_n, hw), dtype=torch.float32, device=fb.device) if self.want_lse else None
         ws = self._workspace(lib, fb, hw, d_key, d_val)
-        banks = fb.bank_array()
         impl = fb.impl if self.impl is None else self.impl
+        # the tcgen05 read takes the live bank sizes from device memory: updates still in flight need not be finished
+        banks = fb.bank_array(bounds_ok=True, impl=int(impl))
         check(lib.vfn_memread(banks, fb.obj_n, ptr(q_in), ptr(q_out), hw, float(self.thres_valid),
                               int(bool(self.update_bank)), ptr(out), ptr(lse), ptr(ws), ws.numel(), int(impl),
                               stream_ptr()), 'vfn_memread')
