@@ -94,3 +94,83 @@ def test_bench_reference_arm_rank_gating(monkeypatch, capsys):
     bench.main_reference(args, rank=0, world=2)
     out = capsys.readouterr().out
     assert called and '"impl": "reference"' in out
+
+
+# ---------------------------------------------------------------------------------------------------
+# sharded LFU eviction: the threshold search over two shards must take the oracle's (= reference's) T sequence and
+# keep exactly the oracle's survivors; the thread communicator must agree with the gloo one
+# ---------------------------------------------------------------------------------------------------
+def _lfu_case(seed):
+    from oracle import afb_oracle as O
+    g = torch.Generator().manual_seed(seed)
+    n, frame, budget_obj, request = 4001, 40, 2000, 700
+    info = torch.zeros(n, 2)
+    info[:, 0] = torch.randint(0, frame, (n,), generator=g).float()
+    info[:, 1] = torch.rand(n, generator=g) * 400
+    info[::7, 1] = 0.0                                   # fresh entries: LFU 0
+    info[5, 1] = 5.0 * (frame - info[5, 0])              # LFU exactly 5.0 (strict > must evict it at T=5)
+    ofb = O.OracleFeatureBank(1, budget_obj, 'cpu')
+    ofb.init_bank([torch.zeros(8, n)], [torch.zeros(8, n)])
+    ofb.info[0] = info.clone()
+    dec = ofb._remove(0, request, frame)
+    lfu = info[:, 1] / (frame - info[:, 0])
+    return lfu, float(ofb.class_budget), request, dec
+
+
+def _lfu_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from vfloodnet_b200 import sharded
+        ok = True
+        for seed in (0, 1, 2):
+            lfu, budget, request, dec = _lfu_case(seed)
+            # interleaved ownership (what the chunked appends produce), local order preserved
+            own = torch.arange(lfu.numel()) % world == rank
+            kl, kg, T, thr = sharded.lfu_threshold_search(lfu[own], budget, request, sharded.DistComm())
+            keep = lfu[own] > float(T)
+            ok = ok and thr == dec.thresholds and kg == int(dec.keep_mask.sum()) and kl == int(keep.sum())
+            ok = ok and torch.equal(keep, dec.keep_mask[own]) and len(thr) > 1
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_lfu_threshold_search_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_lfu_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res), res
+
+
+def test_thread_comm_matches_reference_search_and_raises_like_it():
+    import threading
+    import pytest
+    from vfloodnet_b200 import sharded
+    lfu, budget, request, dec = _lfu_case(3)
+    world = 3
+    comms = sharded.ThreadComm.make(world)
+    out = [None] * world
+
+    def body(r):
+        own = torch.arange(lfu.numel()) % world == r
+        out[r] = sharded.lfu_threshold_search(lfu[own], budget, request, comms[r])
+
+    th = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    [t.start() for t in th]
+    [t.join(timeout=60) for t in th]
+    assert all(o is not None and o[3] == dec.thresholds and o[1] == int(dec.keep_mask.sum()) for o in out)
+    assert sum(o[0] for o in out) == out[0][1]
+    # error behaviour on one rank == the reference's exceptions (FeatureBank.py:123,136)
+    solo = sharded.ThreadComm.make(1)[0]
+    with pytest.raises(ValueError):
+        sharded.lfu_threshold_search(torch.tensor([1.0, float('nan')]), 10.0, 1, solo)
+    with pytest.raises(RuntimeError):
+        sharded.lfu_threshold_search(torch.tensor([1.0, 2.0]), 1.0, 5, solo)
