@@ -160,6 +160,10 @@ class ClockSampler(threading.Thread):
         except Exception:
             self.nvml = None
 
+    def mark(self):
+        """samples from here on belong to the timed region"""
+        self.first = len(self.samples)
+
     def run(self):
         while not self.stop_flag:
             try:
@@ -184,13 +188,14 @@ class ClockSampler(threading.Thread):
             time.sleep(0.3 if self.nvml is not None else 0.6)
 
     def summary(self):
-        if not self.samples:
+        samples = self.samples[getattr(self, 'first', 0):] or self.samples[-1:]
+        if not samples:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['clock query unavailable']}
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        sm = sorted(int(s[0]) for s in samples if s[0].isdigit())
         names = list(self.BITS)
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples)]
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': int(self.samples[0][1]), 'reasons': reasons,
-                'samples': len(self.samples), 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in samples)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': int(samples[0][1]), 'reasons': reasons,
+                'samples': len(samples), 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -278,27 +283,40 @@ def main_ours(args, rank, world, local_rank):
     out_host = torch.empty((2, 2 * R1_H, 2 * R1_W), dtype=torch.float32).pin_memory()
     torch.cuda.synchronize()
 
+    # the clock sampler starts BEFORE the warm-up: the first NVML queries of a process are slow and hold a driver lock
+    # that kernel launches also take (gpurun_out/q1: a sampler started at the timed region doubled its step time)
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and not os.environ.get('VFN_BENCH_NO_SAMPLER'):
+        sampler.start()
     for _ in range(args.warmup):
         run_clip_gpu(vfn, dev_clip, dev, args.read_impl)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     # timed region: K clips, no per-kernel events (bracketing every kernel with timing events serialises the stream:
     # profiles/r1h measured 1.48 ms/frame with them against 1.16 ms without)
     l0 = lib.vfn_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    step_ev = []
+    fb = out = prob = None
     for _ in range(args.steps):
+        # one bank per stream: the previous clip's bank is released before the next clip builds its own, exactly as in
+        # the warm-up (gpurun_out/host1: with the old bank still referenced the second timed clip had to cudaMalloc a
+        # second set of slabs inside the timed region: one step of 780 ms among steps of 105 ms)
+        fb = out = prob = None
         fb, out, prob = run_clip_gpu(vfn, dev_clip, dev, args.read_impl)
+        step_ev.append(torch.cuda.Event(enable_timing=True))
+        step_ev[-1].record()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    ms_steps = [a.elapsed_time(b) for a, b in zip([e0] + step_ev[:-1], step_ev)]
     launches = lib.vfn_launch_count() - l0
     final_n = [fb.bank_n(c) for c in range(2)]
     # roofline pass: the same K clips again with the library's CUDA events around each dominant kernel (recorded on the
     # launching stream), bank sizes read back every frame so that the algorithmic work per launch is exact
+    sampler.stop_flag = True                      # the clocks line covers the timed region only
     lib.vfn_profile_enable(1)
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
@@ -310,7 +328,6 @@ def main_ours(args, rank, world, local_rank):
     prof = (ctypes.c_double * 24)()
     _lib.check(lib.vfn_profile_collect(prof, 8), 'profile_collect')
     lib.vfn_profile_enable(0)
-    sampler.stop_flag = True
 
     # e2e: host inputs, copies inside the timed region
     for _ in range(1):
@@ -390,7 +407,8 @@ def main_ours(args, rank, world, local_rank):
                        'read_impl': args.read_impl},
             'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': int(launches), 'roofline': roofline, 'kernels': extra, 'clocks': sampler.summary(),
-            'ms_per_rank': [[round(a / args.steps, 2), round(b / args.steps, 2)] for a, b in per_rank]}
+            'ms_per_rank': [[round(a / args.steps, 2), round(b / args.steps, 2)] for a, b in per_rank],
+            'ms_steps': [round(x, 2) for x in ms_steps]}
     if not args.no_cpu_baseline and world == 1:
         fps, desc, secs = cpu_sample(args.frac_merge)
         line['cpu_baseline'] = {'value': fps, 'unit': 'frames/s', 'cores': os.cpu_count(), 'kind': 'port',
