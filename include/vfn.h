@@ -216,6 +216,31 @@ int vfn_urr_pre(const float* d_p, const float* d_r1, int64_t r1_obj_stride, int3
 int vfn_urr_post(const float* d_p_up, const float* d_unc, const float* d_conf, const float* d_q_local, int32_t obj_n,
                  int32_t h, int32_t w, float* d_prob, void* stream);
 
+/* ---- frame-loop tail: what follows fb.update in the reference's loop, kept on the device ---------
+ * resize_argmax: pred (H,W) u8 = argmax_c bicubic(pred_mask (obj_n,h,w) -> (H,W)); ties to the lowest class
+ *   replaces `TF.resize(pred_mask, ori_size, BICUBIC)` + `torch.argmax(pred[0], dim=0).cpu()` (test_video_seg.py:114-115).
+ *   antialias != 0: F.interpolate(mode='bicubic', antialias=True) (a = -0.5, truncated + re-normalised window;
+ *   torchvision >= 0.17 TF.resize on tensors); 0: a = -0.75, clamped indices (torchvision 0.9.1, README pin).
+ * largest_component: mask (H,W) u8 = the largest 8-connected component of pred != 0; equal sizes resolve like cv2's
+ *   CCL_GRANA label order (first 2x2 block in raster order); an empty pred gives an all-ones mask.  Replaces
+ *   `myutils.postprocessing_pred` (myutils/data.py:19-39) for binary predictions (obj_n == 2).
+ *   d_stats int32[4] = {foreground pixels, components, size of the kept one, its block-raster root id or -1}.
+ * waterlevel: for key point t = (x, y) = d_key_pts[2t], d_key_pts[2t+1]: first row y' > y with mask[y'][x] ==
+ *   water_label_id -> d_level[t] = y' - y (NaN when that is 1); no such row, or x outside the image: d_level[t] is left
+ *   as it is (the reference carries the previous frame's estimate forward).  estimation/reference_tracking.py:190-204.
+ * vfn_frame_tail: the three in sequence on one stream (7 launches, no host synchronisation). */
+size_t vfn_tail_workspace_bytes(int32_t H, int32_t W);
+int vfn_tail_resize_argmax(const float* d_pred_mask, int32_t obj_n, int32_t h, int32_t w, int32_t H, int32_t W,
+                           int32_t antialias, uint8_t* d_pred, void* stream);
+int vfn_tail_largest_component(const uint8_t* d_pred, int32_t H, int32_t W, uint8_t* d_mask, int32_t* d_stats,
+                               void* d_ws, size_t ws_bytes, void* stream);
+int vfn_tail_waterlevel(const uint8_t* d_mask, int32_t H, int32_t W, const int32_t* d_key_pts, int32_t n_pts,
+                        int32_t water_label_id, float* d_level, void* stream);
+int vfn_frame_tail(const float* d_pred_mask, int32_t obj_n, int32_t h, int32_t w, int32_t H, int32_t W,
+                   int32_t antialias, const int32_t* d_key_pts, int32_t n_pts, int32_t water_label_id,
+                   uint8_t* d_pred, uint8_t* d_mask, int32_t* d_stats, float* d_level, void* d_ws, size_t ws_bytes,
+                   void* stream);
+
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------------
  * While enabled, the library brackets its dominant kernels with CUDA events recorded on the launching stream.
  * kinds: 0 read phase A, 1 read phase B, 2 match, 3 compaction move, 4 merge, 5 append, 6 URR local.

@@ -60,6 +60,12 @@ SIGNATURES = {
     'vfn_bank_update_finish': (c_i32, [BANK_P, c_i32, IO_P, c_vp]),
     'vfn_urr_pre': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vfn_urr_post': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    'vfn_tail_workspace_bytes': (c_sz, [c_i32, c_i32]),
+    'vfn_tail_resize_argmax': (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    'vfn_tail_largest_component': (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'vfn_tail_waterlevel': (c_i32, [c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    'vfn_frame_tail': (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp,
+                               c_vp, c_vp, c_sz, c_vp]),
     'vfn_profile_enable': (c_i32, [c_i32]),
     'vfn_profile_collect': (c_i32, [c_vp, c_i32]),
     'vfn_profile_add_work': (c_i32, [c_i32, c_f64]),
