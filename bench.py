@@ -364,19 +364,29 @@ def main_ours(args, rank, world, local_rank):
     u1.record()
     barrier()
     ms_e2e_tail = u0.elapsed_time(u1)
-    # the tail alone, back to back on one stream (working set ~25 MB: L2 resident, stated in the line)
-    prob_dev = dev_clip['urr'][0].new_empty((2, 2 * R1_H, 2 * R1_W)).uniform_()
-    for _ in range(5):
-        ft(prob_dev)
-    tl0 = lib.vfn_launch_count()
-    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    v0.record()
-    for _ in range(50):
-        ft(prob_dev)
-    v1.record()
-    torch.cuda.synchronize()
-    tail_ms = v0.elapsed_time(v1) / 50
-    tail_launches = (lib.vfn_launch_count() - tl0) // 50
+    # the tail alone, back to back on one stream (working set ~25 MB: L2 resident, stated in the line), on a smooth
+    # soft mask (a handful of water bodies, what a trained model emits) and on per-pixel noise (10^5 components: the
+    # labelling's worst case, and what the URR output of this benchmark's random inputs looks like)
+    gt = torch.Generator().manual_seed(5)
+    coarse = torch.randn(1, 2, 10, 16, generator=gt).to(dev) * 4
+    smooth = torch.softmax(torch.nn.functional.interpolate(coarse, size=(2 * R1_H, 2 * R1_W), mode='bicubic',
+                                                           align_corners=False), dim=1)[0].contiguous()
+    noise = torch.rand((2, 2 * R1_H, 2 * R1_W), generator=gt).to(dev)
+    tail_ms = {}
+    tail_launches = 0
+    for nm, src in (('smooth', smooth), ('noise', noise)):
+        for _ in range(5):
+            ft(src)
+        tl0 = lib.vfn_launch_count()
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record()
+        for _ in range(50):
+            ft(src)
+        v1.record()
+        torch.cuda.synchronize()
+        tail_ms[nm] = v0.elapsed_time(v1) / 50
+        tail_launches = (lib.vfn_launch_count() - tl0) // 50
+    tail_stats = ft.stats.tolist()
 
     t_ms = torch.tensor([ms, ms_e2e, ms_e2e_tail], dtype=torch.float64, device=dev)
     per_rank = [[ms, ms_e2e, ms_e2e_tail]]
@@ -434,10 +444,12 @@ def main_ours(args, rank, world, local_rank):
                 else:
                     d.update(achieved=rate / 1e9, unit='GB/s', frac_of_hbm_peak=rate / 1e9 / hbm_peak)
             extra[nm] = d
-    tail_bytes = 4.0 * prob_dev.numel() + TAIL_SIZE[0] * TAIL_SIZE[1]      # read the soft mask once, write the u8 mask
-    extra['frame_tail'] = {'launches_per_frame': int(tail_launches), 'avg_ms': tail_ms, 'out_size': list(TAIL_SIZE),
-                           'achieved': tail_bytes / (tail_ms * 1e-3) / 1e9, 'unit': 'GB/s',
-                           'frac_of_hbm_peak': tail_bytes / (tail_ms * 1e-3) / 1e9 / hbm_peak,
+    tail_bytes = 4.0 * smooth.numel() + TAIL_SIZE[0] * TAIL_SIZE[1]        # read the soft mask once, write the u8 mask
+    extra['frame_tail'] = {'launches_per_frame': int(tail_launches), 'avg_ms': tail_ms['smooth'],
+                           'avg_ms_noise_input': tail_ms['noise'], 'out_size': list(TAIL_SIZE),
+                           'achieved': tail_bytes / (tail_ms['smooth'] * 1e-3) / 1e9, 'unit': 'GB/s',
+                           'frac_of_hbm_peak': tail_bytes / (tail_ms['smooth'] * 1e-3) / 1e9 / hbm_peak,
+                           'noise_input_stats': dict(zip(['fg_pixels', 'components', 'kept', 'root'], tail_stats)),
                            'note': 'resize+argmax, largest 8-connected component, water-level scan; working set is L2 '
                                    'resident (25 MB), latency bound: 7 dependent launches'}
     line = {'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,

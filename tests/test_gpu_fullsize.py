@@ -194,3 +194,16 @@ def test_eviction_at_capacity_is_order_preserving(vfn):
         assert torch.equal(fb.keys[c][:, :kept], keys[c][:, keep])
         assert torch.equal(fb.values[c][:, :kept], vals[c][:, keep])
         assert torch.equal(fb.keys[c][:, kept:], pk[c].to(dev))                   # appended raw (FeatureBank.py:105-107)
+    # the compaction re-derives the tensor-core operand arrays (fp16 hi/lo, fp8) from the fp32 masters it moves: a
+    # tcgen05 read of the compacted bank must agree with the fp32 SIMT read of the same masters, counts included
+    q_in, q_out = synth.gen_query(g, 700)
+    fb1 = vfn.FeatureBank(2, 250000, dev, impl=1)
+    fb1.load_state([fb.keys[c].clone() for c in range(2)], [fb.values[c].clone() for c in range(2)],
+                   [fb.info[c].clone() for c in range(2)])
+    m = vfn.Matcher(update_bank=True)
+    o_tc = m(fb, q_in.to(dev), q_out.to(dev))
+    o_f32 = m(fb1, q_in.to(dev), q_out.to(dev))
+    assert (o_tc - o_f32).abs().max().item() <= 1e-3
+    for c in range(2):
+        assert (fb.info[c][:, 1] - fb1.info[c][:, 1]).abs().max().item() <= 0.7     # at most one count flip (ln 2)
+        assert ((fb.info[c][:, 1] - fb1.info[c][:, 1]).abs() > 1e-5).sum().item() <= 4

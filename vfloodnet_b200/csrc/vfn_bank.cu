@@ -554,6 +554,48 @@ __global__ void __launch_bounds__(CP_THREADS) compact_move_kernel(vfn_bank src, 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t base_dst = block_off[blockIdx.x];
   const int dk = src.d_key, dv = src.d_val;
+  if (src.kh && dk == 128 && dv == 512) {
+    // AFB-URR dims with tensor-core operand arrays: a warp reads the fp32 masters of a row (keys, nk, values: 3080 B,
+    // all loads in flight before the first store) and re-derives the seven fp16/fp8 operand arrays with the same
+    // element-wise conversions that wrote them (bit-identical), instead of copying another 3584 B per row.
+    // Two rows per warp iteration keep 12 independent 16-byte loads per lane in flight.
+    for (int e = 2 * wid; e < tot; e += 2 * (CP_THREADS / 32)) {
+      const bool two = e + 1 < tot;
+      const int64_t s0 = (int64_t)blockIdx.x * CP_THREADS + list[e];
+      const int64_t s1 = two ? (int64_t)blockIdx.x * CP_THREADS + list[e + 1] : s0;
+      const int64_t d0 = base_dst + e, d1 = d0 + 1;
+      float4 k[2], nk[2], v[2][4];
+      float2 inf[2];
+      k[0] = __ldg(reinterpret_cast<const float4*>(src.keys + s0 * 128) + lane);
+      k[1] = __ldg(reinterpret_cast<const float4*>(src.keys + s1 * 128) + lane);
+      nk[0] = __ldg(reinterpret_cast<const float4*>(src.nk + s0 * 128) + lane);
+      nk[1] = __ldg(reinterpret_cast<const float4*>(src.nk + s1 * 128) + lane);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[0][j] = __ldg(reinterpret_cast<const float4*>(src.values + s0 * 512) + lane + 32 * j);
+        v[1][j] = __ldg(reinterpret_cast<const float4*>(src.values + s1 * 512) + lane + 32 * j);
+      }
+      if (lane < 2) inf[0] = __ldg(reinterpret_cast<const float2*>(src.info) + (lane ? s1 : s0));
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        if (r == 1 && !two) break;
+        const int64_t d = r ? d1 : d0;
+        reinterpret_cast<float4*>(dst.keys + d * 128)[lane] = k[r];
+        store_key_ops4(dst.kh, dst.kl, d * 128 + 4 * lane, k[r]);
+        store_nk4(dst.nk, dst.nkh, dst.nkl, d * 128 + 4 * lane, nk[r]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          reinterpret_cast<float4*>(dst.values + d * 512)[lane + 32 * j] = v[r][j];
+          store_val_ops4(dst.vh, dst.v8, dst.vl, d * 512 + 4 * (lane + 32 * j), v[r][j]);
+        }
+      }
+      if (lane == 0 || (lane == 1 && two)) {
+        reinterpret_cast<float2*>(dst.info)[lane ? d1 : d0] = inf[0];
+        dst.cnt[lane ? d1 : d0] = 0;
+      }
+    }
+    return;
+  }
   for (int e = wid; e < tot; e += CP_THREADS / 32) {
     const int64_t s = (int64_t)blockIdx.x * CP_THREADS + list[e];
     const int64_t d = base_dst + e;

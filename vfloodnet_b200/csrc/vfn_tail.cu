@@ -33,18 +33,20 @@ struct AxisAA {
 __device__ __forceinline__ AxisAA axis_aa(int i, int in_size, float scale) {
   AxisAA r;
   const float support = (scale >= 1.f) ? 2.f * scale : 2.f;
-  const float center = scale * (i + 0.5f);
-  r.lo = max((int)(center - support + 0.5f), 0);
-  r.size = min((int)(center + support + 0.5f), in_size) - r.lo;
-  r.center_off = (float)r.lo - center;
+  // every step rounded on its own (no FMA contraction): near the right border `center` is ~10^3 and half an ulp of an
+  // unrounded product moves the weights by 1e-5 against ATen's separately rounded float arithmetic
+  const float center = __fmul_rn(scale, i + 0.5f);
+  r.lo = max((int)__fadd_rn(__fsub_rn(center, support), 0.5f), 0);
+  r.size = min((int)__fadd_rn(__fadd_rn(center, support), 0.5f), in_size) - r.lo;
+  r.center_off = __fsub_rn((float)r.lo, center);
   r.invscale = (scale >= 1.f) ? 1.f / scale : 1.f;
   float t = 0.f;
-  for (int j = 0; j < r.size; ++j) t += cubic_aa((j + r.center_off + 0.5f) * r.invscale);
+  for (int j = 0; j < r.size; ++j) t += cubic_aa(__fmul_rn(__fadd_rn(__fadd_rn((float)j, r.center_off), 0.5f), r.invscale));
   r.total = t;
   return r;
 }
 __device__ __forceinline__ float axis_w(const AxisAA& a, int j) {
-  const float w = cubic_aa((j + a.center_off + 0.5f) * a.invscale);
+  const float w = cubic_aa(__fmul_rn(__fadd_rn(__fadd_rn((float)j, a.center_off), 0.5f), a.invscale));
   return a.total != 0.f ? w / a.total : w;
 }
 
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(256) resize_argmax_kernel(const float* __restr
       }
     }
   } else {
-    const float ry = scale_y * (Y + 0.5f) - 0.5f, rx = scale_x * (X + 0.5f) - 0.5f;
+    const float ry = __fsub_rn(__fmul_rn(scale_y, Y + 0.5f), 0.5f), rx = __fsub_rn(__fmul_rn(scale_x, X + 0.5f), 0.5f);
     const float fy = floorf(ry), fx = floorf(rx);
     const int iy = (int)fy, ix = (int)fx;
     float cx[4], cy[4];
@@ -168,15 +170,35 @@ __device__ __forceinline__ void uf_union(int* lab, int a, int b) {
   } while (!done);
 }
 
-// parent = left neighbour inside a horizontal run (a valid forest: the left id is always smaller); sizes zeroed
+// parent = first pixel of the horizontal run inside this CTA's 256-pixel span (found from the warps' ballots, so a find
+// never walks along a run); a run that continues from the previous span links its first pixel to the pixel on its
+// left.  Parents always carry a smaller id.  Sizes zeroed.
 __global__ void __launch_bounds__(256) cc_init_kernel(const uint8_t* __restrict__ pred, int H, int W, int wb,
                                                       int* __restrict__ lab, int* __restrict__ size) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= W) return;
+  __shared__ unsigned fg_bits[8];
+  const int x0 = blockIdx.x * 256, x = x0 + threadIdx.x, y = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint8_t* row = pred + (size_t)y * W;
+  const bool fg = x < W && row[x] != 0;
+  const unsigned bits = __ballot_sync(0xffffffffu, fg);
+  if (lane == 0) fg_bits[warp] = bits;
+  __syncthreads();
+  if (x >= W) return;
   const int id = pix_id(x, y, wb);
   int l = -1;
-  if (row[x]) l = (x > 0 && row[x - 1]) ? pix_id(x - 1, y, wb) : id;
+  if (fg) {
+    // nearest background pixel to the left inside the span -> the run starts right after it
+    int start = x0;
+    unsigned zeros = ~bits & ((1u << lane) - 1u);
+    int k = warp;
+    while (true) {
+      if (zeros) { start = x0 + 32 * k + (32 - __clz(zeros)); break; }
+      if (--k < 0) break;
+      zeros = ~fg_bits[k];
+    }
+    if (start < x) l = pix_id(start, y, wb);
+    else l = (x == x0 && x0 > 0 && row[x0 - 1]) ? pix_id(x0 - 1, y, wb) : id;
+  }
   lab[id] = l;
   size[id] = 0;
 }
