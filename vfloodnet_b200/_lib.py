@@ -73,6 +73,7 @@ SIGNATURES = {
     'vfn_debug_set_dump': (c_i32, [c_vp]),
     'vfn_debug_set_pair': (c_i32, [c_i32]),
     'vfn_debug_set_urr_stream': (c_i32, [c_i32]),
+    'vfn_debug_set_tail': (c_i32, [c_i32]),
 }
 
 _lib = None
