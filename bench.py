@@ -214,30 +214,41 @@ def expected_bank_size(frame, frac_merge):
     return int(min(hw + (1 - frac_merge) * hw * frame, 0.8 * (BUDGET // 2)))
 
 
-def cpu_sample(frac_merge, sample_frames=(25, 50, 75, 100), seed=0):
+def cpu_sample(frac_merge, sample_frames=(25, 50, 75, 100), seed=0, device='cpu'):
     """Times oracle read + URR + update at the bank sizes the clip has at `sample_frames` (synthetic bank contents of
-    the clip's analytic size trajectory).  Returns (frames_per_sec, description, seconds)."""
+    the clip's analytic size trajectory).  Returns (frames_per_sec, description, seconds).
+    device='cuda:N' runs the same plain-torch restatement with ATen/cuBLAS kernels on the GPU ("reference torch ops" of
+    BASELINE.json configs[1]); timed with a device synchronisation on both sides of every step."""
     from oracle import afb_oracle as O
     from vfloodnet_b200 import synth
-    torch.set_num_threads(os.cpu_count())
+    on_gpu = str(device) != 'cpu'
+    if not on_gpu:
+        torch.set_num_threads(os.cpu_count())
     hw = HW_H * HW_W
     total = 0.0
+    D = (lambda t: t.to(device)) if on_gpu else (lambda t: t)
     for f in sample_frames:
         g = torch.Generator().manual_seed(seed + f)
         n = expected_bank_size(f, frac_merge)
-        fb = O.OracleFeatureBank(2, BUDGET, 'cpu')
+        fb = O.OracleFeatureBank(2, BUDGET, device)
         keys, vals = zip(*[synth.gen_bank(g, n) for _ in range(2)])
-        fb.init_bank(list(keys), list(vals))
+        fb.init_bank([D(k) for k in keys], [D(v) for v in vals])
         for c in range(2):
-            fb.info[c] = synth.gen_info(g, n, f)
+            fb.info[c] = D(synth.gen_info(g, n, f))
         q_in, q_out = synth.gen_query(g, hw)
         pk, pv = zip(*[synth.gen_candidates(g, keys[c], vals[c], hw, frac_merge) for c in range(2)])
         p, r1, q_local = synth.gen_urr_inputs(g, 2, R1_H, R1_W)
+        args = (D(q_in), D(q_out), [D(k) for k in pk], [D(v) for v in pv])
+        urr = (D(p), D(r1).expand(2, -1, -1, -1), D(q_local), (1, 2, R1_H, R1_W))
+        if on_gpu:
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
-        O.hot_path_step(fb, q_in, q_out, list(pk), list(pv), f,
-                        urr_in=(p, r1.expand(2, -1, -1, -1), q_local, (1, 2, R1_H, R1_W)))
+        O.hot_path_step(fb, *args, f, urr_in=urr)
+        if on_gpu:
+            torch.cuda.synchronize()
         total += time.perf_counter() - t0
-    desc = (f'oracle port (torch CPU fp32) of read+URR+update on frames {list(sample_frames)} of the clip, bank sizes '
+    where = 'torch CUDA ops (ATen/cuBLAS fp32) on the same GPU' if on_gpu else 'torch CPU fp32'
+    desc = (f'oracle port ({where}) of read+URR+update on frames {list(sample_frames)} of the clip, bank sizes '
             f'{[expected_bank_size(f, frac_merge) for f in sample_frames]} slots/object (analytic trajectory)')
     return len(sample_frames) / total, desc, total
 
@@ -467,6 +478,17 @@ def main_ours(args, rank, world, local_rank):
             'gpu_launches': int(launches), 'roofline': roofline, 'kernels': extra, 'clocks': sampler.summary(),
             'ms_per_rank': [[round(x / args.steps, 2) for x in r] for r in per_rank],
             'ms_steps': [round(x, 2) for x in ms_steps]}
+    if world == 1:
+        # BASELINE.json configs[1]: "... vs reference torch ops" - the plain-torch restatement on this GPU (baseline only)
+        try:
+            torch.backends.cuda.matmul.allow_tf32 = False
+            cpu_sample(args.frac_merge, sample_frames=(5,), device=dev)                   # cuBLAS / allocator warm-up
+            fps_t, desc_t, secs_t = cpu_sample(args.frac_merge, device=dev)
+            line['torch_gpu_baseline'] = {'value': fps_t, 'unit': 'frames/s', 'kind': 'port', 'sample': desc_t,
+                                          'seconds': secs_t}
+        except Exception as e:                                                            # reported, never hidden
+            line['torch_gpu_baseline'] = {'value': None, 'error': f'{type(e).__name__}: {e}'[:300]}
+        torch.cuda.empty_cache()
     if not args.no_cpu_baseline and world == 1:
         fps, desc, secs = cpu_sample(args.frac_merge)
         line['cpu_baseline'] = {'value': fps, 'unit': 'frames/s', 'cores': os.cpu_count(), 'kind': 'port',

@@ -188,7 +188,7 @@ class OracleFeatureBank:
             slot_of_sel = related_bank_idx[0, sel[:, 0]]                                 # :72
             touched, _cnt = slot_of_sel.unique(dim=0, return_counts=True)                # :73
 
-            key_bank_update = torch.zeros((d_key, bank_n), dtype=torch.float)            # :76
+            key_bank_update = torch.zeros((d_key, bank_n), dtype=torch.float, device=self.device)   # :76
             key_bank_idx = slot_of_sel.unsqueeze(0).expand(d_key, -1)                    # :77
             scatter_mean_2_0_8(normed_prev_key[:, sel[:, 0]], key_bank_idx, 1, key_bank_update)   # :78
             self.keys[c][:, touched] = mag_keys[touched] * (                             # :81-84
@@ -197,7 +197,7 @@ class OracleFeatureBank:
             normed_values = NF.normalize(self.values[c], dim=0)                          # :87
             normed_prev_value = NF.normalize(prev_value[c], dim=0)                       # :88
             mag_values = self.values[c].norm(p=2, dim=0)                                 # :89
-            val_bank_update = torch.zeros((d_val, bank_n), dtype=torch.float)            # :90
+            val_bank_update = torch.zeros((d_val, bank_n), dtype=torch.float, device=self.device)   # :90
             val_bank_idx = slot_of_sel.unsqueeze(0).expand(d_val, -1)                    # :91
             scatter_mean_2_0_8(normed_prev_value[:, sel[:, 0]], val_bank_idx, 1, val_bank_update)  # :92
             self.values[c][:, touched] = mag_values[touched] * (                         # :94-97
@@ -228,8 +228,8 @@ class OracleFeatureBank:
         LFU = self.info[class_idx][:, 1] / LFU                                # :122
         thres_dynamic = int(LFU.min()) + 1                                    # :123
         thresholds = [thres_dynamic]
-        keep_total = torch.ones(old_size, dtype=torch.bool)
-        alive = torch.arange(old_size)
+        keep_total = torch.ones(old_size, dtype=torch.bool, device=LFU.device)
+        alive = torch.arange(old_size, device=LFU.device)
         while True:
             selected = LFU > thres_dynamic                                    # :127
             self.keys[class_idx] = self.keys[class_idx][:, selected]

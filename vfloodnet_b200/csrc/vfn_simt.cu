@@ -367,22 +367,64 @@ __global__ void __launch_bounds__(ST_THREADS) simt_readout_kernel(BankSet banks,
 }
 
 // out[obj][c][j] = sum_s po[obj][s][c][j] (c < dv) ; out[obj][dv + c][j] = q_out[c][j]     (AFB_URR.py:159,176)
-__global__ void combine_out_kernel(const float* __restrict__ po, int n_split, const int32_t* __restrict__ n_split_dev,
-                                   int64_t plane /* dv*hw */, int obj_n, const float* __restrict__ q_out,
-                                   float* __restrict__ out, int with_qout) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// V = 4: 128-bit accesses (plane % 4 == 0 and 16-byte aligned bases), same per-element summation order as V = 1
+template <int V>
+__global__ void __launch_bounds__(256) combine_out_kernel(const float* __restrict__ po, int n_split,
+                                                          const int32_t* __restrict__ n_split_dev,
+                                                          int64_t plane /* dv*hw */, int obj_n,
+                                                          const float* __restrict__ q_out, float* __restrict__ out,
+                                                          int with_qout) {
+  const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
   const int64_t total = plane * obj_n;
   if (idx >= total) return;
   if (n_split_dev) n_split = *n_split_dev;
   const int64_t obj = idx / plane, r = idx % plane;
-  float s = 0.f;
-  for (int k = 0; k < n_split; ++k) s += po[((int64_t)obj * n_split + k) * plane + r];
-  if (with_qout) {
-    out[obj * 2 * plane + r] = s;
-    out[obj * 2 * plane + plane + r] = q_out[r];
+  if (V == 4) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* base = po + (int64_t)obj * n_split * plane + r;
+    int k = 0;
+    for (; k + 4 <= n_split; k += 4) {          // four partial planes in flight, added in plane order
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(base + (k + 0) * plane));
+      const float4 b = __ldcs(reinterpret_cast<const float4*>(base + (k + 1) * plane));
+      const float4 c = __ldcs(reinterpret_cast<const float4*>(base + (k + 2) * plane));
+      const float4 d = __ldcs(reinterpret_cast<const float4*>(base + (k + 3) * plane));
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
+      s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w;
+      s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+    }
+    for (; k < n_split; ++k) {
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(base + k * plane));
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    }
+    if (with_qout) {
+      *reinterpret_cast<float4*>(out + obj * 2 * plane + r) = s;
+      *reinterpret_cast<float4*>(out + obj * 2 * plane + plane + r) = __ldg(reinterpret_cast<const float4*>(q_out + r));
+    } else {
+      *reinterpret_cast<float4*>(out + obj * plane + r) = s;
+    }
   } else {
-    out[obj * plane + r] = s;
+    float s = 0.f;
+    for (int k = 0; k < n_split; ++k) s += po[((int64_t)obj * n_split + k) * plane + r];
+    if (with_qout) {
+      out[obj * 2 * plane + r] = s;
+      out[obj * 2 * plane + plane + r] = q_out[r];
+    } else {
+      out[obj * plane + r] = s;
+    }
   }
+}
+
+static void launch_combine_out(const float* po, int n_split, const int32_t* n_split_dev, int64_t plane, int obj_n,
+                               const float* q_out, float* out, int with_qout, cudaStream_t st) {
+  const bool vec = plane % 4 == 0 && ((uintptr_t)po % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+                   (!with_qout || (uintptr_t)q_out % 16 == 0);
+  if (vec)
+    combine_out_kernel<4><<<(unsigned)cdiv(plane * obj_n / 4, 256), 256, 0, st>>>(po, n_split, n_split_dev, plane, obj_n,
+                                                                                q_out, out, with_qout);
+  else
+    combine_out_kernel<1><<<(unsigned)cdiv(plane * obj_n, 256), 256, 0, st>>>(po, n_split, n_split_dev, plane, obj_n,
+                                                                            q_out, out, with_qout);
 }
 
 // info[:,1] += log(cnt+1) ; cnt = 0                                                       (AFB_URR.py:174)
@@ -558,9 +600,8 @@ int vfn_memread_phase_b(const vfn_bank* banks, int32_t obj_n, const float* d_q_i
   // phase A of the same call sequence left Q (and the tcgen05 operands) in the workspace
   if (int rc = run_phase_b(set, p, d_lse, thres_valid, update_bank, ws, st)) return rc;
   const int64_t plane = (int64_t)set.b[0].d_val * hw;
-  combine_out_kernel<<<(unsigned)cdiv(plane * obj_n, 256), 256, 0, st>>>(reinterpret_cast<float*>(ws + p.off_po),
-                                                                        p.split_b, p.dev_b, plane, obj_n, nullptr,
-                                                                        d_partial_out, 0);
+  launch_combine_out(reinterpret_cast<float*>(ws + p.off_po), p.split_b, p.dev_b, plane, obj_n, nullptr, d_partial_out, 0,
+                     st);
   if (update_bank) {
     dim3 g((unsigned)cdiv(n_max, 256), obj_n);
     finalize_counts_kernel<<<g, 256, 0, st>>>(set, obj_n);
@@ -592,9 +633,7 @@ int vfn_memread(const vfn_bank* banks, int32_t obj_n, const float* d_q_in_dm, co
   VFN_LAUNCH_OK();
   if (int rc = run_phase_b(set, p, lse, thres_valid, update_bank, ws, st)) return rc;
   const int64_t plane = (int64_t)set.b[0].d_val * hw;
-  combine_out_kernel<<<(unsigned)cdiv(plane * obj_n, 256), 256, 0, st>>>(reinterpret_cast<float*>(ws + p.off_po),
-                                                                        p.split_b, p.dev_b, plane, obj_n, d_q_out_dm,
-                                                                        d_out, 1);
+  launch_combine_out(reinterpret_cast<float*>(ws + p.off_po), p.split_b, p.dev_b, plane, obj_n, d_q_out_dm, d_out, 1, st);
   if (update_bank) {
     dim3 g((unsigned)cdiv(n_max, 256), obj_n);
     finalize_counts_kernel<<<g, 256, 0, st>>>(set, obj_n);
