@@ -260,6 +260,9 @@ int vfn_debug_set_pair(int32_t mask);
 /* 1 (default): streaming (warp-shuffle, register-ring) URR local kernel when w % 4 == 0; 0: tiled shared-memory kernel */
 int vfn_debug_set_urr_stream(int32_t on);
 
+/* 1 (default): kernels that support it are queued with programmatic dependent launch (their CTAs are placed while the
+ * predecessor drains); 0: plain stream-ordered launches */
+int vfn_debug_set_pdl(int32_t on);
 /* tail labelling cross-check: bit 1 = no per-CTA size aggregation (every warp adds to global memory) */
 int vfn_debug_set_tail(int32_t flags);
 

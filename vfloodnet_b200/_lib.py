@@ -74,6 +74,7 @@ SIGNATURES = {
     'vfn_debug_set_pair': (c_i32, [c_i32]),
     'vfn_debug_set_urr_stream': (c_i32, [c_i32]),
     'vfn_debug_set_tail': (c_i32, [c_i32]),
+    'vfn_debug_set_pdl': (c_i32, [c_i32]),
 }
 
 _lib = None

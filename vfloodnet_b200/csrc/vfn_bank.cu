@@ -54,6 +54,8 @@ constexpr int PREP_CHUNK = 128;
 struct PrepJobs { PrepJob j[PREP_MAX_JOBS]; };
 
 __global__ void __launch_bounds__(256) prep_rows_kernel(const __grid_constant__ PrepJobs jobs) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float tile[32][33];
   __shared__ float part[8][32];
   __shared__ float denom[32];
@@ -125,7 +127,7 @@ int launch_prep(const PrepJob* jobs, int n_jobs, cudaStream_t st) {
   }
   if (n_max == 0) return VFN_OK;
   dim3 block(32, 8), grid((unsigned)cdiv(n_max, 32), n_jobs, (unsigned)cdiv(d_max, PREP_CHUNK));
-  prep_rows_kernel<<<grid, block, 0, st>>>(pj);
+  VFN_CUDA_OK(launch_pdl(prep_rows_kernel, grid, block, 0, st, pj));
   VFN_LAUNCH_OK();
   count_launches(1);
   return VFN_OK;
@@ -142,6 +144,8 @@ struct AppendSet { AppendObj o[4]; };
 // grid (rows, objects)
 __global__ void __launch_bounds__(128) append_rows_kernel(const __grid_constant__ AppendSet set, float info0,
                                                           float info1) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[32];
   const AppendObj& ao = set.o[blockIdx.y];
   const vfn_bank& bank = ao.bank;
@@ -344,6 +348,8 @@ struct PlanObj {
 struct PlanSet { PlanObj o[4]; };
 // one CTA per object (blockIdx.x)
 __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(const __grid_constant__ PlanSet set, int hw, float thres) {
+  pdl_wait();
+  pdl_trigger();
   const PlanObj& p = set.o[blockIdx.x];
   plan_body(p.match_idx, p.match_corr, hw, thres, p.merge_q, p.merge_slot, p.run_off, p.append_q, p.counts, p.h_counts,
             p.gkeys, p.n_live);
@@ -361,6 +367,8 @@ struct MergeSet { MergeObj o[4]; };
 // grid (runs, objects)
 __global__ void __launch_bounds__(MERGE_THREADS) merge_runs_kernel(const __grid_constant__ MergeSet set, float omr,
                                                                    float r) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[32];
   const MergeObj& mo = set.o[blockIdx.y];
   const vfn_bank& bank = mo.bank;
@@ -622,6 +630,8 @@ struct ClampSet { float* info[4]; int64_t n[4]; int32_t* n_live[4]; int64_t comm
 // grid (rows / 256, objects).  Last kernel of an update: also commits the bank's device-resident live count (nothing in
 // this kernel reads it; rows are bounded by the host-side upper bound).
 __global__ void clamp_info_kernel(const __grid_constant__ ClampSet set) {
+  pdl_wait();
+  pdl_trigger();
   float* __restrict__ info = set.info[blockIdx.y];
   const int64_t n = set.n[blockIdx.y];
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -663,7 +673,7 @@ int launch_plan(const UpdObj* o, int n_obj, int64_t hw, float thres_close, cudaS
     set.o[c] = PlanObj{o[c].match_idx, o[c].match_corr, o[c].merge_q, o[c].merge_slot, o[c].run_off, o[c].append_q,
                        o[c].counts, o[c].h_counts, reinterpret_cast<unsigned long long*>(o[c].plan_ws), o[c].n_live};
   }
-  plan_kernel<<<n_obj, PLAN_THREADS, 0, st>>>(set, (int)hw, thres_close);
+  VFN_CUDA_OK(launch_pdl(plan_kernel, dim3(n_obj), dim3(PLAN_THREADS), 0, st, set, (int)hw, thres_close));
   VFN_LAUNCH_OK();
   count_launches(1);
   return VFN_OK;
@@ -685,7 +695,7 @@ int launch_merge(const UpdObj* o, int n_obj, int64_t hw, float update_rate, cuda
   const float omr = (float)(1.0 - (double)update_rate);
   dim3 grid((unsigned)(hw < 148 * 8 ? hw : 148 * 8), n_obj);
   prof_begin(PROF_MERGE, st);
-  merge_runs_kernel<<<grid, MERGE_THREADS, 0, st>>>(set, omr, update_rate);
+  VFN_CUDA_OK(launch_pdl(merge_runs_kernel, grid, dim3(MERGE_THREADS), 0, st, set, omr, update_rate));
   prof_end(PROF_MERGE, st, 0.0);
   VFN_LAUNCH_OK();
   count_launches(1);
@@ -712,7 +722,7 @@ int launch_append(const UpdObj* o, int n_obj, float info0, float info1, cudaStre
   if (n_max == 0) return VFN_OK;
   dim3 grid((unsigned)(n_max < 148 * 16 ? n_max : 148 * 16), n_obj);
   prof_begin(PROF_APPEND, st);
-  append_rows_kernel<<<grid, 128, 0, st>>>(set, info0, info1);
+  VFN_CUDA_OK(launch_pdl(append_rows_kernel, grid, dim3(128), 0, st, set, info0, info1));
   // algorithmic bytes: read + write of the appended rows (keys, values, info)
   prof_end(PROF_APPEND, st, bytes);
   VFN_LAUNCH_OK();
@@ -736,7 +746,7 @@ int launch_clamp(const vfn_bank* banks, int n_obj, cudaStream_t st, const int64_
   if (n_max == 0 && any_live) n_max = 1;          // the commit must still happen
   if (n_max == 0) return VFN_OK;
   dim3 grid((unsigned)cdiv(n_max, 256), n_obj);
-  clamp_info_kernel<<<grid, 256, 0, st>>>(set);
+  VFN_CUDA_OK(launch_pdl(clamp_info_kernel, grid, dim3(256), 0, st, set));
   VFN_LAUNCH_OK();
   count_launches(1);
   return VFN_OK;

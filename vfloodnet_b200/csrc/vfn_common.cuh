@@ -64,6 +64,30 @@ int launch_clamp(const vfn_bank* banks, int n_obj, cudaStream_t st, const int64_
 
 #define VFN_LAUNCH_OK() VFN_CUDA_OK(cudaPeekAtLastError())
 
+// Programmatic dependent launch: the kernel is queued behind its predecessor on the stream with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs can be placed on the SMs while the predecessor drains;
+// every kernel launched this way calls pdl_wait() before it touches memory (griddepcontrol.wait = the predecessor has
+// completed and its writes are visible) and pdl_trigger() right after, which lets ITS successor be placed early too.
+// vfn_debug_set_pdl(0) falls back to plain launches (the device calls are no-ops then).
+extern int g_pdl;
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

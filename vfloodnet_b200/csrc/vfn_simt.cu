@@ -194,6 +194,8 @@ __global__ void __launch_bounds__(ST_THREADS) simt_score_kernel(BankSet banks, c
 // n_split_dev (optional): the split chosen on the device (banks with live counts, vfn_tc.cu split_plan_kernel)
 __global__ void lse_combine_kernel(const float2* __restrict__ part, int n_split, const int32_t* __restrict__ n_split_dev,
                                    int64_t hw, int obj_n, float* __restrict__ lse, float* __restrict__ lse_copy) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= hw * obj_n) return;
   if (n_split_dev) n_split = *n_split_dev;
@@ -374,6 +376,8 @@ __global__ void __launch_bounds__(256) combine_out_kernel(const float* __restric
                                                           int64_t plane /* dv*hw */, int obj_n,
                                                           const float* __restrict__ q_out, float* __restrict__ out,
                                                           int with_qout) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
   const int64_t total = plane * obj_n;
   if (idx >= total) return;
@@ -420,15 +424,17 @@ static void launch_combine_out(const float* po, int n_split, const int32_t* n_sp
   const bool vec = plane % 4 == 0 && ((uintptr_t)po % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
                    (!with_qout || (uintptr_t)q_out % 16 == 0);
   if (vec)
-    combine_out_kernel<4><<<(unsigned)cdiv(plane * obj_n / 4, 256), 256, 0, st>>>(po, n_split, n_split_dev, plane, obj_n,
-                                                                                q_out, out, with_qout);
+    launch_pdl(combine_out_kernel<4>, dim3((unsigned)cdiv(plane * obj_n / 4, 256)), dim3(256), 0, st, po, n_split, n_split_dev,
+               plane, obj_n, q_out, out, with_qout);
   else
-    combine_out_kernel<1><<<(unsigned)cdiv(plane * obj_n, 256), 256, 0, st>>>(po, n_split, n_split_dev, plane, obj_n,
-                                                                            q_out, out, with_qout);
+    launch_pdl(combine_out_kernel<1>, dim3((unsigned)cdiv(plane * obj_n, 256)), dim3(256), 0, st, po, n_split, n_split_dev,
+               plane, obj_n, q_out, out, with_qout);
 }
 
 // info[:,1] += log(cnt+1) ; cnt = 0                                                       (AFB_URR.py:174)
 __global__ void finalize_counts_kernel(BankSet banks, int obj_n) {
+  pdl_wait();
+  pdl_trigger();
   const int obj = blockIdx.y;
   const vfn_bank bk = banks.b[obj];
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -604,7 +610,7 @@ int vfn_memread_phase_b(const vfn_bank* banks, int32_t obj_n, const float* d_q_i
                      st);
   if (update_bank) {
     dim3 g((unsigned)cdiv(n_max, 256), obj_n);
-    finalize_counts_kernel<<<g, 256, 0, st>>>(set, obj_n);
+    launch_pdl(finalize_counts_kernel, g, dim3(256), 0, st, set, obj_n);
   }
   VFN_LAUNCH_OK();
   return VFN_OK;
@@ -628,15 +634,15 @@ int vfn_memread(const vfn_bank* banks, int32_t obj_n, const float* d_q_in_dm, co
   if (int rc = run_phase_a(set, p, d_q_in_dm, ws, st)) return rc;
   float* lse = reinterpret_cast<float*>(ws + p.off_lse);
   const int64_t rows = hw * obj_n;
-  lse_combine_kernel<<<(unsigned)cdiv(rows, 256), 256, 0, st>>>(reinterpret_cast<float2*>(ws + p.off_part), p.split_a,
-                                                                p.dev_a, hw, obj_n, lse, d_lse);
+  launch_pdl(lse_combine_kernel, dim3((unsigned)cdiv(rows, 256)), dim3(256), 0, st,
+             reinterpret_cast<const float2*>(ws + p.off_part), p.split_a, p.dev_a, hw, obj_n, lse, d_lse);
   VFN_LAUNCH_OK();
   if (int rc = run_phase_b(set, p, lse, thres_valid, update_bank, ws, st)) return rc;
   const int64_t plane = (int64_t)set.b[0].d_val * hw;
   launch_combine_out(reinterpret_cast<float*>(ws + p.off_po), p.split_b, p.dev_b, plane, obj_n, d_q_out_dm, d_out, 1, st);
   if (update_bank) {
     dim3 g((unsigned)cdiv(n_max, 256), obj_n);
-    finalize_counts_kernel<<<g, 256, 0, st>>>(set, obj_n);
+    launch_pdl(finalize_counts_kernel, g, dim3(256), 0, st, set, obj_n);
   }
   VFN_LAUNCH_OK();
   count_launches(2 + (update_bank ? 1 : 0));

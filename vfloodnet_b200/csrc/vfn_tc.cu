@@ -1408,6 +1408,8 @@ struct RescoreArgs {
 };
 
 __global__ void __launch_bounds__(256) match_rescore_kernel(const float2* __restrict__ part, RescoreArgs a) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int obj = blockIdx.y;
   const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -1838,7 +1840,7 @@ int tc_match(const vfn_bank* banks, int obj_n, const float* const* nck_em, int64
   prof_end(PROF_MATCH, st, work);
   r.obj_n = obj_n; r.pieces = pieces; r.hw = (int)hw; r.band = a.band;
   dim3 grid((unsigned)cdiv(hw, 8), obj_n);
-  match_rescore_kernel<<<grid, 256, 0, st>>>(part, r);
+  VFN_CUDA_OK(launch_pdl(match_rescore_kernel, grid, dim3(256), 0, st, (const float2*)part, r));
   VFN_LAUNCH_OK();
   count_launches(2);
   return VFN_OK;

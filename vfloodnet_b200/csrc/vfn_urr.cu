@@ -24,6 +24,8 @@ __device__ __forceinline__ float bilerp(const float* __restrict__ pl, int win, i
 constexpr int URR_MAX_OBJ = 8;
 __global__ void urr_seg_kernel(const float* __restrict__ p, int obj_n, int h, int w, float* __restrict__ p_up,
                                float* __restrict__ seg, float* __restrict__ unc) {
+  pdl_wait();
+  pdl_trigger();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   if (x >= w) return;
@@ -59,6 +61,8 @@ __global__ void urr_seg_kernel(const float* __restrict__ p, int obj_n, int h, in
 // stage 2: conf = 7x7 max of seg (-inf pad), avg = 7x7 mean of seg (zero pad, /49)
 __global__ void urr_window_kernel(const float* __restrict__ seg, int obj_n, int h, int w, float* __restrict__ conf,
                                   float* __restrict__ avg) {
+  pdl_wait();
+  pdl_trigger();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, o = blockIdx.z;
   if (x >= w) return;
@@ -91,6 +95,8 @@ __global__ void __launch_bounds__(URR_LOCAL_THREADS) urr_local_kernel(const floa
                                                                       const float* __restrict__ seg,
                                                                       const float* __restrict__ avg,
                                                                       float* __restrict__ lm) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sr1[UHH][UW];
   __shared__ float prod[URR_LOCAL_MAX_OBJ][UHH][UW];
   const int ch = blockIdx.z;
@@ -169,6 +175,8 @@ template <int NO>
 __global__ void __launch_bounds__(UL_WARPS * 32) urr_local_stream_kernel(
     const float* __restrict__ r1, int64_t r1_obj_stride, int c_n, int obj_n, int h, int w, int band,
     const float* __restrict__ seg, const float* __restrict__ avg, float* __restrict__ lm) {
+  pdl_wait();
+  pdl_trigger();
   // the warps of a CTA take DIFFERENT channels of the same (band, column range): their seg / avg loads coincide and are
   // served by L1 after the first warp's miss (seg and avg are re-read by every channel: 4 planes x 64 channels)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -263,6 +271,8 @@ __global__ void __launch_bounds__(UL_WARPS * 32) urr_local_stream_kernel(
 __global__ void urr_post_kernel(const float* __restrict__ p_up, const float* __restrict__ unc,
                                 const float* __restrict__ conf, const float* __restrict__ ql, int obj_n, int h, int w,
                                 float* __restrict__ prob) {
+  pdl_wait();
+  pdl_trigger();
   const int X = blockIdx.x * blockDim.x + threadIdx.x;
   const int Y = blockIdx.y, o = blockIdx.z;
   const int H = 2 * h, W = 2 * w;
@@ -300,9 +310,15 @@ __global__ void urr_post_kernel(const float* __restrict__ p_up, const float* __r
 
 using namespace vfn;
 
+namespace vfn { int g_pdl = 1; }
 static int g_urr_stream = 1;   // vfn_debug_set_urr_stream(0): tiled shared-memory kernel (cross-check in tests/)
 
 extern "C" {
+
+int vfn_debug_set_pdl(int32_t on) {
+  vfn::g_pdl = on ? 1 : 0;
+  return VFN_OK;
+}
 
 int vfn_debug_set_urr_stream(int32_t on) {
   g_urr_stream = on ? 1 : 0;
@@ -318,9 +334,9 @@ int vfn_urr_pre(const float* d_p, const float* d_r1, int64_t r1_obj_stride, int3
   VFN_CHECK_ARG(c > 0, "urr_pre: channels must be positive");
   cudaStream_t st = as_stream(stream);
   dim3 g1((unsigned)cdiv(w, 128), h);
-  urr_seg_kernel<<<g1, 128, 0, st>>>(d_p, obj_n, h, w, d_p_up, d_seg, d_unc);
+  launch_pdl(urr_seg_kernel, g1, dim3(128), 0, st, d_p, obj_n, h, w, d_p_up, d_seg, d_unc);
   dim3 g2((unsigned)cdiv(w, 128), h, obj_n);
-  urr_window_kernel<<<g2, 128, 0, st>>>(d_seg, obj_n, h, w, d_conf, d_avg);
+  launch_pdl(urr_window_kernel, g2, dim3(128), 0, st, d_seg, obj_n, h, w, d_conf, d_avg);
   dim3 g3((unsigned)cdiv(w, UT_W), (unsigned)cdiv(h, UT_H), c);
   prof_begin(PROF_URR, st);
   if (w % 4 == 0 && g_urr_stream) {
@@ -340,11 +356,11 @@ int vfn_urr_pre(const float* d_p, const float* d_r1, int64_t r1_obj_stride, int3
     if (band < 8) band = 8;
     dim3 gs((unsigned)cdiv(w / 4, UL_COLS), (unsigned)cdiv(h, band), (unsigned)(cdiv(c, UL_WARPS) * cdiv(obj_n, no)));
     if (no == 2)
-      urr_local_stream_kernel<2><<<gs, UL_WARPS * 32, 0, st>>>(d_r1, r1_obj_stride, c, obj_n, h, w, band, d_seg, d_avg, d_local_match);
+      launch_pdl(urr_local_stream_kernel<2>, gs, dim3(UL_WARPS * 32), 0, st, d_r1, r1_obj_stride, c, obj_n, h, w, band, d_seg, d_avg, d_local_match);
     else
-      urr_local_stream_kernel<1><<<gs, UL_WARPS * 32, 0, st>>>(d_r1, r1_obj_stride, c, obj_n, h, w, band, d_seg, d_avg, d_local_match);
+      launch_pdl(urr_local_stream_kernel<1>, gs, dim3(UL_WARPS * 32), 0, st, d_r1, r1_obj_stride, c, obj_n, h, w, band, d_seg, d_avg, d_local_match);
   } else {
-    urr_local_kernel<<<g3, URR_LOCAL_THREADS, 0, st>>>(d_r1, r1_obj_stride, c, obj_n, h, w, d_seg, d_avg, d_local_match);
+    launch_pdl(urr_local_kernel, g3, dim3(URR_LOCAL_THREADS), 0, st, d_r1, r1_obj_stride, c, obj_n, h, w, d_seg, d_avg, d_local_match);
   }
   // algorithmic bytes: read r1 once, write [r1 ; r1_local] per object, + small planes
   prof_end(PROF_URR, st, 4.0 * (double)h * w * ((r1_obj_stride ? obj_n : 1) * (double)c + obj_n * (2.0 * c + 8.0)));
@@ -358,7 +374,7 @@ int vfn_urr_post(const float* d_p_up, const float* d_unc, const float* d_conf, c
   VFN_CHECK_ARG(d_p_up && d_unc && d_conf && d_q_local && d_prob, "urr_post: NULL argument");
   VFN_CHECK_ARG(obj_n >= 1 && h > 0 && w > 0, "urr_post: bad shape");
   dim3 g((unsigned)cdiv(2 * w, 128), 2 * h, obj_n);
-  urr_post_kernel<<<g, 128, 0, as_stream(stream)>>>(d_p_up, d_unc, d_conf, d_q_local, obj_n, h, w, d_prob);
+  launch_pdl(urr_post_kernel, g, dim3(128), 0, as_stream(stream), d_p_up, d_unc, d_conf, d_q_local, obj_n, h, w, d_prob);
   VFN_LAUNCH_OK();
   count_launches(1);
   return VFN_OK;
