@@ -603,6 +603,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = *tmem_base_p;
+  // programmatic dependent launch: barriers, TMEM and the cluster handshake above overlap the predecessor's tail;
+  // nothing before this point reads global memory
+  pdl_wait();
+  pdl_trigger();
 
   // work items = (split, object, query-tile pair), dealt round-robin to the persistent clusters
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
@@ -1143,6 +1147,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = *tmem_base_p;
+  pdl_wait();        // programmatic dependent launch: the prologue above overlaps the predecessor's tail
+  pdl_trigger();
 
   // work items = (split, object, query-tile pair, channel half), round-robin over the clusters
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
@@ -1549,6 +1555,8 @@ struct SplitPlanArgs {
   int32_t* out;
 };
 __global__ void split_plan_kernel(SplitPlanArgs a) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x;
   long long tmin = 0x7fffffffffffffffll, tmax = 0;
   for (int o = 0; o < a.obj_n; ++o) {
@@ -1592,7 +1600,7 @@ static int launch_split_plan(const vfn_bank* banks, int obj_n, int tile, int com
   sp.obj_n = obj_n; sp.tile = tile; sp.combos = combos; sp.overhead = overhead; sp.G = G; sp.chain_max = chain_max;
   for (int o = 0; o < obj_n; ++o) sp.n_live[o] = banks[o].n_live;
   sp.out = out;
-  split_plan_kernel<<<1, 32, 0, st>>>(sp);
+  VFN_CUDA_OK(launch_pdl(split_plan_kernel, dim3(1), dim3(32), 0, st, sp));
   VFN_LAUNCH_OK();
   count_launches(1);
   return VFN_OK;
@@ -1699,7 +1707,7 @@ int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t h
   for (int o = 0; o < obj_n; ++o) work += 2.0 * DK * (double)banks[o].n * (double)hw;
   prof_begin(PROF_READ_A, st);
   if (pair)
-    tc_scan_pair_kernel<MODE_LSE><<<num_sms(), TC_THREADS, SP_SMEM, st>>>(maps, a, part);
+    VFN_CUDA_OK(launch_pdl(tc_scan_pair_kernel<MODE_LSE>, dim3(num_sms()), dim3(TC_THREADS), SP_SMEM, st, maps, a, part));
   else
     tc_scan_kernel<MODE_LSE><<<num_sms(), TC_THREADS, SC_SMEM, st>>>(maps, a, part);
   prof_end(PROF_READ_A, st, work);
@@ -1745,7 +1753,7 @@ int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const 
   for (int o = 0; o < obj_n; ++o) work += 2.0 * DV * (double)banks[o].n * (double)hw;
   prof_begin(PROF_READ_B, st);
   if (pair)
-    tc_phase_b_pair_kernel<<<num_sms(), TC_THREADS, P_SMEM, st>>>(maps, a, lse, thres_valid, update_bank, po);
+    VFN_CUDA_OK(launch_pdl(tc_phase_b_pair_kernel, dim3(num_sms()), dim3(TC_THREADS), P_SMEM, st, maps, a, lse, thres_valid, update_bank, po));
   else
     tc_phase_b_kernel<<<num_sms(), TC_THREADS, B_SMEM, st>>>(maps, a, lse, thres_valid, update_bank, po);
   prof_end(PROF_READ_B, st, work);
@@ -1834,7 +1842,7 @@ int tc_match(const vfn_bank* banks, int obj_n, const float* const* nck_em, int64
   float2* part = reinterpret_cast<float2*>(ws);
   prof_begin(PROF_MATCH, st);
   if (pair)
-    tc_scan_pair_kernel<MODE_MATCH><<<num_sms(), TC_THREADS, SP_SMEM, st>>>(maps, a, part);
+    VFN_CUDA_OK(launch_pdl(tc_scan_pair_kernel<MODE_MATCH>, dim3(num_sms()), dim3(TC_THREADS), SP_SMEM, st, maps, a, part));
   else
     tc_scan_kernel<MODE_MATCH><<<num_sms(), TC_THREADS, SC_SMEM, st>>>(maps, a, part);
   prof_end(PROF_MATCH, st, work);
