@@ -440,6 +440,7 @@ __global__ void finalize_counts_kernel(BankSet banks, int obj_n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= live_n(bk)) return;
   const int c = bk.cnt[i];
+  if (c == 0) return;            // log(0 + 1) = 0: info unchanged (most slots of a large bank; skips the fp64 log)
   bk.cnt[i] = 0;
   // bank_cnt + 1 is exact in fp32; log evaluated in double and rounded once
   bk.info[2 * i + 1] += (float)log((double)((float)c + 1.0f));
