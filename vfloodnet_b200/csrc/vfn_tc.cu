@@ -507,12 +507,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const __grid_con
           if (cm > m_run + args.band) cnt = 0;
           const float m_new = fmaxf(m_run, cm);
           const float thr = row_live ? m_new - args.band : INFINITY;
+          // once the running maximum is established almost no tile holds a score inside the band: the 32 compares
+          // below only run for the lanes' tiles whose own maximum reaches it
+          if (cm >= thr) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float sv = __uint_as_float(v[i]);
-            if (sv >= thr) {
-              ring[cnt & (MATCH_RING - 1)] = make_float2(sv, __int_as_float(slot0 + i));
-              ++cnt;
+            for (int i = 0; i < 32; ++i) {
+              const float sv = __uint_as_float(v[i]);
+              if (sv >= thr) {
+                ring[cnt & (MATCH_RING - 1)] = make_float2(sv, __int_as_float(slot0 + i));
+                ++cnt;
+              }
             }
           }
           m_run = m_new;
@@ -730,12 +734,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           if (cm > m_run + args.band) cnt = 0;
           const float m_new = fmaxf(m_run, cm);
           const float thr = row_live ? m_new - args.band : INFINITY;
+          // once the running maximum is established almost no tile holds a score inside the band: the 32 compares
+          // below only run for the lanes' tiles whose own maximum reaches it
+          if (cm >= thr) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float sv = __uint_as_float(v[i]);
-            if (sv >= thr) {
-              ring[cnt & (MATCH_RING - 1)] = make_float2(sv, __int_as_float(slot0 + i));
-              ++cnt;
+            for (int i = 0; i < 32; ++i) {
+              const float sv = __uint_as_float(v[i]);
+              if (sv >= thr) {
+                ring[cnt & (MATCH_RING - 1)] = make_float2(sv, __int_as_float(slot0 + i));
+                ++cnt;
+              }
             }
           }
           m_run = m_new;
