@@ -311,12 +311,15 @@ constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 struct TcMaps {
   CUtensorMap kh[TC_MAX_OBJ], kl[TC_MAX_OBJ], vh[TC_MAX_OBJ], v8[TC_MAX_OBJ], vl[TC_MAX_OBJ];
 };
+constexpr int TC_MAX_SPLIT = 24;
 struct TcArgs {
   int obj_n, hw, q_tiles, pieces;       // pieces = partial slots per combo
   int n[TC_MAX_OBJ];                    // live slots per object (an upper bound when n_live[obj] is set)
   int tiles[TC_MAX_OBJ];                // slot tiles per object for this phase (same)
   const int32_t* n_live[TC_MAX_OBJ];    // device-resident live count (vfn_bank::n_live) or NULL
-  const int32_t* pieces_dev;            // with live counts: `pieces` chosen on the device by split_plan_kernel, else NULL
+  int32_t* pieces_dev;                  // with live counts: `pieces` is chosen on the device (tc_pieces) from the plan_*
+                                        // parameters and published here for the combine kernels that follow; else NULL
+  int plan_tile, plan_combos, plan_overhead, plan_G, plan_chain_max;
   const uint16_t* qh;                   // (rows, 128) fp16 hi of the A operand (q * log2e/sqrt(d), or 16 * normalised candidate)
   const uint16_t* ql;
   long long a_obj_stride;               // elements between objects in qh/ql (0: one query set for all objects)
@@ -324,6 +327,44 @@ struct TcArgs {
   float band;                           // match: candidate band in the (scaled) score domain
   float* dbg;
 };
+
+// Work split of a launch.  Host-tracked sizes: args.pieces.  Device-resident live counts: every warp of every CTA
+// evaluates the host's best_split() on the live counts (lane s-1 takes split s; integer costs, ties -> smallest s, the
+// first minimum of the host loop), so a launch issued against bounds partitions the work exactly like one issued after
+// reading the sizes back; CTA 0 publishes the choice for the combine kernels.  Must be called by full warps, after
+// pdl_wait().  (A separate 1-warp kernel did this before: three extra launches per frame.)
+__device__ __forceinline__ int tc_pieces(const TcArgs& a) {
+  if (!a.pieces_dev) return a.pieces;
+  const int lane = threadIdx.x & 31;
+  long long tmin = 0x7fffffffffffffffll, tmax = 0;
+  for (int o = 0; o < a.obj_n; ++o) {
+    const long long n = *reinterpret_cast<const volatile int32_t*>(a.n_live[o]);
+    const long long t = (n + a.plan_tile - 1) / a.plan_tile;
+    tmin = t < tmin ? t : tmin;
+    tmax = t > tmax ? t : tmax;
+  }
+  int s_min = 1;
+  if (a.plan_chain_max > 0) s_min = (int)((tmax * a.plan_tile + a.plan_chain_max - 1) / a.plan_chain_max);
+  if (s_min < 1) s_min = 1;
+  if (s_min > TC_MAX_SPLIT) s_min = TC_MAX_SPLIT;
+  if (s_min > tmin) s_min = (int)(tmin > 1 ? tmin : 1);
+  const int sp = lane + 1;
+  long long cost = 0x7fffffffffffffffll;
+  if (sp >= s_min && sp <= TC_MAX_SPLIT && sp <= tmin) {
+    const long long rounds = ((long long)a.plan_combos * sp + a.plan_G - 1) / a.plan_G;
+    cost = rounds * ((tmax + sp - 1) / sp + a.plan_overhead);
+  }
+  int best = sp;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const long long oc = __shfl_xor_sync(0xffffffffu, cost, o);
+    const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+    if (oc < cost || (oc == cost && ob < best)) { cost = oc; best = ob; }
+  }
+  const int pieces = (cost == 0x7fffffffffffffffll) ? s_min : best;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.pieces_dev = pieces;
+  return pieces;
+}
 
 // A operand (128 rows x 128 d, fp16 hi and lo) -> TMEM columns [col_h, col_h+64) and [col_l, col_l+64).
 // Epilogue warp (quarter q, column group cg): cg 0,1 -> hi halves, cg 2,3 -> lo halves; 32 columns (64 fp16) each.
@@ -392,7 +433,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const __grid_con
   // work items = (split, object, query tile), dealt round-robin to the persistent CTAs: in any round all CTAs
   // stream the same few slot ranges, so the tiles are served from L2 (profiles/r1a_summary.md).
   const int n_combos = args.obj_n * args.q_tiles;
-  const int pieces = args.pieces_dev ? *reinterpret_cast<const volatile int32_t*>(args.pieces_dev) : args.pieces;
+  const int pieces = tc_pieces(args);
   const int n_items = n_combos * pieces;
   uint32_t tile_ctr = 0;        // tiles streamed so far by this CTA (all roles agree)
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -616,7 +657,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   const int qpairs = (args.q_tiles + 1) >> 1;
   const int n_combos = args.obj_n * qpairs;
-  const int pieces = args.pieces_dev ? *reinterpret_cast<const volatile int32_t*>(args.pieces_dev) : args.pieces;
+  const int pieces = tc_pieces(args);
   const int n_items = n_combos * pieces;
   uint32_t tile_ctr = 0;        // tiles streamed so far by this cluster (all roles agree)
   for (int item = cluster_id; item < n_items; item += n_clusters) {
@@ -885,7 +926,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_phase_b_kernel(const __grid_
   // work items = (split, object, query tile, channel half), round-robin over the persistent CTAs
   const int cpo = args.q_tiles * 2;
   const int n_combos = args.obj_n * cpo;
-  const int pieces = args.pieces_dev ? *reinterpret_cast<const volatile int32_t*>(args.pieces_dev) : args.pieces;
+  const int pieces = tc_pieces(args);
   const int n_items = n_combos * pieces;
   uint32_t k_it = 0;            // tiles streamed so far (K/V stage = k_it & 1)
   uint32_t buf_it[2] = {0, 0};  // uses of each S/P buffer so far
@@ -1163,7 +1204,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   const int qpairs = (args.q_tiles + 1) >> 1;
   const int cpo = qpairs * 2;
   const int n_combos = args.obj_n * cpo;
-  const int pieces = args.pieces_dev ? *reinterpret_cast<const volatile int32_t*>(args.pieces_dev) : args.pieces;
+  const int pieces = tc_pieces(args);
   const int n_items = n_combos * pieces;
   uint32_t k_it = 0;            // tiles streamed so far (stage = k_it & 3)
   uint32_t buf_it[2] = {0, 0};  // uses of each S/P buffer so far
@@ -1535,7 +1576,6 @@ bool tc_shapes_ok(int d_key, int d_val) { return d_key == DK && d_val == DV; }
 static int64_t map_rows(const vfn_bank& b) { return b.n_live ? b.cap : b.n; }
 static int64_t n_low(const vfn_bank& b) { return b.n_live ? b.n_min : b.n; }
 
-constexpr int TC_MAX_SPLIT = 24;
 constexpr int B_CHAIN_MAX = 8192;      // slots accumulated into one TMEM readout accumulator (see tc_phase_b)
 
 // number of slot splits per (object, query tile[, half]) combo: minimise rounds x (tiles per item + fixed per-item
@@ -1554,46 +1594,6 @@ static int best_split(int combos, int64_t tiles_min, int64_t tiles_max, int over
   return best;
 }
 
-// best_split evaluated on the device from the live counts (banks with vfn_bank::n_live): the same choice the host makes
-// from exact sizes, so a read / match issued against bounds is bit-identical to one issued after reading the sizes back.
-// One warp: lane s-1 evaluates split s; integer costs, ties -> smallest s (the host loop keeps the first minimum).
-struct SplitPlanArgs {
-  int obj_n, tile, combos, overhead, G, chain_max;     // chain_max > 0: s_min = cdiv(tiles_max * tile, chain_max)
-  const int32_t* n_live[TC_MAX_OBJ];
-  int32_t* out;
-};
-__global__ void split_plan_kernel(SplitPlanArgs a) {
-  pdl_wait();
-  pdl_trigger();
-  const int lane = threadIdx.x;
-  long long tmin = 0x7fffffffffffffffll, tmax = 0;
-  for (int o = 0; o < a.obj_n; ++o) {
-    const long long n = *reinterpret_cast<const volatile int32_t*>(a.n_live[o]);
-    const long long t = (n + a.tile - 1) / a.tile;
-    tmin = t < tmin ? t : tmin;
-    tmax = t > tmax ? t : tmax;
-  }
-  int s_min = 1;
-  if (a.chain_max > 0) s_min = (int)((tmax * a.tile + a.chain_max - 1) / a.chain_max);
-  if (s_min < 1) s_min = 1;
-  if (s_min > TC_MAX_SPLIT) s_min = TC_MAX_SPLIT;
-  if (s_min > tmin) s_min = (int)(tmin > 1 ? tmin : 1);
-  const int sp = lane + 1;
-  long long cost = 0x7fffffffffffffffll;
-  if (sp >= s_min && sp <= TC_MAX_SPLIT && sp <= tmin) {
-    const long long rounds = ((long long)a.combos * sp + a.G - 1) / a.G;
-    cost = rounds * ((tmax + sp - 1) / sp + a.overhead);
-  }
-  int best = sp;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const long long oc = __shfl_xor_sync(0xffffffffu, cost, o);
-    const int ob = __shfl_xor_sync(0xffffffffu, best, o);
-    if (oc < cost || (oc == cost && ob < best)) { cost = oc; best = ob; }
-  }
-  if (lane == 0) *a.out = (cost == 0x7fffffffffffffffll) ? s_min : best;
-}
-
 // all banks of a call carry a live count, or none does
 static int live_mode(const vfn_bank* banks, int obj_n, bool* live) {
   *live = banks[0].n_live != nullptr;
@@ -1602,16 +1602,9 @@ static int live_mode(const vfn_bank* banks, int obj_n, bool* live) {
   return VFN_OK;
 }
 
-static int launch_split_plan(const vfn_bank* banks, int obj_n, int tile, int combos, int overhead, int G, int chain_max,
-                             int32_t* out, cudaStream_t st) {
-  SplitPlanArgs sp{};
-  sp.obj_n = obj_n; sp.tile = tile; sp.combos = combos; sp.overhead = overhead; sp.G = G; sp.chain_max = chain_max;
-  for (int o = 0; o < obj_n; ++o) sp.n_live[o] = banks[o].n_live;
-  sp.out = out;
-  VFN_CUDA_OK(launch_pdl(split_plan_kernel, dim3(1), dim3(32), 0, st, sp));
-  VFN_LAUNCH_OK();
-  count_launches(1);
-  return VFN_OK;
+static void set_split_plan(TcArgs* a, int tile, int combos, int overhead, int G, int chain_max, int32_t* cell) {
+  a->plan_tile = tile; a->plan_combos = combos; a->plan_overhead = overhead; a->plan_G = G; a->plan_chain_max = chain_max;
+  a->pieces_dev = cell;
 }
 
 void tc_pick_splits(int obj_n, int64_t n_max, int64_t hw, int* split_a, int* split_b) {
@@ -1699,10 +1692,7 @@ int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t h
   *pieces_dev_out = nullptr;
   if (live) {
     int32_t* cell = tc_plan_cell(ws_tc, hw);
-    if (int rc = launch_split_plan(banks, obj_n, SC_TILE, obj_n * (int)cdiv(hw, pair ? 2 * QT : QT), 2,
-                                   pair ? num_sms() / 2 : num_sms(), 0, cell, st))
-      return rc;
-    a.pieces_dev = cell;
+    set_split_plan(&a, SC_TILE, obj_n * (int)cdiv(hw, pair ? 2 * QT : QT), 2, pair ? num_sms() / 2 : num_sms(), 0, cell);
     *pieces_dev_out = cell;
   }
   // Q hi/lo of q * log2(e)/sqrt(d): logits land in the log2 domain; pad rows zeroed
@@ -1752,9 +1742,7 @@ int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const 
   *pieces_dev_out = nullptr;
   if (live) {
     int32_t* cell = tc_plan_cell(ws_tc, hw) + 1;
-    if (int rc = launch_split_plan(banks, obj_n, B_TILE, combos, 4, pair ? num_sms() / 2 : num_sms(), B_CHAIN_MAX, cell, st))
-      return rc;
-    a.pieces_dev = cell;
+    set_split_plan(&a, B_TILE, combos, 4, pair ? num_sms() / 2 : num_sms(), B_CHAIN_MAX, cell);
     *pieces_dev_out = cell;
   }
   double work = 0;
@@ -1825,13 +1813,12 @@ int tc_match(const vfn_bank* banks, int obj_n, const float* const* nck_em, int64
   bool live;
   if (int rc = live_mode(banks, obj_n, &live)) return rc;
   a.obj_n = obj_n; a.hw = (int)hw; a.q_tiles = (int)cdiv(hw, QT); a.pieces = pieces;
-  a.pieces_dev = r.pieces_dev = nullptr;
+  a.pieces_dev = nullptr;
+  r.pieces_dev = nullptr;
   if (live) {
     int32_t* cell = reinterpret_cast<int32_t*>(ws + tc_match_workspace_bytes(obj_n, hw) - 256);
-    if (int rc = launch_split_plan(banks, obj_n, SC_TILE, obj_n * (int)cdiv(hw, pair ? 2 * QT : QT), 2,
-                                   pair ? num_sms() / 2 : num_sms(), 0, cell, st))
-      return rc;
-    a.pieces_dev = r.pieces_dev = cell;
+    set_split_plan(&a, SC_TILE, obj_n * (int)cdiv(hw, pair ? 2 * QT : QT), 2, pair ? num_sms() / 2 : num_sms(), 0, cell);
+    r.pieces_dev = cell;
   }
   a.qh = tc_match_cand_hi(ws, obj_n, hw, 0);
   a.ql = tc_match_cand_lo(ws, obj_n, hw, 0);
