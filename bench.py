@@ -34,6 +34,25 @@ NCU_PHASE_B_TRAFFIC = {'bytes': 610.84e6 + 90.05e6,
                                'bytes streamed once = 512 MB; the bench launches average fewer slots'}
 TAIL_SIZE = (1080, 1920)      # original frame size the mask is resized back to (test_video_seg.py:103,114)
 TAIL_KEY_PTS = [(480, 300), (960, 200), (1440, 400), (1800, 100)]
+# --workload: the default is BASELINE.json configs[1] (the metric's configuration); '1080p-capacity' is configs[2]'s regime
+# (long-video stress: native 1080p query grid, bank pre-filled to its 100000-slot budget so that LFU eviction fires on
+# every frame), offered for measurement only - the driver's line is always the default workload.
+WORKLOADS = {
+    '480p-2obj-100frame-clip-hotpath': dict(hw=(30, 54), r1=(240, 432), frames=100, n_init=None, start_frame=0),
+    '1080p-2obj-bank-at-capacity': dict(hw=(68, 120), r1=(544, 960), frames=30, n_init=100000, start_frame=50),
+}
+WORKLOAD = '480p-2obj-100frame-clip-hotpath'
+START_FRAME, N_INIT = 0, None
+
+
+def select_workload(name, frames=None):
+    global HW_H, HW_W, R1_H, R1_W, WORKLOAD, START_FRAME, N_INIT
+    w = WORKLOADS[name]
+    (HW_H, HW_W), (R1_H, R1_W) = w['hw'], w['r1']
+    WORKLOAD, START_FRAME, N_INIT = name, w['start_frame'], w['n_init']
+    return frames or w['frames']
+
+
 METRIC = '480p frames/sec (1/2/4/8 B200); mem-read tensor util; bank-update HBM GB/s'
 
 
@@ -43,11 +62,14 @@ def parse():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--frames', type=int, default=100)
+    ap.add_argument('--frames', type=int, default=None)
+    ap.add_argument('--workload', default='480p-2obj-100frame-clip-hotpath', choices=list(WORKLOADS))
     ap.add_argument('--frac-merge', type=float, default=0.1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--read-impl', type=int, default=0, help='0 auto (tcgen05), 1 fp32 SIMT, 2 tcgen05')
-    return ap.parse_args()
+    args = ap.parse_args()
+    args.frames = select_workload(args.workload, args.frames)
+    return args
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -55,7 +77,8 @@ def parse():
 # ---------------------------------------------------------------------------------------------------
 def make_clip(seed, frames, frac_merge, pin):
     from vfloodnet_b200 import synth
-    gen = synth.ClipGenerator(seed=seed, obj_n=2, hw=HW_H * HW_W, d_key=D_KEY, d_val=D_VAL, frac_merge=frac_merge)
+    gen = synth.ClipGenerator(seed=seed, obj_n=2, hw=HW_H * HW_W, d_key=D_KEY, d_val=D_VAL, frac_merge=frac_merge,
+                              n_init=N_INIT)
     keys0, vals0 = gen.init()
     fr = []
     for _ in range(frames):
@@ -68,14 +91,25 @@ def make_clip(seed, frames, frac_merge, pin):
         keys0, vals0 = [P(k) for k in keys0], [P(v) for v in vals0]
         fr = [(P(a), P(b), [P(k) for k in pk], [P(v) for v in pv]) for a, b, pk, pv in fr]
         urr = tuple(P(t) for t in urr)
-    return dict(keys0=keys0, vals0=vals0, frames=fr, urr=urr)
+    clip = dict(keys0=keys0, vals0=vals0, frames=fr, urr=urr)
+    if N_INIT:   # a bank that has lived for START_FRAME frames: insertion frames in order, usage counts spread (regime C)
+        info0 = []
+        for _ in range(2):
+            i = synth.gen_info(g, N_INIT, START_FRAME)
+            i[:, 0] = torch.sort(i[:, 0]).values
+            info0.append(P(i) if pin else i)
+        clip['info0'] = info0
+    return clip
 
 
 def to_device(clip, dev):
     D = lambda t: t.to(dev, non_blocking=True)
-    return dict(keys0=[D(k) for k in clip['keys0']], vals0=[D(v) for v in clip['vals0']],
-                frames=[(D(a), D(b), [D(k) for k in pk], [D(v) for v in pv]) for a, b, pk, pv in clip['frames']],
-                urr=tuple(D(t) for t in clip['urr']))
+    out = dict(keys0=[D(k) for k in clip['keys0']], vals0=[D(v) for v in clip['vals0']],
+               frames=[(D(a), D(b), [D(k) for k in pk], [D(v) for v in pv]) for a, b, pk, pv in clip['frames']],
+               urr=tuple(D(t) for t in clip['urr']))
+    if 'info0' in clip:
+        out['info0'] = [D(i) for i in clip['info0']]
+    return out
 
 
 def run_clip_gpu(vfn, clip, dev, read_impl, host_inputs=False, out_host=None, exact_sizes=False, tail=None,
@@ -101,7 +135,7 @@ def run_clip_gpu(vfn, clip, dev, read_impl, host_inputs=False, out_host=None, ex
                 ev.record(copy_stream)
             return tens, ev
 
-        fb.init_bank([H(k) for k in clip['keys0']], [H(v) for v in clip['vals0']])
+        _start_bank(fb, clip, H)
         nxt = stage(0)
     out = prob = None
     for t in range(len(clip['frames'])):
@@ -114,14 +148,14 @@ def run_clip_gpu(vfn, clip, dev, read_impl, host_inputs=False, out_host=None, ex
                 x.record_stream(cur)
         else:
             if t == 0:
-                fb.init_bank(list(clip['keys0']), list(clip['vals0']))
+                _start_bank(fb, clip, lambda x: x)
             q_in, q_out, pk, pv = clip['frames'][t]
             urr = clip['urr']
         p, r1, q_local = urr
         out = m(fb, q_in, q_out)
         p_up, unc, conf, local_match = vfn.urr_pre(p, r1.expand(2, -1, -1, -1), (1, 2, R1_H, R1_W))
         prob = vfn.urr_post(p_up, unc, conf, q_local)
-        fb.update(pk, pv, t + 1)
+        fb.update(pk, pv, START_FRAME + t + 1)
         if tail is not None:
             # device-resident loop tail: resize to the original frame size, arg-max, largest component,
             # water-level column scan; only the levels go back to the host
@@ -138,6 +172,13 @@ def run_clip_gpu(vfn, clip, dev, read_impl, host_inputs=False, out_host=None, ex
     if out_host is not None and tail is None:
         cur.wait_stream(_d2h_stream(dev))          # the step's result is on the host when the step's work is done
     return fb, out, prob
+
+
+def _start_bank(fb, clip, H):
+    if 'info0' in clip:          # pre-filled bank (capacity workload)
+        fb.load_state([H(k) for k in clip['keys0']], [H(v) for v in clip['vals0']], [H(i) for i in clip['info0']])
+    else:                        # test_video_seg.py:100-101
+        fb.init_bank([H(k) for k in clip['keys0']], [H(v) for v in clip['vals0']])
 
 
 _COPY_STREAMS = {}
@@ -226,16 +267,23 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------------
 def expected_bank_size(frame, frac_merge):
     hw = HW_H * HW_W
+    if N_INIT:
+        return int(min(N_INIT, 0.8 * (BUDGET // 2)))
     return int(min(hw + (1 - frac_merge) * hw * frame, 0.8 * (BUDGET // 2)))
 
 
-def cpu_sample(frac_merge, sample_frames=(25, 50, 75, 100), seed=0, device='cpu'):
+def default_samples():
+    return (START_FRAME + 10,) if N_INIT else (25, 50, 75, 100)
+
+
+def cpu_sample(frac_merge, sample_frames=None, seed=0, device='cpu'):
     """Times oracle read + URR + update at the bank sizes the clip has at `sample_frames` (synthetic bank contents of
     the clip's analytic size trajectory).  Returns (frames_per_sec, description, seconds).
     device='cuda:N' runs the same plain-torch restatement with ATen/cuBLAS kernels on the GPU ("reference torch ops" of
     BASELINE.json configs[1]); timed with a device synchronisation on both sides of every step."""
     from oracle import afb_oracle as O
     from vfloodnet_b200 import synth
+    sample_frames = sample_frames or default_samples()
     on_gpu = str(device) != 'cpu'
     if not on_gpu:
         torch.set_num_threads(os.cpu_count())
@@ -277,13 +325,13 @@ def main_reference(args, rank, world):
     n_frames = 0
     for _ in range(args.steps):
         fps, desc, secs = cpu_sample(args.frac_merge)
-        n_frames += 4
+        n_frames += len(default_samples())
     el = time.perf_counter() - t0
     v = n_frames / el
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'frames/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * el / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': '480p-2obj-100frame-clip-hotpath', 'hw': HW_H * HW_W, 'budget': BUDGET,
+            'config': {'workload': WORKLOAD, 'hw': HW_H * HW_W, 'budget': BUDGET,
                        'frames': args.frames, 'frac_merge': args.frac_merge},
             'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': desc},
             'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -483,7 +531,7 @@ def main_ours(args, rank, world, local_rank):
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f16 hi/lo + f8 split operands, f32 accumulate (read, match); f32 (update, URR)',
             'data': 'synthetic',
-            'config': {'workload': '480p-2obj-100frame-clip-hotpath', 'hw': HW_H * HW_W, 'budget': BUDGET,
+            'config': {'workload': WORKLOAD, 'hw': HW_H * HW_W, 'budget': BUDGET,
                        'frames': args.frames, 'frac_merge': args.frac_merge, 'streams_per_gpu': 1,
                        'final_bank_slots': final_n, 'l2_policy': 'inputs_exceed_l2 (bank operands 0.5-1.1 GB >> 126 MB)',
                        'read_impl': args.read_impl},

@@ -194,6 +194,43 @@ __global__ void __launch_bounds__(128) append_rows_kernel(const __grid_constant_
   }
 }
 
+// append, AFB-URR dims with tensor-core operand arrays and normalised candidates supplied (the update path): one WARP
+// per row, all six 16-byte loads of the row (raw key, normalised key, four value quarters) in flight before the first
+// store; the same element-wise conversions as append_rows_kernel, so the rows are bit-identical.
+__global__ void __launch_bounds__(128) append_rows_warp_kernel(const __grid_constant__ AppendSet set, float info0,
+                                                               float info1) {
+  pdl_wait();
+  pdl_trigger();
+  const AppendObj& ao = set.o[blockIdx.y];
+  const vfn_bank& bank = ao.bank;
+  const int64_t n_sel = ao.n_sel_dev ? (int64_t)*ao.n_sel_dev : ao.n_sel_upper;
+  const int64_t n_base = live_n(bank);
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * 4;
+  for (int64_t i = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5); i < n_sel; i += warps) {
+    const int64_t s = ao.sel ? (int64_t)ao.sel[i] : i;
+    const int64_t d = n_base + i;
+    const float4 k = __ldg(reinterpret_cast<const float4*>(ao.ck + s * 128) + lane);
+    const float4 nk = __ldg(reinterpret_cast<const float4*>(ao.nck + s * 128) + lane);
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(ao.cv + s * 512) + lane + 32 * j);
+    reinterpret_cast<float4*>(bank.keys + d * 128)[lane] = k;
+    store_key_ops4(bank.kh, bank.kl, d * 128 + 4 * lane, k);
+    store_nk4(bank.nk, bank.nkh, bank.nkl, d * 128 + 4 * lane, nk);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      reinterpret_cast<float4*>(bank.values + d * 512)[lane + 32 * j] = v[j];
+      store_val_ops4(bank.vh, bank.v8, bank.vl, d * 512 + 4 * (lane + 32 * j), v[j]);
+    }
+    if (lane == 0) {
+      bank.info[d * 2 + 0] = info0;
+      bank.info[d * 2 + 1] = info1;
+      bank.cnt[d] = 0;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128) refresh_rows_kernel(vfn_bank bank, int64_t first, int64_t count) {
   __shared__ float red[32];
   const int dk4 = bank.d_key >> 2, dv4 = bank.d_val >> 2;
@@ -721,8 +758,17 @@ int launch_append(const UpdObj* o, int n_obj, float info0, float info1, cudaStre
   }
   if (n_max == 0) return VFN_OK;
   dim3 grid((unsigned)(n_max < 148 * 16 ? n_max : 148 * 16), n_obj);
+  bool warp_rows = true;        // every object: 128/512 dims, operand arrays, normalised candidates given
+  for (int c = 0; c < n_obj; ++c)
+    warp_rows = warp_rows && o[c].bank.d_key == 128 && o[c].bank.d_val == 512 && o[c].bank.kh && o[c].bank.nkh && o[c].nck;
   prof_begin(PROF_APPEND, st);
-  VFN_CUDA_OK(launch_pdl(append_rows_kernel, grid, dim3(128), 0, st, set, info0, info1));
+  if (warp_rows) {
+    const int64_t blocks = cdiv(n_max, 4);
+    dim3 gw((unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), n_obj);
+    VFN_CUDA_OK(launch_pdl(append_rows_warp_kernel, gw, dim3(128), 0, st, set, info0, info1));
+  } else {
+    VFN_CUDA_OK(launch_pdl(append_rows_kernel, grid, dim3(128), 0, st, set, info0, info1));
+  }
   // algorithmic bytes: read + write of the appended rows (keys, values, info)
   prof_end(PROF_APPEND, st, bytes);
   VFN_LAUNCH_OK();
