@@ -125,17 +125,28 @@ def run_clip_gpu(vfn, clip, dev, read_impl, host_inputs=False, out_host=None, ex
     if host_inputs:
         copy_stream = _copy_stream(dev)
         H = lambda t: t.to(dev, non_blocking=True)
+        # two resident staging sets on the device (frame t uses set t & 1): no allocation inside the loop - allocating
+        # each frame's inputs on the side stream made one clip in ~10 take 30 ms longer (gpurun_out/t12, r1m2: the
+        # caching allocator has to cudaMalloc when record_stream'ed blocks are not reusable yet)
+        stg = _staging(dev, clip)
+        done = [None, None]
 
         def stage(t):
-            copy_stream.wait_stream(cur) if t == 0 else None
+            b = t & 1
+            q_in, q_out, pk, pv = clip['frames'][t]
+            src = (q_in, q_out, *pk, *pv, *clip['urr'])
             with torch.cuda.stream(copy_stream):
-                q_in, q_out, pk, pv = clip['frames'][t]
-                tens = (H(q_in), H(q_out), [H(k) for k in pk], [H(v) for v in pv], tuple(H(x) for x in clip['urr']))
+                if done[b] is not None:
+                    copy_stream.wait_event(done[b])          # frame t-2 has consumed this set
+                for d_, s_ in zip(stg[b], src):
+                    d_.copy_(s_, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
-            return tens, ev
+            q = stg[b]
+            return (q[0], q[1], [q[2], q[3]], [q[4], q[5]], (q[6], q[7], q[8])), ev
 
         _start_bank(fb, clip, H)
+        copy_stream.wait_stream(cur)
         nxt = stage(0)
     out = prob = None
     for t in range(len(clip['frames'])):
@@ -144,8 +155,6 @@ def run_clip_gpu(vfn, clip, dev, read_impl, host_inputs=False, out_host=None, ex
             if t + 1 < len(clip['frames']):
                 nxt = stage(t + 1)
             cur.wait_event(ev)
-            for x in (q_in, q_out, *pk, *pv, *urr):
-                x.record_stream(cur)
         else:
             if t == 0:
                 _start_bank(fb, clip, lambda x: x)
@@ -169,6 +178,9 @@ def run_clip_gpu(vfn, clip, dev, read_impl, host_inputs=False, out_host=None, ex
             with torch.cuda.stream(d2h):
                 out_host.copy_(prob, non_blocking=True)
             prob.record_stream(d2h)
+        if host_inputs:
+            done[t & 1] = torch.cuda.Event()
+            done[t & 1].record(cur)
     if out_host is not None and tail is None:
         cur.wait_stream(_d2h_stream(dev))          # the step's result is on the host when the step's work is done
     return fb, out, prob
@@ -183,6 +195,17 @@ def _start_bank(fb, clip, H):
 
 _COPY_STREAMS = {}
 _D2H_STREAMS = {}
+_STAGING = {}
+
+
+def _staging(dev, clip):
+    q_in, q_out, pk, pv = clip['frames'][0]
+    src = (q_in, q_out, *pk, *pv, *clip['urr'])
+    key = (str(dev), tuple(tuple(t.shape) for t in src))
+    if key not in _STAGING:
+        assert len(src) == 9, 'two objects: q_in, q_out, 2 keys, 2 values, 3 URR tensors'
+        _STAGING[key] = [[torch.empty(t.shape, dtype=t.dtype, device=dev) for t in src] for _ in range(2)]
+    return _STAGING[key]
 
 
 def _d2h_stream(dev):
