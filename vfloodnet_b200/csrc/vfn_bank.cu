@@ -65,7 +65,11 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const __grid_constant__ 
   const int64_t n = jb.n;
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int64_t q0 = (int64_t)blockIdx.x * 32;
-  if (q0 >= n || (int)blockIdx.z * PREP_CHUNK >= d) return;
+  // jobs without a norm (the read's query operand) are cut into 32-row chunks: four times as many CTAs for a job that
+  // would otherwise run on 51; normalising jobs keep PREP_CHUNK rows per CTA (every CTA re-reads the whole column for
+  // the norm)
+  const int chunk = (jb.normed || jb.split_normed) ? PREP_CHUNK : 32;
+  if (q0 >= n || (int)blockIdx.z * chunk >= d) return;
   const int64_t q = q0 + tx;
   if (jb.normed || jb.split_normed) {
     float ss = 0.f;
@@ -86,8 +90,8 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const __grid_constant__ 
   }
   // blockIdx.z takes PREP_CHUNK of the d rows (the norm above is over all of them: cheap re-reads from L2), so that a
   // 512-channel job spreads over four times as many CTAs as a 128-channel one
-  const int k_end = min(d, (int)(blockIdx.z + 1) * PREP_CHUNK);
-  for (int k0 = blockIdx.z * PREP_CHUNK; k0 < k_end; k0 += 32) {
+  const int k_end = min(d, (int)(blockIdx.z + 1) * chunk);
+  for (int k0 = blockIdx.z * chunk; k0 < k_end; k0 += 32) {
     for (int r = ty; r < 32; r += 8) {
       int k = k0 + r;
       tile[r][tx] = (k < d && q < n) ? src[(int64_t)k * n + q] : 0.f;
@@ -126,7 +130,12 @@ int launch_prep(const PrepJob* jobs, int n_jobs, cudaStream_t st) {
     if (jobs[i].d > d_max) d_max = jobs[i].d;
   }
   if (n_max == 0) return VFN_OK;
-  dim3 block(32, 8), grid((unsigned)cdiv(n_max, 32), n_jobs, (unsigned)cdiv(d_max, PREP_CHUNK));
+  int z_max = 1;
+  for (int i = 0; i < n_jobs; ++i) {
+    const int chunk = (jobs[i].normed || jobs[i].split_normed) ? PREP_CHUNK : 32;
+    z_max = max(z_max, (int)cdiv(jobs[i].d, chunk));
+  }
+  dim3 block(32, 8), grid((unsigned)cdiv(n_max, 32), n_jobs, (unsigned)z_max);
   VFN_CUDA_OK(launch_pdl(prep_rows_kernel, grid, block, 0, st, pj));
   VFN_LAUNCH_OK();
   count_launches(1);

@@ -378,36 +378,41 @@ __global__ void __launch_bounds__(256) combine_out_kernel(const float* __restric
                                                           int with_qout) {
   pdl_wait();
   pdl_trigger();
-  const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
   const int64_t total = plane * obj_n;
-  if (idx >= total) return;
   if (n_split_dev) n_split = *n_split_dev;
-  const int64_t obj = idx / plane, r = idx % plane;
   if (V == 4) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* base = po + (int64_t)obj * n_split * plane + r;
-    int k = 0;
-    for (; k + 4 <= n_split; k += 4) {          // four partial planes in flight, added in plane order
-      const float4 a = __ldcs(reinterpret_cast<const float4*>(base + (k + 0) * plane));
-      const float4 b = __ldcs(reinterpret_cast<const float4*>(base + (k + 1) * plane));
-      const float4 c = __ldcs(reinterpret_cast<const float4*>(base + (k + 2) * plane));
-      const float4 d = __ldcs(reinterpret_cast<const float4*>(base + (k + 3) * plane));
-      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
-      s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
-      s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w;
-      s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
-    }
-    for (; k < n_split; ++k) {
-      const float4 a = __ldcs(reinterpret_cast<const float4*>(base + k * plane));
-      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
-    }
-    if (with_qout) {
-      *reinterpret_cast<float4*>(out + obj * 2 * plane + r) = s;
-      *reinterpret_cast<float4*>(out + obj * 2 * plane + plane + r) = __ldg(reinterpret_cast<const float4*>(q_out + r));
-    } else {
-      *reinterpret_cast<float4*>(out + obj * plane + r) = s;
+    // grid-stride over float4 positions: a few CTAs per SM, each thread keeps up to four partial planes in flight
+    for (int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x * 4) {
+      const int64_t obj = idx / plane, r = idx % plane;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* base = po + (int64_t)obj * n_split * plane + r;
+      int k = 0;
+      for (; k + 4 <= n_split; k += 4) {          // added in plane order
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(base + (k + 0) * plane));
+        const float4 b = __ldcs(reinterpret_cast<const float4*>(base + (k + 1) * plane));
+        const float4 c = __ldcs(reinterpret_cast<const float4*>(base + (k + 2) * plane));
+        const float4 d = __ldcs(reinterpret_cast<const float4*>(base + (k + 3) * plane));
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
+        s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w;
+        s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+      }
+      for (; k < n_split; ++k) {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(base + k * plane));
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      }
+      if (with_qout) {
+        *reinterpret_cast<float4*>(out + obj * 2 * plane + r) = s;
+        *reinterpret_cast<float4*>(out + obj * 2 * plane + plane + r) = __ldg(reinterpret_cast<const float4*>(q_out + r));
+      } else {
+        *reinterpret_cast<float4*>(out + obj * plane + r) = s;
+      }
     }
   } else {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int64_t obj = idx / plane, r = idx % plane;
     float s = 0.f;
     for (int k = 0; k < n_split; ++k) s += po[((int64_t)obj * n_split + k) * plane + r];
     if (with_qout) {
@@ -423,9 +428,10 @@ static void launch_combine_out(const float* po, int n_split, const int32_t* n_sp
                                const float* q_out, float* out, int with_qout, cudaStream_t st) {
   const bool vec = plane % 4 == 0 && ((uintptr_t)po % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
                    (!with_qout || (uintptr_t)q_out % 16 == 0);
+  const int64_t need = cdiv(plane * obj_n / 4, 256);
   if (vec)
-    launch_pdl(combine_out_kernel<4>, dim3((unsigned)cdiv(plane * obj_n / 4, 256)), dim3(256), 0, st, po, n_split, n_split_dev,
-               plane, obj_n, q_out, out, with_qout);
+    launch_pdl(combine_out_kernel<4>, dim3((unsigned)(need < 148 * 4 ? need : 148 * 4)), dim3(256), 0, st, po, n_split,
+               n_split_dev, plane, obj_n, q_out, out, with_qout);
   else
     launch_pdl(combine_out_kernel<1>, dim3((unsigned)cdiv(plane * obj_n, 256)), dim3(256), 0, st, po, n_split, n_split_dev,
                plane, obj_n, q_out, out, with_qout);
