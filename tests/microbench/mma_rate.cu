@@ -140,6 +140,10 @@ int main() {
   for (int N : {128, 256}) run<K_F8, 0, 0>("TS f8  1-CTA", N, 1);
   for (int N : {64, 128, 256}) run<K_F8, 0, 0>("TS f8  1-CTA", N, 0);
   for (int N : {64, 128, 256}) run<K_F16, 1, 0>("TS f16 pair", N, 0);
+  // intermediate widths (is the N = 64 penalty a fixed per-instruction cost?): candidates for 96-slot S tiles
+  for (int N : {32, 48, 80, 96, 112, 160, 192}) run<K_F16, 1, 0>("TS f16 pair", N, 0);
+  for (int N : {96, 192}) run<K_F16, 1, 1>("SS f16 pair", N, 0);
+  for (int N : {96, 192}) run<K_F8, 1, 0>("TS f8  pair", N, 1);
   for (int N : {64, 128, 256}) run<K_F16, 1, 1>("SS f16 pair", N, 0);
   for (int N : {128, 256}) run<K_F16, 1, 0>("TS f16 pair", N, 1);
   for (int N : {128, 256}) run<K_F8, 1, 0>("TS f8  pair", N, 1);
