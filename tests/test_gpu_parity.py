@@ -451,7 +451,7 @@ def test_read_pair_and_single_cta_kernels(vfn, n, hw):
     rr, _ = _oracle_read(list(keys), list(vals), info, q_in, q_out)
     outs, infos = [], []
     try:
-        for pair in (3, 0, 1):                     # bit 0: pair phase B, bit 1: pair score scan (phase A)
+        for pair in (3, 0, 1, 7):                  # bit 0: pair phase B, bit 1: pair score scan, bit 2: 96-slot tiles
             lib.vfn_debug_set_pair(pair)
             fb = vfn.FeatureBank(2, 10 ** 6, 'cuda', impl=2)
             fb.load_state(list(keys), list(vals), info)
@@ -462,7 +462,7 @@ def test_read_pair_and_single_cta_kernels(vfn, n, hw):
             infos.append([fb.info[c].cpu().clone() for c in range(2)])
     finally:
         lib.vfn_debug_set_pair(3)
-    for k in (1, 2):
+    for k in (1, 2, 3):
         assert (outs[0] - outs[k]).abs().max().item() <= 2e-4
         for c in range(2):
             # same logits and LSE in all kernels: identical usage counts up to threshold-band flips

@@ -101,6 +101,8 @@ def load(build_if_missing: bool = True):
         fn = getattr(lib, name)       # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
+    if os.environ.get('VFN_PAIR'):          # debug override of the tensor-kernel selection mask (vfn_debug_set_pair)
+        lib.vfn_debug_set_pair(int(os.environ['VFN_PAIR']))
     _lib = lib
     return lib
 
