@@ -3,6 +3,7 @@
 // One CTA (or CTA pair) per SM; one thread issues `reps` back-to-back MMAs into the same accumulator and commits;
 // operands are zero-filled smem / TMEM (timing does not depend on the values).
 #include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -108,6 +109,116 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int bmn, int reps, 
   }
 }
 
+// Phase-B-shaped instruction mix on a CTA pair: per "tile" n_s S-MMAs (f16, K-major B of N_s slots, D = S buffer,
+// A = Q in TMEM) followed by n_o O-MMAs (N = 256, MN-major B, D = O accumulator, A = the S buffer: half of them f16,
+// half f8f6f4 when mix_f8).  stream != 0: every instruction reads a different B tile (5 distinct 16 KB windows) instead
+// of the same one.  Prints cycles per tile.
+template <int n_s, int N_s, int n_o, int mix_f8, int stream>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mix_kernel(int tiles, int rnd, int commits, long long* out_cycles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint64_t bar2[4];   // commit targets inside the tile loop (nobody waits on them)
+  __shared__ uint32_t tmem_p;
+  // rnd: operands are pseudo-random finite fp16 / fp8 bit patterns (|x| < 2) instead of zeros - does the data matter?
+  for (int i = threadIdx.x; i < 160 * 1024 / 16; i += blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+    uint4 v;
+    h ^= h >> 15; h *= 2246822519u; v.x = rnd ? (h & 0xbbffbbffu) & 0xb7ffb7ffu : 0u;
+    h ^= h >> 13; h *= 3266489917u; v.y = rnd ? (h & 0xb7ffb7ffu) : 0u;
+    h ^= h >> 16; h *= 668265263u;  v.z = rnd ? (h & 0xb7ffb7ffu) : 0u;
+    h ^= h >> 15; h *= 374761393u;  v.w = rnd ? (h & 0xb7ffb7ffu) : 0u;
+    reinterpret_cast<uint4*>(smem)[i] = v;
+  }
+  uint32_t rank = 0;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_p)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_p;
+  {
+    const uint32_t taddr = tmem + (((threadIdx.x >> 5) * 32u) << 16) + 256;
+    for (int c = 0; c < 256; c += 8)
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr + c), "r"(rnd ? (((threadIdx.x * 2654435761u + c * 40503u) >> 3) & 0x37ff37ffu) : 0u) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t idesc_s = make_idesc(256, N_s, 0, 0, 0, 0);
+  const uint32_t idesc_o = make_idesc(256, 256, 0, 0, 0, 1);
+  const uint32_t b_smem = smem_u32(smem + 65536);
+  if (threadIdx.x == 0 && rank == 0) {
+    long long t0 = clock64();
+    for (int t = 0; t < tiles; ++t) {
+      // fully unrolled, every descriptor a compile-time offset from b_smem: the issuing thread spends 2-3 instructions
+      // per MMA, as the production kernels do
+#pragma unroll
+      for (int i = 0; i < n_s; ++i) {
+        const uint32_t win = stream ? (uint32_t)(i % 5) * 16384u : 0u;
+        const uint64_t bd = make_sdesc(b_smem + win + (i & 3) * 32u, 16, 1024);
+        mma<K_F16, 1, 0>(tmem + 384, tmem + 256 + (i & 7) * 8, 0, bd, idesc_s);
+      }
+      // commits as the production kernel issues them: after the S group (K stage free, S ready), after the O group
+      if (commits >= 1) asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(&bar2[0])), "h"((uint16_t)3) : "memory");
+      if (commits >= 3) asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(&bar2[1])), "h"((uint16_t)3) : "memory");
+#pragma unroll
+      for (int i = 0; i < n_o; ++i) {
+        const uint32_t win = stream ? (uint32_t)((i + 2) % 5) * 16384u : 0u;
+        if (mix_f8 && i >= n_o / 2) {
+          const uint64_t bd = make_sdesc(b_smem + win, 8192, 1024);
+          mma<K_F8, 1, 0>(tmem, tmem + 384 + (i & 3) * 8, 0, bd, idesc_o);
+        } else {
+          const uint64_t bd = make_sdesc(b_smem + win + (i & 3) * 2048u, 8192, 1024);
+          mma<K_F16, 1, 0>(tmem, tmem + 384 + (i & 3) * 8, 0, bd, idesc_o);
+        }
+      }
+      if (commits >= 2) asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(&bar2[2])), "h"((uint16_t)3) : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{.reg .pred P1; mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], 0; selp.u32 %0, 1, 0, P1;}" : "=r"(done) : "r"(smem_u32(&bar)) : "memory");
+    long long t1 = clock64();
+    if (blockIdx.x == 0) *out_cycles = t1 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+template <int n_s, int N_s, int n_o, int mix_f8, int stream>
+void run_mix(const char* name, int rnd = 0, int commits = 0) {
+  long long* d;
+  cudaMalloc(&d, 8);
+  const int tiles = getenv("MIX_TILES") ? atoi(getenv("MIX_TILES")) : 256, smem = 160 * 1024 + 2048;
+  const int launches = getenv("MIX_LAUNCHES") ? atoi(getenv("MIX_LAUNCHES")) : 2;
+  auto k = mix_kernel<n_s, N_s, n_o, mix_f8, stream>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int it = 0; it < launches; ++it) k<<<148, 128, smem>>>(tiles, rnd, commits, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long h = 0;
+  cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+  const double model = n_s * (N_s >= 96 ? N_s / 2.0 : 45.6) + n_o * 128.0;
+  printf("mix %-22s %s S: %2d x N=%3d  O: %2d x N=256 %s %s  %8.1f cyc/tile  (sum of isolated rates %7.1f)  %s\n", name, rnd ? "random" : "zeros ", n_s, N_s, n_o,
+         mix_f8 ? "f16+f8" : "f16   ", stream ? "stream B" : "same B  ", (double)h / tiles, model,
+         e == cudaSuccess ? "" : cudaGetErrorString(e));
+  cudaFree(d);
+}
+
 template <int KIND, int PAIR, int SS>
 void run(const char* name, int N, int bmn, int same_b = 0) {
   long long* d;
@@ -132,7 +243,30 @@ void run(const char* name, int N, int bmn, int same_b = 0) {
   cudaFree(d);
 }
 
-int main() {
+int main(int argc, char** argv) {
+  if (argc > 1) {   // phase-B-shaped mixes only
+    run_mix<24, 64, 8, 1, 1>("64-slot, 0 commits", 1, 0);
+    run_mix<24, 64, 8, 1, 1>("64-slot, 1 commit", 1, 1);
+    run_mix<24, 64, 8, 1, 1>("64-slot, 2 commits", 1, 2);
+    run_mix<24, 64, 8, 1, 1>("64-slot, 3 commits", 1, 3);
+    run_mix<24, 96, 12, 1, 1>("96-slot, 3 commits", 1, 3);
+    run_mix<24, 64, 8, 1, 1>("64-slot tile", 1);
+    run_mix<24, 96, 12, 1, 1>("96-slot tile", 1);
+    run_mix<0, 64, 8, 1, 1>("O only f16+f8", 1);
+    run_mix<24, 64, 0, 0, 1>("S only N=64", 1);
+    run_mix<24, 64, 8, 1, 0>("64-slot tile");
+    run_mix<24, 96, 12, 1, 0>("96-slot tile");
+    run_mix<24, 64, 8, 1, 1>("64-slot tile");
+    run_mix<24, 96, 12, 1, 1>("96-slot tile");
+    run_mix<24, 128, 16, 1, 1>("128-slot tile");
+    run_mix<24, 64, 8, 0, 1>("64-slot, f16 only");
+    run_mix<24, 64, 0, 0, 1>("S only N=64");
+    run_mix<24, 96, 0, 0, 1>("S only N=96");
+    run_mix<0, 64, 8, 0, 1>("O only f16");
+    run_mix<0, 64, 8, 1, 1>("O only f16+f8");
+    run_mix<8, 64, 8, 1, 1>("8 S + 8 O (1-pass S)");
+    return 0;
+  }
   for (int N : {64, 128, 256}) run<K_F16, 0, 0>("TS f16 1-CTA", N, 0);
   for (int N : {64, 128, 256}) run<K_F16, 0, 0>("TS f16 1-CTA same B", N, 0, 1);
   for (int N : {64, 128, 256}) run<K_F16, 0, 1>("SS f16 1-CTA", N, 0);
