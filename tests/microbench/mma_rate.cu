@@ -114,11 +114,14 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int bmn, int reps, 
 // half f8f6f4 when mix_f8).  stream != 0: every instruction reads a different B tile (5 distinct 16 KB windows) instead
 // of the same one.  Prints cycles per tile.
 template <int n_s, int N_s, int n_o, int mix_f8, int stream>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mix_kernel(int tiles, int rnd, int commits, long long* out_cycles) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mix_kernel(int tiles, int rnd, int commits, const uint8_t* fill_src, int fill_bytes, long long* out_cycles) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
   __shared__ uint64_t bar2[4];   // commit targets inside the tile loop (nobody waits on them)
+  __shared__ uint64_t fbar;
+  __shared__ volatile int stop_fill;
+  __shared__ long long fill_count;
   __shared__ uint32_t tmem_p;
   // rnd: operands are pseudo-random finite fp16 / fp8 bit patterns (|x| < 2) instead of zeros - does the data matter?
   for (int i = threadIdx.x; i < 160 * 1024 / 16; i += blockDim.x) {
@@ -135,6 +138,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mix_kernel(i
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
     for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2[i])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&fbar)));
+    stop_fill = 0;
+    fill_count = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 32) {
@@ -160,6 +166,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mix_kernel(i
   const uint32_t idesc_s = make_idesc(256, N_s, 0, 0, 0, 0);
   const uint32_t idesc_o = make_idesc(256, 256, 0, 0, 0, 1);
   const uint32_t b_smem = smem_u32(smem + 65536);
+  // background fill (both CTAs): warp 1 streams fill_bytes-sized bulk copies from global memory into the unused A region
+  // of shared memory, back to back, while the MMA loop runs - the TMA fills of the production kernels
+  if (fill_src && threadIdx.x == 32) {
+    uint32_t ph = 0;
+    long long n = 0;
+    const uint8_t* src = fill_src + (size_t)blockIdx.x * 65536;
+    while (!stop_fill) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&fbar)), "r"(fill_bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem)),
+                   "l"(src + (n & 3) * 16384), "r"(fill_bytes), "r"(smem_u32(&fbar))
+                   : "memory");
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{.reg .pred P1; mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2; selp.u32 %0, 1, 0, P1;}" : "=r"(done) : "r"(smem_u32(&fbar)), "r"(ph) : "memory");
+      ph ^= 1;
+      ++n;
+    }
+    fill_count = n;
+  }
   if (threadIdx.x == 0 && rank == 0) {
     long long t0 = clock64();
     for (int t = 0; t < tiles; ++t) {
@@ -194,6 +219,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mix_kernel(i
     long long t1 = clock64();
     if (blockIdx.x == 0) *out_cycles = t1 - t0;
   }
+  if (threadIdx.x == 0) stop_fill = 1;
+  if (threadIdx.x == 0 && rank != 0) { /* the peer stops when the leader's cluster barrier arrives */ }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -201,18 +228,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mix_kernel(i
 }
 
 template <int n_s, int N_s, int n_o, int mix_f8, int stream>
-void run_mix(const char* name, int rnd = 0, int commits = 0) {
+void run_mix(const char* name, int rnd = 0, int commits = 0, int fill_bytes = 0) {
   long long* d;
   cudaMalloc(&d, 8);
   const int tiles = getenv("MIX_TILES") ? atoi(getenv("MIX_TILES")) : 256, smem = 160 * 1024 + 2048;
   const int launches = getenv("MIX_LAUNCHES") ? atoi(getenv("MIX_LAUNCHES")) : 2;
   auto k = mix_kernel<n_s, N_s, n_o, mix_f8, stream>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  for (int it = 0; it < launches; ++it) k<<<148, 128, smem>>>(tiles, rnd, commits, d);
+  static uint8_t* fsrc = nullptr;
+  if (!fsrc) { cudaMalloc(&fsrc, 148 * 65536 + 65536); cudaMemset(fsrc, 1, 148 * 65536 + 65536); }
+  for (int it = 0; it < launches; ++it) k<<<148, 128, smem>>>(tiles, rnd, commits, fill_bytes ? fsrc : nullptr, fill_bytes, d);
   cudaError_t e = cudaDeviceSynchronize();
   long long h = 0;
   cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
   const double model = n_s * (N_s >= 96 ? N_s / 2.0 : 45.6) + n_o * 128.0;
+  if (fill_bytes) printf("[+ background bulk fills of %d B] ", fill_bytes);
   printf("mix %-22s %s S: %2d x N=%3d  O: %2d x N=256 %s %s  %8.1f cyc/tile  (sum of isolated rates %7.1f)  %s\n", name, rnd ? "random" : "zeros ", n_s, N_s, n_o,
          mix_f8 ? "f16+f8" : "f16   ", stream ? "stream B" : "same B  ", (double)h / tiles, model,
          e == cudaSuccess ? "" : cudaGetErrorString(e));
@@ -245,6 +275,10 @@ void run(const char* name, int N, int bmn, int same_b = 0) {
 
 int main(int argc, char** argv) {
   if (argc > 1) {   // phase-B-shaped mixes only
+    run_mix<24, 64, 8, 1, 1>("64-slot + fills", 1, 3, 16384);
+    run_mix<24, 64, 8, 1, 1>("64-slot + fills", 1, 3, 4096);
+    run_mix<0, 64, 8, 1, 1>("O only + fills", 1, 0, 16384);
+    run_mix<24, 64, 0, 0, 1>("S only + fills", 1, 0, 16384);
     run_mix<24, 64, 8, 1, 1>("64-slot, 0 commits", 1, 0);
     run_mix<24, 64, 8, 1, 1>("64-slot, 1 commit", 1, 1);
     run_mix<24, 64, 8, 1, 1>("64-slot, 2 commits", 1, 2);
