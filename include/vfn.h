@@ -252,6 +252,9 @@ int vfn_profile_add_work(int32_t kind, double work);
 int64_t vfn_launch_count(void);
 
 /* ---- self-test hooks for the tcgen05/TMA building blocks (used by tests/, not by the product path) ---- */
+/* d_ptr != NULL (74 x 64 x 8 int64, zeroed): the CTA-pair phase-B kernel stamps clock64 per cluster and work item:
+ * {item start, P of the first tile ready, P of the last tile ready, item end, tiles} (tests/debug_item_times.py) */
+int vfn_debug_set_tstamp(long long* d_ptr);
 /* d_ptr != NULL: the next tcgen05 read launches dump the first S^T tile of CTA 0 (128 x tile floats) there. */
 int vfn_debug_set_dump(float* d_ptr);
 /* bit mask, default 3: bit 0 = CTA-pair (cta_group::2) phase B, bit 1 = CTA-pair score scan (phase A, match),

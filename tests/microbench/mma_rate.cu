@@ -187,7 +187,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mix_kernel(i
   }
   if (threadIdx.x == 0 && rank == 0) {
     long long t0 = clock64();
+    const int fences = commits / 10;
+    commits %= 10;
     for (int t = 0; t < tiles; ++t) {
+      if (fences & 1) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (fences & 2) { uint32_t d_; asm volatile("{.reg .pred P1; mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], 1; selp.u32 %0, 1, 0, P1;}" : "=r"(d_) : "r"(smem_u32(&bar2[3])) : "memory"); }
       // fully unrolled, every descriptor a compile-time offset from b_smem: the issuing thread spends 2-3 instructions
       // per MMA, as the production kernels do
 #pragma unroll
@@ -196,6 +200,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mix_kernel(i
         const uint64_t bd = make_sdesc(b_smem + win + (i & 3) * 32u, 16, 1024);
         mma<K_F16, 1, 0>(tmem + 384, tmem + 256 + (i & 7) * 8, 0, bd, idesc_s);
       }
+      if (fences & 1) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (fences & 2) { uint32_t d_; asm volatile("{.reg .pred P1; mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], 1; selp.u32 %0, 1, 0, P1;}" : "=r"(d_) : "r"(smem_u32(&bar2[3])) : "memory"); }
       // commits as the production kernel issues them: after the S group (K stage free, S ready), after the O group
       if (commits >= 1) asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(&bar2[0])), "h"((uint16_t)3) : "memory");
       if (commits >= 3) asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(&bar2[1])), "h"((uint16_t)3) : "memory");
@@ -275,6 +281,9 @@ void run(const char* name, int N, int bmn, int same_b = 0) {
 
 int main(int argc, char** argv) {
   if (argc > 1) {   // phase-B-shaped mixes only
+    run_mix<24, 64, 8, 1, 1>("64: 3 commits+fences", 1, 13);
+    run_mix<24, 64, 8, 1, 1>("64: 3 commits+try_wait", 1, 23);
+    run_mix<24, 64, 8, 1, 1>("64: commits+fence+wait", 1, 33);
     run_mix<24, 64, 8, 1, 1>("64-slot + fills", 1, 3, 16384);
     run_mix<24, 64, 8, 1, 1>("64-slot + fills", 1, 3, 4096);
     run_mix<0, 64, 8, 1, 1>("O only + fills", 1, 0, 16384);

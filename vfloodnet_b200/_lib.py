@@ -71,6 +71,7 @@ SIGNATURES = {
     'vfn_profile_add_work': (c_i32, [c_i32, c_f64]),
     'vfn_launch_count': (c_i64, []),
     'vfn_debug_set_dump': (c_i32, [c_vp]),
+    'vfn_debug_set_tstamp': (c_i32, [c_vp]),
     'vfn_debug_set_pair': (c_i32, [c_i32]),
     'vfn_debug_set_urr_stream': (c_i32, [c_i32]),
     'vfn_debug_set_tail': (c_i32, [c_i32]),

@@ -348,6 +348,7 @@ struct TcArgs {
   int32_t* cnt[TC_MAX_OBJ];
   float band;                           // match: candidate band in the (scaled) score domain
   float* dbg;
+  long long* tstamp;                    // vfn_debug_set_tstamp: per cluster and item {start, first O issued, last O issued, end, tiles}
 };
 
 // Work split of a launch.  Host-tracked sizes: args.pieces.  Device-resident live counts: every warp of every CTA
@@ -716,7 +717,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       }
       __syncwarp();
     } else if (warp == 1) {
-      if (leader) {
+      if (leader && elect_one()) {   // ONE thread runs the whole issue loop of the item (see tc_phase_b_pair_kernel)
         constexpr uint32_t idesc = make_idesc(256, SC_TILE, FMT_F16, FMT_F16, 0, 0);
         for (int t = 0; t < ntile; ++t) {
           const uint32_t c = tile_ctr + t, st = c % SP_STAGES, ph = (c / SP_STAGES) & 1;
@@ -726,7 +727,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           tc_fence_after();
           const uint32_t kbase = smem_u32(kst + st * SP_STAGE_BYTES);
           const uint32_t d_t = tmem + TS_S + sb * SC_TILE;
-          if (elect_one()) {
+          {
             // passes: (Ah,Bh) (Al,Bh) (Ah,Bl); each CTA's smem holds its 64 slots of the 128-slot B tile
 #pragma unroll
             for (int pass = 0; pass < 3; ++pass) {
@@ -741,9 +742,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             tc_commit_pair(&k_empty[st]);
             tc_commit_pair(&s_full[sb]);
           }
-          __syncwarp();
         }
       }
+      __syncwarp();
     } else if (warp >= 4) {
       const int quarter = warp & 3, cg = (warp - 4) >> 2;
       const int row = (quarter << 5) + lane;
@@ -1276,7 +1277,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       }
       __syncwarp();
     } else if (warp == 1) {
-      if (leader) {
+      // ONE elected thread runs the whole issue loop of the item (waits, MMAs, commits).  With an elect + __syncwarp around
+      // every MMA group the steady tile period was 2092 clk; like this it is 1902 (tests/debug_item_times.py) against
+      // an MMA floor of 1795 (tests/microbench/mma_rate.cu mix): every instruction the issuing warp spends between two
+      // MMAs shows up in the tile period.
+      if (leader && elect_one()) {
         constexpr uint32_t idesc_s = make_idesc(256, B_TILE, FMT_F16, FMT_F16, 0, 0);
         constexpr uint32_t idesc_o = make_idesc(256, 256, FMT_F16, FMT_F16, 0, 1);
         constexpr uint32_t idesc_o8 = make_idesc(256, 256, FMT_E4M3, FMT_E4M3, 0, 1);
@@ -1288,7 +1293,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           tc_fence_after();
           const uint32_t kbase = smem_u32(kst + st * P_KSTAGE_BYTES);
           const uint32_t d_t = tmem + TM_S + (uint32_t)b * 64;
-          if (elect_one()) {
+          {
 #pragma unroll
             for (int pass = 0; pass < 3; ++pass) {
               const uint32_t a_col = (pass == 1) ? TM_QL : TM_QH;
@@ -1302,20 +1307,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             tc_commit_pair(&k_empty[st]);
             tc_commit_pair(&s_full[b]);
           }
-          __syncwarp();
         };
+        long long* ts = args.tstamp ? args.tstamp + ((size_t)cluster_id * 64 + (size_t)(item / n_clusters)) * 8 : nullptr;
+        if (ts && item / n_clusters < 64) { ts[0] = clock64(); ts[4] = ntile; }
         if (ntile > 0) issue_s(0);
         if (ntile > 1) issue_s(1);
         for (int t = 0; t < ntile; ++t) {
           const uint32_t kit = k_it + t, st = kit & 3, ph = (kit >> 2) & 1;
           const int b = t & 1;
           mbar_wait(&p_full[b], buf_it[b] & 1);
+          if (ts && item / n_clusters < 64) { if (t == 0) ts[1] = clock64(); if (t == ntile - 1) ts[2] = clock64(); }
           ++buf_it[b];
           mbar_wait(&v_full[st], ph);
           tc_fence_after();
           const uint32_t vbase = smem_u32(vst + st * P_VSTAGE_BYTES);
           const uint32_t pcol = tmem + TM_S + (uint32_t)b * 64;
-          if (elect_one()) {
+          {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint64_t bd = make_sdesc(vbase + ks * 2048u, 8192, 1024);
@@ -1331,12 +1338,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             }
             tc_commit_pair(&v_empty[st]);
           }
-          __syncwarp();
           if (t + 2 < ntile) issue_s(t + 2);
         }
-        if (elect_one()) tc_commit_pair(o_full);
-        __syncwarp();
+        tc_commit_pair(o_full);
       }
+      __syncwarp();
     } else if (warp >= 4) {
       // every softmax warp works on every tile: slot group sg = 16 of the tile's 64 slots, for its 32 query rows
       const int quarter = warp & 3, sg = (warp - 4) >> 2;
@@ -1441,6 +1447,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     ++seg_it;
     tc_fence_before();
     __syncthreads();
+    if (args.tstamp && leader && threadIdx.x == 0 && item / n_clusters < 64)
+      args.tstamp[((size_t)cluster_id * 64 + (size_t)(item / n_clusters)) * 8 + 3] = clock64();
     tc_fence_after();
   }
   tc_fence_before();
@@ -1958,6 +1966,7 @@ static int num_sms() {
 }
 
 static float* g_dbg = nullptr;
+static long long* g_tstamp = nullptr;   // vfn_debug_set_tstamp()
 static int g_pair = 3;    // bit 0: CTA-pair (cta_group::2) phase B, bit 1: CTA-pair scan (phase A, match); vfn_debug_set_pair()
 
 bool tc_shapes_ok(int d_key, int d_val) { return d_key == DK && d_val == DV; }
@@ -2042,6 +2051,7 @@ static int fill_args(const vfn_bank* banks, int obj_n, int64_t hw, int pieces, i
   a->pieces_dev = nullptr;
   a->band = 0.f;
   a->dbg = g_dbg;
+  a->tstamp = g_tstamp;
   for (int o = 0; o < obj_n; ++o) {
     VFN_CHECK_ARG(banks[o].kh && banks[o].vh, "bank %d has no tensor-core operand arrays", o);
     VFN_CHECK_ARG(banks[o].n < (1ll << 31), "bank too large");
@@ -2222,6 +2232,7 @@ int tc_match(const vfn_bank* banks, int obj_n, const float* const* nck_em, int64
   a.a_obj_stride = (long long)(a_operand_bytes(hw) / sizeof(uint16_t));
   a.band = MATCH_BAND * NK_SCALE * NK_SCALE;
   a.dbg = g_dbg;
+  a.tstamp = nullptr;
   if (!cand_split) {
     VFN_CUDA_OK(cudaMemsetAsync(const_cast<uint16_t*>(a.qh), 0, 2 * (size_t)obj_n * a_operand_bytes(hw), st));
     for (int o = 0; o < obj_n; ++o) {
@@ -2250,6 +2261,11 @@ int tc_match(const vfn_bank* banks, int obj_n, const float* const* nck_em, int64
 
 extern "C" int vfn_debug_set_pair(int32_t mask) {
   vfn::g_pair = mask & 7;
+  return VFN_OK;
+}
+
+extern "C" int vfn_debug_set_tstamp(long long* d_ptr) {
+  vfn::g_tstamp = d_ptr;
   return VFN_OK;
 }
 
