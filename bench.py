@@ -261,8 +261,12 @@ class ClockSampler(threading.Thread):
                         r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
                     except Exception:
                         r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                    try:
+                        pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                    except Exception:
+                        pw = None
                     self.samples.append([str(sm), str(self.sm_max)] +
-                                        [('Active' if r & b else 'Not Active') for b in self.BITS.values()])
+                                        [('Active' if r & b else 'Not Active') for b in self.BITS.values()] + [pw])
                 else:
                     o = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i',
                                         str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
@@ -281,8 +285,12 @@ class ClockSampler(threading.Thread):
         sm = sorted(int(s[0]) for s in samples if s[0].isdigit())
         names = list(self.BITS)
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in samples)]
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': int(samples[0][1]), 'reasons': reasons,
-                'samples': len(samples), 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
+        pw = sorted(s[6] for s in samples if len(s) > 6 and s[6] is not None)
+        out = {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': int(samples[0][1]), 'reasons': reasons,
+               'samples': len(samples), 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
+        if pw:
+            out['power_w'] = round(pw[len(pw) // 2], 1)      # the tensor kernels run the board at its power limit
+        return out
 
 
 # ---------------------------------------------------------------------------------------------------
