@@ -174,3 +174,20 @@ def test_thread_comm_matches_reference_search_and_raises_like_it():
         sharded.lfu_threshold_search(torch.tensor([1.0, float('nan')]), 10.0, 1, solo)
     with pytest.raises(RuntimeError):
         sharded.lfu_threshold_search(torch.tensor([1.0, 2.0]), 1.0, 5, solo)
+
+
+def test_bench_workload_selection(monkeypatch):
+    """--workload switches the query grid, the r1 grid, the pre-filled bank and the frame numbering together"""
+    import importlib
+    bench = importlib.import_module('bench')
+    try:
+        frames = bench.select_workload('1080p-2obj-bank-at-capacity')
+        assert (bench.HW_H * bench.HW_W, bench.R1_H, bench.R1_W) == (8160, 544, 960)
+        assert bench.N_INIT == 100000 and bench.START_FRAME == 50 and frames == 30
+        assert bench.expected_bank_size(60, 0.1) == 100000
+        assert bench.default_samples() == (60,)
+        assert bench.select_workload('480p-2obj-100frame-clip-hotpath', 7) == 7
+    finally:
+        assert bench.select_workload('480p-2obj-100frame-clip-hotpath') == 100
+    assert (bench.HW_H * bench.HW_W, bench.R1_H, bench.R1_W, bench.N_INIT, bench.START_FRAME) == (1620, 240, 432, None, 0)
+    assert bench.default_samples() == (25, 50, 75, 100)
