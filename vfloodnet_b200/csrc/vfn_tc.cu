@@ -481,13 +481,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const __grid_con
         for (int t = 0; t < ntile; ++t) {
           const uint32_t c = tile_ctr + t, st = c % SC_STAGES, ph = (c / SC_STAGES) & 1;
           mbar_wait(&k_empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&k_full[st], SC_STAGE_BYTES);
+          // the match reads only the hi half of the bank operand (two passes, see SCAN_PASSES)
+          mbar_arrive_expect_tx(&k_full[st], MODE == MODE_MATCH ? SC_STAGE_BYTES / 2 : SC_STAGE_BYTES);
           uint8_t* dst = kst + st * SC_STAGE_BYTES;
           const int row0 = (t0 + t) * SC_TILE;
           tma_load_2d(dst, &maps.kh[obj], &k_full[st], 0, row0);
           tma_load_2d(dst + 16384, &maps.kh[obj], &k_full[st], 64, row0);
-          tma_load_2d(dst + 32768, &maps.kl[obj], &k_full[st], 0, row0);
-          tma_load_2d(dst + 49152, &maps.kl[obj], &k_full[st], 64, row0);
+          if (MODE != MODE_MATCH) {
+            tma_load_2d(dst + 32768, &maps.kl[obj], &k_full[st], 0, row0);
+            tma_load_2d(dst + 49152, &maps.kl[obj], &k_full[st], 64, row0);
+          }
         }
       }
       __syncwarp();
@@ -504,7 +507,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_scan_kernel(const __grid_con
         if (elect_one()) {
           // passes: (Ah,Bh) (Al,Bh) (Ah,Bl)
 #pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
+          for (int pass = 0; pass < (MODE == MODE_MATCH ? 2 : 3); ++pass) {
             const uint32_t a_col = (pass == 1) ? TS_AL : TS_AH;
             const uint32_t kb = kbase + ((pass == 2) ? 32768u : 0u);
 #pragma unroll
@@ -705,14 +708,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         for (int t = 0; t < ntile; ++t) {
           const uint32_t c = tile_ctr + t, st = c % SP_STAGES, ph = (c / SP_STAGES) & 1;
           mbar_wait(&k_empty[st], ph ^ 1);
-          if (leader) mbar_arrive_expect_tx(&k_full[st], 2 * SP_STAGE_BYTES);
+          if (leader) mbar_arrive_expect_tx(&k_full[st], MODE == MODE_MATCH ? SP_STAGE_BYTES : 2 * SP_STAGE_BYTES);
           const uint32_t kf = mapa_u32(smem_u32(&k_full[st]), 0);
           uint8_t* dst = kst + st * SP_STAGE_BYTES;
           const int row0 = (t0 + t) * SC_TILE + (int)rank * 64;     // this CTA's 64 of the tile's 128 slots
           tma_load_2d_pair(dst, &maps.kh[obj], kf, 0, row0);
           tma_load_2d_pair(dst + 8192, &maps.kh[obj], kf, 64, row0);
-          tma_load_2d_pair(dst + 16384, &maps.kl[obj], kf, 0, row0);
-          tma_load_2d_pair(dst + 24576, &maps.kl[obj], kf, 64, row0);
+          if (MODE != MODE_MATCH) {                                 // the match reads only the hi half (SCAN_PASSES)
+            tma_load_2d_pair(dst + 16384, &maps.kl[obj], kf, 0, row0);
+            tma_load_2d_pair(dst + 24576, &maps.kl[obj], kf, 64, row0);
+          }
         }
       }
       __syncwarp();
@@ -730,7 +735,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           {
             // passes: (Ah,Bh) (Al,Bh) (Ah,Bl); each CTA's smem holds its 64 slots of the 128-slot B tile
 #pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
+            for (int pass = 0; pass < (MODE == MODE_MATCH ? 2 : 3); ++pass) {
               const uint32_t a_col = (pass == 1) ? TS_AL : TS_AH;
               const uint32_t kb = kbase + ((pass == 2) ? 16384u : 0u);
 #pragma unroll
@@ -1833,7 +1838,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 // FMA chain the SIMT kernel uses (bit-identical values and ordering, ties -> lowest slot).  An overflow marker (more
 // than four near-ties in one column group of one item) sends that query to an exact scan of all slots.
 // ------------------------------------------------------------------------------------------------
-constexpr float MATCH_BAND = 2e-5f;
+// The scan runs TWO passes for the match, (Ah + Al) x Bh: the candidate is exact to ~2^-22, the bank operand is the fp16
+// rounding of 16 * nk, so |approximate - exact| <= 2^-11 * sum |a_i b_i| <= 2^-11 (unit vectors) + the accumulate
+// truncation.  Any slot that can be the true arg-max lies within twice that bound of the approximate maximum: the band.
+// (Three passes with a 2e-5 band cost a third more MMA work - and energy, which is what these kernels are bound by -
+// for the same exact result after the re-score.)
+constexpr float MATCH_BAND = 1.05e-3f;
 
 __device__ __forceinline__ float exact_dot128(const float* __restrict__ nk, const float* __restrict__ q, int64_t slot) {
   const float4* a = reinterpret_cast<const float4*>(nk + slot * DK);
