@@ -1,0 +1,193 @@
+"""Whole-model harness for BASELINE.json configs[0]/[1]: the reference's own frame loop
+(test_video_seg.py:99-112, without resize / post-processing / PNG) over a seeded synthetic 480p 2-object clip, run with
+
+  * the UNMODIFIED reference (baseline/refshim.py: `AFB_URR`, `FeatureBank`) on any torch device, and
+  * the same model instance's weights with `vfloodnet_b200.patch_model` + `vfloodnet_b200.FeatureBank` (the drop-in).
+
+Test / bench infrastructure (tests/test_gpu_dropin.py, bench.py --workload 480p-model-clip); never imported by the
+product package.  Regime B of the survey: random-init weights, `torch.manual_seed(0)` before construction, BatchNorm
+statistics calibrated by three train-mode passes (`momentum=None`) over seeded frames, then `.eval()`.
+"""
+from __future__ import annotations
+
+import copy
+import math
+import time
+from typing import Callable, List, Optional
+
+import torch
+from torch.nn import functional as F
+
+H480, W480 = 480, 854          # test_video_seg.py:46 downsample_size = 480 of a 16:9 frame
+BUDGET = 250000                # test_video_seg.py:24
+
+
+# ---------------------------------------------------------------------------------------------------
+# clip
+# ---------------------------------------------------------------------------------------------------
+def make_frame(t: int, seed: int = 0, h: int = H480, w: int = W480) -> torch.Tensor:
+    """(1,3,h,w) fp32 in [0,1]: a smooth moving sinusoid pattern + 0.3 * uniform noise (CPU, seeded per frame)."""
+    g = torch.Generator().manual_seed(seed * 100003 + t)
+    yy = torch.arange(h, dtype=torch.float32).view(h, 1) / h
+    xx = torch.arange(w, dtype=torch.float32).view(1, w) / w
+    chans = []
+    for c in range(3):
+        ph = 0.7 * c + 0.37 * seed
+        base = 0.5 + 0.25 * torch.sin(2 * math.pi * (3 * xx + 0.020 * t) + ph) * \
+            torch.cos(2 * math.pi * (2 * yy - 0.013 * t) + 0.5 * ph)
+        chans.append(base)
+    base = torch.stack(chans, 0)
+    noise = torch.rand(3, h, w, generator=g)
+    return (0.7 * base + 0.3 * noise).clamp_(0, 1).unsqueeze(0)
+
+
+def first_mask(h: int = H480, w: int = W480) -> torch.Tensor:
+    """(1,2,h,w) one-hot: lower half water (object 1), upper half background (object 0)."""
+    m = torch.zeros(1, 2, h, w)
+    m[:, 1, h // 2:, :] = 1
+    m[:, 0, :h // 2, :] = 1
+    return m
+
+
+def make_clip(frames: int, seed: int = 0, h: int = H480, w: int = W480, pin: bool = False):
+    fr = [make_frame(t, seed, h, w) for t in range(frames + 1)]      # frame 0 is the annotated first frame
+    if pin:
+        fr = [f.pin_memory() for f in fr]
+    return fr
+
+
+# ---------------------------------------------------------------------------------------------------
+# model
+# ---------------------------------------------------------------------------------------------------
+def build_reference_model(ns, device, seed: int = 0, calib_frames: Optional[List[torch.Tensor]] = None):
+    """ns: baseline.refshim.load().  Construction and BN calibration happen on the CPU so that every device (and the
+    CPU arm) starts from bit-identical weights; the result is moved to `device`."""
+    import warnings
+    torch.manual_seed(seed)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        model = ns.AFB_URR('cpu', update_bank=True, load_imagenet_params=False)
+    if calib_frames is None:
+        calib_frames = [make_frame(1000 + i, seed) for i in range(3)]
+    bns = [m for m in model.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    for b in bns:
+        b.reset_running_stats()
+        b.momentum = None                         # cumulative average over the calibration passes
+    model.train()
+    mask = first_mask(*calib_frames[0].shape[-2:])
+    with torch.no_grad():
+        for f in calib_frames:
+            model.memorize(f, mask)               # encoder_m statistics
+            [fp], _ = ns.myutils.pad_divide_by([f], 16, f.shape[-2:])
+            model.encoder_q(fp)                   # encoder_q statistics
+    model.eval()
+    model.device = device
+    model.decoder.device = device
+    return model.to(device)
+
+
+def patched_copy(model, vfn):
+    """deep copy of the reference model with the B200 hot path installed (vfloodnet_b200.patch_model)"""
+    m = copy.deepcopy(model)
+    vfn.patch_model(m)
+    return m.eval()
+
+
+# ---------------------------------------------------------------------------------------------------
+# loop (test_video_seg.py:99-112)
+# ---------------------------------------------------------------------------------------------------
+class StageTimer:
+    """per-stage time of the frame loop: CUDA events on the current stream (GPU) or perf_counter (CPU)"""
+
+    def __init__(self, device):
+        self.cuda = torch.device(device).type == 'cuda'
+        self.acc = {}
+        self._open = []
+
+    def start(self, name):
+        if self.cuda:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            return (name, e)
+        return (name, time.perf_counter())
+
+    def stop(self, tok):
+        name, t0 = tok
+        if self.cuda:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._open.append((name, t0, e))
+        else:
+            self.acc[name] = self.acc.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+
+    def totals(self):
+        if self.cuda:
+            torch.cuda.synchronize()
+            for name, a, b in self._open:
+                self.acc[name] = self.acc.get(name, 0.0) + a.elapsed_time(b)
+            self._open = []
+        return dict(self.acc)
+
+
+def instrument(model, timer: StageTimer):
+    """time the read (global_matcher) inside segment with forward hooks; returns the hook handles"""
+    tok = {}
+
+    def pre(_m, _inp):
+        tok['t'] = timer.start('read')
+
+    def post(_m, _inp, _out):
+        timer.stop(tok.pop('t'))
+
+    return [model.global_matcher.register_forward_pre_hook(pre), model.global_matcher.register_forward_hook(post)]
+
+
+def run_clip(model, bank_cls, frames: List[torch.Tensor], device, budget: int = BUDGET, thres_close: float = 0.95,
+             update_rate: float = 0.1, timer: Optional[StageTimer] = None, warm_frames: int = 0,
+             on_frame: Optional[Callable] = None, keep_masks: bool = True, frames_on_host: bool = False):
+    """The reference loop: memorize(first frame, first mask) -> init_bank; per frame segment -> softmax -> memorize ->
+    update.  frames[0] is the annotated frame.  Returns dict(fb=, masks=[(h,w) uint8 arg-max per frame], probs_last=).
+    on_frame(t, frame, score, pred_mask, k4, v4, fb) is called after every update (tests hook comparisons there).
+    frames_on_host: frames are (pinned) host tensors copied in every frame and the arg-max mask is copied back (e2e)."""
+    dev = torch.device(device)
+    f0 = frames[0].to(dev, non_blocking=True)
+    m0 = first_mask(*f0.shape[-2:]).to(dev)
+    fb = bank_cls(2, budget, dev, update_rate=update_rate, thres_close=thres_close)
+    masks = []
+    host_mask = None
+    with torch.no_grad():
+        k4, v4 = model.memorize(f0, m0)
+        fb.init_bank(k4, v4)
+        for t in range(1, len(frames)):
+            timed = timer is not None and t > warm_frames
+            frame = frames[t].to(dev, non_blocking=True)
+            a = timer.start('segment') if timed else None
+            score, _ = model.segment(frame, fb)
+            pred_mask = F.softmax(score, dim=1)
+            if timed:
+                timer.stop(a)
+                a = timer.start('memorize')
+            k4, v4 = model.memorize(frame, pred_mask)
+            if timed:
+                timer.stop(a)
+                a = timer.start('update')
+            fb.update(k4, v4, t)
+            if timed:
+                timer.stop(a)
+            am = torch.argmax(pred_mask[0], dim=0).to(torch.uint8)
+            if frames_on_host:
+                if host_mask is None:
+                    host_mask = torch.empty(am.shape, dtype=torch.uint8).pin_memory()
+                host_mask.copy_(am, non_blocking=True)
+            if keep_masks:
+                masks.append(am)
+            if on_frame is not None:
+                on_frame(t, frame, score, pred_mask, k4, v4, fb)
+    return dict(fb=fb, masks=masks, last_score=score, host_mask=host_mask)
+
+
+def iou(a: torch.Tensor, b: torch.Tensor) -> float:
+    """IoU of the water class (label 1) of two arg-max masks; two empty masks count as 1."""
+    a1, b1 = a == 1, b == 1
+    union = (a1 | b1).sum().item()
+    return 1.0 if union == 0 else (a1 & b1).sum().item() / union

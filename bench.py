@@ -7,7 +7,11 @@ init_bank.  `value` = frames/s with the clip resident in HBM; `e2e` = the same t
 HOST (pinned) inputs copied in and the refined mask copied out every frame.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (CUDA kernels)
-    python bench.py --impl reference ...                           # reference algorithm on the host cores (oracle port)
+    python bench.py --impl reference ...                           # the reference's own read+update on the host cores:
+                                                                   # the SAME clip, free-running (true bank trajectory)
+    python bench.py --workload 480p-model-clip                     # whole reference model, unpatched vs patch_model
+    python bench.py --workload 1080p-2obj-bank-at-capacity --frames 2000      # BASELINE configs[2]
+    python bench.py --workload 480p-64-streams --gpus G                         # BASELINE configs[3]
 """
 import argparse
 import json
@@ -40,6 +44,9 @@ TAIL_KEY_PTS = [(480, 300), (960, 200), (1440, 400), (1800, 100)]
 WORKLOADS = {
     '480p-2obj-100frame-clip-hotpath': dict(hw=(30, 54), r1=(240, 432), frames=100, n_init=None, start_frame=0),
     '1080p-2obj-bank-at-capacity': dict(hw=(68, 120), r1=(544, 960), frames=30, n_init=100000, start_frame=50),
+    # whole reference model (encoders, KeyValue, decoder convolutions stay cuDNN) around the hot path: the unmodified
+    # reference on the GPU against the same weights with vfloodnet_b200.patch_model (BASELINE configs[1])
+    '480p-model-clip': dict(hw=(30, 54), r1=(240, 432), frames=100, n_init=None, start_frame=0),
 }
 WORKLOAD = '480p-2obj-100frame-clip-hotpath'
 START_FRAME, N_INIT = 0, None
@@ -67,6 +74,8 @@ def parse():
     ap.add_argument('--frac-merge', type=float, default=0.1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--read-impl', type=int, default=0, help='0 auto (tcgen05), 1 fp32 SIMT, 2 tcgen05')
+    ap.add_argument('--no-torch-baseline', action='store_true', help='skip the reference-torch-ops-on-this-GPU leg')
+    ap.add_argument('--no-affinity', action='store_true', help='do not bind the process to the GPU-local CPUs')
     args = ap.parse_args()
     args.frames = select_workload(args.workload, args.frames)
     return args
@@ -113,7 +122,7 @@ def to_device(clip, dev):
 
 
 def run_clip_gpu(vfn, clip, dev, read_impl, host_inputs=False, out_host=None, exact_sizes=False, tail=None,
-                 levels_host=None):
+                 levels_host=None, before_frame=None, copy_only=False):
     """one step: the whole clip through the drop-in API.  Returns (bank, last readout, last refined mask).
     host_inputs: every frame's tensors start in pinned HOST memory; their H2D copies are issued on a side stream one
     frame ahead (double buffering) and the refined mask is copied back to the host every frame."""
@@ -160,6 +169,13 @@ def run_clip_gpu(vfn, clip, dev, read_impl, host_inputs=False, out_host=None, ex
                 _start_bank(fb, clip, lambda x: x)
             q_in, q_out, pk, pv = clip['frames'][t]
             urr = clip['urr']
+        if copy_only:          # the host->device leg alone (same staging, same events), no kernels
+            if host_inputs:
+                done[t & 1] = torch.cuda.Event()
+                done[t & 1].record(cur)
+            continue
+        if before_frame is not None:
+            before_frame(t, fb, (q_in, q_out, pk, pv))
         p, r1, q_local = urr
         out = m(fb, q_in, q_out)
         p_up, unc, conf, local_match = vfn.urr_pre(p, r1.expand(2, -1, -1, -1), (1, 2, R1_H, R1_W))
@@ -294,80 +310,186 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU arm: the reference algorithm (oracle port, torch CPU, all host threads) on a bounded sample
+# Reference arm: the reference's own read + update (unmodified classes from baseline/_ref when staged, else the oracle
+# port) on plain torch ops, over THE SAME CLIP as our arm (same ClipGenerator seed), free-running from init_bank so that
+# every frame sees the true bank state (sizes, usage counts, evictions) of the clip.
 # ---------------------------------------------------------------------------------------------------
-def expected_bank_size(frame, frac_merge):
-    hw = HW_H * HW_W
-    if N_INIT:
-        return int(min(N_INIT, 0.8 * (BUDGET // 2)))
-    return int(min(hw + (1 - frac_merge) * hw * frame, 0.8 * (BUDGET // 2)))
+def config_dict(args):
+    """identical in both arms (the driver compares it)"""
+    return {'workload': WORKLOAD, 'hw': HW_H * HW_W, 'budget': BUDGET, 'frames': args.frames,
+            'frac_merge': args.frac_merge,
+            'l2_policy': 'inputs_exceed_l2 (bank operands 0.5-1.1 GB per object >> 126 MB L2)'}
 
 
-def default_samples():
-    return (START_FRAME + 10,) if N_INIT else (25, 50, 75, 100)
-
-
-def cpu_sample(frac_merge, sample_frames=None, seed=0, device='cpu'):
-    """Times oracle read + URR + update at the bank sizes the clip has at `sample_frames` (synthetic bank contents of
-    the clip's analytic size trajectory).  Returns (frames_per_sec, description, seconds).
-    device='cuda:N' runs the same plain-torch restatement with ATen/cuBLAS kernels on the GPU ("reference torch ops" of
-    BASELINE.json configs[1]); timed with a device synchronisation on both sides of every step."""
-    from oracle import afb_oracle as O
+def _ref_clip_source(seed, frames, frac_merge):
+    """frame generator of the clip (CPU tensors, produced one frame ahead of use: a whole clip is 4 GB)"""
     from vfloodnet_b200 import synth
-    sample_frames = sample_frames or default_samples()
+    gen = synth.ClipGenerator(seed=seed, obj_n=2, hw=HW_H * HW_W, d_key=D_KEY, d_val=D_VAL, frac_merge=frac_merge,
+                              n_init=N_INIT)
+    keys0, vals0 = gen.init()
+    g = torch.Generator().manual_seed(seed + 1000)
+    urr = synth.gen_urr_inputs(g, 2, R1_H, R1_W)
+    return gen, keys0, vals0, urr
+
+
+def reference_free_run(frac_merge, frames, seed, device='cpu', steps=1, timed_from=0, max_seconds=None):
+    """Runs the clip free from init_bank through the reference arm.  Every frame is timed on its own; frame t belongs to
+    step (t mod steps) - each step is a bounded sample (every steps-th frame) of the one clip, and together the steps
+    are the whole clip.  Returns dict(kind, seconds_per_step[steps], frames_per_step[steps], sizes, desc)."""
+    from baseline.ref_arm import RefArm
     on_gpu = str(device) != 'cpu'
     if not on_gpu:
         torch.set_num_threads(os.cpu_count())
-    hw = HW_H * HW_W
-    total = 0.0
-    D = (lambda t: t.to(device)) if on_gpu else (lambda t: t)
-    for f in sample_frames:
-        g = torch.Generator().manual_seed(seed + f)
-        n = expected_bank_size(f, frac_merge)
-        fb = O.OracleFeatureBank(2, BUDGET, device)
-        keys, vals = zip(*[synth.gen_bank(g, n) for _ in range(2)])
-        fb.init_bank([D(k) for k in keys], [D(v) for v in vals])
-        for c in range(2):
-            fb.info[c] = D(synth.gen_info(g, n, f))
-        q_in, q_out = synth.gen_query(g, hw)
-        pk, pv = zip(*[synth.gen_candidates(g, keys[c], vals[c], hw, frac_merge) for c in range(2)])
-        p, r1, q_local = synth.gen_urr_inputs(g, 2, R1_H, R1_W)
-        args = (D(q_in), D(q_out), [D(k) for k in pk], [D(v) for v in pv])
-        urr = (D(p), D(r1).expand(2, -1, -1, -1), D(q_local), (1, 2, R1_H, R1_W))
+    else:
+        torch.backends.cuda.matmul.allow_tf32 = False      # the reference's default: true fp32 GEMMs (SURVEY App. A 17)
+    gen, keys0, vals0, urr = _ref_clip_source(seed, frames, frac_merge)
+    arm = RefArm(BUDGET, device)
+    arm.init(keys0, vals0)
+    if N_INIT:
+        from vfloodnet_b200 import synth
+        g = torch.Generator().manual_seed(seed + 1000)
+        synth.gen_urr_inputs(g, 2, R1_H, R1_W)
+        info0 = []
+        for _ in range(2):
+            i = synth.gen_info(g, N_INIT, START_FRAME)
+            i[:, 0] = torch.sort(i[:, 0]).values
+            info0.append(i)
+        arm.load(keys0, vals0, info0)
+    p, r1, q_local = [arm.D(t) for t in urr]
+    urr_in = (p, r1.expand(2, -1, -1, -1), q_local, (1, 2, R1_H, R1_W))
+    secs, cnt, sizes = [0.0] * steps, [0] * steps, []
+    t_all = time.perf_counter()
+    done = 0
+    for t in range(frames):
+        q_in, q_out, pk, pv = gen.frame()
+        a = (arm.D(q_in), arm.D(q_out), [arm.D(k) for k in pk], [arm.D(v) for v in pv])
         if on_gpu:
             torch.cuda.synchronize()
         t0 = time.perf_counter()
-        O.hot_path_step(fb, *args, f, urr_in=urr)
+        arm.frame(*a, urr_in, START_FRAME + t + 1)
         if on_gpu:
             torch.cuda.synchronize()
-        total += time.perf_counter() - t0
-    where = 'torch CUDA ops (ATen/cuBLAS fp32) on the same GPU' if on_gpu else 'torch CPU fp32'
-    desc = (f'oracle port ({where}) of read+URR+update on frames {list(sample_frames)} of the clip, bank sizes '
-            f'{[expected_bank_size(f, frac_merge) for f in sample_frames]} slots/object (analytic trajectory)')
-    return len(sample_frames) / total, desc, total
+        dt = time.perf_counter() - t0
+        sizes.append(arm.sizes())
+        done += 1
+        if t >= timed_from:
+            secs[t % steps] += dt
+            cnt[t % steps] += 1
+        if max_seconds is not None and time.perf_counter() - t_all > max_seconds:
+            break
+    where = 'torch CUDA ops (ATen/cuBLAS fp32, allow_tf32=False) on the same GPU' if on_gpu else 'torch CPU fp32, all host threads'
+    what = ('unmodified reference FeatureBank + Matcher (baseline/_ref), URR block via the oracle restatement'
+            if arm.kind == 'reference' else 'oracle port of the reference (baseline/_ref not staged)')
+    desc = (f'{what}; {where}; read+URR+update of frames 1..{done} of the same clip (seed {seed}), free-running from '
+            f'init_bank: true bank trajectory, mean {sum(sum(x) for x in sizes) / (2 * len(sizes)):.0f} slots/object, '
+            f'final {sizes[-1]}')
+    return dict(kind=arm.kind, secs=secs, cnt=cnt, sizes=sizes, desc=desc, frames_done=done, arm=arm)
 
 
 def main_reference(args, rank, world):
     if rank != 0:
         return
-    for _ in range(args.warmup and 1):
-        cpu_sample(args.frac_merge, sample_frames=(5,))
-    t0 = time.perf_counter()
-    n_frames = 0
-    for _ in range(args.steps):
-        fps, desc, secs = cpu_sample(args.frac_merge)
-        n_frames += len(default_samples())
-    el = time.perf_counter() - t0
+    if WORKLOAD == '480p-model-clip':
+        return main_reference_model(args)
+    if args.warmup:                                   # one short untimed pass (allocator, thread pools, MKL plans)
+        reference_free_run(args.frac_merge, min(3, args.frames), seed=99, steps=1)
+    r = reference_free_run(args.frac_merge, args.frames, seed=100, steps=args.steps)
+    el = sum(r['secs'])
+    n_frames = sum(r['cnt'])
     v = n_frames / el
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'frames/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * el / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'hw': HW_H * HW_W, 'budget': BUDGET,
-                       'frames': args.frames, 'frac_merge': args.frac_merge},
-            'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': desc},
+            'config': config_dict(args),
+            'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': os.cpu_count(), 'kind': r['kind'],
+                             'sample': r['desc'] + f'; step k = frames t with t mod {args.steps} == k '
+                                                   f'({n_frames} frames in all)'},
             'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-            'gpu_launches': 0}
+            'gpu_launches': 0, 'final_bank_slots': r['sizes'][-1]}
     print(json.dumps(line))
+
+
+def cpu_sample_true_state(vfn, dev_clip, dev, read_impl, frac_merge, sample_frames):
+    """cpu_baseline of OUR arm: a bounded sample of the same clip.  The GPU run is paused before the read of each sample
+    frame, its bank (the true state of the clip at that frame) is copied to the host, and the reference arm (CPU) is
+    timed on that one frame.  sample_frames are 0-based clip positions."""
+    from baseline.ref_arm import RefArm
+    torch.set_num_threads(os.cpu_count())
+    secs, sizes, kind = [], [], [None]
+    p, r1, q_local = [t.cpu() for t in dev_clip['urr']]
+    urr_in = (p, r1.expand(2, -1, -1, -1), q_local, (1, 2, R1_H, R1_W))
+
+    def before_frame(t, fb, frame):
+        if t not in sample_frames:
+            return
+        torch.cuda.synchronize()
+        arm = RefArm(BUDGET, 'cpu')
+        arm.load([fb.keys[c].cpu() for c in range(2)], [fb.values[c].cpu() for c in range(2)],
+                 [fb.info[c].cpu() for c in range(2)])
+        kind[0] = arm.kind
+        q_in, q_out, pk, pv = frame
+        a = (q_in.cpu(), q_out.cpu(), [k.cpu() for k in pk], [v.cpu() for v in pv])
+        sizes.append(arm.sizes())
+        t0 = time.perf_counter()
+        arm.frame(*a, urr_in, START_FRAME + t + 1)
+        secs.append(time.perf_counter() - t0)
+
+    run_clip_gpu(vfn, dev_clip, dev, read_impl, before_frame=before_frame)
+    total = sum(secs)
+    desc = (f'reference arm ({kind[0]}; torch CPU fp32, all host threads) on frames {[t + 1 for t in sample_frames]} of the '
+            f'same clip, each started from the TRUE bank state of the clip at that frame (copied from the GPU run), bank '
+            f'sizes {sizes} slots/object')
+    return len(secs) / total, desc, total, kind[0]
+
+
+# ---------------------------------------------------------------------------------------------------
+# host placement: bind the process (and so its pinned allocations: first touch) to the CPUs / NUMA node of its GPU
+# ---------------------------------------------------------------------------------------------------
+def bind_to_gpu_node(index):
+    """at 8 GPUs the per-frame H2D copies of ranks 0-3 ran at 2/3 of the speed of ranks 4-7 - pinned buffers
+    had been allocated wherever the launcher happened to start the process.  Must run BEFORE any pin_memory().
+    Returns a description for the bench line."""
+    info = {'bound': False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        try:
+            info['pci'] = pynvml.nvmlDeviceGetPciInfo(h).busId
+            if isinstance(info['pci'], bytes):
+                info['pci'] = info['pci'].decode()
+        except Exception:
+            pass
+        node = None
+        if info.get('pci'):
+            pth = f"/sys/bus/pci/devices/{info['pci'].lower()[-12:]}/numa_node"
+            if os.path.exists(pth):
+                node = int(open(pth).read().strip())
+        info['numa_node'] = node
+        cpus = None
+        if node is not None and node >= 0 and os.path.exists(f'/sys/devices/system/node/node{node}/cpulist'):
+            cpus = set()
+            for part in open(f'/sys/devices/system/node/node{node}/cpulist').read().strip().split(','):
+                a, _, b = part.partition('-')
+                cpus.update(range(int(a), int(b or a) + 1))
+        else:
+            try:                                                    # NVML's ideal CPU set of the device
+                n_words = (os.cpu_count() + 63) // 64
+                mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+                cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+            except Exception:
+                cpus = None
+        allowed = os.sched_getaffinity(0)
+        if cpus:
+            cpus = cpus & allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            info.update(bound=True, cpus=len(cpus))
+        else:
+            info['cpus'] = len(allowed)
+    except Exception as e:
+        info['error'] = f'{type(e).__name__}: {e}'[:120]
+    return info
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -380,6 +502,7 @@ def main_ours(args, rank, world, local_rank):
     lib = _lib.load()
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
+    placement = {'bound': False, 'note': 'disabled'} if args.no_affinity else bind_to_gpu_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -453,6 +576,16 @@ def main_ours(args, rank, world, local_rank):
     t1.record()
     barrier()
     ms_e2e = t0.elapsed_time(t1)
+    # the host->device leg of that loop alone (every rank at once): what the host memory / PCIe path sustains
+    run_clip_gpu(vfn, host_clip, dev, args.read_impl, host_inputs=True, copy_only=True)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(args.steps):
+        run_clip_gpu(vfn, host_clip, dev, args.read_impl, host_inputs=True, copy_only=True)
+    c1.record()
+    barrier()
+    ms_copy = c0.elapsed_time(c1)
 
     # e2e with the device-resident tail: per frame the refined probabilities are resized to 1080x1920, reduced to the
     # largest water component and scanned for the water level at 4 key points; 16 bytes per frame return to the host
@@ -494,14 +627,14 @@ def main_ours(args, rank, world, local_rank):
         tail_launches = (lib.vfn_launch_count() - tl0) // 50
     tail_stats = ft.stats.tolist()
 
-    t_ms = torch.tensor([ms, ms_e2e, ms_e2e_tail], dtype=torch.float64, device=dev)
-    per_rank = [[ms, ms_e2e, ms_e2e_tail]]
+    t_ms = torch.tensor([ms, ms_e2e, ms_e2e_tail, ms_copy], dtype=torch.float64, device=dev)
+    per_rank = [[ms, ms_e2e, ms_e2e_tail, ms_copy]]
     if dist is not None:
         allt = [torch.empty_like(t_ms) for _ in range(world)]
         dist.all_gather(allt, t_ms)
         per_rank = [t.tolist() for t in allt]
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_e2e_tail = t_ms.tolist()
+    ms, ms_e2e, ms_e2e_tail, ms_copy = t_ms.tolist()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -558,39 +691,210 @@ def main_ours(args, rank, world, local_rank):
                            'noise_input_stats': dict(zip(['fg_pixels', 'components', 'kept', 'root'], tail_stats)),
                            'note': 'resize+argmax, largest 8-connected component, water-level scan; working set is L2 '
                                    'resident (25 MB), latency bound: 7 dependent launches'}
+    copy_gbs = h2d * args.steps / (ms_copy * 1e-3) / 1e9
     line = {'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f16 hi/lo + f8 split operands, f32 accumulate (read, match); f32 (update, URR)',
-            'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'hw': HW_H * HW_W, 'budget': BUDGET,
-                       'frames': args.frames, 'frac_merge': args.frac_merge, 'streams_per_gpu': 1,
-                       'final_bank_slots': final_n, 'l2_policy': 'inputs_exceed_l2 (bank operands 0.5-1.1 GB >> 126 MB)',
-                       'read_impl': args.read_impl},
+            'data': 'synthetic', 'config': config_dict(args),
+            'run': {'streams_per_gpu': 1, 'final_bank_slots': final_n, 'read_impl': args.read_impl, 'seed': 100,
+                    'host_placement': placement},
             'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'e2e_tail': {'value': frames_total / (ms_e2e_tail / 1e3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d,
                          'd2h_bytes_per_step': args.frames * 4 * len(TAIL_KEY_PTS),
                          'note': 'e2e + device-resident loop tail (1080x1920 mask, largest component, 4 water levels)'},
+            'h2d_copy_only': {'gb_per_s_per_gpu': copy_gbs, 'ms_per_step': ms_copy / args.steps,
+                              'frames_per_s_bound': frames_total / (ms_copy / 1e3),
+                              'note': 'the e2e loop with its kernels removed: pinned-host -> device copies of every '
+                                      "frame's boundary tensors on all ranks at once (max over ranks); e2e cannot exceed it"},
             'gpu_launches': int(launches), 'roofline': roofline, 'kernels': extra, 'clocks': sampler.summary(),
             'ms_per_rank': [[round(x / args.steps, 2) for x in r] for r in per_rank],
             'ms_steps': [round(x, 2) for x in ms_steps]}
-    if world == 1:
-        # BASELINE.json configs[1]: "... vs reference torch ops" - the plain-torch restatement on this GPU (baseline only)
+    if world == 1 and not args.no_torch_baseline:
+        # BASELINE.json configs[1]: "... vs reference torch ops": the reference's own classes on this GPU over the same clip
         try:
-            torch.backends.cuda.matmul.allow_tf32 = False
-            cpu_sample(args.frac_merge, sample_frames=(5,), device=dev)                   # cuBLAS / allocator warm-up
-            fps_t, desc_t, secs_t = cpu_sample(args.frac_merge, device=dev)
-            line['torch_gpu_baseline'] = {'value': fps_t, 'unit': 'frames/s', 'kind': 'port', 'sample': desc_t,
-                                          'seconds': secs_t}
+            reference_free_run(args.frac_merge, 3, seed=99, device=dev)                   # cuBLAS / allocator warm-up
+            r = reference_free_run(args.frac_merge, args.frames, seed=100, device=dev)
+            line['torch_gpu_baseline'] = {'value': sum(r['cnt']) / sum(r['secs']), 'unit': 'frames/s', 'kind': r['kind'],
+                                          'sample': r['desc'], 'seconds': sum(r['secs']),
+                                          'final_bank_slots': r['sizes'][-1]}
+            del r
         except Exception as e:                                                            # reported, never hidden
             line['torch_gpu_baseline'] = {'value': None, 'error': f'{type(e).__name__}: {e}'[:300]}
         torch.cuda.empty_cache()
     if not args.no_cpu_baseline and world == 1:
-        fps, desc, secs = cpu_sample(args.frac_merge)
-        line['cpu_baseline'] = {'value': fps, 'unit': 'frames/s', 'cores': os.cpu_count(), 'kind': 'port',
+        n_f = args.frames
+        sample = sorted({min(n_f - 1, int((i + 0.5) * n_f / 8)) for i in range(8)})      # midpoints of 8 equal parts
+        fps, desc, secs, kind = cpu_sample_true_state(vfn, dev_clip, dev, args.read_impl, args.frac_merge, sample)
+        line['cpu_baseline'] = {'value': fps, 'unit': 'frames/s', 'cores': os.cpu_count(), 'kind': kind,
                                 'sample': desc, 'seconds': secs}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
+# --workload 480p-model-clip: the whole reference model around the hot path
+# ---------------------------------------------------------------------------------------------------
+def _stage_table(tot, frames):
+    """per-frame ms: CNN = segment + memorize minus the stages timed inside them"""
+    seg, mem, upd = tot.get('segment', 0.0), tot.get('memorize', 0.0), tot.get('update', 0.0)
+    read, urr = tot.get('read', 0.0), tot.get('urr', 0.0)
+    d = {'cnn': (seg - read - urr + mem) / frames, 'read': read / frames, 'update': upd / frames,
+         'total': (seg + mem + upd) / frames}
+    if 'urr' in tot:
+        d['urr'] = urr / frames
+    else:
+        d['urr'] = None          # inlined in Decoder.forward between convolutions in the unpatched reference: inside cnn
+    return {k: (round(v, 4) if v is not None else None) for k, v in d.items()}
+
+
+def main_model_clip(args, rank, world, local_rank):
+    import vfloodnet_b200 as vfn
+    from vfloodnet_b200 import _lib, urr as vurr
+    from baseline import refshim, model_clip as MC
+    lib = _lib.load()
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    placement = {'bound': False, 'note': 'disabled'} if args.no_affinity else bind_to_gpu_node(local_rank)
+    if not refshim.available():
+        print(json.dumps({'metric': METRIC, 'config': config_dict(args),
+                          'unavailable': 'reference model definition not staged (python baseline/make_ref.py)'}))
+        return
+    ns = refshim.load()
+    model_ref = MC.build_reference_model(ns, dev)
+    model_ours = MC.patched_copy(model_ref, vfn)
+    host_clip = MC.make_clip(args.frames, seed=rank, pin=True)
+    dev_clip = [f.to(dev) for f in host_clip]
+    torch.cuda.synchronize()
+
+    def clip_ours(frames, **kw):
+        return MC.run_clip(model_ours, vfn.FeatureBank, frames, dev, budget=BUDGET, **kw)
+
+    def clip_ref(frames, **kw):
+        return MC.run_clip(model_ref, ns.FeatureBank, frames, dev, budget=BUDGET, **kw)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and not os.environ.get('VFN_BENCH_NO_SAMPLER'):
+        sampler.start()
+    for _ in range(max(args.warmup, 1)):
+        clip_ours(dev_clip, keep_masks=False)
+    torch.cuda.synchronize()
+    sampler.mark()
+    l0 = lib.vfn_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        o = clip_ours(dev_clip, keep_masks=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = lib.vfn_launch_count() - l0
+    final_n = [o['fb'].bank_n(c) for c in range(2)]
+    sampler.stop_flag = True
+    # e2e: every frame starts in pinned host memory, the arg-max mask returns to the host
+    clip_ours(host_clip, keep_masks=False, frames_on_host=True)
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        clip_ours(host_clip, keep_masks=False, frames_on_host=True)
+    t1.record()
+    torch.cuda.synchronize()
+    ms_e2e = t0.elapsed_time(t1)
+    # per-stage times, our arm (URR stages timed through wrappers around the two fused entry points)
+    tm = MC.StageTimer(dev)
+    hooks = MC.instrument(model_ours, tm)
+    pre0, post0 = vurr.urr_pre, vurr.urr_post
+
+    def timed(fn):
+        def w(*a, **k):
+            tok = tm.start('urr')
+            r = fn(*a, **k)
+            tm.stop(tok)
+            return r
+        return w
+
+    vurr.urr_pre, vurr.urr_post = timed(pre0), timed(post0)
+    try:
+        ours_run = clip_ours(dev_clip, timer=tm)
+    finally:
+        vurr.urr_pre, vurr.urr_post = pre0, post0
+        for h in hooks:
+            h.remove()
+    st_ours = _stage_table(tm.totals(), args.frames)
+    # the unmodified reference on the same GPU: same weights, same clip
+    torch.backends.cuda.matmul.allow_tf32 = False
+    clip_ref(dev_clip[:4], keep_masks=False)
+    torch.cuda.synchronize()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    clip_ref(dev_clip, keep_masks=False)
+    r1.record()
+    torch.cuda.synchronize()
+    ms_ref = r0.elapsed_time(r1)
+    tm_r = MC.StageTimer(dev)
+    hooks = MC.instrument(model_ref, tm_r)
+    ref_run = clip_ref(dev_clip, timer=tm_r)
+    for h in hooks:
+        h.remove()
+    st_ref = _stage_table(tm_r.totals(), args.frames)
+    ious = [MC.iou(a, b) for a, b in zip(ref_run['masks'], ours_run['masks'])]
+    n_ref = [int(ref_run['fb'].keys[c].shape[1]) for c in range(2)]
+    if rank != 0:
+        return
+    frames_total = args.frames * args.steps
+    frame_bytes = host_clip[1].numel() * 4
+    line = {'metric': METRIC, 'value': frames_total / (ms / 1e3), 'unit': 'frames/s', 'n_gpus': 1, 'steps': args.steps,
+            'warmup': max(args.warmup, 1), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32 convolutions (cuDNN, TF32 allowed: the reference default); hot path as in '
+                                          'the default workload', 'data': 'synthetic',
+            'config': config_dict(args),
+            'run': {'final_bank_slots': final_n, 'host_placement': placement,
+                    'model': 'reference AFB_URR (random init seed 0, BN-calibrated), patch_model + vfloodnet_b200.FeatureBank'},
+            'e2e': {'value': frames_total / (ms_e2e / 1e3), 'unit': 'frames/s',
+                    'h2d_bytes_per_step': (args.frames + 1) * frame_bytes,
+                    'd2h_bytes_per_step': args.frames * host_clip[1].shape[-1] * host_clip[1].shape[-2]},
+            'gpu_launches': int(launches), 'stages_ms_per_frame': st_ours,
+            'reference_gpu': {'value': args.frames / (ms_ref / 1e3), 'unit': 'frames/s', 'kind': 'reference',
+                              'sample': 'unmodified reference AFB_URR + FeatureBank (baseline/_ref), torch CUDA ops on '
+                                        'the same GPU, same weights, same clip, free-running',
+                              'stages_ms_per_frame': st_ref, 'final_bank_slots': n_ref},
+            'parity': {'min_mask_iou': min(ious), 'frames_identical': sum(1 for x in ious if x == 1.0),
+                       'bank_sizes_equal': n_ref == [ours_run['fb'].bank_n(c) for c in range(2)]},
+            'clocks': sampler.summary()}
+    print(json.dumps(line))
+
+
+def main_reference_model(args):
+    """the unmodified reference model on the host cores: the first frames of the same clip, free-running, bounded"""
+    from baseline import refshim, model_clip as MC
+    if not refshim.available():
+        print(json.dumps({'impl': 'reference', 'unavailable': 'reference not staged (python baseline/make_ref.py)'}))
+        return
+    torch.set_num_threads(os.cpu_count())
+    ns = refshim.load()
+    model = MC.build_reference_model(ns, 'cpu')
+    n = min(args.frames, int(os.environ.get('VFN_REF_MODEL_FRAMES', '12')))
+    clip = MC.make_clip(n)
+    tm = MC.StageTimer('cpu')
+    hooks = MC.instrument(model, tm)
+    MC.run_clip(model, ns.FeatureBank, clip, 'cpu', budget=BUDGET, timer=tm, warm_frames=min(args.warmup, 1),
+                keep_masks=False)
+    for h in hooks:
+        h.remove()
+    tot = tm.totals()
+    timed = n - min(args.warmup, 1)
+    secs = (tot['segment'] + tot['memorize'] + tot['update']) / 1e3
+    v = timed / secs
+    print(json.dumps({'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'frames/s', 'n_gpus': args.gpus,
+                      'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * secs / args.steps,
+                      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                      'data': 'synthetic', 'config': config_dict(args),
+                      'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': os.cpu_count(), 'kind': 'reference',
+                                       'sample': f'unmodified reference model, frames 1..{n} of the clip (bank still small)'},
+                      'stages_ms_per_frame': _stage_table(tot, timed),
+                      'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                      'gpu_launches': 0}))
 
 
 def main():
@@ -606,7 +910,10 @@ def main():
             cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
                    '--master-addr', '127.0.0.1', '--master-port', '29517', os.path.abspath(__file__)] + sys.argv[1:]
             sys.exit(subprocess.call(cmd))
-        main_ours(args, rank, world, local_rank)
+        if WORKLOAD == '480p-model-clip':
+            main_model_clip(args, rank, world, local_rank)
+        else:
+            main_ours(args, rank, world, local_rank)
 
 
 if __name__ == '__main__':

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VFN_VERSION 100
+#define VFN_VERSION 101
 
 #define VFN_OK 0
 #define VFN_E_ARG (-1)       /* bad argument / unsupported shape */
@@ -66,6 +66,10 @@ int vfn_version(void);
 const char* vfn_last_error(void);
 /* 1 if the running device is compute capability 10.x (tcgen05/TMEM/TMA kernels usable) */
 int vfn_device_is_sm100(void);
+/* sizeof(vfn_bank) / sizeof(vfn_update_io) as compiled into the library: a binding checks them against its own layout
+ * before the first call (a stale library with other struct layouts must not be driven silently) */
+int vfn_abi_sizeof_bank(void);
+int vfn_abi_sizeof_update_io(void);
 
 /* ---- candidate / query preparation ------------------------------------------------------------
  * (d, n) dm  ->  (n, d) em copies: raw and L2-normalised (x / max(|x|, 1e-12)), + optional fp16 hi/lo of raw*scale
@@ -141,6 +145,8 @@ int vfn_bank_merge(const vfn_bank* bank, const float* d_nck_em, const float* d_n
  * LFU_i = info[i,1]/(frame_idx - info[i,0]); T = int(min LFU)+1; keep LFU > T; while
  * class_budget - kept - request_n < 0: T = int(min of survivors)+1.
  * d_plan (int32[72]) = {status, kept, n_iter, T_final, thresholds[0..63]...}; mirrored to h_plan if non-NULL.
+ * The search runs until the balance is met (no iteration cap, like the reference); n_iter counts every threshold tried,
+ * of which the first 64 are recorded.
  * status: 0 ok, 1 = survivors empty while balance<0 (reference raises), 2 = non-finite LFU minimum (reference raises). */
 int vfn_bank_evict_plan(const vfn_bank* bank, float frame_idx, double class_budget, int64_t request_n,
                         int32_t* d_plan, int32_t* h_plan, float* d_lfu_scratch, void* stream);
@@ -178,7 +184,7 @@ typedef struct vfn_update_io {
   int32_t swapped;               /* 1 if banks[c] / alts[c] were exchanged */
   int32_t evict_status;          /* 0 ok, 1 = survivors empty (reference raises), 2 = non-finite LFU minimum */
   int32_t kept, n_iter;
-  int32_t thresholds[64];        /* T sequence of remove() */
+  int32_t thresholds[64];        /* T sequence of remove(): the first min(n_iter, 64) thresholds */
   int64_t n_before;              /* bank size before this update */
   int32_t deferred;              /* 1: counts not read back yet - call vfn_bank_update_finish() after the event */
   int32_t reserved;

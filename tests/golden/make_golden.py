@@ -184,6 +184,9 @@ def golden_misc():
 if __name__ == '__main__':
     install_shims()
     torch.set_num_threads(1)   # deterministic reduction order for the committed vectors
+    if 'real_dims_evict' in sys.argv[1:]:      # added in round 2: regenerate this file alone
+        golden_update('real_dims_evict', 13, 128, 512, 100, 64, 3, budget=350, s_k=3.0)
+        sys.exit(0)
     golden_read('real_dims', 1, 128, 512, (96, 77), 40)
     golden_read('one_slot', 2, 16, 24, (1, 3), 7)
     golden_update('small_evict', 3, 16, 24, 20, 24, 8, budget=150)          # class_budget 60.0 -> eviction fires
@@ -191,5 +194,7 @@ if __name__ == '__main__':
     golden_update('small_allmerge', 4, 16, 24, 30, 16, 3, budget=10 ** 5, thres_close=-1.0, frac_merge=1.0)
     golden_update('small_allappend', 6, 16, 24, 30, 16, 3, budget=10 ** 5, thres_close=2.0, frac_merge=0.0)
     golden_update('real_dims', 7, 128, 512, 64, 36, 2, budget=260)          # class_budget 104.0
+    # d_k=128 / d_v=512 WITH LFU eviction (class_budget 140.0, peaked softmax): the only dims the tcgen05 match/read serve
+    golden_update('real_dims_evict', 13, 128, 512, 100, 64, 3, budget=350, s_k=3.0)
     golden_urr('h32w48', 8, 32, 48)
     golden_misc()

@@ -184,10 +184,9 @@ def test_bench_workload_selection(monkeypatch):
         frames = bench.select_workload('1080p-2obj-bank-at-capacity')
         assert (bench.HW_H * bench.HW_W, bench.R1_H, bench.R1_W) == (8160, 544, 960)
         assert bench.N_INIT == 100000 and bench.START_FRAME == 50 and frames == 30
-        assert bench.expected_bank_size(60, 0.1) == 100000
-        assert bench.default_samples() == (60,)
         assert bench.select_workload('480p-2obj-100frame-clip-hotpath', 7) == 7
     finally:
         assert bench.select_workload('480p-2obj-100frame-clip-hotpath') == 100
     assert (bench.HW_H * bench.HW_W, bench.R1_H, bench.R1_W, bench.N_INIT, bench.START_FRAME) == (1620, 240, 432, None, 0)
-    assert bench.default_samples() == (25, 50, 75, 100)
+    cfg = bench.config_dict(type('A', (), dict(frames=100, frac_merge=0.1))())
+    assert set(cfg) == {'workload', 'hw', 'budget', 'frames', 'frac_merge', 'l2_policy'}     # same keys in both arms

@@ -1,0 +1,211 @@
+"""The drop-in run AS a drop-in (north star): the UNMODIFIED reference `AFB_URR` + `FeatureBank`
+(baseline/_ref, staged by baseline/make_ref.py) against the same weights with `vfloodnet_b200.patch_model` +
+`vfloodnet_b200.FeatureBank`, through the reference's own frame loop (test_video_seg.py:99-112,
+AFB_URR.py:255-318) on the seeded 480p 2-object clip of SURVEY 8d config 1/2 (regime B: random init, BN-calibrated).
+
+  * teacher-forced, frame by frame: both arms start every read and every update from the reference's bank state;
+    readout <= 1e-3, usage-count effect on `info` equal up to threshold-band flips, bank after the update equal
+    (sizes / eviction / insertion frames exact, appended rows bit-exact, merged rows <= 1e-5), decisions equal to the
+    oracle's (which is pinned to the reference) - match index, merge pairs, append set, evicted set, thresholds;
+  * free-running: per-frame mask IoU >= 0.999, first-divergence frame reported, final bank sizes / replace_n equal.
+
+A JSON report goes to gpurun_out/dropin_report_*.json (copied to profiles/ by hand).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import afb_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FRAMES = int(os.environ.get('VFN_DROPIN_FRAMES', '100'))
+
+
+@pytest.fixture(scope='module')
+def env():
+    from baseline import refshim, model_clip
+    if not refshim.available():
+        pytest.skip('reference not staged: run `python baseline/make_ref.py` in the build container')
+    import vfloodnet_b200 as vfn
+    ns = refshim.load()
+    dev = torch.device('cuda', 0)
+    model_ref = model_clip.build_reference_model(ns, dev)
+    model_ours = model_clip.patched_copy(model_ref, vfn)
+    return dict(ns=ns, vfn=vfn, MC=model_clip, dev=dev, ref=model_ref, ours=model_ours)
+
+
+def _report(name, d):
+    out = os.path.join(ROOT, 'gpurun_out')
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, f'dropin_report_{name}.json'), 'w') as f:
+        json.dump(d, f, indent=1)
+
+
+def _capture_readout(model):
+    box = {}
+    h = model.global_matcher.register_forward_hook(lambda _m, _i, out: box.__setitem__('out', out.detach().clone()))
+    return box, h
+
+
+def _lockstep(env, frames, budget, thres_close, name):
+    """teacher-forced comparison over the whole clip; returns the statistics that were asserted"""
+    ns, vfn, MC, dev = env['ns'], env['vfn'], env['MC'], env['dev']
+    ref, ours = env['ref'], env['ours']
+    clip = MC.make_clip(frames)
+    fb_ref = ns.FeatureBank(2, budget, dev, thres_close=thres_close)
+    fb_ours = vfn.FeatureBank(2, budget, dev, thres_close=thres_close)
+    box_r, h_r = _capture_readout(ref)
+    box_o, h_o = _capture_readout(ours)
+    stats = dict(name=name, frames=frames, budget=budget, thres_close=thres_close, readout_err=[], count_flips=[],
+                 bank_n=[], evicted=[], n_merge=[], n_append=[], mask_iou=[], prob_err=[], near_ties=[],
+                 thresholds=[])
+    try:
+        with torch.no_grad():
+            f0 = clip[0].to(dev)
+            k4, v4 = ref.memorize(f0, MC.first_mask().to(dev))
+            fb_ref.init_bank(k4, v4)
+            for t in range(1, frames + 1):
+                frame = clip[t].to(dev)
+                keys0 = [k.clone() for k in fb_ref.keys]
+                vals0 = [v.clone() for v in fb_ref.values]
+                info0 = [i.clone() for i in fb_ref.info]
+                # ---- read + decode: reference, then the drop-in from the same bank state
+                score_r, _ = ref.segment(frame, fb_ref)
+                fb_ours.load_state(keys0, vals0, info0)
+                score_o, _ = ours.segment(frame, fb_ours)
+                err = (box_o['out'][:, :, :512] - box_r['out'][:, :, :512]).abs().max().item()
+                assert err <= 1e-3, (t, err)
+                assert torch.equal(box_o['out'][:, :, 512:], box_r['out'][:, :, 512:])
+                stats['readout_err'].append(err)
+                flips = 0
+                for c in range(2):
+                    d = (fb_ours.info[c][:, 1] - fb_ref.info[c][:, 1]).abs()
+                    bad = d > 2e-5
+                    flips += int(bad.sum())
+                    # a flip is one usage count of difference: |log(cnt+2) - log(cnt+1)| <= log 2
+                    assert float(d.max()) <= 0.7, (t, c, float(d.max()))
+                    assert torch.equal(fb_ours.info[c][:, 0], fb_ref.info[c][:, 0])
+                n_tot = sum(int(i.shape[0]) for i in info0)
+                assert flips <= max(4, int(2e-4 * n_tot)), (t, flips, n_tot)
+                stats['count_flips'].append(flips)
+                pm_r, pm_o = torch.softmax(score_r, 1), torch.softmax(score_o, 1)
+                stats['prob_err'].append((pm_r - pm_o).abs().max().item())
+                iou = MC.iou(pm_r[0].argmax(0), pm_o[0].argmax(0))
+                stats['mask_iou'].append(iou)
+                assert iou >= 0.999, (t, iou)
+                # ---- update: all arms start from the reference's post-read state and the reference's candidates
+                k4, v4 = ref.memorize(frame, pm_r)
+                keys1 = [k.clone() for k in fb_ref.keys]
+                vals1 = [v.clone() for v in fb_ref.values]
+                info1 = [i.clone() for i in fb_ref.info]
+                fb_ours.load_state(keys1, vals1, info1)
+                ofb = O.OracleFeatureBank(2, budget, dev, thres_close=thres_close)
+                ofb.init_bank([k.clone() for k in keys1], [v.clone() for v in vals1])
+                ofb.info = [i.clone() for i in info1]
+                rep_r, rep_o = fb_ref.replace_n.copy(), fb_ours.replace_n.copy()
+                fb_ref.update([k.clone() for k in k4], [v.clone() for v in v4], t)
+                ofb.update([k.clone() for k in k4], [v.clone() for v in v4], t)
+                fb_ours.update([k.clone() for k in k4], [v.clone() for v in v4], t)
+                ev, nm, na, ties, thr = [], [], [], 0, []
+                for c in range(2):
+                    d, dg = ofb.last_decisions[c], fb_ours.last_decisions[c]
+                    n_r = fb_ref.keys[c].shape[1]
+                    assert fb_ours.bank_n(c) == n_r == ofb.keys[c].shape[1], (t, c)
+                    gidx = dg['match_idx'].long()
+                    clear = d.margin > 4e-6
+                    ties += int((~clear).sum())
+                    assert torch.equal(gidx[clear], d.match_idx[clear]), (t, c, 'match index')
+                    n_m, n_a = dg['n_merge'], dg['n_append']
+                    if bool(clear.all()):
+                        assert n_m == len(d.merge_q) and n_a == len(d.append_q)
+                        order = torch.argsort(d.merge_slot * (10 ** 6) + d.merge_q)
+                        assert torch.equal(dg['merge_q'][:n_m].long(), d.merge_q[order]), (t, c, 'merge set')
+                        assert torch.equal(dg['merge_slot'][:n_m].long(), d.merge_slot[order]), (t, c, 'merge slots')
+                        assert torch.equal(dg['append_q'][:n_a].long(), d.append_q), (t, c, 'append set')
+                    assert dg['evicted'] == (d.remove is not None), (t, c, 'eviction decision')
+                    if d.remove is not None:
+                        assert fb_ours.last_thresholds_obj[c] == d.remove.thresholds, (t, c, 'LFU thresholds')
+                        thr.append(d.remove.thresholds)
+                    # the evicted set: insertion frames of the survivors in order (exact), then every row
+                    assert torch.equal(fb_ours.info[c][:, 0], fb_ref.info[c][:, 0]), (t, c, 'evicted / appended set')
+                    np.testing.assert_allclose(fb_ours.info[c][:, 1].cpu().numpy(), fb_ref.info[c][:, 1].cpu().numpy(),
+                                               rtol=0, atol=1e-5)
+                    kd = (fb_ours.keys[c] - fb_ref.keys[c]).abs().max().item()
+                    vd = (fb_ours.values[c] - fb_ref.values[c]).abs().max().item()
+                    assert kd <= 1e-4 and vd <= 1e-4, (t, c, kd, vd)
+                    if n_a:   # appended rows are raw copies of the candidates: bit-exact
+                        assert torch.equal(fb_ours.keys[c][:, n_r - n_a:], fb_ref.keys[c][:, n_r - n_a:])
+                        assert torch.equal(fb_ours.values[c][:, n_r - n_a:], fb_ref.values[c][:, n_r - n_a:])
+                    ev.append(bool(dg['evicted'])); nm.append(int(n_m)); na.append(int(n_a))
+                np.testing.assert_array_equal(fb_ref.replace_n - rep_r, fb_ours.replace_n - rep_o)
+                stats['bank_n'].append([int(fb_ref.keys[c].shape[1]) for c in range(2)])
+                stats['evicted'].append(ev); stats['n_merge'].append(nm); stats['n_append'].append(na)
+                stats['near_ties'].append(ties); stats['thresholds'].append(thr)
+                del ofb, keys0, vals0, info0, keys1, vals1, info1
+    finally:
+        h_r.remove(); h_o.remove()
+    stats['summary'] = dict(max_readout_err=max(stats['readout_err']), total_count_flips=sum(stats['count_flips']),
+                            min_mask_iou=min(stats['mask_iou']), frames_with_eviction=sum(any(e) for e in stats['evicted']),
+                            total_merged=int(np.sum(stats['n_merge'])), total_appended=int(np.sum(stats['n_append'])),
+                            near_ties=sum(stats['near_ties']), final_bank=stats['bank_n'][-1],
+                            replace_n=fb_ref.replace_n.tolist())
+    _report(name, stats)
+    return stats
+
+
+def test_dropin_teacher_forced_480p_clip(env):
+    """the reference configuration: budget 250000, merge threshold 0.95 (test_video_seg.py:24,32)"""
+    st = _lockstep(env, FRAMES, 250000, 0.95, 'teacher_forced_480p')
+    if FRAMES >= 70:
+        assert st['summary']['frames_with_eviction'] > 0, 'the clip must reach the budget (LFU eviction on real features)'
+
+
+def test_dropin_teacher_forced_merge_mix(env):
+    """--merge-thres 0.70 (regime-B best-cosine quartiles 0.67/0.69/0.70: a merge/append mix on real features) with a
+    small budget so that merges, appends and multi-threshold evictions all occur within 24 frames"""
+    st = _lockstep(env, min(FRAMES, 24), 40000, 0.70, 'teacher_forced_merge_mix')
+    assert st['summary']['total_merged'] > 0 and st['summary']['total_appended'] > 0
+    if FRAMES >= 24:
+        assert st['summary']['frames_with_eviction'] > 0
+
+
+@pytest.mark.parametrize('budget,thres,name', [(250000, 0.95, 'free_480p'), (40000, 0.70, 'free_merge_mix')])
+def test_dropin_free_running(env, budget, thres, name):
+    """both arms run the whole clip on their own: masks must agree (IoU >= 0.999 per frame), bank bookkeeping equal"""
+    ns, vfn, MC, dev = env['ns'], env['vfn'], env['MC'], env['dev']
+    frames = FRAMES if budget == 250000 else min(FRAMES, 40)
+    clip = MC.make_clip(frames)
+    r = MC.run_clip(env['ref'], ns.FeatureBank, clip, dev, budget=budget, thres_close=thres)
+    o = MC.run_clip(env['ours'], vfn.FeatureBank, clip, dev, budget=budget, thres_close=thres)
+    ious = [MC.iou(a, b) for a, b in zip(r['masks'], o['masks'])]
+    agree = [float((a == b).float().mean()) for a, b in zip(r['masks'], o['masks'])]
+    first_div = next((t + 1 for t, (a, b) in enumerate(zip(r['masks'], o['masks'])) if not torch.equal(a, b)), None)
+    n_r = [int(r['fb'].keys[c].shape[1]) for c in range(2)]
+    n_o = [o['fb'].bank_n(c) for c in range(2)]
+    rep = dict(name=name, frames=frames, min_iou=min(ious), min_pixel_agreement=min(agree),
+               first_divergent_frame=first_div, bank_ref=n_r, bank_ours=n_o,
+               replace_ref=r['fb'].replace_n.tolist(), replace_ours=o['fb'].replace_n.tolist(),
+               peak_ref=r['fb'].peak_n.tolist(), peak_ours=o['fb'].peak_n.tolist(),
+               water_fraction=[float((m == 1).float().mean()) for m in r['masks'][::10]], iou=ious)
+    _report(name, rep)
+    assert min(ious) >= 0.999, rep
+    assert min(agree) >= 0.9999, rep
+    assert n_r == n_o and np.array_equal(r['fb'].replace_n, o['fb'].replace_n), rep
+    assert np.array_equal(r['fb'].peak_n, o['fb'].peak_n)
+    for c in range(2):      # the same slots survived: insertion frames in order
+        assert torch.equal(r['fb'].info[c][:, 0], o['fb'].info[c][:, 0])
+
+
+def test_patch_model_surface(env):
+    """patch_model swaps exactly the matcher and the decoder's forward; every parameter stays the reference's"""
+    ref, ours = env['ref'], env['ours']
+    assert type(ours.global_matcher).__module__.startswith('vfloodnet_b200')
+    assert ours.global_matcher.update_bank is True and ours.global_matcher.thres_valid == ref.global_matcher.thres_valid
+    sr, so = ref.state_dict(), ours.state_dict()
+    assert sr.keys() == so.keys()
+    assert all(torch.equal(sr[k], so[k]) for k in sr)

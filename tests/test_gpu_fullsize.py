@@ -207,3 +207,90 @@ def test_eviction_at_capacity_is_order_preserving(vfn):
     for c in range(2):
         assert (fb.info[c][:, 1] - fb1.info[c][:, 1]).abs().max().item() <= 0.7     # at most one count flip (ln 2)
         assert ((fb.info[c][:, 1] - fb1.info[c][:, 1]).abs() > 1e-5).sum().item() <= 4
+
+
+# ---------------------------------------------------------------------------------------------------
+# the ORACLE at the benchmarked sizes (VERDICT r1 "what's weak" 1): one read + update with eviction against a bank at
+# capacity, N = 100 000 slots, at the 480p grid (two objects) and at the 1080p grid (one object; the CPU oracle needs
+# ~1 min and ~16 GB there).  Same bars as tests/test_gpu_parity.py.
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('hw,obj_n', [(1620, 2), (8160, 1)])
+def test_read_and_update_vs_oracle_at_capacity(vfn, hw, obj_n):
+    import gc
+    from oracle import afb_oracle as O
+    from vfloodnet_b200 import synth
+    dev = torch.device('cuda')
+    g = torch.Generator().manual_seed(7 + hw)
+    n, frame = CAP, 60
+    budget = 250000 if obj_n == 2 else 100000           # class_budget 100000 either way (FeatureBank.py:20-22)
+    keys, vals = zip(*[synth.gen_bank(g, n) for _ in range(obj_n)])
+    info = []
+    for c in range(obj_n):
+        i = synth.gen_info(g, n, frame)
+        i[:, 0] = torch.sort(i[:, 0]).values
+        info.append(i)
+    q_in, q_out = synth.gen_query(g, hw)
+    pk, pv = zip(*[synth.gen_candidates(g, keys[c], vals[c], hw, 0.5) for c in range(obj_n)])
+    # ---- CUDA path (tcgen05 read + match: what bench.py times)
+    fb = vfn.FeatureBank(obj_n, budget, dev)
+    assert fb.class_budget == float(CAP)
+    fb.load_state(list(keys), list(vals), info)
+    m = vfn.Matcher(update_bank=True)
+    m.want_lse = True
+    out = m(fb, q_in.to(dev), q_out.to(dev)).cpu()
+    lse = m.last_lse.cpu()
+    info_read = [fb.info[c].cpu().clone() for c in range(obj_n)]
+    fb.update([k.to(dev) for k in pk], [v.to(dev) for v in pv], frame)
+    dec_g = [{k: (v.cpu() if torch.is_tensor(v) else v) for k, v in fb.last_decisions[c].items()} for c in range(obj_n)]
+    thr_g = [fb.last_thresholds_obj[c] for c in range(obj_n)]
+    # ---- oracle, one object at a time (the N x HW matrices of one object are all the host has to hold)
+    flips = 0
+    for c in range(obj_n):
+        info_o = [info[c].clone()]
+        rr = O.matcher_forward([keys[c]], [vals[c]], info_o, q_in, q_out, 1e-3, update_bank=True, keep_p=True)
+        err = (out[0, c, :512] - rr.out[0, 0, :512]).abs().max().item()
+        assert err <= 1e-3, (c, err)
+        assert torch.equal(out[0, c, 512:], q_out[0])
+        assert (lse[c] - rr.lse[0]).abs().max().item() <= 2e-4
+        delta = info_read[c][:, 1] - info[c][:, 1]
+        cnt_gpu = torch.round(torch.exp(delta.double()) - 1).long()
+        p = rr.p[0][0]
+        lo = (p > 1e-3 * (1 + 2e-4)).sum(dim=1)
+        hi = (p > 1e-3 * (1 - 2e-4)).sum(dim=1)
+        assert torch.all(cnt_gpu >= lo) and torch.all(cnt_gpu <= hi), 'usage count outside the threshold band'
+        flips += int((cnt_gpu != (p > 1e-3).sum(dim=1)).sum())
+        del rr, p, lo, hi
+        gc.collect()
+        # update from the ORACLE's post-read state against the GPU's decisions: a usage count that flipped inside the
+        # band may not change what is evicted here, or the test says so
+        ofb = O.OracleFeatureBank(1, budget // obj_n if obj_n == 2 else budget, 'cpu')
+        ofb.class_budget = float(CAP)
+        ofb.init_bank([keys[c].clone()], [vals[c].clone()])
+        ofb.info = [info_o[0]]
+        ofb.update([pk[c].clone()], [pv[c].clone()], frame)
+        d, dg = ofb.last_decisions[0], dec_g[c]
+        gidx = dg['match_idx'].long()
+        clear = d.margin > 4e-6
+        assert float(clear.float().mean()) > 0.99
+        assert torch.equal(gidx[clear], d.match_idx[clear]), 'match index'
+        np.testing.assert_allclose(dg['match_corr'][clear].numpy(), d.match_corr[clear].numpy(), rtol=0, atol=2e-6)
+        if bool(clear.all()):
+            nm, na = dg['n_merge'], dg['n_append']
+            assert nm == len(d.merge_q) and na == len(d.append_q) and dg['n_runs'] == len(d.touched)
+            order = torch.argsort(d.merge_slot * (10 ** 6) + d.merge_q)
+            assert torch.equal(dg['merge_q'][:nm].long(), d.merge_q[order])
+            assert torch.equal(dg['merge_slot'][:nm].long(), d.merge_slot[order])
+            assert torch.equal(dg['append_q'][:na].long(), d.append_q)
+            assert dg['evicted'] and d.remove is not None, 'the bank is at capacity: remove() must run'
+            assert thr_g[c] == d.remove.thresholds, (thr_g[c], d.remove.thresholds)
+            assert fb.bank_n(c) == d.n_after
+            # evicted set: the survivors' rows, in order, are the oracle's
+            assert torch.equal(fb.info[c][:, 0].cpu(), ofb.info[0][:, 0])
+            np.testing.assert_allclose(fb.keys[c].cpu().numpy(), ofb.keys[0].numpy(), rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(fb.values[c].cpu().numpy(), ofb.values[0].numpy(), rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(fb.info[c][:, 1].cpu().numpy(), ofb.info[0][:, 1].numpy(), rtol=0, atol=0.7)
+            assert int(((fb.info[c][:, 1].cpu() - ofb.info[0][:, 1]).abs() > 1e-5).sum()) <= max(flips, 0) + 0
+            assert fb.replace_n[c] == ofb.replace_n[0]
+        del ofb
+        gc.collect()
+    print(f'capacity parity hw={hw}: usage counts differing from the oracle (inside the 2e-4 band): {flips}')

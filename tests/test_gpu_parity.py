@@ -105,7 +105,8 @@ def test_read_vs_oracle(vfn, n, hw, seed):
 # update (teacher forced per frame against the reference-generated vectors)
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('name,impl', [('small_evict', 1), ('small_evict2', 1), ('small_allmerge', 1),
-                                       ('small_allappend', 1)] + [('real_dims', i) for i in IMPLS])
+                                       ('small_allappend', 1)] + [('real_dims', i) for i in IMPLS] +
+                         [('real_dims_evict', i) for i in IMPLS])
 def test_update_golden_teacher_forced(vfn, golden_dir, name, impl):
     g = load(golden_dir, f'update_{name}.npz')
     obj_n = int(g['obj_n'])
@@ -128,21 +129,25 @@ def test_update_golden_teacher_forced(vfn, golden_dir, name, impl):
         replace_prev = g[f'f{t}_replace_n'].copy()
 
 
-@pytest.mark.parametrize('name', ['small_evict2', 'real_dims'])
-def test_loop_golden_free_running(vfn, golden_dir, name):
-    """read + update free-running over the whole golden clip (no teacher forcing)."""
+@pytest.mark.parametrize('name,impl', [('small_evict2', 1)] + [('real_dims', i) for i in IMPLS] +
+                         [('real_dims_evict', i) for i in IMPLS])
+def test_loop_golden_free_running(vfn, golden_dir, name, impl):
+    """read + update free-running over the whole golden clip (no teacher forcing), on the fp32 SIMT path and on the
+    tcgen05 path the benchmark times (impl 2): readouts, LFU bookkeeping, evicted sets and final keys vs the reference."""
     g = load(golden_dir, f'update_{name}.npz')
     obj_n = int(g['obj_n'])
-    fb = vfn.FeatureBank(obj_n, int(g['budget']), 'cuda', thres_close=float(g['thres_close']), impl=1)
+    fb = vfn.FeatureBank(obj_n, int(g['budget']), 'cuda', thres_close=float(g['thres_close']), impl=impl)
     fb.init_bank([T(g[f'key_init{c}']) for c in range(obj_n)], [T(g[f'val_init{c}']) for c in range(obj_n)])
     m = vfn.Matcher(update_bank=True)
     for t in range(1, int(g['frames']) + 1):
         out = m(fb, T(g[f'f{t}_q_in']).cuda(), T(g[f'f{t}_q_out']).cuda())
-        assert (out.cpu() - T(g[f'f{t}_out'])).abs().max().item() <= 1e-4
+        assert (out.cpu() - T(g[f'f{t}_out'])).abs().max().item() <= READ_TOL[impl]
         fb.update([T(g[f'f{t}_pk{c}']).cuda() for c in range(obj_n)], [T(g[f'f{t}_pv{c}']).cuda() for c in range(obj_n)], t)
         for c in range(obj_n):
             assert tuple(fb.keys[c].shape) == g[f'f{t}_key{c}'].shape, (t, c)
             np.testing.assert_allclose(fb.info[c].cpu().numpy(), g[f'f{t}_info{c}'], rtol=0, atol=2e-5)
+            # the same slots survived and were appended: every row lines up with the reference's
+            np.testing.assert_allclose(fb.keys[c].cpu().numpy(), g[f'f{t}_key{c}'], rtol=1e-4, atol=1e-4)
         np.testing.assert_array_equal(fb.peak_n, g[f'f{t}_peak_n'])
         np.testing.assert_array_equal(fb.replace_n, g[f'f{t}_replace_n'])
     for c in range(obj_n):
@@ -173,7 +178,8 @@ def _run_update_pair(vfn, n, hw, seed, budget, frame_idx=12, frac_merge=0.5, thr
                                               (3000, 257, 3, 10 ** 6)])
 @pytest.mark.parametrize('impl', IMPLS)
 def test_update_vs_oracle_decisions(vfn, n, hw, seed, budget, impl):
-    """impl 1: fp32 SIMT match; impl 2: 3xTF32 tcgen05 match.  Everything downstream (plan/merge/evict/append) is shared."""
+    """impl 1: fp32 SIMT match; impl 2: tcgen05 two-pass fp16 band scan + exact fp32 re-score.  Everything downstream
+    (plan/merge/evict/append) is shared."""
     ofb, fb = _run_update_pair(vfn, n, hw, seed, budget, impl=impl)
     for c in range(2):
         d, dg = ofb.last_decisions[c], fb.last_decisions[c]
@@ -494,3 +500,69 @@ def test_match_pair_and_single_cta_kernels(vfn, n, hw):
     for c in range(2):
         assert torch.equal(res[0][0][c], res[1][0][c]) and torch.equal(res[0][1][c], res[1][1][c])
         assert torch.equal(res[0][2][c], res[1][2][c])
+
+
+# ---------------------------------------------------------------------------------------------------
+# the benchmark's own clip, free-running on the tcgen05 path (what bench.py times), against the reference arm
+# ---------------------------------------------------------------------------------------------------
+def test_bench_clip_free_running_tcgen05_vs_reference_arm(vfn):
+    """bench.py's 100-frame 480p clip (ClipGenerator seed 100, init_bank -> read -> update per frame, budget 250000) run
+    free on the product path (impl 0 = tcgen05, deferred updates, as benchmarked) and through the reference arm - the
+    UNMODIFIED reference FeatureBank + Matcher when baseline/_ref is staged, else the oracle port - with plain torch ops
+    on the same GPU (cuBLAS fp32, allow_tf32=False).  Neither run is teacher-forced.
+
+    Asserted per frame: bank sizes, the evicted / appended sets (insertion-frame column of every surviving row) and
+    replace_n are identical; at checkpoints every key row lines up.  Reported: usage-count differences (threshold-band
+    flips) as they accumulate in info[:,1], and whether any of them ever changed an eviction."""
+    import json
+    import os
+    from baseline.ref_arm import RefArm
+    from vfloodnet_b200 import synth
+    frames = int(os.environ.get('VFN_CLIP_FRAMES', '100'))
+    dev = torch.device('cuda')
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gen = synth.ClipGenerator(seed=100, obj_n=2, hw=1620, frac_merge=0.1)
+    keys0, vals0 = gen.init()
+    arm = RefArm(250000, dev)
+    arm.init(keys0, vals0)
+    fb = vfn.FeatureBank(2, 250000, dev)
+    fb.init_bank([k.to(dev) for k in keys0], [v.to(dev) for v in vals0])
+    m = vfn.Matcher(update_bank=True)
+    rep = dict(kind=arm.kind, frames=frames, sizes=[], info_diffs=[], readout_err=[], evictions=0)
+    for t in range(frames):
+        q_in, q_out, pk, pv = gen.frame()
+        q_in, q_out = q_in.to(dev), q_out.to(dev)
+        pk, pv = [k.to(dev) for k in pk], [v.to(dev) for v in pv]
+        out = m(fb, q_in, q_out)
+        n_before = arm.sizes()
+        out_ref, _ = arm.frame(q_in, q_out, [k.clone() for k in pk], [v.clone() for v in pv], None, t + 1)
+        err = (out[0, :, :512] - out_ref[0, :, :512]).abs().max().item()
+        assert err <= 1e-3, (t, err)
+        fb.update(pk, pv, t + 1)
+        sizes = [fb.bank_n(c) for c in range(2)]
+        assert sizes == arm.sizes(), (t, sizes, arm.sizes())
+        diffs = 0
+        for c in range(2):
+            assert torch.equal(fb.info[c][:, 0], arm.fb.info[c][:, 0]), (t, c, 'evicted / appended set differs')
+            d = (fb.info[c][:, 1] - arm.fb.info[c][:, 1]).abs()
+            diffs += int((d > 1e-5).sum())
+            if sizes[c] < n_before[c] + 1:
+                rep['evictions'] += 1
+            if t % 10 == 9 or t == frames - 1:
+                kd = (fb.keys[c] - arm.fb.keys[c]).abs().max().item()
+                vd = (fb.values[c] - arm.fb.values[c]).abs().max().item()
+                assert kd <= 1e-4 and vd <= 1e-4, (t, c, kd, vd)
+        assert np.array_equal(fb.replace_n, arm.fb.replace_n), (t, fb.replace_n, arm.fb.replace_n)
+        rep['sizes'].append(sizes); rep['info_diffs'].append(diffs); rep['readout_err'].append(err)
+    assert np.array_equal(fb.peak_n, arm.fb.peak_n)
+    if frames >= 80:
+        assert rep['evictions'] > 0, 'the clip must reach the budget'
+    rep['summary'] = dict(max_readout_err=max(rep['readout_err']), final_sizes=rep['sizes'][-1],
+                          rows_with_usage_count_difference_at_end=rep['info_diffs'][-1],
+                          max_rows_with_difference=max(rep['info_diffs']), replace_n=fb.replace_n.tolist(),
+                          evicted_sets_identical_every_frame=True)
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, 'free_run_clip_report.json'), 'w') as f:
+        json.dump(rep, f)
+    print('free-running bench clip:', rep['summary'])

@@ -58,7 +58,8 @@ def test_read_golden(golden_dir, name):
         np.testing.assert_allclose(np.log(rr.cnt[c].numpy() + 1), delta, atol=2e-6)
 
 
-@pytest.mark.parametrize('name', ['small_evict', 'small_evict2', 'small_allmerge', 'small_allappend', 'real_dims'])
+@pytest.mark.parametrize('name', ['small_evict', 'small_evict2', 'small_allmerge', 'small_allappend', 'real_dims',
+                                  'real_dims_evict'])
 def test_update_golden(golden_dir, name):
     g = load(golden_dir, f'update_{name}.npz')
     obj_n = int(g['obj_n'])

@@ -36,6 +36,8 @@ SIGNATURES = {
     'vfn_version': (c_i32, []),
     'vfn_last_error': (C.c_char_p, []),
     'vfn_device_is_sm100': (c_i32, []),
+    'vfn_abi_sizeof_bank': (c_i32, []),
+    'vfn_abi_sizeof_update_io': (c_i32, []),
     'vfn_prep_rows': (c_i32, [c_vp, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp]),
     'vfn_bank_append_rows': (c_i32, [BANK_P, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_f32, c_f32, c_vp]),
     'vfn_bank_set_live': (c_i32, [BANK_P, c_i64, c_vp]),
@@ -79,6 +81,7 @@ SIGNATURES = {
 }
 
 _lib = None
+VFN_VERSION = 101      # include/vfn.h
 
 
 class VfnError(RuntimeError):
@@ -86,22 +89,31 @@ class VfnError(RuntimeError):
 
 
 def load(build_if_missing: bool = True):
-    """dlopen the in-tree library.  Raises ImportError loudly if it is absent and cannot be built."""
+    """dlopen the in-tree library.  Raises ImportError loudly if it is absent and cannot be built.
+    With nvcc at hand a library older than its sources (csrc/*, include/vfn.h) is rebuilt first (build.build() is a no-op
+    when it is current), so a stale .so with other struct layouts is never loaded silently; without nvcc (the GPU box
+    receives the prebuilt library) the ABI version export is checked instead."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        if build_if_missing and (shutil.which('nvcc') or os.path.exists('/usr/local/cuda/bin/nvcc')):
-            from . import build as _build
+    have_nvcc = bool(shutil.which('nvcc') or os.path.exists('/usr/local/cuda/bin/nvcc'))
+    if build_if_missing and have_nvcc:
+        from . import build as _build
+        if _build.needs_build():
             _build.build()
-        else:
-            raise ImportError(f'{LIB_PATH} is missing and nvcc is not available: the CUDA extension must be built '
-                              f'(python -m vfloodnet_b200.build); there is no CPU fallback')
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f'{LIB_PATH} is missing and nvcc is not available: the CUDA extension must be built '
+                          f'(python -m vfloodnet_b200.build); there is no CPU fallback')
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)       # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
+    if lib.vfn_version() != VFN_VERSION or lib.vfn_abi_sizeof_bank() != C.sizeof(VfnBank) or \
+            lib.vfn_abi_sizeof_update_io() != C.sizeof(VfnUpdateIO):
+        raise ImportError(f'{LIB_PATH} does not match this binding (version {lib.vfn_version()} vs {VFN_VERSION}, '
+                          f'struct sizes {lib.vfn_abi_sizeof_bank()}/{lib.vfn_abi_sizeof_update_io()} vs '
+                          f'{C.sizeof(VfnBank)}/{C.sizeof(VfnUpdateIO)}): rebuild with python -m vfloodnet_b200.build')
     if os.environ.get('VFN_PAIR'):          # debug override of the tensor-kernel selection mask (vfn_debug_set_pair)
         lib.vfn_debug_set_pair(int(os.environ['VFN_PAIR']))
     _lib = lib
@@ -119,6 +131,14 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """cudaStream_t of torch's current stream on `device` (None: the current device)"""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def on_device(device):
+    """context: make `device` the current CUDA device for the library calls inside (the library launches on the calling
+    thread's current device; banks, matchers and tails may live on any GPU of the process, like the reference's)"""
+    import torch
+    return torch.cuda.device(device)

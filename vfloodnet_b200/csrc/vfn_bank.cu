@@ -3,6 +3,8 @@
 // Reference behaviour restated: video_module/model/FeatureBank.py:27-143 (see include/vfn.h per entry point).
 #include "vfn_common.cuh"
 
+#include <atomic>
+#include <mutex>
 #include <vector>
 
 namespace vfn {
@@ -19,13 +21,16 @@ void set_error(const char* fmt, ...) {
 // measurement hooks
 // ------------------------------------------------------------------------------------------------
 struct ProfRec { cudaEvent_t a, b; int kind; double work; };
-static bool g_prof_on = false;
+// The library may be driven from several host threads (one per rank in the thread-rank sharded tests): the launch counter
+// is atomic, the open event of a bracket is per thread, and the shared record list / event pool sit behind one mutex.
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_ev_pool;
-static cudaEvent_t g_open[PROF_KINDS];
-static long long g_launches = 0;
+static thread_local cudaEvent_t g_open[PROF_KINDS];
+static std::atomic<long long> g_launches{0};
 
-static cudaEvent_t get_event() {
+static cudaEvent_t get_event() {   // caller holds g_prof_mu
   if (!g_ev_pool.empty()) { cudaEvent_t e = g_ev_pool.back(); g_ev_pool.pop_back(); return e; }
   cudaEvent_t e;
   cudaEventCreate(&e);
@@ -33,16 +38,20 @@ static cudaEvent_t get_event() {
 }
 void prof_begin(int kind, cudaStream_t st) {
   if (!g_prof_on) return;
-  g_open[kind] = get_event();
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_open[kind] = get_event();
+  }
   cudaEventRecord(g_open[kind], st);
 }
 void prof_end(int kind, cudaStream_t st, double work) {
   if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   cudaEvent_t e = get_event();
   cudaEventRecord(e, st);
   g_prof.push_back({g_open[kind], e, kind, work});
 }
-void count_launches(int n) { g_launches += n; }
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------------------------------------
 // prep_rows: (d, n) dimension-major  ->  (n, d) entry-major raw / L2-normalised / fp16 hi+lo.
@@ -527,7 +536,9 @@ __global__ void __launch_bounds__(EV_THREADS) evict_plan_kernel(const float* __r
     status = 2;                                       // int(nan)/int(inf)/min(empty) raise in the reference
   } else {
     T = (int)truncf(mn) + 1;                          // int(LFU.min()) + 1           (:123)
-    for (; it < 64; ++it) {
+    // no iteration cap (the reference has none): T strictly increases and LFU <= 1e5, so the search terminates;
+    // only the first 64 thresholds are kept for inspection, `it` counts all of them
+    for (;; ++it) {
       float m2 = INFINITY;
       int c2 = 0, nf = 0;
       const float Tf = (float)T;
@@ -537,7 +548,7 @@ __global__ void __launch_bounds__(EV_THREADS) evict_plan_kernel(const float* __r
       }
       block_min_count(m2, c2, nf, sf, si);
       kept = c2;
-      if (tid == 0) plan[4 + it] = T;
+      if (tid == 0 && it < 64) plan[4 + it] = T;
       const double balance = (class_budget - (double)kept) - (double)request_n;   // (:134)
       if (balance < 0) {
         if (kept == 0) { status = 1; ++it; break; }   // LFU.min() of an empty tensor raises
@@ -826,6 +837,7 @@ int vfn_bank_set_live(const vfn_bank* bank, int64_t n, void* stream) {
 }
 
 int vfn_profile_enable(int32_t on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   for (auto& r : g_prof) { g_ev_pool.push_back(r.a); g_ev_pool.push_back(r.b); }
   g_prof.clear();
   if (on) {   // pre-create events so that recording inside a timed region never calls cudaEventCreate
@@ -843,6 +855,7 @@ int vfn_profile_enable(int32_t on) {
 int vfn_profile_collect(double* h_out, int32_t n_kinds) {
   VFN_CHECK_ARG(h_out && n_kinds >= 1 && n_kinds <= PROF_KINDS, "profile_collect: bad args");
   for (int k = 0; k < n_kinds * 3; ++k) h_out[k] = 0.0;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   for (auto& r : g_prof) {
     VFN_CUDA_OK(cudaEventSynchronize(r.b));
     float ms = 0.f;
@@ -852,15 +865,19 @@ int vfn_profile_collect(double* h_out, int32_t n_kinds) {
   return VFN_OK;
 }
 
-int64_t vfn_launch_count(void) { return g_launches; }
+int64_t vfn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int vfn_profile_add_work(int32_t kind, double work) {
   VFN_CHECK_ARG(kind >= 0 && kind < PROF_KINDS, "profile_add_work: bad kind");
   if (!g_prof_on) return VFN_OK;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   for (auto it = g_prof.rbegin(); it != g_prof.rend(); ++it)
     if (it->kind == kind) { it->work += work; break; }
   return VFN_OK;
 }
+
+int vfn_abi_sizeof_bank(void) { return (int)sizeof(vfn_bank); }
+int vfn_abi_sizeof_update_io(void) { return (int)sizeof(vfn_update_io); }
 
 int vfn_device_is_sm100(void) {
   int dev = 0, major = 0;

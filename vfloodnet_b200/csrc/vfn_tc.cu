@@ -1964,15 +1964,19 @@ static int make_map(CUtensorMap* m, const void* base, int64_t rows, int cols, in
   return VFN_OK;
 }
 
+// SM count of the CURRENT device (the caller's context: the Python host enters the bank's device around every call),
+// cached per device ordinal - a process may drive banks on several GPUs
 static int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!n[dev]) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
 }
 
 static float* g_dbg = nullptr;

@@ -174,7 +174,7 @@ int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_i
       if (!io[c].evicted) continue;
       const int32_t* hp = h_plan + 72 * c;
       io[c].evict_status = hp[0]; io[c].kept = hp[1]; io[c].n_iter = hp[2];
-      for (int k = 0; k < 64; ++k) io[c].thresholds[k] = (k < hp[2]) ? hp[4 + k] : 0;
+      for (int k = 0; k < 64; ++k) io[c].thresholds[k] = (k < hp[2]) ? hp[4 + k] : 0;   // first 64 of n_iter
       if (hp[0] != 0) continue;                             // the caller raises like the reference
       VFN_CHECK_ARG(alts[c].keys != nullptr && alts[c].cap >= hp[1] + hw, "bank_update: eviction needs alts[%d] with cap >= kept + hw", c);
       alts[c].n = 0;

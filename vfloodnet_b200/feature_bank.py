@@ -17,7 +17,20 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import VfnBank, VfnUpdateIO, check, ptr, stream_ptr
+import functools
+
+from ._lib import VfnBank, VfnUpdateIO, check, on_device, ptr, stream_ptr
+
+
+def _on_bank_device(fn):
+    """run a FeatureBank method with the bank's GPU as the current CUDA device: the library launches on the calling
+    thread's current device and stream_ptr() is that device's current stream (a bank may live on any GPU, like the
+    reference's `device` argument)"""
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        with on_device(self.device):
+            return fn(self, *a, **k)
+    return wrapped
 
 
 class _Slab:
@@ -128,14 +141,33 @@ class FeatureBank:
         # lead over the GPU.  Anything that needs an exact size (keys/values/info views, bank_n, an update that may evict,
         # capacity growth) finishes everything first (_resolve).
         self.defer = True
-        self.run_ahead = 3
-        self._ring = 4                          # pinned count slots / events; > run_ahead
-        self._h_pinned = torch.zeros((self._ring, obj_n * 80), dtype=torch.int32).pin_memory()
-        self._events = [None] * self._ring
+        self._run_ahead = 3
+        self._ring = 0
+        self._size_ring(self._run_ahead + 1)    # pinned count slots / events: one more than the updates in flight
         self._seq = 0
         self._pending = collections.deque()     # unfinished updates, oldest first
         self._n_hi = [0] * obj_n                # upper bound of the live count (== _n when nothing is pending)
         self._n_live = torch.zeros((obj_n, 2), dtype=torch.int32, device=self.device)
+
+    def _size_ring(self, ring: int):
+        if ring > self._ring:
+            self._ring = ring
+            self._h_pinned = torch.zeros((ring, self.obj_n * 80), dtype=torch.int32).pin_memory()
+            self._events = [None] * ring
+
+    @property
+    def run_ahead(self):
+        """updates that may stay unfinished behind the host (0: every update is finished before the next call)"""
+        return self._run_ahead
+
+    @run_ahead.setter
+    def run_ahead(self, depth: int):
+        depth = int(depth)
+        if depth < 0:
+            raise ValueError('run_ahead must be >= 0')
+        self._resolve()                         # nothing in flight while the ring of count slots is replaced
+        self._run_ahead = depth
+        self._size_ring(depth + 1)
 
     # ---- reference attribute surface -------------------------------------------------------------
     @property
@@ -157,6 +189,8 @@ class FeatureBank:
 
     @property
     def last_decisions(self):
+        """per object: counts of the last finished update + its decision tensors.  The tensors are scratch buffers shared
+        by all updates: they hold the data of the most recently ISSUED update (read them before the next update())."""
         self._resolve()
         return self._last_decisions
 
@@ -197,6 +231,7 @@ class FeatureBank:
         """finish every deferred update: bank sizes are exact afterwards"""
         self._drain(0)
 
+    @_on_bank_device
     def _set_live(self, c: int):
         """device-resident live count := exact host count (after ingest / remove, which bypass vfn_bank_update)"""
         s = self._slabs[c]
@@ -226,6 +261,7 @@ class FeatureBank:
     def _budget_cap(self):
         return int(math.ceil(self.class_budget))
 
+    @_on_bank_device
     def _ensure_capacity(self, c: int, needed: int, d_key: int, d_val: int, slack: int = 0):
         """grow geometrically up to the budget (+ one frame of candidates: update() needs cap >= n + hw)"""
         s = self._slabs[c]
@@ -251,6 +287,7 @@ class FeatureBank:
             self._scratch[name] = t
         return t[:numel].view(*shape)
 
+    @_on_bank_device
     def _ingest(self, c: int, key_dm: torch.Tensor, val_dm: torch.Tensor, info0: float, info1: float):
         """append all columns of (d, n) tensors as new slots (init_bank / append)."""
         self._resolve()
@@ -288,6 +325,7 @@ class FeatureBank:
         else:
             self.init_bank(keys, values, frame_idx)
 
+    @_on_bank_device
     def update(self, prev_key, prev_value, frame_idx, update_rate=-1):
         """FeatureBank.py:53-115: cosine match -> merge -> (LFU evict) -> append -> clamp, for all objects, as ONE call
         into the library (vfn_bank_update orders the kernel launches in C++)."""
@@ -364,7 +402,7 @@ class FeatureBank:
         for c in range(obj_n):
             r = io[c]
             if r.evicted:
-                self.last_thresholds = [int(r.thresholds[k]) for k in range(r.n_iter)]
+                self.last_thresholds = [int(r.thresholds[k]) for k in range(min(r.n_iter, 64))]   # first 64 kept
                 self.last_thresholds_obj[c] = list(self.last_thresholds)
                 if r.evict_status == 1:
                     err = err or RuntimeError('FeatureBank.remove: every entry was evicted and the budget is still '
@@ -383,6 +421,7 @@ class FeatureBank:
         if err is not None:
             raise err
 
+    @_on_bank_device
     def _launch_evict_plan(self, c: int, request_n: int, frame_idx):
         self._resolve()
         lib, st = self._lib, stream_ptr()
@@ -394,11 +433,12 @@ class FeatureBank:
                                       ptr(plan), self._h_plan[c].data_ptr(), ptr(lfu), st), 'evict_plan')
         self.launches += 1
 
+    @_on_bank_device
     def _finish_evict(self, c: int, request_n: int):
         lib, st = self._lib, stream_ptr()
         hp = self._h_plan.numpy()[c]
         status, kept, n_iter = int(hp[0]), int(hp[1]), int(hp[2])
-        self.last_thresholds = [int(v) for v in hp[4:4 + n_iter]]
+        self.last_thresholds = [int(v) for v in hp[4:4 + min(n_iter, 64)]]
         if status == 1:
             raise RuntimeError('FeatureBank.remove: every entry was evicted and the budget is still exceeded '
                                '(the reference raises on LFU.min() of an empty tensor, FeatureBank.py:136)')
@@ -424,6 +464,7 @@ class FeatureBank:
         self.replace_n[c] += n - kept                                             # FeatureBank.py:140-141
         return (self.class_budget - kept) - request_n
 
+    @_on_bank_device
     def remove(self, class_idx, request_n, frame_idx):
         """FeatureBank.py:117-143; returns `balance`."""
         self._launch_evict_plan(class_idx, request_n, frame_idx)
@@ -436,6 +477,7 @@ class FeatureBank:
         print(f'Obj num: {self.obj_n}.', f'Budget / obj: {self.class_budget}.', f'UR: {ur}.', f'Replace: {rr}.')
 
     # ---- test / parity helpers (not in the reference) ---------------------------------------------
+    @_on_bank_device
     def load_state(self, keys, values, info):
         """Teacher forcing: overwrite the bank with (d,N) keys/values and (N,2) info tensors."""
         self._resolve()

@@ -10,7 +10,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from ._lib import check, ptr, stream_ptr
+from ._lib import check, on_device, ptr, stream_ptr
 from .feature_bank import FeatureBank
 
 
@@ -26,6 +26,9 @@ class Matcher(nn.Module):
         self.launches = 0
 
     def _workspace(self, lib, fb: FeatureBank, hw: int, d_key: int, d_val: int):
+        if any(s is None for s in fb._slabs):
+            raise RuntimeError('Matcher.forward on an empty feature bank: call init_bank() first '
+                               '(the reference fails on fb.keys[i].size() of None, AFB_URR.py:141)')
         n_max = max(max(s.cap for s in fb._slabs), 1)
         need = lib.vfn_memread_workspace_bytes(fb.obj_n, n_max, hw, d_key, d_val)
         if self._ws is None or self._ws.numel() < need or self._ws.device != fb.device:
@@ -37,6 +40,10 @@ class Matcher(nn.Module):
             raise TypeError('vfloodnet_b200.Matcher needs a vfloodnet_b200.FeatureBank (device slabs); '
                             'there is no fallback for other bank types')
         fb = feature_bank
+        with on_device(fb.device):
+            return self._forward(fb, q_in, q_out)
+
+    def _forward(self, fb, q_in, q_out):
         lib = _lib.load()
         if q_in.dim() != 3 or q_in.shape[0] != 1:
             raise ValueError('inference read expects q_in of shape (1, d_key, HW)')   # bs>1 is training only

@@ -16,7 +16,7 @@ from typing import Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import check, ptr, stream_ptr
+from ._lib import check, on_device, ptr, stream_ptr
 
 water_label_id = 1   # estimation/reference_tracking.py:21
 
@@ -46,8 +46,9 @@ def resize_argmax(pred_mask: torch.Tensor, ori_size, antialias: bool = True) -> 
     H, W = int(ori_size[0]), int(ori_size[1])
     src = pred_mask.to(torch.float32).contiguous()
     pred = torch.empty((H, W), dtype=torch.uint8, device=src.device)
-    check(_lib.load().vfn_tail_resize_argmax(ptr(src), obj_n, h, w, H, W, int(bool(antialias)), ptr(pred), stream_ptr()),
-          'vfn_tail_resize_argmax')
+    with on_device(src.device):
+        check(_lib.load().vfn_tail_resize_argmax(ptr(src), obj_n, h, w, H, W, int(bool(antialias)), ptr(pred),
+                                                 stream_ptr()), 'vfn_tail_resize_argmax')
     return pred
 
 
@@ -65,8 +66,9 @@ def postprocessing_pred(pred: torch.Tensor, return_stats: bool = False):
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pred.device)
     mask = torch.empty_like(pred)
     stats = torch.empty(4, dtype=torch.int32, device=pred.device)
-    check(lib.vfn_tail_largest_component(ptr(pred), H, W, ptr(mask), ptr(stats), ptr(ws), ws_bytes, stream_ptr()),
-          'vfn_tail_largest_component')
+    with on_device(pred.device):
+        check(lib.vfn_tail_largest_component(ptr(pred), H, W, ptr(mask), ptr(stats), ptr(ws), ws_bytes, stream_ptr()),
+              'vfn_tail_largest_component')
     return (mask, stats) if return_stats else mask
 
 
@@ -106,9 +108,10 @@ class FrameTail:
             pred_mask = pred_mask[0]
         obj_n, h, w = pred_mask.shape
         src = pred_mask.to(torch.float32).contiguous()
-        check(self.lib.vfn_frame_tail(ptr(src), obj_n, h, w, self.H, self.W, int(self.antialias),
-                                      ptr(self.key_pts) if self.n_pts else None, self.n_pts, self.label_id,
-                                      ptr(self.pred), ptr(self.mask), ptr(self.stats),
-                                      ptr(self.levels) if self.n_pts else None, ptr(self.ws), self.ws_bytes,
-                                      stream_ptr()), 'vfn_frame_tail')
+        with on_device(self.device):
+            check(self.lib.vfn_frame_tail(ptr(src), obj_n, h, w, self.H, self.W, int(self.antialias),
+                                          ptr(self.key_pts) if self.n_pts else None, self.n_pts, self.label_id,
+                                          ptr(self.pred), ptr(self.mask), ptr(self.stats),
+                                          ptr(self.levels) if self.n_pts else None, ptr(self.ws), self.ws_bytes,
+                                          stream_ptr()), 'vfn_frame_tail')
         return self.mask, self.levels

@@ -13,7 +13,7 @@ import torch
 from torch.nn import functional as NF
 
 from . import _lib
-from ._lib import check, ptr, stream_ptr
+from ._lib import check, on_device, ptr, stream_ptr
 
 
 def urr_pre(p: torch.Tensor, r1: torch.Tensor, feature_shape):
@@ -40,8 +40,9 @@ def urr_pre(p: torch.Tensor, r1: torch.Tensor, feature_shape):
     conf = torch.empty((obj_n, 1, h, w), **f32)
     avg = torch.empty((obj_n, h, w), **f32)
     local_match = torch.empty((obj_n, 2 * c, h, w), **f32)
-    check(lib.vfn_urr_pre(ptr(p), ptr(r1c), obj_stride, obj_n, c, h, w, ptr(p_up), ptr(seg), ptr(unc), ptr(conf),
-                          ptr(avg), ptr(local_match), stream_ptr()), 'vfn_urr_pre')
+    with on_device(dev):
+        check(lib.vfn_urr_pre(ptr(p), ptr(r1c), obj_stride, obj_n, c, h, w, ptr(p_up), ptr(seg), ptr(unc), ptr(conf),
+                              ptr(avg), ptr(local_match), stream_ptr()), 'vfn_urr_pre')
     return p_up, unc.view(1, 1, h, w).expand(obj_n, -1, -1, -1), conf, local_match
 
 
@@ -52,8 +53,9 @@ def urr_post(p_up: torch.Tensor, uncertainty: torch.Tensor, r1_conf: torch.Tenso
     unc_plane = uncertainty[0, 0].contiguous()
     q_local = q_local.to(torch.float32).contiguous()
     prob = torch.empty((obj_n, 2 * h, 2 * w), dtype=torch.float32, device=p_up.device)
-    check(lib.vfn_urr_post(ptr(p_up), ptr(unc_plane), ptr(r1_conf), ptr(q_local), obj_n, h, w, ptr(prob),
-                           stream_ptr()), 'vfn_urr_post')
+    with on_device(p_up.device):
+        check(lib.vfn_urr_post(ptr(p_up), ptr(unc_plane), ptr(r1_conf), ptr(q_local), obj_n, h, w, ptr(prob),
+                               stream_ptr()), 'vfn_urr_post')
     return prob
 
 
