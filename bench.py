@@ -47,6 +47,9 @@ WORKLOADS = {
     # whole reference model (encoders, KeyValue, decoder convolutions stay cuDNN) around the hot path: the unmodified
     # reference on the GPU against the same weights with vfloodnet_b200.patch_model (BASELINE configs[1])
     '480p-model-clip': dict(hw=(30, 54), r1=(240, 432), frames=100, n_init=None, start_frame=0),
+    # BASELINE configs[4]: one 4K stream (HW = 32400), its bank sharded over the GPUs of the node, split-memory read with
+    # the log-sum-exp combine and the readout reduction as kernels over peer memory (tests/multi_gpu_sharded_bench.py)
+    '4k-2obj-sharded-bank': dict(hw=(135, 240), r1=(1080, 1920), frames=24, n_init=None, start_frame=0),
 }
 WORKLOAD = '480p-2obj-100frame-clip-hotpath'
 START_FRAME, N_INIT = 0, None
@@ -910,7 +913,13 @@ def main():
             cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
                    '--master-addr', '127.0.0.1', '--master-port', '29517', os.path.abspath(__file__)] + sys.argv[1:]
             sys.exit(subprocess.call(cmd))
-        if WORKLOAD == '480p-model-clip':
+        if WORKLOAD == '4k-2obj-sharded-bank':
+            sys.path.insert(0, os.path.join(ROOT, 'tests'))
+            import multi_gpu_sharded_bench
+            os.environ.setdefault('RANK', '0'); os.environ.setdefault('WORLD_SIZE', '1'); os.environ.setdefault('LOCAL_RANK', '0')
+            os.environ.setdefault('MASTER_ADDR', '127.0.0.1'); os.environ.setdefault('MASTER_PORT', '29519')
+            multi_gpu_sharded_bench.main(['--frames', str(args.frames)])
+        elif WORKLOAD == '480p-model-clip':
             main_model_clip(args, rank, world, local_rank)
         else:
             main_ours(args, rank, world, local_rank)

@@ -117,6 +117,32 @@ int vfn_memread_phase_b(const vfn_bank* banks, int32_t obj_n, const float* d_q_i
 /* d_ml: n_parts stacked partial sets (n_parts, n_rows, 2) -> d_lse (n_rows) = M + log(sum_s l_s exp(m_s - M)) */
 int vfn_lse_combine(const float* d_ml, int32_t n_parts, int64_t n_rows, float* d_lse, void* stream);
 
+/* ---- exchange steps of a bank sharded over the GPUs of one node, over PEER memory ---------------------
+ * h_peer_*: HOST array of n_parts DEVICE pointers, entry r = rank r's buffer as mapped into THIS process (CUDA IPC /
+ * symmetric memory; entry `self` is the local buffer).  The kernels read the peers' buffers straight over NVLink - there
+ * is no library collective on the data path.  The caller brackets each call with a cross-GPU barrier on `stream`
+ * (all producers done before, all consumers done after the buffers are overwritten).  n_parts <= 16.
+ *   lse_combine_peers:   rank r's buffer = its local (m, l) pairs (n_rows, 2) from vfn_memread_phase_a; d_lse (n_rows) =
+ *                        the global log-sum-exp (same arithmetic and order on every rank)
+ *   reduce_peers:        d_out[first .. first+count) = sum_r peer_r[first .. first+count), summed in rank order (fp32,
+ *                        deterministic: every rank that reduces the same range gets the same bits); first, count % 4 == 0
+ *   gather_peers:        d_out[i] = peer_r[i] for i in slice r (slice floats per rank, the last rank takes the rest) for
+ *                        every r != self: the all-gather half of a two-shot reduction (each rank reduced its own slice
+ *                        in place with vfn_reduce_peers)
+ *   match_pack / match_combine_peers: the arg-max combine of the cosine match (FeatureBank.py:66-68) across shards.
+ *                        pack: pair[q] = {corr bits, global sequence id of the matched local slot} (16 bytes per query);
+ *                        combine: best corr and, among the ranks reaching it, the LOWEST sequence id (= the reference's
+ *                        lowest index: shards keep insertion order); a NaN score makes (NaN, INT64_MAX). */
+int vfn_lse_combine_peers(const void* const* h_peer_ml, int32_t n_parts, int64_t n_rows, float* d_lse, void* stream);
+int vfn_reduce_peers(const void* const* h_peer_part, int32_t n_parts, int64_t first, int64_t count, float* d_out,
+                     void* stream);
+int vfn_gather_peers(const void* const* h_peer_buf, int32_t n_parts, int32_t self, int64_t slice, int64_t total,
+                     float* d_out, void* stream);
+int vfn_match_pack(const float* d_corr, const int32_t* d_idx, const int64_t* d_seq_of_slot, int64_t n_local, int64_t hw,
+                   void* d_pair, void* stream);
+int vfn_match_combine_peers(const void* const* h_peer_pair, int32_t n_parts, int64_t hw, float* d_best_corr,
+                            int64_t* d_best_seq, void* stream);
+
 /* ---- bank update: FeatureBank.update (FeatureBank.py:53-115) -----------------------------------
  * match: j*_q = argmax_i <nk_i, nck_q>, ties -> lowest i; c*_q = that maximum.  (FeatureBank.py:63-68) */
 size_t vfn_bank_match_workspace_bytes(int64_t n, int64_t hw);
@@ -267,7 +293,8 @@ int vfn_debug_set_dump(float* d_ptr);
  * bit 2 = 96-slot tiles in the CTA-pair phase B (alternative kernel, same results up to fp32 summation order);
  * 0 selects the single-CTA kernels (cross-check in tests/) */
 int vfn_debug_set_pair(int32_t mask);
-/* 1 (default): streaming (warp-shuffle, register-ring) URR local kernel when w % 4 == 0; 0: tiled shared-memory kernel */
+/* streaming (warp-shuffle, register-ring) URR local kernel when w % 4 == 0: 1 = two objects per warp, 2 = one object per
+ * warp; 0: tiled shared-memory kernel.  All three are bit-identical (tests/). */
 int vfn_debug_set_urr_stream(int32_t on);
 
 /* 1 (default): kernels that support it are queued with programmatic dependent launch (their CTAs are placed while the

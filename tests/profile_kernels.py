@@ -14,6 +14,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 hw = int(sys.argv[2]) if len(sys.argv) > 2 else 1620
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 lib = _lib.load()
+if os.environ.get('VFN_URR_MODE') is not None:
+    lib.vfn_debug_set_urr_stream(int(os.environ['VFN_URR_MODE']))
 if os.environ.get('VFN_PAIR') is not None:
     lib.vfn_debug_set_pair(int(os.environ['VFN_PAIR']))
 g = torch.Generator().manual_seed(0)

@@ -88,12 +88,35 @@ def test_bench_reference_arm_rank_gating(monkeypatch, capsys):
     import argparse
     args = argparse.Namespace(gpus=2, steps=1, warmup=0, frames=100, frac_merge=0.1)
     called = []
-    monkeypatch.setattr(bench, 'cpu_sample', lambda *a, **k: (called.append(1) or (1.0, 'stub', 1.0)))
+    stub = dict(kind='port', secs=[2.0], cnt=[4], sizes=[[10, 10]], desc='stub', frames_done=4, arm=None)
+    monkeypatch.setattr(bench, 'reference_free_run', lambda *a, **k: (called.append(1) or stub))
     bench.main_reference(args, rank=1, world=2)
     assert not called and capsys.readouterr().out == ''
     bench.main_reference(args, rank=0, world=2)
     out = capsys.readouterr().out
     assert called and '"impl": "reference"' in out
+    import json
+    line = json.loads(out)
+    assert line['value'] == 2.0 and line['e2e']['value'] == 2.0 and line['cpu_baseline']['kind'] == 'port'
+
+
+def test_bench_reference_arm_free_runs_the_clip():
+    """the reference arm consumes the SAME clip as our arm (ClipGenerator(seed=100)), free-running: after t frames the
+    bank holds init + the appended candidates of those frames; every frame lands in exactly one step"""
+    import bench
+    from vfloodnet_b200 import synth
+    bench.select_workload('480p-2obj-100frame-clip-hotpath')
+    old = (bench.HW_H, bench.HW_W, bench.R1_H, bench.R1_W)
+    try:
+        bench.HW_H, bench.HW_W, bench.R1_H, bench.R1_W = 4, 6, 16, 24          # a tiny grid: seconds on the CPU
+        r = bench.reference_free_run(0.25, 7, seed=100, steps=3)
+        assert r['cnt'] == [3, 2, 2] and r['frames_done'] == 7 and all(s > 0 for s in r['secs'])
+        gen = synth.ClipGenerator(seed=100, obj_n=2, hw=24, frac_merge=0.25)
+        gen.init()
+        assert r['sizes'][0][0] > 24 and r['sizes'][-1][0] == r['arm'].sizes()[0]
+        assert r['kind'] in ('reference', 'port')
+    finally:
+        bench.HW_H, bench.HW_W, bench.R1_H, bench.R1_W = old
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -380,12 +380,13 @@ def test_urr_local_streaming_equals_tiled(vfn, obj_n, c, h, w, shared):
     try:
         lib.vfn_debug_set_urr_stream(0)
         ref = vfn.urr_pre(p, r1, (1, obj_n, h, w))[3].clone()
-        lib.vfn_debug_set_urr_stream(1)
-        got = vfn.urr_pre(p, r1, (1, obj_n, h, w))[3]
-        torch.cuda.synchronize()
+        for mode in (1, 2):                  # two objects per warp / one object per warp
+            lib.vfn_debug_set_urr_stream(mode)
+            got = vfn.urr_pre(p, r1, (1, obj_n, h, w))[3]
+            torch.cuda.synchronize()
+            assert torch.equal(ref, got), (mode, (ref - got).abs().max().item())
     finally:
         lib.vfn_debug_set_urr_stream(1)
-    assert torch.equal(ref, got), (ref - got).abs().max().item()
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -505,15 +506,38 @@ def test_match_pair_and_single_cta_kernels(vfn, n, hw):
 # ---------------------------------------------------------------------------------------------------
 # the benchmark's own clip, free-running on the tcgen05 path (what bench.py times), against the reference arm
 # ---------------------------------------------------------------------------------------------------
+def _lfu_search(lfu, class_budget, request_n):
+    """FeatureBank.remove's threshold search (FeatureBank.py:121-138) on a vector of LFU values -> (T list, keep mask)"""
+    keep = torch.ones_like(lfu, dtype=torch.bool)
+    T = int(lfu.min()) + 1
+    seq = [T]
+    while True:
+        keep = keep & (lfu > T)
+        if (class_budget - int(keep.sum())) - request_n < 0:
+            T = int(lfu[keep].min()) + 1
+            seq.append(T)
+        else:
+            return seq, keep
+
+
 def test_bench_clip_free_running_tcgen05_vs_reference_arm(vfn):
     """bench.py's 100-frame 480p clip (ClipGenerator seed 100, init_bank -> read -> update per frame, budget 250000) run
     free on the product path (impl 0 = tcgen05, deferred updates, as benchmarked) and through the reference arm - the
     UNMODIFIED reference FeatureBank + Matcher when baseline/_ref is staged, else the oracle port - with plain torch ops
     on the same GPU (cuBLAS fp32, allow_tf32=False).  Neither run is teacher-forced.
 
-    Asserted per frame: bank sizes, the evicted / appended sets (insertion-frame column of every surviving row) and
-    replace_n are identical; at checkpoints every key row lines up.  Reported: usage-count differences (threshold-band
-    flips) as they accumulate in info[:,1], and whether any of them ever changed an eviction."""
+    What can and cannot be bit-exact here: two fp32-grade evaluations of p = softmax(K.q/sqrt(128)) (the reference's
+    cuBLAS + ATen, ours) agree to ~3e-6 relative, so a handful of the 1.6e8 p_ij per object and frame fall on different
+    sides of `p > 1e-3` (the reference's own CPU and CUDA back ends differ the same way).  A usage
+    count that differs by one moves that row's LFU by log((c+2)/(c+1))/age, and if the row's LFU sits that close to the
+    integer eviction threshold the two runs evict different rows.  The test therefore asserts, frame by frame:
+      * readout <= 1e-3; match / merge / append sets as the reference (bank rows line up);
+      * the threshold sequences T of every eviction are identical;
+      * every row evicted by one run and kept by the other is a BAND case: its distance to T is no larger than the LFU
+        difference between the two runs for that row (caused by an earlier usage-count flip) - anything else fails;
+      * such rows are < 0.1 % of the evicted rows.
+    After a frame with band cases the product bank is re-synchronised to the reference's so that later frames are
+    compared on equal terms; the report says how often that happened (gpurun_out/free_run_clip_report.json)."""
     import json
     import os
     from baseline.ref_arm import RefArm
@@ -528,41 +552,105 @@ def test_bench_clip_free_running_tcgen05_vs_reference_arm(vfn):
     fb = vfn.FeatureBank(2, 250000, dev)
     fb.init_bank([k.to(dev) for k in keys0], [v.to(dev) for v in vals0])
     m = vfn.Matcher(update_bank=True)
-    rep = dict(kind=arm.kind, frames=frames, sizes=[], info_diffs=[], readout_err=[], evictions=0)
+    rep = dict(kind=arm.kind, frames=frames, sizes=[], rows_with_count_difference=[], readout_err=[], evictions=0,
+               evicted_rows=0, band_rows=0, resyncs=[], first_band_frame=None)
     for t in range(frames):
         q_in, q_out, pk, pv = gen.frame()
         q_in, q_out = q_in.to(dev), q_out.to(dev)
         pk, pv = [k.to(dev) for k in pk], [v.to(dev) for v in pv]
         out = m(fb, q_in, q_out)
-        n_before = arm.sizes()
-        out_ref, _ = arm.frame(q_in, q_out, [k.clone() for k in pk], [v.clone() for v in pv], None, t + 1)
+        out_ref = arm.matcher(arm.fb, q_in, q_out) if arm.matcher is not None else \
+            O.matcher_forward(arm.fb.keys, arm.fb.values, arm.fb.info, q_in, q_out, 1e-3, update_bank=True).out
         err = (out[0, :, :512] - out_ref[0, :, :512]).abs().max().item()
         assert err <= 1e-3, (t, err)
+        n_before = arm.sizes()
+        pre_o = [fb.info[c].clone() for c in range(2)]          # post-read, pre-update: what remove() will see
+        pre_r = [arm.fb.info[c].clone() for c in range(2)]
+        diffs = sum(int(((a[:, 1] - b[:, 1]).abs() > 1e-5).sum()) for a, b in zip(pre_o, pre_r))
+        arm.fb.update([k.clone() for k in pk], [v.clone() for v in pv], t + 1)
         fb.update(pk, pv, t + 1)
-        sizes = [fb.bank_n(c) for c in range(2)]
-        assert sizes == arm.sizes(), (t, sizes, arm.sizes())
-        diffs = 0
+        resync = False
         for c in range(2):
-            assert torch.equal(fb.info[c][:, 0], arm.fb.info[c][:, 0]), (t, c, 'evicted / appended set differs')
-            d = (fb.info[c][:, 1] - arm.fb.info[c][:, 1]).abs()
-            diffs += int((d > 1e-5).sum())
-            if sizes[c] < n_before[c] + 1:
+            d = fb.last_decisions[c]
+            n_app = d['n_append']
+            if d['evicted']:
                 rep['evictions'] += 1
-            if t % 10 == 9 or t == frames - 1:
-                kd = (fb.keys[c] - arm.fb.keys[c]).abs().max().item()
-                vd = (fb.values[c] - arm.fb.values[c]).abs().max().item()
-                assert kd <= 1e-4 and vd <= 1e-4, (t, c, kd, vd)
-        assert np.array_equal(fb.replace_n, arm.fb.replace_n), (t, fb.replace_n, arm.fb.replace_n)
-        rep['sizes'].append(sizes); rep['info_diffs'].append(diffs); rep['readout_err'].append(err)
-    assert np.array_equal(fb.peak_n, arm.fb.peak_n)
+                age = (t + 1) - pre_o[c][:, 0]
+                lfu_o, lfu_r = pre_o[c][:, 1] / age, pre_r[c][:, 1] / age
+                seq_o, keep_o = _lfu_search(lfu_o, fb.class_budget, n_app)
+                seq_r, keep_r = _lfu_search(lfu_r, fb.class_budget, n_app)
+                assert fb.last_thresholds_obj[c] == seq_o, (t, c, 'device threshold search')
+                assert seq_o == seq_r, (t, c, seq_o, seq_r, 'threshold sequences differ between the runs')
+                rep['evicted_rows'] += int((~keep_r).sum())
+                bad = keep_o != keep_r
+                if bool(bad.any()):
+                    T = float(seq_r[-1])
+                    # crossing any threshold of the sequence counts; the final one decides almost always
+                    dist = torch.stack([(lfu_o[bad] - float(x)).abs() for x in seq_r]).min(dim=0).values
+                    gap = (lfu_o[bad] - lfu_r[bad]).abs()
+                    assert bool((dist <= gap + 1e-6).all()), (t, c, 'eviction differs outside the usage-count band',
+                                                                dist.tolist()[:8], gap.tolist()[:8], T)
+                    rep['band_rows'] += int(bad.sum())
+                    rep['first_band_frame'] = rep['first_band_frame'] or t + 1
+                    resync = True
+            if not resync:
+                assert fb.bank_n(c) == arm.sizes()[c], (t, c, fb.bank_n(c), arm.sizes()[c])
+                assert torch.equal(fb.info[c][:, 0], arm.fb.info[c][:, 0]), (t, c, 'evicted / appended set differs')
+                if t % 10 == 9 or t == frames - 1:
+                    kd = (fb.keys[c] - arm.fb.keys[c]).abs().max().item()
+                    vd = (fb.values[c] - arm.fb.values[c]).abs().max().item()
+                    assert kd <= 1e-4 and vd <= 1e-4, (t, c, kd, vd)
+        if resync:
+            rep['resyncs'].append(t + 1)
+            fb.load_state([k.clone() for k in arm.fb.keys], [v.clone() for v in arm.fb.values],
+                          [i.clone() for i in arm.fb.info])
+            fb.replace_n[:] = arm.fb.replace_n
+        else:
+            assert np.array_equal(fb.replace_n, arm.fb.replace_n), (t, fb.replace_n, arm.fb.replace_n)
+        rep['sizes'].append(arm.sizes()); rep['rows_with_count_difference'].append(diffs); rep['readout_err'].append(err)
     if frames >= 80:
         assert rep['evictions'] > 0, 'the clip must reach the budget'
+    assert rep['band_rows'] <= max(2, 1e-3 * rep['evicted_rows']), rep
     rep['summary'] = dict(max_readout_err=max(rep['readout_err']), final_sizes=rep['sizes'][-1],
-                          rows_with_usage_count_difference_at_end=rep['info_diffs'][-1],
-                          max_rows_with_difference=max(rep['info_diffs']), replace_n=fb.replace_n.tolist(),
-                          evicted_sets_identical_every_frame=True)
+                          evictions=rep['evictions'], evicted_rows=rep['evicted_rows'], band_rows=rep['band_rows'],
+                          frames_resynchronised=rep['resyncs'], first_band_frame=rep['first_band_frame'],
+                          max_rows_with_count_difference=max(rep['rows_with_count_difference']))
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
     os.makedirs(out_dir, exist_ok=True)
     with open(os.path.join(out_dir, 'free_run_clip_report.json'), 'w') as f:
         json.dump(rep, f)
     print('free-running bench clip:', rep['summary'])
+
+
+def test_usage_counts_against_fp64_counts_at_capacity(vfn):
+    """How far are the usage counts from EXACT arithmetic, next to the reference's own fp32 ones?  One object at
+    capacity (N = 100 000, HW = 1620): counts from a float64 evaluation of AFB_URR.py:144-165, from the reference's fp32
+    torch ops on this GPU (cuBLAS, allow_tf32=False), and from the tcgen05 read.  The product may not be further from the
+    exact counts than twice the reference's fp32 evaluation is (plus 4)."""
+    from vfloodnet_b200 import synth
+    dev = torch.device('cuda')
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator().manual_seed(17)
+    n, hw = 100000, 1620
+    k, v = synth.gen_bank(g, n)
+    q_in, q_out = synth.gen_query(g, hw)
+    kd, qd = k.to(dev), q_in.to(dev)
+    s64 = torch.matmul(kd.double().t(), qd.double()[0]) / (128 ** 0.5)
+    p64 = torch.softmax(s64, dim=0)
+    cnt64 = (p64 > 1e-3).sum(dim=1)
+    near = ((p64 / 1e-3 - 1).abs() < 1e-5).sum().item()           # elements within 1e-5 relative of the threshold
+    del s64
+    p32 = torch.softmax(torch.matmul(kd.t(), qd) / (128 ** 0.5), dim=1)       # the reference's expression (bs = 1)
+    cnt32 = (p32[0] > 1e-3).sum(dim=1)
+    del p32
+    fb = vfn.FeatureBank(1, 10 ** 6, dev)
+    info = torch.zeros(n, 2)
+    fb.load_state([k], [v], [info])
+    vfn.Matcher(update_bank=True)(fb, qd, q_out.to(dev))
+    cnt_g = torch.round(torch.exp(fb.info[0][:, 1].double()) - 1).long()
+    flips_ref = int((cnt32 != cnt64).sum())
+    flips_ours = int((cnt_g != cnt64).sum())
+    assert int((cnt_g - cnt64).abs().max()) <= 1
+    print(f'usage counts vs fp64 at N={n}: reference fp32 differs in {flips_ref} slots, tcgen05 read in {flips_ours}; '
+          f'{near} of {n * hw} p_ij lie within 1e-5 (relative) of the threshold')
+    assert flips_ours <= 2 * flips_ref + 4, (flips_ours, flips_ref)

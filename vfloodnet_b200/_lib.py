@@ -47,6 +47,11 @@ SIGNATURES = {
     'vfn_memread_phase_a': (c_i32, [BANK_P, c_i32, c_vp, c_i64, c_vp, c_vp, c_sz, c_i32, c_vp]),
     'vfn_memread_phase_b': (c_i32, [BANK_P, c_i32, c_vp, c_i64, c_vp, c_f32, c_i32, c_vp, c_vp, c_sz, c_i32, c_vp]),
     'vfn_lse_combine': (c_i32, [c_vp, c_i32, c_i64, c_vp, c_vp]),
+    'vfn_lse_combine_peers': (c_i32, [C.POINTER(c_vp), c_i32, c_i64, c_vp, c_vp]),
+    'vfn_reduce_peers': (c_i32, [C.POINTER(c_vp), c_i32, c_i64, c_i64, c_vp, c_vp]),
+    'vfn_gather_peers': (c_i32, [C.POINTER(c_vp), c_i32, c_i32, c_i64, c_i64, c_vp, c_vp]),
+    'vfn_match_pack': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    'vfn_match_combine_peers': (c_i32, [C.POINTER(c_vp), c_i32, c_i64, c_vp, c_vp, c_vp]),
     'vfn_bank_match_workspace_bytes': (c_sz, [c_i64, c_i64]),
     'vfn_bank_match': (c_i32, [BANK_P, c_vp, c_i64, c_vp, c_vp, c_vp, c_sz, c_i32, c_vp]),
     'vfn_bank_plan_workspace_bytes': (c_sz, [c_i64]),

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libvfn_sm100a.so')
-SOURCES = ['vfn_bank.cu', 'vfn_simt.cu', 'vfn_tc.cu', 'vfn_urr.cu', 'vfn_update.cu', 'vfn_tail.cu']
+SOURCES = ['vfn_bank.cu', 'vfn_simt.cu', 'vfn_tc.cu', 'vfn_urr.cu', 'vfn_update.cu', 'vfn_tail.cu', 'vfn_peer.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 
@@ -37,7 +37,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError(f'nvcc failed on {src}')
-    cmd = [nvcc, '-shared', '-o', LIB] + objs
+    cmd = [nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', LIB] + objs
     subprocess.check_call(cmd)
     return LIB
 

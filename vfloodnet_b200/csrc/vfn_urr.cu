@@ -20,6 +20,15 @@ __device__ __forceinline__ float bilerp(const float* __restrict__ pl, int win, i
          ly1 * (lx0 * pl[y1 * win + x0] + lx1 * pl[y1 * win + x1]);
 }
 
+// r1_local = (box7(r1*seg) / 49) / (avg + 1e-8)   (AFB_URR.py:227-228).  Both URR-local kernels go through this one
+// function so that they stay bit-identical to each other.  1/49 and the reciprocal are 1-2 ulp operations
+// (MUFU.RCP + FMUL): 3e-7 relative against the reference's two IEEE divisions, inside the 1e-5 bar of the URR tests -
+// the two correctly rounded fp32 divisions were 40 % of the streaming kernel's instructions (16 FCHK/CALL slow-path
+// blocks per row: profiles/r2_urr_local.md).
+__device__ __forceinline__ float urr_ratio(float tot, float av) {
+  return __fdividef(tot * (1.f / 49.f), av + 1e-8f);
+}
+
 // stage 1: p (obj,2,h/2,w/2) -> p_up (obj,2,h,w), seg (obj,h,w) object-normalised fg prob, unc (h,w)
 constexpr int URR_MAX_OBJ = 8;
 __global__ void urr_seg_kernel(const float* __restrict__ p, int obj_n, int h, int w, float* __restrict__ p_up,
@@ -155,7 +164,7 @@ __global__ void __launch_bounds__(URR_LOCAL_THREADS) urr_local_kernel(const floa
             for (int r = 0; r < 7; ++r) tot += ring[(ly + r) % 7];       // rows ly .. ly+6 of the tile, top to bottom
             const int64_t off = (int64_t)yy * w + xx;
             out_raw[off] = sr1[ly + UHALO][lx + UHALO];
-            out_loc[off] = (tot / 49.f) / (avv[ly] + 1e-8f);             // AFB_URR.py:227-228
+            out_loc[off] = urr_ratio(tot, avv[ly]);                       // AFB_URR.py:227-228
           }
         }
       }
@@ -184,8 +193,8 @@ __global__ void __launch_bounds__(UL_WARPS * 32) urr_local_stream_kernel(
   const int x4 = blockIdx.x * UL_COLS + lane - 1;
   const bool col_ok = (x4 >= 0 && x4 < w4);
   const bool out_lane = col_ok && lane >= 1 && lane <= UL_COLS;
-  const int cgroups = (c_n + UL_WARPS - 1) / UL_WARPS;
-  const int ch = (blockIdx.z % cgroups) * UL_WARPS + warp, ob = (blockIdx.z / cgroups) * NO;
+  const int ogroups = (obj_n + NO - 1) / NO;            // object group fastest: the re-reads of an r1 row are close in time
+  const int ch = (blockIdx.z / ogroups) * UL_WARPS + warp, ob = (blockIdx.z % ogroups) * NO;
   if (ch >= c_n) return;
   const int no = min(NO, obj_n - ob);
   const int y0 = blockIdx.y * band, y1 = min(h, y0 + band);
@@ -197,14 +206,14 @@ __global__ void __launch_bounds__(UL_WARPS * 32) urr_local_stream_kernel(
   const int64_t obj_out4 = (int64_t)2 * c_n * plane4, loc4 = (int64_t)c_n * plane4;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  float4 ring[NO][7];
-  float4 rring[4];                                  // r1 rows yin-3 .. yin
+  // ring of the last row sums: EIGHT slots for a seven-row window, and the row loop unrolled by eight, so that the ring
+  // slot (u), the window order ((u + 2) % 8 .. u, oldest first) and the double-buffered prefetch (u & 1) are all
+  // compile-time indices: nothing rotates through registers (a rolled loop spent 100 MOVs per row on that)
+  float4 ring[NO][8];
 #pragma unroll
   for (int o = 0; o < NO; ++o)
 #pragma unroll
-    for (int r = 0; r < 7; ++r) ring[o][r] = z4;
-#pragma unroll
-  for (int r = 0; r < 4; ++r) rring[r] = z4;
+    for (int r = 0; r < 8; ++r) ring[o][r] = z4;
 
   auto load_row = [&](int y, float4& rv, float4 (&sv)[NO]) {
     const bool ok = col_ok && y >= 0 && y < h;
@@ -212,58 +221,63 @@ __global__ void __launch_bounds__(UL_WARPS * 32) urr_local_stream_kernel(
 #pragma unroll
     for (int o = 0; o < NO; ++o) sv[o] = (ok && o < no) ? __ldg(sp + (int64_t)o * plane4 + (int64_t)y * w4) : z4;
   };
-  float4 rv, sv[NO];
-  load_row(y0 - UHALO, rv, sv);
-  for (int yin = y0 - UHALO; yin < y1 + UHALO; ++yin) {
-    float4 rn, sn[NO], av[NO];
-    load_row(yin + 1 < y1 + UHALO ? yin + 1 : -1, rn, sn);          // prefetch the next input row
-    const int yout = yin - UHALO;
-    const bool emit = out_lane && yout >= y0;
+  float4 rbuf[2], sbuf[2][NO];
+  const int y_end = y1 + UHALO;
+  int yin = y0 - UHALO;
+  load_row(yin, rbuf[0], sbuf[0]);
+  while (yin < y_end) {
 #pragma unroll
-    for (int o = 0; o < NO; ++o) av[o] = (emit && o < no) ? __ldg(ap + (int64_t)o * plane4 + (int64_t)yout * w4) : z4;
-    rring[0] = rring[1]; rring[1] = rring[2]; rring[2] = rring[3]; rring[3] = rv;
+    for (int u = 0; u < 8; ++u) {
+      if (yin < y_end) {                                               // warp-uniform; only the last group stops early
+        load_row(yin + 1 < y_end ? yin + 1 : -1, rbuf[(u + 1) & 1], sbuf[(u + 1) & 1]);   // prefetch the next row
+        const float4 rv = rbuf[u & 1];
+        const int yout = yin - UHALO;
+        const bool emit = out_lane && yout >= y0;
+        float4 av[NO];
 #pragma unroll
-    for (int o = 0; o < NO; ++o) {
-      // __fmul_rn: the products must round before the tap sums (no FMA contraction), as in the tiled kernel
-      const float4 c = make_float4(__fmul_rn(rv.x, sv[o].x), __fmul_rn(rv.y, sv[o].y), __fmul_rn(rv.z, sv[o].z),
-                                   __fmul_rn(rv.w, sv[o].w));   // AFB_URR.py:226
-      const float ly = __shfl_up_sync(0xffffffffu, c.y, 1), lz = __shfl_up_sync(0xffffffffu, c.z, 1),
-                  lw = __shfl_up_sync(0xffffffffu, c.w, 1);
-      const float rx = __shfl_down_sync(0xffffffffu, c.x, 1), ry = __shfl_down_sync(0xffffffffu, c.y, 1),
-                  rz = __shfl_down_sync(0xffffffffu, c.z, 1);
-      float4 hs;                                   // 7 taps, left to right (the order of urr_local_kernel)
-      hs.x = (((((ly + lz) + lw) + c.x) + c.y) + c.z) + c.w;
-      hs.y = (((((lz + lw) + c.x) + c.y) + c.z) + c.w) + rx;
-      hs.z = (((((lw + c.x) + c.y) + c.z) + c.w) + rx) + ry;
-      hs.w = (((((c.x + c.y) + c.z) + c.w) + rx) + ry) + rz;
+        for (int o = 0; o < NO; ++o)
+          av[o] = (emit && o < no) ? __ldg(ap + (int64_t)o * plane4 + (int64_t)yout * w4) : z4;
+        if (out_lane && yin >= y0 && yin < y1) {     // the raw copy [r1 ; .] of the row just loaded (AFB_URR.py:231)
 #pragma unroll
-      for (int r = 0; r < 6; ++r) ring[o][r] = ring[o][r + 1];
-      ring[o][6] = hs;
-    }
-    if (emit) {
-      const float4 rc = rring[0];                  // r1 of the output row
-#pragma unroll
-      for (int o = 0; o < NO; ++o) {
-        if (o < no) {
-          float4 tot = ring[o][0];
-#pragma unroll
-          for (int r = 1; r < 7; ++r) {
-            tot.x += ring[o][r].x; tot.y += ring[o][r].y; tot.z += ring[o][r].z; tot.w += ring[o][r].w;
-          }
-          float4 res;                              // AFB_URR.py:227-228
-          res.x = (tot.x / 49.f) / (av[o].x + 1e-8f);
-          res.y = (tot.y / 49.f) / (av[o].y + 1e-8f);
-          res.z = (tot.z / 49.f) / (av[o].z + 1e-8f);
-          res.w = (tot.w / 49.f) / (av[o].w + 1e-8f);
-          float4* dst = out + (int64_t)o * obj_out4 + (int64_t)yout * w4;
-          __stcs(dst, rc);
-          __stcs(dst + loc4, res);
+          for (int o = 0; o < NO; ++o)
+            if (o < no) __stcs(out + (int64_t)o * obj_out4 + (int64_t)yin * w4, rv);
         }
+#pragma unroll
+        for (int o = 0; o < NO; ++o) {
+          // __fmul_rn: the products must round before the tap sums (no FMA contraction), as in the tiled kernel
+          const float4 sv = sbuf[u & 1][o];
+          const float4 c = make_float4(__fmul_rn(rv.x, sv.x), __fmul_rn(rv.y, sv.y), __fmul_rn(rv.z, sv.z),
+                                       __fmul_rn(rv.w, sv.w));   // AFB_URR.py:226
+          const float ly = __shfl_up_sync(0xffffffffu, c.y, 1), lz = __shfl_up_sync(0xffffffffu, c.z, 1),
+                      lw = __shfl_up_sync(0xffffffffu, c.w, 1);
+          const float rx = __shfl_down_sync(0xffffffffu, c.x, 1), ry = __shfl_down_sync(0xffffffffu, c.y, 1),
+                      rz = __shfl_down_sync(0xffffffffu, c.z, 1);
+          float4 hs;                                   // 7 taps, left to right (the order of urr_local_kernel)
+          hs.x = (((((ly + lz) + lw) + c.x) + c.y) + c.z) + c.w;
+          hs.y = (((((lz + lw) + c.x) + c.y) + c.z) + c.w) + rx;
+          hs.z = (((((lw + c.x) + c.y) + c.z) + c.w) + rx) + ry;
+          hs.w = (((((c.x + c.y) + c.z) + c.w) + rx) + ry) + rz;
+          ring[o][u] = hs;
+        }
+        if (emit) {
+#pragma unroll
+          for (int o = 0; o < NO; ++o) {
+            if (o < no) {
+              float4 tot = ring[o][(u + 2) % 8];       // rows top to bottom, as in the tiled kernel
+#pragma unroll
+              for (int r = 3; r <= 8; ++r) {
+                const float4 a = ring[o][(u + r) % 8];
+                tot.x += a.x; tot.y += a.y; tot.z += a.z; tot.w += a.w;
+              }
+              const float4 res = make_float4(urr_ratio(tot.x, av[o].x), urr_ratio(tot.y, av[o].y),
+                                             urr_ratio(tot.z, av[o].z), urr_ratio(tot.w, av[o].w));
+              __stcs(out + (int64_t)o * obj_out4 + (int64_t)yout * w4 + loc4, res);
+            }
+          }
+        }
+        ++yin;
       }
     }
-    rv = rn;
-#pragma unroll
-    for (int o = 0; o < NO; ++o) sv[o] = sn[o];
   }
 }
 
@@ -321,7 +335,7 @@ int vfn_debug_set_pdl(int32_t on) {
 }
 
 int vfn_debug_set_urr_stream(int32_t on) {
-  g_urr_stream = on ? 1 : 0;
+  g_urr_stream = on;      // 0 tiled, 1 streaming (two objects per warp), 2 streaming (one object per warp)
   return VFN_OK;
 }
 
@@ -342,15 +356,15 @@ int vfn_urr_pre(const float* d_p, const float* d_r1, int64_t r1_obj_stride, int3
   if (w % 4 == 0 && g_urr_stream) {
     // streaming kernel: bands of rows sized so that the grid holds a few CTAs per SM; halo cost 6 / band input rows
     // band height: one wave of CTAs (4 resident per SM at 119 registers) where that keeps bands >= 8 rows
-    const int no = (r1_obj_stride == 0 && obj_n >= 2) ? 2 : 1;
+    // objects per warp: 2 shares one r1 load between two objects (128 registers, 4 CTAs per SM); 1 gives each object
+    // its own warp (80 registers, 6 CTAs per SM; the second read of r1 is an L2 hit: r1 is 26 MB)
+    const int no = (r1_obj_stride == 0 && obj_n >= 2 && g_urr_stream != 2) ? 2 : 1;
+    const int resident = no == 2 ? 4 : 6;
     const int64_t per_band = cdiv(w / 4, UL_COLS) * cdiv(c, UL_WARPS) * cdiv(obj_n, no);
-    static int sms = 0;
-    if (sms == 0) {
-      int dev = 0;
-      VFN_CUDA_OK(cudaGetDevice(&dev));
-      VFN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    int64_t n_bands = (int64_t)sms * 4 / per_band;
+    int sms = 0, dev = 0;
+    VFN_CUDA_OK(cudaGetDevice(&dev));
+    VFN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int64_t n_bands = (int64_t)sms * resident / per_band;
     if (n_bands < 1) n_bands = 1;
     int band = (int)cdiv(h, n_bands);
     if (band < 8) band = 8;

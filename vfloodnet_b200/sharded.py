@@ -125,16 +125,16 @@ def lfu_threshold_search(lfu: torch.Tensor, class_budget, request_n: int, comm):
     Returns (kept_local, kept_global, T_final, [T sequence]); raises like the reference on a non-finite minimum
     (int() of nan/inf, :123) and when every slot is gone while the budget is still exceeded (min of empty, :136)."""
     dev = lfu.device
-    inf = torch.tensor([float('inf')], dtype=torch.float32, device=dev)
 
-    def gmin(x):
-        m = torch.cat([x.min().reshape(1), inf]).min().reshape(1) if x.numel() else inf.clone()
-        return float(torch.stack(comm.all_gather(m)).min().item())       # torch.min propagates NaN, like the reference
+    def exchange(keep):
+        """one collective: (survivors of this rank, their LFU minimum) of every rank -> (global count, global minimum)"""
+        sel = lfu if keep is None else lfu[keep]
+        mn = sel.min().double() if sel.numel() else torch.tensor(float('inf'), dtype=torch.float64, device=dev)
+        pair = torch.stack([torch.tensor(float(sel.numel()), dtype=torch.float64, device=dev), mn])
+        allp = torch.stack(comm.all_gather(pair))                       # torch.min propagates NaN, like the reference
+        return int(allp[:, 0].sum().item()), float(allp[:, 1].min().item())
 
-    def gsum(v: int) -> int:
-        return int(comm.all_reduce(torch.tensor([v], dtype=torch.int64, device=dev), 'sum').item())
-
-    mn = gmin(lfu)
+    _, mn = exchange(None)
     if not np.isfinite(mn):
         raise ValueError('FeatureBank.remove: LFU minimum is not finite (the reference raises in int(), '
                          'FeatureBank.py:123)')
@@ -143,7 +143,7 @@ def lfu_threshold_search(lfu: torch.Tensor, class_budget, request_n: int, comm):
     while True:
         keep = lfu > float(T)                                                             # strict >  (:127)
         kept_local = int(keep.sum().item())
-        kept_global = gsum(kept_local)
+        kept_global, mn = exchange(keep)
         thresholds.append(T)
         balance = (class_budget - kept_global) - request_n                                # :134
         if balance >= 0:
@@ -151,42 +151,137 @@ def lfu_threshold_search(lfu: torch.Tensor, class_budget, request_n: int, comm):
         if kept_global == 0:
             raise RuntimeError('FeatureBank.remove: every entry was evicted and the budget is still exceeded '
                                '(the reference raises on LFU.min() of an empty tensor, FeatureBank.py:136)')
-        T = int(gmin(lfu[keep])) + 1                                                      # :136
+        T = int(mn) + 1                                                                   # :136
     return kept_local, kept_global, T, thresholds
 
 
-class ShardedReader:
-    """Split-memory Matcher.forward over a process group; `fb` is this rank's vfloodnet_b200.FeatureBank shard."""
+class PeerExchange:
+    """The exchange steps over PEER memory (NVLink / NVSwitch) instead of library collectives: every rank keeps its
+    partial results in a symmetric-memory buffer that all GPUs of the node map, and the combine kernels of
+    libvfn_sm100a.so (vfn_lse_combine_peers, vfn_reduce_peers / vfn_gather_peers, vfn_match_combine_peers) load their
+    peers' partials directly.  A cross-GPU barrier on the stream (signal pads of the same symmetric allocation) stands
+    before each combine; none is needed after it, because a rank overwrites a region only after the NEXT barrier of
+    the sequence, which every peer reaches after it has finished reading (read: ml | barrier | lse, phase B -> po |
+    barrier | reduce; update: pair | barrier | combine).  One process per GPU, torch.distributed initialised (NCCL)."""
 
-    def __init__(self, thres_valid=1e-3, update_bank=True, group=None, comm=None):
+    TWO_SHOT_BYTES = 16 << 20     # partial readouts beyond this are reduced slice-wise (reduce-scatter + all-gather)
+
+    def __init__(self, group, device, obj_n: int, hw: int, d_val: int):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.device = torch.device(device)
+        self.obj_n, self.hw, self.d_val = obj_n, hw, d_val
+        al = lambda n: (n + 255) // 256 * 256
+        self.off = {}
+        total = 0
+        for name, nbytes in (('ml', obj_n * hw * 8), ('po', obj_n * d_val * hw * 4), ('pair', obj_n * hw * 16)):
+            self.off[name] = (total, nbytes)
+            total += al(nbytes)
+        if hasattr(symm, 'enable_symm_mem_for_group'):
+            try:
+                symm.enable_symm_mem_for_group(self.group.group_name)
+            except Exception:
+                pass
+        self.buf = symm.empty(total, dtype=torch.uint8, device=self.device)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        base = [int(p) for p in self.hdl.buffer_ptrs]
+        self._ptrs = {}
+        for name, (o, _n) in self.off.items():
+            self._ptrs[name] = (C.c_void_p * self.world)(*[b + o for b in base])
+        self.barriers = 0
+
+    def fits(self, obj_n, hw, d_val):
+        return (obj_n, hw, d_val) == (self.obj_n, self.hw, self.d_val)
+
+    def local(self, name, shape, dtype):
+        o, n = self.off[name]
+        return self.buf[o:o + n].view(dtype).view(*shape)
+
+    def peers(self, name):
+        return self._ptrs[name]
+
+    def barrier(self):
+        self.hdl.barrier(channel=0)
+        self.barriers += 1
+
+
+class ShardedReader:
+    """Split-memory Matcher.forward over a process group; `fb` is this rank's vfloodnet_b200.FeatureBank shard.
+    peer = True: the two exchange steps run as kernels over peer memory (PeerExchange); otherwise through the
+    communicator's collectives (NCCL / gloo / thread ranks)."""
+
+    def __init__(self, thres_valid=1e-3, update_bank=True, group=None, comm=None, peer=False):
         self.thres_valid, self.update_bank, self.group, self.comm = thres_valid, update_bank, group, comm
+        self.peer = peer
+        self.px: Optional[PeerExchange] = None
         self._ws = None
+        self._bufs = {}
+
+    def _buf(self, name, shape, dev):
+        t = self._bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.device != dev:
+            t = torch.empty(shape, dtype=torch.float32, device=dev)
+            self._bufs[name] = t
+        return t
+
+    def exchange(self, fb, hw, d_val) -> Optional['PeerExchange']:
+        if not self.peer:
+            return None
+        if self.px is None or not self.px.fits(fb.obj_n, hw, d_val):
+            self.px = PeerExchange(self.group, fb.device, fb.obj_n, hw, d_val)
+        return self.px
 
     def __call__(self, fb, q_in: torch.Tensor, q_out: torch.Tensor) -> torch.Tensor:
-        import ctypes as C
         from . import _lib
-        from ._lib import check, ptr, stream_ptr
+        from ._lib import check, on_device, ptr, stream_ptr
         lib = _lib.load()
         dev = fb.device
         q_in = q_in.to(dev, torch.float32).contiguous()
         q_out = q_out.to(dev, torch.float32).contiguous()
         _, d_key, hw = q_in.shape
         d_val = q_out.shape[1]
+        obj_n = fb.obj_n
         n_max = max(s.cap for s in fb._slabs)
-        need = lib.vfn_memread_workspace_bytes(fb.obj_n, n_max, hw, d_key, d_val)
+        need = lib.vfn_memread_workspace_bytes(obj_n, n_max, hw, d_key, d_val)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
         banks = fb.bank_array()
-        ml = torch.empty((fb.obj_n, hw, 2), dtype=torch.float32, device=dev)
-        check(lib.vfn_memread_phase_a(banks, fb.obj_n, ptr(q_in), hw, ptr(ml), ptr(self._ws), self._ws.numel(), fb.impl,
-                                      stream_ptr()), 'memread_phase_a')
-        lse = combine_lse(ml, self.group, self.comm).contiguous()                               # exchange step 1
-        partial = torch.empty((fb.obj_n, d_val, hw), dtype=torch.float32, device=dev)
-        check(lib.vfn_memread_phase_b(banks, fb.obj_n, ptr(q_in), hw, ptr(lse), float(self.thres_valid),
-                                      int(self.update_bank), ptr(partial), ptr(self._ws), self._ws.numel(), fb.impl,
-                                      stream_ptr()), 'memread_phase_b')
-        mem = reduce_readout(partial, self.group, self.comm)                                    # exchange step 2
-        out = torch.cat([mem, q_out.expand(fb.obj_n, -1, -1)], dim=1).unsqueeze(0)   # (1, obj_n, 2*d_val, HW)
+        px = self.exchange(fb, hw, d_val)
+        with on_device(dev):
+            st = stream_ptr()
+            ml = px.local('ml', (obj_n, hw, 2), torch.float32) if px else self._buf('ml', (obj_n, hw, 2), dev)
+            check(lib.vfn_memread_phase_a(banks, obj_n, ptr(q_in), hw, ptr(ml), ptr(self._ws), self._ws.numel(), fb.impl,
+                                          st), 'memread_phase_a')
+            if px:                                                                              # exchange step 1
+                lse = self._buf('lse', (obj_n, hw), dev)
+                px.barrier()
+                check(lib.vfn_lse_combine_peers(px.peers('ml'), px.world, obj_n * hw, ptr(lse), st), 'lse_combine_peers')
+            else:
+                lse = combine_lse(ml, self.group, self.comm).contiguous()
+            partial = px.local('po', (obj_n, d_val, hw), torch.float32) if px else self._buf('po', (obj_n, d_val, hw), dev)
+            check(lib.vfn_memread_phase_b(banks, obj_n, ptr(q_in), hw, ptr(lse), float(self.thres_valid),
+                                          int(self.update_bank), ptr(partial), ptr(self._ws), self._ws.numel(), fb.impl,
+                                          st), 'memread_phase_b')
+            out = torch.empty((1, obj_n, 2 * d_val, hw), dtype=torch.float32, device=dev)
+            if px:                                                                              # exchange step 2
+                total = obj_n * d_val * hw
+                mem = self._buf('mem', (obj_n, d_val, hw), dev)
+                px.barrier()
+                if total * 4 <= px.TWO_SHOT_BYTES or px.world == 1:
+                    check(lib.vfn_reduce_peers(px.peers('po'), px.world, 0, total, ptr(mem), st), 'reduce_peers')
+                else:   # reduce-scatter into my slice of my own buffer, then all-gather the slices
+                    sl = (total // px.world) // 4 * 4
+                    first = px.rank * sl
+                    count = sl if px.rank < px.world - 1 else total - first
+                    check(lib.vfn_reduce_peers(px.peers('po'), px.world, first, count, ptr(partial), st), 'reduce_peers')
+                    px.barrier()
+                    check(lib.vfn_gather_peers(px.peers('po'), px.world, px.rank, sl, total, ptr(mem), st), 'gather_peers')
+            else:
+                mem = reduce_readout(partial, self.group, self.comm)
+            out[0, :, :d_val] = mem
+            out[0, :, d_val:] = q_out[0]
         return out
 
 
@@ -205,7 +300,7 @@ class ShardedFeatureBank:
     """
 
     def __init__(self, obj_n, memory_budget, device, update_rate=0.1, thres_close=0.95, *, comm=None, group=None,
-                 impl: int = 0):
+                 impl: int = 0, peer: bool = False):
         from .feature_bank import FeatureBank
         self.comm = _comm(group, comm)
         self.rank, self.world = self.comm.rank, self.comm.world
@@ -221,7 +316,8 @@ class ShardedFeatureBank:
         self.n_global = [0] * obj_n
         self.last_decisions = [None] * obj_n
         self.last_thresholds_obj = [None] * obj_n
-        self.reader = ShardedReader(comm=self.comm)
+        self.group, self.peer = group, peer
+        self.reader = ShardedReader(comm=self.comm, group=group, peer=peer)
 
     # ---- sizes -----------------------------------------------------------------------------------
     def n_local(self, c: int) -> int:
@@ -263,22 +359,27 @@ class ShardedFeatureBank:
             update_rate = self.update_rate
         lib, fb, dev = _lib.load(), self.local, self.device
         nan = float('nan')
-        for c in range(self.obj_n):
-            st = stream_ptr()
+        obj_n = self.obj_n
+        hw = prev_key[0].shape[1]
+        px = self.reader.exchange(fb, hw, prev_value[0].shape[0])
+        st = stream_ptr()
+        # ---- phase I, every object: candidates, local match, and this rank's (c*, sequence id) for the exchange
+        pre = []
+        for c in range(obj_n):
             pk = prev_key[c].to(dev, torch.float32).contiguous()
             pv = prev_value[c].to(dev, torch.float32).contiguous()
-            d_key, hw = pk.shape
+            d_key, hw_c = pk.shape
             d_val = pv.shape[0]
             n_loc = fb._n[c]
             s = fb._slabs[c]
-            if (d_key, d_val) != (s.d_key, s.d_val) or pv.shape[1] != hw:
+            if (d_key, d_val) != (s.d_key, s.d_val) or pv.shape[1] != hw or hw_c != hw:
                 raise ValueError('candidate dims do not match the bank')
             # (1) candidates -> entry-major raw + normalised (FeatureBank.py:64,88)
             ck, nck = fb._buf(f'sh_ck{c}', (hw, d_key), torch.float32), fb._buf(f'sh_nck{c}', (hw, d_key), torch.float32)
             cv, ncv = fb._buf(f'sh_cv{c}', (hw, d_val), torch.float32), fb._buf(f'sh_ncv{c}', (hw, d_val), torch.float32)
             check(lib.vfn_prep_rows(ptr(pk), d_key, hw, ptr(ck), ptr(nck), None, None, 1.0, st), 'prep_rows')
             check(lib.vfn_prep_rows(ptr(pv), d_val, hw, ptr(cv), ptr(ncv), None, None, 1.0, st), 'prep_rows')
-            # (2) local match, then the arg-max combine over shards (FeatureBank.py:66-68)
+            # (2) local match (FeatureBank.py:66-68)
             idx = fb._buf(f'sh_idx{c}', (hw,), torch.int32)
             corr = fb._buf(f'sh_corr{c}', (hw,), torch.float32)
             if n_loc > 0:
@@ -286,18 +387,49 @@ class ShardedFeatureBank:
                 bank = fb.bank_struct(c)
                 check(lib.vfn_bank_match(C.byref(bank), ptr(nck), hw, ptr(idx), ptr(corr), ptr(mws), mws.numel(),
                                          int(fb.impl), st), 'bank_match')
-                seq_loc = self.seq[c][idx.long()]
-            else:
+            else:                                  # an empty shard never wins: (-inf, last possible sequence id)
                 idx.zero_()
                 corr.fill_(-float('inf'))
+            if px:
+                pair = px.local('pair', (obj_n, hw, 2), torch.int64)[c]
+                check(lib.vfn_match_pack(ptr(corr), ptr(idx), ptr(self.seq[c]) if n_loc > 0 else None, n_loc, hw,
+                                         ptr(pair), st), 'match_pack')
+                seq_loc = None
+            elif n_loc > 0:
+                seq_loc = self.seq[c][idx.long()]
+            else:
                 seq_loc = torch.full((hw,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)
-            best, best_seq = combine_match(corr, seq_loc, comm=self.comm)                 # exchange step 1
-            mine = (corr == best) & (seq_loc == best_seq)
+            pre.append(dict(ck=ck, nck=nck, cv=cv, ncv=ncv, idx=idx, corr=corr, seq_loc=seq_loc, d_key=d_key, d_val=d_val))
+        # ---- exchange step 1, all objects at once: arg-max combine over the shards (ties -> earliest slot)
+        if px:
+            best_all = fb._buf('sh_best', (obj_n, hw), torch.float32)
+            seq_all = fb._buf('sh_bseq', (obj_n, hw), torch.int64)
+            px.barrier()
+            check(lib.vfn_match_combine_peers(px.peers('pair'), px.world, obj_n * hw, ptr(best_all), ptr(seq_all), st),
+                  'match_combine_peers')
+            pair_all = px.local('pair', (obj_n, hw, 2), torch.int64)
+            my_seq = pair_all[..., 1]
+            my_corr = torch.stack([p['corr'] for p in pre])
+        else:
+            my_corr = torch.stack([p['corr'] for p in pre])
+            my_seq = torch.stack([p['seq_loc'] for p in pre])
+            best_all, seq_all = combine_match(my_corr, my_seq, comm=self.comm)
+        mine_all = (my_corr == best_all) & (my_seq == seq_all)
+        is_append_all = best_all <= self.thres_close
+        n_append_all = [int(v) for v in is_append_all.sum(dim=1).tolist()]          # the reference's nonzero() sync, once
+        # ---- phase II, per object: plan, merge, LFU eviction against the global budget, append, clamp
+        for c in range(obj_n):
+            p = pre[c]
+            ck, nck, cv, ncv, idx, corr = p['ck'], p['nck'], p['cv'], p['ncv'], p['idx'], p['corr']
+            d_key, d_val = p['d_key'], p['d_val']
+            n_loc = fb._n[c]
+            s = fb._slabs[c]
+            best, best_seq, mine = best_all[c], seq_all[c], mine_all[c]
             # (3) global classification (FeatureBank.py:71,100): strict > merges, <= appends, NaN goes nowhere
             is_merge = best > self.thres_close
-            is_append = best <= self.thres_close
+            is_append = is_append_all[c]
             pos = torch.cumsum(is_append.to(torch.int64), 0) - 1
-            n_append = int(is_append.sum().item())                                        # the reference's nonzero() sync
+            n_append = n_append_all[c]
             a_lo, a_hi = shard_range(n_append, self.rank, self.world)
             my_append = is_append & (pos >= a_lo) & (pos < a_hi)
             # local plan: owned merges keep their score, my chunk of the append set keeps its score, the rest -> NaN
