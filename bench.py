@@ -47,6 +47,9 @@ WORKLOADS = {
     # whole reference model (encoders, KeyValue, decoder convolutions stay cuDNN) around the hot path: the unmodified
     # reference on the GPU against the same weights with vfloodnet_b200.patch_model (BASELINE configs[1])
     '480p-model-clip': dict(hw=(30, 54), r1=(240, 432), frames=100, n_init=None, start_frame=0),
+    # BASELINE configs[3]: 64 independent 480p water-level streams, 64/G per GPU, several of them in flight per GPU on
+    # their own CUDA streams; the step is one pass over all of a rank's streams (read -> URR -> update -> frame tail)
+    '480p-64-streams': dict(hw=(30, 54), r1=(240, 432), frames=100, n_init=None, start_frame=0),
     # BASELINE configs[4]: one 4K stream (HW = 32400), its bank sharded over the GPUs of the node, split-memory read with
     # the log-sum-exp combine and the readout reduction as kernels over peer memory (tests/multi_gpu_sharded_bench.py)
     '4k-2obj-sharded-bank': dict(hw=(135, 240), r1=(1080, 1920), frames=24, n_init=None, start_frame=0),
@@ -79,6 +82,8 @@ def parse():
     ap.add_argument('--read-impl', type=int, default=0, help='0 auto (tcgen05), 1 fp32 SIMT, 2 tcgen05')
     ap.add_argument('--no-torch-baseline', action='store_true', help='skip the reference-torch-ops-on-this-GPU leg')
     ap.add_argument('--no-affinity', action='store_true', help='do not bind the process to the GPU-local CPUs')
+    ap.add_argument('--total-streams', type=int, default=64, help='480p-64-streams: video streams over all GPUs')
+    ap.add_argument('--concurrency', type=int, default=8, help='480p-64-streams: streams in flight per GPU')
     args = ap.parse_args()
     args.frames = select_workload(args.workload, args.frames)
     return args
@@ -900,6 +905,145 @@ def main_reference_model(args):
                       'gpu_launches': 0}))
 
 
+# ---------------------------------------------------------------------------------------------------
+# --workload 480p-64-streams (BASELINE configs[3])
+# ---------------------------------------------------------------------------------------------------
+def main_streams(args, rank, world, local_rank):
+    """64 seeded video streams, stream s on GPU s mod G; per GPU `concurrency` of them run at a time, each on its own
+    CUDA stream with its own bank, matcher workspace and frame tail (no shared state, no inter-GPU traffic).  The host
+    issues frame t of every stream of a wave round-robin, so kernels of different streams overlap on the device (the
+    small-bank frames are launch-latency bound on their own: 0.32 ms for 0.1 ms of work).  Clips are generated in HBM by
+    a seeded CUDA generator (stream seed 1000 + s) before the timed region; a stream's result (bank sizes, replace_n,
+    the water levels of every frame) does not depend on G or on its GPU - `stream_checksums` lets two runs be compared."""
+    import hashlib
+    import vfloodnet_b200 as vfn
+    from vfloodnet_b200 import _lib, synth, tail as vtail
+    lib = _lib.load()
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    placement = {'bound': False, 'note': 'disabled'} if args.no_affinity else bind_to_gpu_node(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    mine = [s for s in range(args.total_streams) if s % world == rank]
+    conc = max(1, min(args.concurrency, len(mine)))
+    hw = HW_H * HW_W
+    clips = {}
+    for s_id in mine:
+        gen = synth.ClipGenerator(seed=1000 + s_id, obj_n=2, hw=hw, frac_merge=args.frac_merge, device=dev)
+        keys0, vals0 = gen.init()
+        frames = [gen.frame() for _ in range(args.frames)]
+        g = torch.Generator(device=dev).manual_seed(5000 + s_id)
+        clips[s_id] = dict(keys0=keys0, vals0=vals0, frames=frames, urr=synth.gen_urr_inputs(g, 2, R1_H, R1_W))
+    cuda_streams = [torch.cuda.Stream(dev) for _ in range(conc)]
+    levels_all = {s_id: torch.zeros((args.frames, len(TAIL_KEY_PTS)), device=dev) for s_id in mine}
+    results = {}
+
+    def run_pass(record):
+        for w0 in range(0, len(mine), conc):
+            wave = mine[w0:w0 + conc]
+            st = []
+            for i, s_id in enumerate(wave):
+                with torch.cuda.stream(cuda_streams[i]):
+                    fb = vfn.FeatureBank(2, BUDGET, dev, impl=args.read_impl)
+                    c = clips[s_id]
+                    fb.init_bank(c['keys0'], c['vals0'])
+                    st.append((fb, vfn.Matcher(update_bank=True), vtail.FrameTail(TAIL_SIZE, TAIL_KEY_PTS, dev)))
+            for t in range(args.frames):
+                for i, s_id in enumerate(wave):
+                    fb, m, ft = st[i]
+                    c = clips[s_id]
+                    q_in, q_out, pk, pv = c['frames'][t]
+                    p, r1, q_local = c['urr']
+                    with torch.cuda.stream(cuda_streams[i]):
+                        m(fb, q_in, q_out)
+                        p_up, unc, conf, _lm = vfn.urr_pre(p, r1.expand(2, -1, -1, -1), (1, 2, R1_H, R1_W))
+                        prob = vfn.urr_post(p_up, unc, conf, q_local)
+                        fb.update(pk, pv, t + 1)
+                        _, levels = ft(prob)
+                        if record:
+                            levels_all[s_id][t].copy_(levels)
+            for i, s_id in enumerate(wave):
+                cuda_streams[i].synchronize()
+                if record:
+                    fb = st[i][0]
+                    results[s_id] = dict(bank=[fb.bank_n(c) for c in range(2)], replace_n=fb.replace_n.tolist())
+            del st
+
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and not os.environ.get('VFN_BENCH_NO_SAMPLER'):
+        sampler.start()
+    for _ in range(args.warmup):
+        run_pass(False)
+    barrier()
+    sampler.mark()
+    l0 = lib.vfn_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        run_pass(k == args.steps - 1)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.vfn_launch_count() - l0
+    sampler.stop_flag = True
+    # the same pass with ONE stream in flight per GPU: what the concurrency buys
+    conc_saved, conc = conc, 1
+    run_pass(False)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    run_pass(False)
+    s1.record()
+    barrier()
+    ms_serial = s0.elapsed_time(s1)
+    conc = conc_saved
+    sums = {}
+    for s_id in mine:
+        h = hashlib.sha256(levels_all[s_id].cpu().numpy().tobytes())
+        h.update(json.dumps(results[s_id], sort_keys=True).encode())
+        sums[s_id] = h.hexdigest()[:16]
+    t_ms = torch.tensor([ms, ms_serial], dtype=torch.float64, device=dev)
+    all_sums = [sums]
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        all_sums = [None] * world
+        dist.all_gather_object(all_sums, sums)
+    ms, ms_serial = t_ms.tolist()
+    if rank == 0:
+        merged = {}
+        for d in all_sums:
+            merged.update(d)
+        frames_total = args.frames * args.total_streams * args.steps
+        fleet = hashlib.sha256(json.dumps(sorted(merged.items())).encode()).hexdigest()[:16]
+        line = {'metric': METRIC, 'value': frames_total / (ms / 1e3), 'unit': 'frames/s', 'n_gpus': world,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+                'scaling': 'strong', 'vs_baseline': None,
+                'dtype': 'f16 hi/lo + f8 split operands, f32 accumulate (read, match); f32 (update, URR, tail)',
+                'data': 'synthetic (seeded CUDA generator, stream seed 1000 + s)', 'config': config_dict(args),
+                'run': {'total_streams': args.total_streams, 'streams_per_gpu': len(mine), 'in_flight_per_gpu': conc,
+                        'host_placement': placement, 'read_impl': args.read_impl},
+                'one_stream_in_flight': {'value': args.frames * args.total_streams / (ms_serial / 1e3), 'unit': 'frames/s',
+                                         'note': 'the same streams, one at a time per GPU'},
+                'gpu_launches': int(launches), 'clocks': sampler.summary(),
+                'stream_checksums': {'all_streams': fleet, 'first': [merged[s] for s in sorted(merged)[:4]],
+                                     'note': 'sha256 over every frame\'s water levels + final bank sizes + replace_n, per '
+                                             'stream; all_streams must not depend on --gpus'},
+                'stream_results_sample': {str(s): results[s] for s in mine[:2]}}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get('RANK', 0))
@@ -921,6 +1065,8 @@ def main():
             multi_gpu_sharded_bench.main(['--frames', str(args.frames)])
         elif WORKLOAD == '480p-model-clip':
             main_model_clip(args, rank, world, local_rank)
+        elif WORKLOAD == '480p-64-streams':
+            main_streams(args, rank, world, local_rank)
         else:
             main_ours(args, rank, world, local_rank)
 

@@ -126,9 +126,9 @@ int vfn_lse_combine(const float* d_ml, int32_t n_parts, int64_t n_rows, float* d
  *                        the global log-sum-exp (same arithmetic and order on every rank)
  *   reduce_peers:        d_out[first .. first+count) = sum_r peer_r[first .. first+count), summed in rank order (fp32,
  *                        deterministic: every rank that reduces the same range gets the same bits); first, count % 4 == 0
- *   gather_peers:        d_out[i] = peer_r[i] for i in slice r (slice floats per rank, the last rank takes the rest) for
- *                        every r != self: the all-gather half of a two-shot reduction (each rank reduced its own slice
- *                        in place with vfn_reduce_peers)
+ *   gather_peers:        d_out[i] = peer_r[i] for i in slice r (slice floats per rank, the last rank takes the rest):
+ *                        the all-gather half of a two-shot reduction (each rank reduced its own slice in place with
+ *                        vfn_reduce_peers; `self` is only range-checked)
  *   match_pack / match_combine_peers: the arg-max combine of the cosine match (FeatureBank.py:66-68) across shards.
  *                        pack: pair[q] = {corr bits, global sequence id of the matched local slot} (16 bytes per query);
  *                        combine: best corr and, among the ranks reaching it, the LOWEST sequence id (= the reference's

@@ -67,13 +67,13 @@ __global__ void reduce_peers_kernel(const __grid_constant__ PeerPtrs peers, int 
   }
 }
 
-// out[r * slice4 + i] = peers[r][r * slice4 + i]: all-gather of the slices each rank reduced (two-shot reduction)
+// out[i] = peers[r][i] for i in the slice rank r reduced (slice4 float4 per rank, the last rank takes the rest): the
+// all-gather half of a two-shot reduction.  The local slice is read through peers[self] like the others.
 __global__ void gather_peers_kernel(const __grid_constant__ PeerPtrs peers, int n_parts, int64_t slice4, int64_t total4,
-                                    int self, float4* __restrict__ out) {
+                                    float4* __restrict__ out) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
     const int r = (int)min((int64_t)(n_parts - 1), i / slice4);
-    if (r == self) continue;                                   // my own slice was reduced in place
     out[i] = ld_peer_f4(reinterpret_cast<const float4*>(peers.p[r]) + i);
   }
 }
@@ -168,7 +168,7 @@ int vfn_gather_peers(const void* const* h_peer_buf, int32_t n_parts, int32_t sel
   VFN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int64_t t4 = total / 4;
   const unsigned grid = (unsigned)std::min<int64_t>(cdiv(t4, 256), (int64_t)sms * 8);
-  gather_peers_kernel<<<grid, 256, 0, as_stream(stream)>>>(pp, n_parts, slice / 4, t4, self, reinterpret_cast<float4*>(d_out));
+  gather_peers_kernel<<<grid, 256, 0, as_stream(stream)>>>(pp, n_parts, slice / 4, t4, reinterpret_cast<float4*>(d_out));
   VFN_LAUNCH_OK();
   count_launches(1);
   return VFN_OK;

@@ -9,12 +9,19 @@ import torch
 S_K = 1.58   # key/query element scale so that logits/sqrt(128) have sigma ~2.5
 
 
+def _dev(g: torch.Generator):
+    """tensors are produced on the generator's device (a CUDA generator builds a clip in HBM without the host)"""
+    return g.device
+
+
 def gen_bank(g: torch.Generator, n: int, d_key=128, d_val=512, s_k=S_K):
-    return torch.randn(d_key, n, generator=g) * s_k, torch.randn(d_val, n, generator=g)
+    d = _dev(g)
+    return torch.randn(d_key, n, generator=g, device=d) * s_k, torch.randn(d_val, n, generator=g, device=d)
 
 
 def gen_query(g: torch.Generator, hw: int, d_key=128, d_val=512, s_k=S_K):
-    return torch.randn(1, d_key, hw, generator=g) * s_k, torch.randn(1, d_val, hw, generator=g)
+    d = _dev(g)
+    return torch.randn(1, d_key, hw, generator=g, device=d) * s_k, torch.randn(1, d_val, hw, generator=g, device=d)
 
 
 def gen_candidates(g: torch.Generator, key: torch.Tensor, value: torch.Tensor, hw: int, frac_merge=0.5, dup=True,
@@ -23,31 +30,34 @@ def gen_candidates(g: torch.Generator, key: torch.Tensor, value: torch.Tensor, h
     duplicated so several candidates hit the same slot); the rest are fresh draws (cos ~0 -> appended)."""
     d_k, n = key.shape
     d_v = value.shape[0]
+    d = _dev(g)
     n_m = int(hw * frac_merge)
-    src = torch.randint(0, n, (n_m,), generator=g)
+    src = torch.randint(0, n, (n_m,), generator=g, device=d)
     if dup and n_m >= 4:
         src[1::4] = src[0::4][: len(src[1::4])]
-    k_m = key[:, src] + noise * s_k * torch.randn(d_k, n_m, generator=g)
-    v_m = value[:, src] + noise * torch.randn(d_v, n_m, generator=g)
-    k_f = torch.randn(d_k, hw - n_m, generator=g) * s_k
-    v_f = torch.randn(d_v, hw - n_m, generator=g)
-    perm = torch.randperm(hw, generator=g)
+    k_m = key[:, src] + noise * s_k * torch.randn(d_k, n_m, generator=g, device=d)
+    v_m = value[:, src] + noise * torch.randn(d_v, n_m, generator=g, device=d)
+    k_f = torch.randn(d_k, hw - n_m, generator=g, device=d) * s_k
+    v_f = torch.randn(d_v, hw - n_m, generator=g, device=d)
+    perm = torch.randperm(hw, generator=g, device=d)
     return torch.cat([k_m, k_f], 1)[:, perm].contiguous(), torch.cat([v_m, v_f], 1)[:, perm].contiguous()
 
 
 def gen_info(g: torch.Generator, n: int, frame_idx: int):
-    info = torch.zeros(n, 2)
-    info[:, 0] = torch.randint(0, max(frame_idx, 1), (n,), generator=g).float()
-    info[:, 1] = torch.rand(n, generator=g) * 50
+    d = _dev(g)
+    info = torch.zeros(n, 2, device=d)
+    info[:, 0] = torch.randint(0, max(frame_idx, 1), (n,), generator=g, device=d).float()
+    info[:, 1] = torch.rand(n, generator=g, device=d) * 50
     return info
 
 
 def gen_urr_inputs(g: torch.Generator, obj_n: int, h: int, w: int, c=64):
     """p: coarse logits (obj_n,2,h/2,w/2); r1 (1,c,h,w) shared by objects; q_local: stand-in for the output of the
     three local convolutions (obj_n,2,h,w)."""
-    p = torch.randn(obj_n, 2, h // 2, w // 2, generator=g) * 2
-    r1 = torch.randn(1, c, h, w, generator=g).relu()
-    q_local = torch.randn(obj_n, 2, h, w, generator=g)
+    d = _dev(g)
+    p = torch.randn(obj_n, 2, h // 2, w // 2, generator=g, device=d) * 2
+    r1 = torch.randn(1, c, h, w, generator=g, device=d).relu()
+    q_local = torch.randn(obj_n, 2, h, w, generator=g, device=d)
     return p, r1, q_local
 
 
@@ -56,8 +66,8 @@ class ClipGenerator:
     update, produced from a seeded generator and a small pool of 'scene prototypes' so that a fraction of the
     candidates re-occur (merge) and the rest are new (append) - the 480p 2-object configuration of BASELINE.json."""
 
-    def __init__(self, seed=0, obj_n=2, hw=1620, d_key=128, d_val=512, frac_merge=0.1, n_init=None):
-        self.g = torch.Generator().manual_seed(seed)
+    def __init__(self, seed=0, obj_n=2, hw=1620, d_key=128, d_val=512, frac_merge=0.1, n_init=None, device='cpu'):
+        self.g = torch.Generator(device=device).manual_seed(seed)
         self.obj_n, self.hw, self.d_key, self.d_val, self.frac_merge = obj_n, hw, d_key, d_val, frac_merge
         self.n_init = n_init or hw
 
