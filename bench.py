@@ -791,13 +791,16 @@ def main_model_clip(args, rank, world, local_rank):
     l0 = lib.vfn_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    o = None
     for _ in range(args.steps):
+        o = None          # one bank at a time: a second live bank makes the caching allocator cudaMalloc inside the region
         o = clip_ours(dev_clip, keep_masks=False)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     launches = lib.vfn_launch_count() - l0
     final_n = [o['fb'].bank_n(c) for c in range(2)]
+    o = None
     sampler.stop_flag = True
     # e2e: every frame starts in pinned host memory, the arg-max mask returns to the host
     clip_ours(host_clip, keep_masks=False, frames_on_host=True)
@@ -824,12 +827,40 @@ def main_model_clip(args, rank, world, local_rank):
 
     vurr.urr_pre, vurr.urr_post = timed(pre0), timed(post0)
     try:
+        clip_ours(dev_clip[:6], keep_masks=False)
+        tm.totals(); tm.acc.clear()
         ours_run = clip_ours(dev_clip, timer=tm)
     finally:
         vurr.urr_pre, vurr.urr_post = pre0, post0
         for h in hooks:
             h.remove()
     st_ours = _stage_table(tm.totals(), args.frames)
+    # the same patched model with its convolution stages replayed as CUDA graphs (vfloodnet_b200.GraphedAFBURR, n4)
+    graphed = None
+    try:
+        gm = vfn.GraphedAFBURR(model_ours, tuple(dev_clip[0].shape))
+        run_g = lambda frames, **kw: MC.run_clip(gm, vfn.FeatureBank, frames, dev, budget=BUDGET, **kw)
+        run_g(dev_clip, keep_masks=False)
+        torch.cuda.synchronize()
+        g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        gr = None
+        g0.record()
+        for _ in range(args.steps):
+            gr = None
+            gr = run_g(dev_clip, keep_masks=False)
+        g1.record()
+        for _ in range(args.steps):
+            run_g(host_clip, keep_masks=False, frames_on_host=True)
+        g2.record()
+        torch.cuda.synchronize()
+        graphed = {'value': args.frames * args.steps / (g0.elapsed_time(g1) / 1e3), 'unit': 'frames/s',
+                   'e2e': args.frames * args.steps / (g1.elapsed_time(g2) / 1e3),
+                   'final_bank_slots': [gr['fb'].bank_n(c) for c in range(2)],
+                   'note': 'encoder_q+KeyValue, decoder trunk, local head and memorize replayed as four CUDA graphs; read, '
+                           'URR and update as in the eager patched model'}
+        del gm, gr
+    except Exception as e:                                                                # reported, never hidden
+        graphed = {'value': None, 'error': f'{type(e).__name__}: {e}'[:300]}
     # the unmodified reference on the same GPU: same weights, same clip
     torch.backends.cuda.matmul.allow_tf32 = False
     clip_ref(dev_clip[:4], keep_masks=False)
@@ -858,11 +889,12 @@ def main_model_clip(args, rank, world, local_rank):
                                           'the default workload', 'data': 'synthetic',
             'config': config_dict(args),
             'run': {'final_bank_slots': final_n, 'host_placement': placement,
-                    'model': 'reference AFB_URR (random init seed 0, BN-calibrated), patch_model + vfloodnet_b200.FeatureBank'},
+                    'model': f'reference AFB_URR (random init seed {MC.MODEL_SEED}, BN statistics and output scale '
+                             'calibrated), patch_model + vfloodnet_b200.FeatureBank'},
             'e2e': {'value': frames_total / (ms_e2e / 1e3), 'unit': 'frames/s',
                     'h2d_bytes_per_step': (args.frames + 1) * frame_bytes,
                     'd2h_bytes_per_step': args.frames * host_clip[1].shape[-1] * host_clip[1].shape[-2]},
-            'gpu_launches': int(launches), 'stages_ms_per_frame': st_ours,
+            'gpu_launches': int(launches), 'stages_ms_per_frame': st_ours, 'graphed_convolutions': graphed,
             'reference_gpu': {'value': args.frames / (ms_ref / 1e3), 'unit': 'frames/s', 'kind': 'reference',
                               'sample': 'unmodified reference AFB_URR + FeatureBank (baseline/_ref), torch CUDA ops on '
                                         'the same GPU, same weights, same clip, free-running',
@@ -1044,6 +1076,79 @@ def main_streams(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------
+# --workload 1080p-2obj-bank-at-capacity --frames 2000   (BASELINE configs[2] as written: long-video stress)
+# ---------------------------------------------------------------------------------------------------
+def main_long(args, rank, world, local_rank):
+    """2000 frames at the native 1080p grid (HW = 8160) against a bank at its 100000-slot budget: LFU eviction on every
+    frame.  Frames are synthesised ON THE DEVICE in chunks of 50 (a resident clip would be 146 GB) by a seeded CUDA
+    generator, outside the timed regions; every chunk is timed with CUDA events.  Reports frames/s over all chunks, the
+    first / last 100 frames, the allocator high-water mark at the start and at the end (growth = leak), peak_n, replace_n
+    and the info clamp (FeatureBank.py:113-115,140-141)."""
+    import vfloodnet_b200 as vfn
+    from vfloodnet_b200 import _lib, synth
+    lib = _lib.load()
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    hw, chunk = HW_H * HW_W, 50
+    gen = synth.ClipGenerator(seed=100 + rank, obj_n=2, hw=hw, frac_merge=args.frac_merge, n_init=N_INIT, device=dev)
+    keys0, vals0 = gen.init()
+    g = torch.Generator(device=dev).manual_seed(1100 + rank)
+    p, r1, q_local = synth.gen_urr_inputs(g, 2, R1_H, R1_W)
+    info0 = []
+    for _ in range(2):
+        i = synth.gen_info(g, N_INIT, START_FRAME)
+        i[:, 0] = torch.sort(i[:, 0]).values
+        info0.append(i)
+    fb = vfn.FeatureBank(2, BUDGET, dev, impl=args.read_impl)
+    fb.load_state(keys0, vals0, info0)
+    del keys0, vals0
+    m = vfn.Matcher(update_bank=True)
+    chunks_ms, sizes, mem = [], [], []
+    l0 = lib.vfn_launch_count()
+    done = 0
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sampler.mark()
+    while done < args.frames:
+        n = min(chunk, args.frames - done)
+        frames = [gen.frame() for _ in range(n)]
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for t, (q_in, q_out, pk, pv) in enumerate(frames):
+            m(fb, q_in, q_out)
+            p_up, unc, conf, _lm = vfn.urr_pre(p, r1.expand(2, -1, -1, -1), (1, 2, R1_H, R1_W))
+            vfn.urr_post(p_up, unc, conf, q_local)
+            fb.update(pk, pv, START_FRAME + done + t + 1)
+        e1.record()
+        torch.cuda.synchronize()
+        chunks_ms.append(e0.elapsed_time(e1))
+        done += n
+        sizes.append([fb.bank_n(c) for c in range(2)])
+        mem.append(torch.cuda.max_memory_allocated(dev) / 2 ** 30)
+        del frames
+    sampler.stop_flag = True
+    total_ms = sum(chunks_ms)
+    per = chunk
+    info_max = max(float(fb.info[c][:, 1].max()) for c in range(2))
+    line = {'metric': METRIC, 'value': args.frames / (total_ms / 1e3), 'unit': 'frames/s', 'n_gpus': 1, 'steps': 1,
+            'warmup': 0, 'ms_per_step': total_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f16 hi/lo + f8 split operands, f32 accumulate (read, match); f32 (update, URR)',
+            'data': 'synthetic (seeded CUDA generator, 50-frame chunks synthesised on the device between timed regions)',
+            'config': config_dict(args),
+            'long_run': {'frames': args.frames, 'ms_per_frame_first_100': sum(chunks_ms[:100 // per]) / 100,
+                         'ms_per_frame_last_100': sum(chunks_ms[-(100 // per):]) / 100,
+                         'ms_per_frame_min_chunk': min(chunks_ms) / per, 'ms_per_frame_max_chunk': max(chunks_ms) / per,
+                         'bank_slots_first_chunk': sizes[0], 'bank_slots_last_chunk': sizes[-1],
+                         'peak_n': fb.peak_n.tolist(), 'replace_n': fb.replace_n.tolist(),
+                         'replace_over_budget': (fb.replace_n / fb.class_budget).tolist(),
+                         'allocator_high_water_gib_after_first_chunk': mem[0], 'allocator_high_water_gib_at_end': mem[-1],
+                         'info_col1_max': info_max, 'info_clamp': 1e5},
+            'gpu_launches': int(lib.vfn_launch_count() - l0), 'clocks': sampler.summary()}
+    print(json.dumps(line))
+
+
 def main():
     args = parse()
     rank = int(os.environ.get('RANK', 0))
@@ -1067,6 +1172,8 @@ def main():
             main_model_clip(args, rank, world, local_rank)
         elif WORKLOAD == '480p-64-streams':
             main_streams(args, rank, world, local_rank)
+        elif WORKLOAD == '1080p-2obj-bank-at-capacity' and args.frames > 200:
+            main_long(args, rank, world, local_rank)
         else:
             main_ours(args, rank, world, local_rank)
 

@@ -289,8 +289,7 @@ int64_t vfn_launch_count(void);
 int vfn_debug_set_tstamp(long long* d_ptr);
 /* d_ptr != NULL: the next tcgen05 read launches dump the first S^T tile of CTA 0 (128 x tile floats) there. */
 int vfn_debug_set_dump(float* d_ptr);
-/* bit mask, default 3: bit 0 = CTA-pair (cta_group::2) phase B, bit 1 = CTA-pair score scan (phase A, match),
- * bit 2 = 96-slot tiles in the CTA-pair phase B (alternative kernel, same results up to fp32 summation order);
+/* bit mask, default 3: bit 0 = CTA-pair (cta_group::2) phase B, bit 1 = CTA-pair score scan (phase A, match);
  * 0 selects the single-CTA kernels (cross-check in tests/) */
 int vfn_debug_set_pair(int32_t mask);
 /* streaming (warp-shuffle, register-ring) URR local kernel when w % 4 == 0: 1 = two objects per warp, 2 = one object per

@@ -290,3 +290,30 @@ def test_patch_model_surface(env):
     sr, so = ref.state_dict(), ours.state_dict()
     assert sr.keys() == so.keys()
     assert all(torch.equal(sr[k], so[k]) for k in sr)
+
+
+def test_graphed_model_equals_eager(env):
+    """vfloodnet_b200.GraphedAFBURR (the convolution stages of segment / memorize as four CUDA graphs)
+    runs the reference's own modules and weights: over a free-running clip its masks, scores and bank must equal the
+    eager patched model's (same kernels in the same order; cuDNN picks the same algorithms)"""
+    ns, vfn, MC, dev = env['ns'], env['vfn'], env['MC'], env['dev']
+    frames = min(FRAMES, 12)
+    clip = [f.to(dev) for f in MC.make_clip(frames)]
+    scores = {}
+
+    def keep(tag):
+        def cb(t, frame, score, pm, k4, v4, fb):
+            scores.setdefault(tag, []).append(score.clone())
+        return cb
+
+    with _conv_math(tf32=True):
+        gm = vfn.GraphedAFBURR(env['ours'], tuple(clip[0].shape))
+        e = MC.run_clip(env['ours'], vfn.FeatureBank, clip, dev, on_frame=keep('eager'))
+        g = MC.run_clip(gm, vfn.FeatureBank, clip, dev, on_frame=keep('graph'))
+    worst = max((a - b).abs().max().item() for a, b in zip(scores['eager'], scores['graph']))
+    ious = [MC.iou(a, b) for a, b in zip(e['masks'], g['masks'])]
+    _report('graphed_vs_eager', dict(frames=frames, max_score_diff=worst, min_iou=min(ious),
+                                     bank_eager=[e['fb'].bank_n(c) for c in range(2)],
+                                     bank_graph=[g['fb'].bank_n(c) for c in range(2)]))
+    assert min(ious) >= 0.9999 and worst <= 1e-3, (min(ious), worst)
+    assert [e['fb'].bank_n(c) for c in range(2)] == [g['fb'].bank_n(c) for c in range(2)]

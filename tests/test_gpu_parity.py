@@ -458,7 +458,7 @@ def test_read_pair_and_single_cta_kernels(vfn, n, hw):
     rr, _ = _oracle_read(list(keys), list(vals), info, q_in, q_out)
     outs, infos = [], []
     try:
-        for pair in (3, 0, 1, 7):                  # bit 0: pair phase B, bit 1: pair score scan, bit 2: 96-slot tiles
+        for pair in (3, 0, 1, 2):                  # bit 0: pair phase B, bit 1: pair score scan
             lib.vfn_debug_set_pair(pair)
             fb = vfn.FeatureBank(2, 10 ** 6, 'cuda', impl=2)
             fb.load_state(list(keys), list(vals), info)

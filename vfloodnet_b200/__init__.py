@@ -4,11 +4,13 @@ Public surface mirrors the reference operator API for this path:
     FeatureBank  (video_module/model/FeatureBank.py)
     Matcher      (video_module/model/AFB_URR.py:130-178)
     urr_pre / urr_post / decoder_forward / patch_model   (AFB_URR.py:208-239)
+    GraphedAFBURR (memorize / segment of AFB_URR.py:255-318 with the convolution stages as CUDA graphs)
 Everything computes in libvfn_sm100a.so (include/vfn.h); importing this package without the built library, or
 calling it without a CUDA device, fails loudly - there is no CPU fallback.
 """
 from .feature_bank import FeatureBank
 from .matcher import Matcher
 from .urr import urr_pre, urr_post, decoder_forward, patch_model
+from .graphed import GraphedAFBURR
 
-__all__ = ['FeatureBank', 'Matcher', 'urr_pre', 'urr_post', 'decoder_forward', 'patch_model']
+__all__ = ['FeatureBank', 'Matcher', 'urr_pre', 'urr_post', 'decoder_forward', 'patch_model', 'GraphedAFBURR']

@@ -1462,376 +1462,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Phase B on CTA pairs with 96-slot tiles.  An MMA instruction never issues faster than every 45.6 clk
-// (profiles/r1m_mma_rate.txt), which the 64-slot S tiles of tc_phase_b_pair_kernel pay on each of their 24 S-MMAs
-// (N = 64: 32 clk of work).  N = 96 runs at its 48-clk floor.  Two 96-column S/P buffers need 192 TMEM columns: the
-// lo half of Q moves to shared memory (32 KB, written once per work item in the K-major 128B-swizzle layout) and the
-// Al x Bh pass is issued in SS mode; Q-hi stays in TMEM.  TMEM: O 256 | Q-hi 64 | S/P 2 x 96.
-// Per CTA and tile: K 48 slots (hi + lo, 24 KB), V 96 slots x 128 channels (fp16 + e4m3 + e5m2, 48 KB), two stages.
-// P keeps the 32-slot sub-layout [hi 16 cols | e4m3(lo) 8 | e4m3(P) 8] three times per buffer; each of the four
-// softmax warps of a lane quarter takes 24 slots = three 8-slot pieces.
-// Predicted from the isolated issue rates: 24 x 48 + 12 x 128 = 2688 clk per 96 slots (1792 per 64) against 2121 per 64.
-// MEASURED (gpurun_out/p96, profiles/r1n_phase_b_96.md): 3263 clk per 96 slots = 2175 per 64 - no gain.  In the running
-// kernel the cost of an S-MMA scales with N between 64 and 96 (the isolated microbenchmark, which re-reads one B tile,
-// does not show that), a deeper K ring / a separate V producer and a softmax without the fp8 conversions change the
-// time by < 4 %.  The kernel is kept as a cross-checked alternative (vfn_debug_set_pair bit 2), not the default.
-// ------------------------------------------------------------------------------------------------
-constexpr int B96 = 96;
-constexpr int Q_KSTAGES = 3, Q_VSTAGES = 2;      // K runs two tiles ahead of V in the MMA order: its own, deeper ring
-constexpr int Q_KBLOCK = 48 * 128;                               // 48 slots x 64 fp16 columns: 6 KB
-constexpr int Q_KSTAGE_BYTES = 4 * Q_KBLOCK;                     // kh c0-63 | kh c64-127 | kl c0-63 | kl c64-127: 24 KB
-constexpr int Q_VBLOCK = B96 * 128;                              // 96 slots x 128 B: 12 KB
-constexpr int Q_VSTAGE_BYTES = 4 * Q_VBLOCK;                     // vh ch0-63 | vh ch64-127 | v8 | vl: 48 KB
-constexpr int Q_QL_BYTES = QT * DK * 2;                          // Q-lo tile: 32 KB
-constexpr int CNT96_TILES = 16;                                  // 16 x 96 = 1536 slots per count chunk
-constexpr int Q_SMEM = Q_KSTAGES * Q_KSTAGE_BYTES + Q_VSTAGES * Q_VSTAGE_BYTES + Q_QL_BYTES + 1024 + 256 + CNT96_TILES * B96 * 4;
-constexpr uint32_t T9_O = 0, T9_QH = 256, T9_S = 320;
-
-// 8 slots of a softmax row: P' = 2^(s - lse2m), fp16 hi (4 words), e4m3 of the residual and of P' (2 words each);
-// bit (7 - i) set iff P'_i > thres_s
-template <bool MASK, bool COUNT>
-__device__ __forceinline__ uint32_t softmax_chunk8(const uint32_t (&s)[8], float lse2m, float thres_s, int lim,
-                                                   uint32_t (&hi)[4], uint32_t (&lo)[2], uint32_t (&p8)[2]) {
-  uint32_t bits = 0u;
-#pragma unroll
-  for (int i = 0; i < 8; i += 2) {
-    float p0 = ex2(__uint_as_float(s[i]) - lse2m), p1 = ex2(__uint_as_float(s[i + 1]) - lse2m);
-    if (MASK) {
-      p0 = (i < lim) ? p0 : 0.f;
-      p1 = (i + 1 < lim) ? p1 : 0.f;
-    }
-    if (COUNT) {
-      bits = __funnelshift_l(__float_as_uint(thres_s - p0), bits, 1);
-      bits = __funnelshift_l(__float_as_uint(thres_s - p1), bits, 1);
-    }
-    const uint32_t h = f16x2_rn(p0, p1);
-    const float2 hf = f16x2_to_f32(h);
-    hi[i >> 1] = h;
-    const uint32_t l = e4m3x2(p0 - hf.x, p1 - hf.y), q = e4m3x2(p0, p1);
-    if ((i & 2) == 0) { lo[i >> 2] = l; p8[i >> 2] = q; }
-    else { lo[i >> 2] |= l << 16; p8[i >> 2] |= q << 16; }
-  }
-  return bits;
-}
-
-// Q tile of a work item: hi -> TMEM columns [T9_QH, T9_QH + 64), lo -> shared memory, K-major with the 128B swizzle a
-// TMA load of a {64 columns, 128 rows} box would produce (two 16 KB column blocks; 16-byte chunk c of row r at
-// (r / 8) * 1024 + (r % 8) * 128 + ((c ^ (r % 8)) * 16)).  Warp (quarter, cg): cg 0,1 -> hi halves, cg 2,3 -> lo halves.
-__device__ __forceinline__ void load_q96(const TcArgs& args, int obj, int qt, uint32_t tmem, uint8_t* ql_smem, int warp,
-                                         int lane) {
-  const int quarter = warp & 3, cg = (warp - 4) >> 2;
-  const int row = (quarter << 5) + lane;
-  const uint16_t* base = (cg < 2 ? args.qh : args.ql) + (size_t)obj * args.a_obj_stride;
-  const uint4* src = reinterpret_cast<const uint4*>(base + ((size_t)qt * QT + row) * DK + (cg & 1) * 64);
-  if (cg < 2) {
-    const uint32_t taddr = tmem + (((uint32_t)quarter * 32u) << 16) + T9_QH + (uint32_t)(cg & 1) * 32u;
-    uint32_t v[32];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const uint4 x = src[i];
-      v[4 * i + 0] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
-    }
-    tmem_st32(taddr, v);
-    tmem_wait_st();
-  } else {
-    uint8_t* blk = ql_smem + (cg & 1) * 16384 + (row >> 3) * 1024 + (row & 7) * 128;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(blk + ((c ^ (row & 7)) << 4)) = src[c];
-    fence_proxy_async_smem();
-  }
-}
-
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-    tc_phase_b_pair96_kernel(const __grid_constant__ TcMaps maps, TcArgs args, const float* __restrict__ lse, float thres,
-                           int do_count, float* __restrict__ po) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* kst = smem;
-  uint8_t* vst = smem + Q_KSTAGES * Q_KSTAGE_BYTES;
-  uint8_t* qls = vst + Q_VSTAGES * Q_VSTAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(qls + Q_QL_BYTES);
-  uint64_t* k_full = bars;             // [4]  (used on the leader)
-  uint64_t* k_empty = bars + 4;        // [4]
-  uint64_t* v_full = bars + 8;         // [4]  (used on the leader)
-  uint64_t* v_empty = bars + 12;       // [4]
-  uint64_t* s_full = bars + 16;        // [2]
-  uint64_t* p_full = bars + 18;        // [2]  (used on the leader: 8 local + 8 remote warps)
-  uint64_t* o_full = bars + 20;        // [1]
-  uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(bars + 21);
-  int* cnt_item = reinterpret_cast<int*>(bars + 32);   // [CNT96_TILES][96] usage counts of the current item
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < Q_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
-    for (int i = 0; i < Q_VSTAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 2 * EPI_WARPS); }
-    mbar_init(o_full, 1);
-    fence_barrier_init();
-  }
-  for (int i = threadIdx.x; i < CNT96_TILES * B96; i += TC_THREADS) cnt_item[i] = 0;
-  if (warp == 2) tmem_alloc_pair(tmem_base_p, 512);
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_base_p;
-  pdl_wait();        // programmatic dependent launch: the prologue above overlaps the predecessor's tail
-  pdl_trigger();
-
-  // work items = (split, object, query-tile pair, channel half), round-robin over the clusters
-  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-  const int qpairs = (args.q_tiles + 1) >> 1;
-  const int cpo = qpairs * 2;
-  const int n_combos = args.obj_n * cpo;
-  const int pieces = tc_pieces(args);
-  const int n_items = n_combos * pieces;
-  uint32_t k_it = 0;            // tiles streamed so far (stage = k_it & 1)
-  uint32_t buf_it[2] = {0, 0};  // uses of each S/P buffer so far
-  uint32_t seg_it = 0;          // items finished (o_full phase)
-  for (int item = cluster_id; item < n_items; item += n_clusters) {
-    const int piece = item / n_combos;
-    const int combo = item - piece * n_combos;
-    const int obj = combo / cpo;
-    const int cidx = combo - obj * cpo;                // qp * 2 + half
-    const int qt = (cidx >> 1) * 2 + (int)rank, half = cidx & 1;
-    const int n_obj = args.n_live[obj] ? *reinterpret_cast<const volatile int32_t*>(args.n_live[obj]) : args.n[obj];
-    const int tiles_o = args.n_live[obj] ? (n_obj + B96 - 1) / B96 : args.tiles[obj];
-    const int t0 = (int)((long long)tiles_o * piece / pieces);
-    const int t1 = (int)((long long)tiles_o * (piece + 1) / pieces);
-    const int ntile = t1 - t0;
-    const bool first_item = (item == cluster_id);
-
-    if (warp >= 4) load_q96(args, obj, qt, tmem, qls, warp, lane);
-    tc_fence_before();
-    cluster_sync_all();      // both CTAs' Q tiles are in TMEM, both epilogues of the previous item are done
-    tc_fence_after();
-
-    if (warp == 0) {            // K producer
-      if (lane == 0) {
-        for (int t = 0; t < ntile; ++t) {
-          const uint32_t kit = k_it + t, st = kit % Q_KSTAGES, ph = (kit / Q_KSTAGES) & 1;
-          const int row0 = (t0 + t) * B96;
-          mbar_wait(&k_empty[st], ph ^ 1);
-          if (leader) mbar_arrive_expect_tx(&k_full[st], 2 * Q_KSTAGE_BYTES);
-          const uint32_t kf = mapa_u32(smem_u32(&k_full[st]), 0);
-          uint8_t* kd = kst + st * Q_KSTAGE_BYTES;
-          const int krow = row0 + (int)rank * 48;
-          tma_load_2d_pair(kd, &maps.kh[obj], kf, 0, krow);
-          tma_load_2d_pair(kd + Q_KBLOCK, &maps.kh[obj], kf, 64, krow);
-          tma_load_2d_pair(kd + 2 * Q_KBLOCK, &maps.kl[obj], kf, 0, krow);
-          tma_load_2d_pair(kd + 3 * Q_KBLOCK, &maps.kl[obj], kf, 64, krow);
-        }
-      }
-      __syncwarp();
-    } else if (warp == 2) {     // V producer: its own thread, so that a V stage waiting for its O-MMAs never holds up
-      if (lane == 0) {          // the K tile that the S-MMAs two tiles ahead need
-        for (int t = 0; t < ntile; ++t) {
-          const uint32_t kit = k_it + t, st = kit & 1, ph = (kit >> 1) & 1;
-          const int row0 = (t0 + t) * B96;
-          mbar_wait(&v_empty[st], ph ^ 1);
-          if (leader) mbar_arrive_expect_tx(&v_full[st], 2 * Q_VSTAGE_BYTES);
-          const uint32_t vf = mapa_u32(smem_u32(&v_full[st]), 0);
-          uint8_t* vd = vst + st * Q_VSTAGE_BYTES;
-          const int ch0 = half * 256 + (int)rank * 128;
-          tma_load_2d_pair(vd, &maps.vh[obj], vf, ch0, row0);
-          tma_load_2d_pair(vd + Q_VBLOCK, &maps.vh[obj], vf, ch0 + 64, row0);
-          tma_load_2d_pair(vd + 2 * Q_VBLOCK, &maps.v8[obj], vf, ch0, row0);
-          tma_load_2d_pair(vd + 3 * Q_VBLOCK, &maps.vl[obj], vf, ch0, row0);
-        }
-      }
-      __syncwarp();
-    } else if (warp == 1) {
-      if (leader) {
-        constexpr uint32_t idesc_s = make_idesc(256, B96, FMT_F16, FMT_F16, 0, 0);
-        constexpr uint32_t idesc_o = make_idesc(256, 256, FMT_F16, FMT_F16, 0, 1);
-        constexpr uint32_t idesc_o8 = make_idesc(256, 256, FMT_E4M3, FMT_E4M3, 0, 1);
-        constexpr uint32_t idesc_ol = make_idesc(256, 256, FMT_E4M3, FMT_E5M2, 0, 1);
-        const uint32_t qlbase = smem_u32(qls);
-        auto issue_s = [&](int t) {
-          const uint32_t kit = k_it + t, st = kit % Q_KSTAGES, ph = (kit / Q_KSTAGES) & 1;
-          const int b = t & 1;
-          mbar_wait(&k_full[st], ph);
-          tc_fence_after();
-          const uint32_t kbase = smem_u32(kst + st * Q_KSTAGE_BYTES);
-          const uint32_t d_t = tmem + T9_S + (uint32_t)b * B96;
-          if (elect_one()) {
-            // passes: (Ah,Bh) TS, (Al,Bh) SS with Al in shared memory, (Ah,Bl) TS
-#pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-              const uint32_t kb = kbase + ((pass == 2) ? 2u * Q_KBLOCK : 0u);
-#pragma unroll
-              for (int ks = 0; ks < 8; ++ks) {
-                const uint64_t bd = make_sdesc(kb + (ks >> 2) * Q_KBLOCK + (ks & 3) * 32u, 16, 1024);
-                if (pass == 1) {
-                  const uint64_t ad = make_sdesc(qlbase + (ks >> 2) * 16384u + (ks & 3) * 32u, 16, 1024);
-                  mma_ss_pair(d_t, ad, bd, idesc_s, 1u);
-                } else {
-                  mma_ts_pair(d_t, tmem + T9_QH + ks * 8, bd, idesc_s, (pass | ks) ? 1u : 0u);
-                }
-              }
-            }
-            tc_commit_pair(&k_empty[st]);
-            tc_commit_pair(&s_full[b]);
-          }
-          __syncwarp();
-        };
-        if (ntile > 0) issue_s(0);
-        if (ntile > 1) issue_s(1);
-        for (int t = 0; t < ntile; ++t) {
-          const uint32_t kit = k_it + t, st = kit & 1, ph = (kit >> 1) & 1;
-          const int b = t & 1;
-          mbar_wait(&p_full[b], buf_it[b] & 1);
-          ++buf_it[b];
-          mbar_wait(&v_full[st], ph);
-          tc_fence_after();
-          const uint32_t vbase = smem_u32(vst + st * Q_VSTAGE_BYTES);
-          const uint32_t pcol = tmem + T9_S + (uint32_t)b * B96;
-          if (elect_one()) {
-#pragma unroll
-            for (int h = 0; h < 3; ++h) {                    // 32-slot thirds of the tile
-#pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t bd = make_sdesc(vbase + (uint32_t)(2 * h + ks) * 2048u, Q_VBLOCK, 1024);
-                mma_ts_pair(tmem + T9_O, pcol + (uint32_t)h * 32u + (uint32_t)ks * 8u, bd, idesc_o, (t | h | ks) ? 1u : 0u);
-              }
-            }
-#pragma unroll
-            for (int h = 0; h < 3; ++h) {
-              const uint64_t b8 = make_sdesc(vbase + 2u * Q_VBLOCK + h * 4096u, Q_VBLOCK, 1024);
-              mma_ts_f8_pair(tmem + T9_O, pcol + (uint32_t)h * 32u + 16u, b8, idesc_o8, 1u);
-              const uint64_t bl = make_sdesc(vbase + 3u * Q_VBLOCK + h * 4096u, Q_VBLOCK, 1024);
-              mma_ts_f8_pair(tmem + T9_O, pcol + (uint32_t)h * 32u + 24u, bl, idesc_ol, 1u);
-            }
-            tc_commit_pair(&v_empty[st]);
-          }
-          __syncwarp();
-          if (t + 2 < ntile) issue_s(t + 2);
-        }
-        if (elect_one()) tc_commit_pair(o_full);
-        __syncwarp();
-      }
-    } else if (warp >= 4) {
-      // every softmax warp works on every tile: slot group sg = 24 of the tile's 96 slots, for its 32 query rows
-      const int quarter = warp & 3, sg = (warp - 4) >> 2;
-      const int row = (quarter << 5) + lane;
-      const int et = threadIdx.x - 128;                          // 0..511
-      const uint32_t tlane = tmem + (((uint32_t)quarter * 32u) << 16);
-      const int j = qt * QT + row;
-      const float lse2m = (j < args.hw) ? (lse[(size_t)obj * args.hw + j] * LOG2E - P_SCALE_LOG2) : INFINITY;
-      const float thres_s = thres * P_SCALE;
-      const bool counting = do_count && (half == 0);
-      const uint32_t pf_leader0 = mapa_u32(smem_u32(&p_full[0]), 0), pf_leader1 = mapa_u32(smem_u32(&p_full[1]), 0);
-      auto flush_counts = [&](int tile_first, int n_tiles) {
-        named_bar_sync(9, EPI_THREADS);
-        for (int idx = et; idx < n_tiles * B96; idx += EPI_THREADS) {
-          const int c = cnt_item[idx];
-          if (c) {
-            atomicAdd(&args.cnt[obj][(size_t)(t0 + tile_first) * B96 + idx], c);
-            cnt_item[idx] = 0;
-          }
-        }
-        named_bar_sync(9, EPI_THREADS);
-      };
-      int chunk0 = 0;                                            // first tile of the current count chunk
-      for (int t = 0; t < ntile; ++t) {
-        const int b = t & 1;
-        mbar_wait(&s_full[b], buf_it[b] & 1);
-        ++buf_it[b];
-        tc_fence_after();
-        const int slot0 = (t0 + t) * B96 + sg * 24;
-        const uint32_t pb = tlane + T9_S + (uint32_t)b * B96;     // this buffer's 96-column S / P region
-        uint32_t sv[3][8];
-        tmem_ld8(pb + (uint32_t)sg * 24, sv[0]);
-        tmem_ld8(pb + (uint32_t)sg * 24 + 8, sv[1]);
-        tmem_ld8(pb + (uint32_t)sg * 24 + 16, sv[2]);
-        tmem_wait_ld();
-        if (args.dbg && blockIdx.x == 0 && first_item && t == 0) {
-#pragma unroll
-          for (int i = 0; i < 24; ++i) args.dbg[row * B96 + sg * 24 + i] = __uint_as_float(sv[i >> 3][i & 7]);
-        }
-        // P is written in place over S and the pieces of different warps interleave inside a 32-slot third: all four
-        // warps of this lane quarter must hold their logits in registers before any of them stores
-        tc_fence_before();
-        named_bar_sync(5 + quarter, 128);
-        tc_fence_after();
-        uint32_t bits = 0u;
-        const int lim = n_obj - slot0;
-#pragma unroll
-        for (int pc = 0; pc < 3; ++pc) {                       // 8-slot piece g = 3 sg + pc of the tile's twelve
-          uint32_t hi[4], lo[2], p8[2];
-          uint32_t bpc;
-          if (lim >= 24) {
-            bpc = counting ? softmax_chunk8<false, true>(sv[pc], lse2m, thres_s, 8, hi, lo, p8)
-                           : softmax_chunk8<false, false>(sv[pc], lse2m, thres_s, 8, hi, lo, p8);
-          } else {
-            bpc = softmax_chunk8<true, true>(sv[pc], lse2m, thres_s, lim - 8 * pc, hi, lo, p8);
-          }
-          bits = (bits << 8) | bpc;
-          const int g = 3 * sg + pc;
-          const uint32_t third = pb + (uint32_t)(g >> 2) * 32u, r = (uint32_t)(g & 3);
-          tmem_st4(third + r * 4u, hi);
-          tmem_st2(third + 16u + r * 2u, lo);
-          tmem_st2(third + 24u + r * 2u, p8);
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(b ? pf_leader1 : pf_leader0);
-        if (counting) {
-          // bit (23 - i) <-> slot slot0 + i of this row; rows beyond hw have lse = +inf, P = 0: no bits
-          int* cdst = cnt_item + (t - chunk0) * B96 + sg * 24;
-          if (__any_sync(0xffffffffu, __popc(bits) > 2)) {
-            int c_mine = 0;
-#pragma unroll
-            for (int c = 0; c < 24; ++c) {
-              const unsigned bal = __ballot_sync(0xffffffffu, (bits >> c) & 1u);
-              if (lane == c) c_mine = __popc(bal);
-            }
-            if (lane < 24 && c_mine) atomicAdd(&cdst[23 - lane], c_mine);
-          } else {
-            while (bits) {
-              const int c = 31 - __clz((int)bits);
-              bits &= ~(1u << c);
-              atomicAdd(&cdst[23 - c], 1);
-            }
-          }
-          if (t - chunk0 + 1 == CNT96_TILES && t + 1 < ntile) {
-            flush_counts(chunk0, CNT96_TILES);
-            chunk0 = t + 1;
-          }
-        }
-      }
-      if (counting && ntile > chunk0) flush_counts(chunk0, ntile - chunk0);
-      mbar_wait(o_full, seg_it & 1);
-      tc_fence_after();
-      if (ntile > 0) {
-        float* dst = po + (((size_t)obj * pieces + piece) * DV + half * 256 + sg * 64) * (size_t)args.hw;
-#pragma unroll 1
-        for (int ch = 0; ch < 2; ++ch) {
-          uint32_t v[32];
-          tmem_ld32(tlane + T9_O + (uint32_t)sg * 64 + ch * 32, v);
-          tmem_wait_ld();
-          if (j < args.hw) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) dst[(size_t)(ch * 32 + i) * args.hw + j] = __uint_as_float(v[i]) * (1.f / P_SCALE);
-          }
-        }
-      }
-    }
-    k_it += ntile;
-    ++seg_it;
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 2) tmem_dealloc_pair(tmem, 512);
-}
-
-// ------------------------------------------------------------------------------------------------
 // Exact fp32 re-score of the tensor-core candidates (FeatureBank.py:66-68): one warp per candidate query.
 // The fp16x3 scores carry the tensor core's truncating accumulation (measured: ~4e-6 systematic bias), so every slot
 // whose approximate score lies within MATCH_BAND of the approximate maximum is re-evaluated with the sequential fp32
@@ -2048,7 +1678,6 @@ static int set_attrs() {
     VFN_CUDA_OK(cudaFuncSetAttribute(tc_scan_pair_kernel<MODE_MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
     VFN_CUDA_OK(cudaFuncSetAttribute(tc_phase_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
     VFN_CUDA_OK(cudaFuncSetAttribute(tc_phase_b_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
-    VFN_CUDA_OK(cudaFuncSetAttribute(tc_phase_b_pair96_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM));
     attr = true;
   }
   return VFN_OK;
@@ -2140,8 +1769,7 @@ int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const 
   TcMaps maps;
   TcArgs a;
   const bool pair = (g_pair & 1) && (num_sms() % 2 == 0);
-  const bool pair96 = pair && (g_pair & 4);          // 96-slot tiles (tc_phase_b_pair96_kernel)
-  const int tile = pair96 ? B96 : B_TILE;
+  const int tile = B_TILE;
   int64_t tmin = INT64_MAX, tmax = 0;
   for (int o = 0; o < obj_n; ++o) {
     const int64_t t = cdiv(banks[o].n, tile), tl = cdiv(n_low(banks[o]), tile);
@@ -2157,7 +1785,7 @@ int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const 
   const int pieces = best_split(combos, tmin, tmax, 4, pair ? num_sms() / 2 : num_sms(), s_min);
   if (pieces > split_b) { set_error("phase B: split %d exceeds workspace bound %d", pieces, split_b); return VFN_E_CAPACITY; }
   *pieces_out = pieces;
-  if (int rc = fill_args(banks, obj_n, hw, pieces, tile, ws_tc, &maps, &a, true, pair96 ? 48 : (pair ? 32 : B_TILE))) return rc;
+  if (int rc = fill_args(banks, obj_n, hw, pieces, tile, ws_tc, &maps, &a, true, pair ? 32 : B_TILE)) return rc;
   *pieces_dev_out = nullptr;
   if (live) {
     int32_t* cell = tc_plan_cell(ws_tc, hw) + 1;
@@ -2167,9 +1795,7 @@ int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const 
   double work = 0;
   for (int o = 0; o < obj_n; ++o) work += 2.0 * DV * (double)banks[o].n * (double)hw;
   prof_begin(PROF_READ_B, st);
-  if (pair96)
-    VFN_CUDA_OK(launch_pdl(tc_phase_b_pair96_kernel, dim3(num_sms()), dim3(TC_THREADS), Q_SMEM, st, maps, a, lse, thres_valid, update_bank, po));
-  else if (pair)
+  if (pair)
     VFN_CUDA_OK(launch_pdl(tc_phase_b_pair_kernel, dim3(num_sms()), dim3(TC_THREADS), P_SMEM, st, maps, a, lse, thres_valid, update_bank, po));
   else
     tc_phase_b_kernel<<<num_sms(), TC_THREADS, B_SMEM, st>>>(maps, a, lse, thres_valid, update_bank, po);

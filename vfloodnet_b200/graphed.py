@@ -1,0 +1,148 @@
+"""The convolutional stages around the hot path as CUDA graphs ("CUDA graphs for the whole frame
+step"; reference: AFB_URR.memorize / AFB_URR.segment, video_module/model/AFB_URR.py:255-318).
+
+Once read + URR + update take ~1 ms per frame, a frame of the reference loop is dominated by its ~350 eager cuDNN / ATen
+launches (encoder_q, KeyValue, decoder, encoder_m for every object): 6.8 of 7.6 ms on a B200, most of it launch-bound.
+`GraphedAFBURR` wraps a reference `AFB_URR` instance (after `patch_model`) and captures its four static-shape stages once:
+
+    enc   frame -> pad -> encoder_q -> KeyValue             (AFB_URR.py:279-285)
+    dec   readout, r3, r2 -> convFM .. pred2 -> coarse logits (AFB_URR.py:209-212; the expand of r3 / r2 included)
+    loc   [r1 ; r1_local] -> local_convFM, local_ResMM, local_pred2   (AFB_URR.py:232-233)
+    mem   frame, mask -> pad -> encoder_m -> KeyValue        (AFB_URR.py:257-272), captured by calling model.memorize
+
+Between the graphs the library's kernels run as before (vfn_memread, vfn_urr_pre / _post, vfn_bank_update): their shapes
+follow the bank.  The modules, weights and the arithmetic are the reference's own; only the launch mechanism changes, so
+`segment` / `memorize` return what the patched model returns (tests/test_gpu_dropin.py::test_graphed_model_equals_eager).
+Same method names and signatures as the reference model: the frame loop of test_video_seg.py:99-112 runs unchanged.
+"""
+from __future__ import annotations
+
+import torch
+from torch.nn import functional as NF
+
+from .urr import urr_post, urr_pre
+
+
+def _pad16(x):
+    """myutils.pad_divide_by([x], 16, x.shape[-2:]) (myutils/data.py:134-151) for one tensor"""
+    h, w = x.shape[-2:]
+    nh, nw = (h + 15) // 16 * 16, (w + 15) // 16 * 16
+    lh, lw = int((nh - h) / 2), int((nw - w) / 2)
+    pad = (lw, nw - w - lw, lh, nh - h - lh)
+    return NF.pad(x, pad), pad
+
+
+class GraphedAFBURR:
+    def __init__(self, model, frame_shape, obj_n: int = 2, warmup: int = 3):
+        """model: a reference AFB_URR (eval mode, on a CUDA device) with vfloodnet_b200.patch_model applied.
+        frame_shape: (1, 3, H, W) of the frames the loop will feed (test_video_seg.py:107 after the resize)."""
+        self.model, self.obj_n = model, obj_n
+        dev = next(model.parameters()).device
+        if dev.type != 'cuda':
+            raise RuntimeError('GraphedAFBURR needs the model on a CUDA device')
+        self.device = dev
+        b, c, h, w = frame_shape
+        if b != 1:
+            raise ValueError('inference path: one frame at a time (bs == 1)')
+        self.frame = torch.zeros(frame_shape, device=dev)
+        self.mask = torch.zeros((1, obj_n, h, w), device=dev)
+        self.mask[:, 0] = 1
+        with torch.no_grad():
+            self._capture(warmup)
+
+    # ---- the four stages as plain functions of the static buffers ---------------------------------
+    def _enc(self):
+        f, pad = _pad16(self.frame)
+        r4, r3, r2, r1 = self.model.encoder_q(f)
+        k4, v4 = self.model.keyval_r4(r4)
+        return k4, v4, r3, r2, r1, pad
+
+    def _dec(self):
+        d, n = self.model.decoder, self.obj_n
+        r3 = self.r3.unsqueeze(1).expand(-1, n, -1, -1, -1).reshape(n, *self.r3.shape[1:])      # AFB_URR.py:291-292
+        r2 = self.r2.unsqueeze(1).expand(-1, n, -1, -1, -1).reshape(n, *self.r2.shape[1:])
+        p = d.ResMM(d.convFM(self.res_global))
+        p = d.RF3(r3, p)
+        p = d.RF2(r2, p)
+        return d.pred2(NF.relu(p))
+
+    def _loc(self):
+        d = self.model.decoder
+        q = d.local_ResMM(d.local_convFM(self.local_match))
+        return d.local_pred2(NF.relu(q))
+
+    def _mem(self):
+        k4, v4 = self.model.memorize(self.frame, self.mask)
+        return torch.stack(k4), torch.stack(v4)
+
+    def _graph(self, fn, warmup):
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                fn()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = fn()
+        return g, out
+
+    def _capture(self, warmup):
+        with torch.cuda.device(self.device):
+            self.g_enc, (self.k4, self.v4, self.r3, self.r2, self.r1, self.pad) = self._graph(self._enc, warmup)
+            n = self.obj_n
+            self.grid4 = (self.r3.shape[2] // 2, self.r3.shape[3] // 2)               # r4 grid (stride 16)
+            self.res_global = torch.zeros((n, 2 * self.v4.shape[1]) + self.grid4, device=self.device)
+            self.g_dec, self.p = self._graph(self._dec, warmup)
+            c1, h1, w1 = self.r1.shape[1:]
+            self.local_match = torch.zeros((n, 2 * c1, h1, w1), device=self.device)
+            self.g_loc, self.q = self._graph(self._loc, warmup)
+            self.g_mem, (self.mk4, self.mv4) = self._graph(self._mem, warmup)
+
+    # ---- reference method surface ------------------------------------------------------------------
+    @property
+    def global_matcher(self):
+        return self.model.global_matcher
+
+    @property
+    def decoder(self):
+        return self.model.decoder
+
+    def eval(self):
+        return self
+
+    @torch.no_grad()
+    def memorize(self, frame, mask):
+        """AFB_URR.memorize (AFB_URR.py:255-272): lists of (128, HW) / (512, HW) per object (views of static buffers,
+        valid until the next memorize)"""
+        if frame.data_ptr() != self.frame.data_ptr():
+            self.frame.copy_(frame, non_blocking=True)
+        self.mask.copy_(mask, non_blocking=True)
+        self.g_mem.replay()
+        return [self.mk4[i] for i in range(self.obj_n)], [self.mv4[i] for i in range(self.obj_n)]
+
+    @torch.no_grad()
+    def segment(self, frame, fb_global):
+        """AFB_URR.segment, inference branch (AFB_URR.py:274-318): returns (score, None)"""
+        n = fb_global.obj_n
+        if n != self.obj_n:
+            raise ValueError('object count differs from the captured graphs')
+        self.frame.copy_(frame, non_blocking=True)
+        self.g_enc.replay()
+        res = self.model.global_matcher(fb_global, self.k4, self.v4)                   # (1, n, 1024, HW): the read
+        self.res_global.copy_(res.reshape(n, -1, *self.grid4))
+        self.g_dec.replay()
+        r1 = self.r1.expand(n, -1, -1, -1)                                             # stride-0 view: never materialised
+        fs = (1, n, self.r1.shape[2], self.r1.shape[3])
+        p_up, unc, conf, _lm = urr_pre(self.p, r1, fs, out_local_match=self.local_match)
+        self.g_loc.replay()
+        prob = urr_post(p_up, unc, conf, self.q)                                       # (n, H, W)
+        score = prob.view(1, n, *prob.shape[-2:])
+        score = torch.clamp(score, 1e-7, 1 - 1e-7)                                     # AFB_URR.py:308-309
+        score = torch.log(score / (1 - score))
+        pad = self.pad
+        if pad[2] + pad[3] > 0:
+            score = score[:, :, pad[2]:score.shape[2] - pad[3], :]
+        if pad[0] + pad[1] > 0:
+            score = score[:, :, :, pad[0]:score.shape[3] - pad[1]]
+        return score, None

@@ -16,10 +16,11 @@ from . import _lib
 from ._lib import check, on_device, ptr, stream_ptr
 
 
-def urr_pre(p: torch.Tensor, r1: torch.Tensor, feature_shape):
+def urr_pre(p: torch.Tensor, r1: torch.Tensor, feature_shape, out_local_match: torch.Tensor = None):
     """p: (obj_n, 2, h/2, w/2) logits of pred2; r1: (obj_n, C, h, w) (may be an expand()ed view of (1,C,h,w)).
     Returns p_up (obj_n,2,h,w), uncertainty (obj_n,1,h,w) [expanded view], r1_conf (obj_n,1,h,w),
-    local_match (obj_n,2C,h,w)."""
+    local_match (obj_n,2C,h,w).  out_local_match: write local_match into this (contiguous fp32) tensor instead of a
+    fresh one (a CUDA-graph input buffer, vfloodnet_b200.graphed)."""
     lib = _lib.load()
     bs, obj_n, h, w = feature_shape
     if bs != 1:
@@ -39,7 +40,13 @@ def urr_pre(p: torch.Tensor, r1: torch.Tensor, feature_shape):
     unc = torch.empty((h, w), **f32)
     conf = torch.empty((obj_n, 1, h, w), **f32)
     avg = torch.empty((obj_n, h, w), **f32)
-    local_match = torch.empty((obj_n, 2 * c, h, w), **f32)
+    if out_local_match is not None:
+        if tuple(out_local_match.shape) != (obj_n, 2 * c, h, w) or out_local_match.dtype != torch.float32 or \
+                not out_local_match.is_contiguous() or out_local_match.device != dev:
+            raise ValueError('out_local_match must be a contiguous fp32 (obj_n, 2C, h, w) tensor on the device of p')
+        local_match = out_local_match
+    else:
+        local_match = torch.empty((obj_n, 2 * c, h, w), **f32)
     with on_device(dev):
         check(lib.vfn_urr_pre(ptr(p), ptr(r1c), obj_stride, obj_n, c, h, w, ptr(p_up), ptr(seg), ptr(unc), ptr(conf),
                               ptr(avg), ptr(local_match), stream_ptr()), 'vfn_urr_pre')
