@@ -31,10 +31,10 @@ R1_H, R1_W = 240, 432
 D_KEY, D_VAL = 128, 512
 BUDGET = 250000               # test_video_seg.py:24  -> class_budget 100000.0
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE tc_phase_b_pair_kernel launch, from the committed `ncu --set full`
-# capture (profiles/r1m_ncu_summary.md): N = 100000 slots/object, 2 objects, HW = 1620.  The operand arrays that launch
+# capture (profiles/r2f_ncu_summary.md): N = 100000 slots/object, 2 objects, HW = 1620.  The operand arrays that launch
 # has to stream once are 2560 B/slot (kh, kl, vh, v8, vl) = 512 MB; its algorithmic work is 3.32e11 flop.
-NCU_PHASE_B_TRAFFIC = {'bytes': 611.70e6 + 91.63e6,
-                       'note': 'per launch at N=100000 slots/object (ncu capture profiles/r1m_ncu_summary.md); operand '
+NCU_PHASE_B_TRAFFIC = {'bytes': 615.17e6 + 93.33e6,
+                       'note': 'per launch at N=100000 slots/object (ncu capture profiles/r2f_ncu_summary.md); operand '
                                'bytes streamed once = 512 MB; the bench launches average fewer slots'}
 TAIL_SIZE = (1080, 1920)      # original frame size the mask is resized back to (test_video_seg.py:103,114)
 TAIL_KEY_PTS = [(480, 300), (960, 200), (1440, 400), (1800, 100)]
@@ -899,8 +899,11 @@ def main_model_clip(args, rank, world, local_rank):
                               'sample': 'unmodified reference AFB_URR + FeatureBank (baseline/_ref), torch CUDA ops on '
                                         'the same GPU, same weights, same clip, free-running',
                               'stages_ms_per_frame': st_ref, 'final_bank_slots': n_ref},
-            'parity': {'min_mask_iou': min(ious), 'frames_identical': sum(1 for x in ious if x == 1.0),
-                       'bank_sizes_equal': n_ref == [ours_run['fb'].bank_n(c) for c in range(2)]},
+            'parity': {'mask_iou_frames_1_to_5': [round(x, 5) for x in ious[:5]],
+                       'frames_with_iou_ge_0_999': next((t for t, x in enumerate(ious) if x < 0.999), len(ious)),
+                       'note': 'two FREE-RUNNING clips with TF32 convolutions: an untrained model is an unstable recurrence and '
+                               'any two arms part ways within ~8 frames; the gated comparison (teacher-forced, exact arm, '
+                               'fp32 convolutions) is tests/test_gpu_dropin.py'},
             'clocks': sampler.summary()}
     print(json.dumps(line))
 
