@@ -654,3 +654,42 @@ def test_usage_counts_against_fp64_counts_at_capacity(vfn):
     print(f'usage counts vs fp64 at N={n}: reference fp32 differs in {flips_ref} slots, tcgen05 read in {flips_ours}; '
           f'{near} of {n * hw} p_ij lie within 1e-5 (relative) of the threshold')
     assert flips_ours <= 2 * flips_ref + 4, (flips_ours, flips_ref)
+
+
+# ---------------------------------------------------------------------------------------------------
+# a bank on a GPU that is not the current device (the library launches on the caller's current device)
+# ---------------------------------------------------------------------------------------------------
+def test_bank_on_a_non_current_device(vfn):
+    """FeatureBank / Matcher / URR / FrameTail accept any `device`, like the reference: with cuda:0 current, a bank on
+    cuda:1 must compute on cuda:1 (every host entry point enters the tensor's device and takes ITS current stream)"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    from vfloodnet_b200 import synth
+    from vfloodnet_b200.tail import FrameTail
+    g = torch.Generator().manual_seed(3)
+    n, hw = 3000, 500
+    keys, vals = zip(*[synth.gen_bank(g, n) for _ in range(2)])
+    info = [synth.gen_info(g, n, 9) for _ in range(2)]
+    q_in, q_out = synth.gen_query(g, hw)
+    pk, pv = zip(*[synth.gen_candidates(g, keys[c], vals[c], hw, 0.5) for c in range(2)])
+    p, r1, q_local = synth.gen_urr_inputs(g, 2, 32, 48)
+    res = []
+    torch.cuda.set_device(0)
+    for dev in ('cuda:0', 'cuda:1'):
+        fb = vfn.FeatureBank(2, 7000, dev)
+        fb.load_state(list(keys), list(vals), info)
+        out = vfn.Matcher(update_bank=True)(fb, q_in.to(dev), q_out.to(dev))
+        fb.update([k.to(dev) for k in pk], [v.to(dev) for v in pv], 9)
+        p_up, unc, conf, lm = vfn.urr_pre(p.to(dev), r1.to(dev).expand(2, -1, -1, -1), (1, 2, 32, 48))
+        prob = vfn.urr_post(p_up, unc, conf, q_local.to(dev))
+        mask, levels = FrameTail((64, 96), [(10, 5)], dev)(prob)
+        torch.cuda.synchronize(dev)
+        assert out.device == torch.device(dev) and prob.device == torch.device(dev)
+        res.append((out.cpu(), [fb.keys[c].cpu() for c in range(2)], [fb.info[c].cpu() for c in range(2)], prob.cpu(),
+                    mask.cpu(), fb.replace_n.copy()))
+    assert torch.cuda.current_device() == 0
+    a, b = res
+    assert torch.equal(a[0], b[0]) and torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
+    for c in range(2):
+        assert torch.equal(a[1][c], b[1][c]) and torch.equal(a[2][c], b[2][c])
+    assert np.array_equal(a[5], b[5]) and a[5].sum() > 0

@@ -62,7 +62,7 @@ int launch_clamp(const vfn_bank* banks, int n_obj, cudaStream_t st, const int64_
     }                                                                                       \
   } while (0)
 
-#define VFN_LAUNCH_OK() VFN_CUDA_OK(cudaPeekAtLastError())
+#define VFN_LAUNCH_OK() VFN_CUDA_OK(cudaGetLastError())   /* reads AND clears: a failed launch fails its own call only */
 
 // Programmatic dependent launch: the kernel is queued behind its predecessor on the stream with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs can be placed on the SMs while the predecessor drains;
@@ -86,6 +86,17 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.attrs = attr;
   cfg.numAttrs = g_pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// true the first time it is called for the CURRENT device with this flag array: per-device one-time setup
+// (cudaFuncSetAttribute is per device; a process may drive banks on several GPUs)
+static inline bool first_use_on_device(bool (&done)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return true;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
 }
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -537,12 +537,10 @@ static int run_phase_b(const BankSet& set, ReadPlan& p, const float* lse, float 
   for (int o = 0; o < p.obj_n; ++o)
     VFN_CHECK_ARG(!set.b[o].n_live || set.b[o].n_min == set.b[o].n,
                   "the fp32 SIMT read needs exact bank sizes (bank %d was passed with bounds)", o);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};
+  if (first_use_on_device(attr_set))
     VFN_CUDA_OK(cudaFuncSetAttribute(simt_readout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(ReadoutSmem)));
-    attr_set = true;
-  }
   dim3 grid(p.q_tiles, p.split_b, p.obj_n * p.n_chunk);
   double work = 0;
   for (int o = 0; o < p.obj_n; ++o) work += 2.0 * p.d_val * (double)set.b[o].n * (double)p.hw;

@@ -1670,15 +1670,14 @@ size_t tc_workspace_bytes(int obj_n, int64_t hw) {
 static int32_t* tc_plan_cell(char* ws_tc, int64_t hw) { return reinterpret_cast<int32_t*>(ws_tc + 2 * a_operand_bytes(hw)); }
 
 static int set_attrs() {
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {false};
+  if (first_use_on_device(attr)) {
     VFN_CUDA_OK(cudaFuncSetAttribute(tc_scan_kernel<MODE_LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
     VFN_CUDA_OK(cudaFuncSetAttribute(tc_scan_kernel<MODE_MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
     VFN_CUDA_OK(cudaFuncSetAttribute(tc_scan_pair_kernel<MODE_LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
     VFN_CUDA_OK(cudaFuncSetAttribute(tc_scan_pair_kernel<MODE_MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
     VFN_CUDA_OK(cudaFuncSetAttribute(tc_phase_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
     VFN_CUDA_OK(cudaFuncSetAttribute(tc_phase_b_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
-    attr = true;
   }
   return VFN_OK;
 }

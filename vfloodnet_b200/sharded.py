@@ -243,6 +243,8 @@ class ShardedReader:
         _, d_key, hw = q_in.shape
         d_val = q_out.shape[1]
         obj_n = fb.obj_n
+        if any(s is None for s in fb._slabs):
+            raise RuntimeError('sharded read on an empty feature bank: call init_bank() first')
         n_max = max(s.cap for s in fb._slabs)
         need = lib.vfn_memread_workspace_bytes(obj_n, n_max, hw, d_key, d_val)
         if self._ws is None or self._ws.numel() < need:

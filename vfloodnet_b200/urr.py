@@ -72,7 +72,14 @@ def decoder_forward(self, patch_match, r3, r2, r1=None, feature_shape=None):
     p = self.RF3(r3, p)
     p = self.RF2(r2, p)
     p = self.pred2(NF.relu(p))
-    p_up, uncertainty, r1_conf, local_match = urr_pre(p, r1, feature_shape)
+    # [r1 ; r1_local] (106 MB at 480p) goes into one buffer kept on the decoder: it is consumed by local_convFM right
+    # below, and a fresh 100 MB allocation per frame is what the caching allocator handles worst
+    bs, obj_n, h, w = feature_shape
+    lm = self.__dict__.get('_vfn_local_match')
+    if lm is None or tuple(lm.shape) != (obj_n, 2 * r1.shape[1], h, w) or lm.device != p.device:
+        lm = torch.empty((obj_n, 2 * r1.shape[1], h, w), dtype=torch.float32, device=p.device)
+        self.__dict__['_vfn_local_match'] = lm
+    p_up, uncertainty, r1_conf, local_match = urr_pre(p, r1, feature_shape, out_local_match=lm)
     q = self.local_ResMM(self.local_convFM(local_match))
     q = self.local_pred2(NF.relu(q))
     return urr_post(p_up, uncertainty, r1_conf, q)
