@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int bmn, int reps, 
 // A = Q in TMEM) followed by n_o O-MMAs (N = 256, MN-major B, D = O accumulator, A = the S buffer: half of them f16,
 // half f8f6f4 when mix_f8).  stream != 0: every instruction reads a different B tile (5 distinct 16 KB windows) instead
 // of the same one.  Prints cycles per tile.
-template <int n_s, int N_s, int n_o, int mix_f8, int stream>
+template <int n_s, int N_s, int n_o, int mix_f8, int stream, int MP = 256>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mix_kernel(int tiles, int rnd, int commits, const uint8_t* fill_src, int fill_bytes, long long* out_cycles) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -163,8 +163,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mix_kernel(i
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t idesc_s = make_idesc(256, N_s, 0, 0, 0, 0);
-  const uint32_t idesc_o = make_idesc(256, 256, 0, 0, 0, 1);
+  // MP = 256: each CTA holds 128 rows (the production kernels); MP = 128: the "2x2" layout, 64 rows per CTA, the shape that
+  // would keep 64 queries x 512 channels in 256 TMEM columns (S computed once for all channels)
+  const uint32_t idesc_s = make_idesc(MP, N_s, 0, 0, 0, 0);
+  const uint32_t idesc_o = make_idesc(MP, 256, 0, 0, 0, 1);
   const uint32_t b_smem = smem_u32(smem + 65536);
   // background fill (both CTAs): warp 1 streams fill_bytes-sized bulk copies from global memory into the unused A region
   // of shared memory, back to back, while the MMA loop runs - the TMA fills of the production kernels
@@ -233,13 +235,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mix_kernel(i
   if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
-template <int n_s, int N_s, int n_o, int mix_f8, int stream>
+template <int n_s, int N_s, int n_o, int mix_f8, int stream, int MP = 256>
 void run_mix(const char* name, int rnd = 0, int commits = 0, int fill_bytes = 0) {
   long long* d;
   cudaMalloc(&d, 8);
   const int tiles = getenv("MIX_TILES") ? atoi(getenv("MIX_TILES")) : 256, smem = 160 * 1024 + 2048;
   const int launches = getenv("MIX_LAUNCHES") ? atoi(getenv("MIX_LAUNCHES")) : 2;
-  auto k = mix_kernel<n_s, N_s, n_o, mix_f8, stream>;
+  auto k = mix_kernel<n_s, N_s, n_o, mix_f8, stream, MP>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   static uint8_t* fsrc = nullptr;
   if (!fsrc) { cudaMalloc(&fsrc, 148 * 65536 + 65536); cudaMemset(fsrc, 1, 148 * 65536 + 65536); }
@@ -280,6 +282,17 @@ void run(const char* name, int N, int bmn, int same_b = 0) {
 }
 
 int main(int argc, char** argv) {
+  if (argc > 1 && argv[1][0] == 'h') {   // the M = 128 cta_group::2 (2x2 layout) question: do 16-clk S-MMAs hide behind the O-MMAs?
+    run_mix<24, 64, 8, 1, 1>("M=256: 24 S + 8 O (today)", 1, 3);
+    run_mix<24, 64, 16, 1, 1, 128>("M=128: 24 S + 16 O", 1, 3);
+    run_mix<24, 64, 16, 1, 1, 128>("M=128: 24 S + 16 O, 0 commits", 1, 0);
+    run_mix<24, 64, 0, 0, 1, 128>("M=128: S only", 1);
+    run_mix<0, 64, 16, 1, 1, 128>("M=128: O only", 1);
+    run_mix<24, 128, 32, 1, 1, 128>("M=128: 24 S(N=128) + 32 O", 1, 3);
+    run_mix<12, 128, 16, 1, 1, 128>("M=128: 12 S(N=128) + 16 O", 1, 3);
+    run_mix<24, 64, 16, 1, 1, 128>("M=128 + fills 16K", 1, 3, 16384);
+    return 0;
+  }
   if (argc > 1) {   // phase-B-shaped mixes only
     run_mix<24, 64, 8, 1, 1>("64: 3 commits+fences", 1, 13);
     run_mix<24, 64, 8, 1, 1>("64: 3 commits+try_wait", 1, 23);
