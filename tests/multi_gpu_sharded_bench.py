@@ -192,6 +192,23 @@ def bench_4k(dev, rank, world, budget, reps):
         res['max_abs_sharded_vs_single_read'] = (outs['peer'] - ref).abs().max().item()
         assert res['max_abs_sharded_vs_single_read'] <= 2e-4, res['max_abs_sharded_vs_single_read']
         res['read_speedup_vs_single_gpu'] = res['ms_read_single_gpu'] / res['ms_read_peer']
+        # the same update (every candidate new, bank at capacity -> LFU eviction) on the single-GPU bank
+        gq = torch.Generator(device=dev).manual_seed(7)
+        torch.randn(1, 128, hw, generator=gq, device=dev); torch.randn(1, 512, hw, generator=gq, device=dev)   # q_in, q_out
+        pk1 = [torch.randn(128, hw, generator=gq, device=dev) * synth.S_K for _ in range(2)]
+        pv1 = [torch.randn(512, hw, generator=gq, device=dev) for _ in range(2)]
+        st0 = ([full.keys[c].clone() for c in range(2)], [full.values[c].clone() for c in range(2)],
+               [full.info[c].clone() for c in range(2)])
+        full.update(pk1, pv1, frame)                    # untimed: allocations
+        full.load_state(*st0)
+        torch.cuda.synchronize()
+        a = ev()
+        full.update(pk1, pv1, frame)
+        b = ev()
+        torch.cuda.synchronize()
+        res['ms_update_single_gpu'] = a.elapsed_time(b)
+        res['update_single_gpu_bank_after'] = [full.bank_n(c) for c in range(2)]
+        res['update_speedup_vs_single_gpu'] = res['ms_update_single_gpu'] / res['ms_update_peer']
         res['algorithmic_tflops_read_sharded'] = 1280.0 * class_budget * hw * 2 / (res['ms_read_peer'] * 1e-3) / 1e12
     dist.barrier()
     return res
