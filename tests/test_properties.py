@@ -11,8 +11,10 @@ from hypothesis import HealthCheck, given, settings, strategies as st
 
 from oracle import afb_oracle as O
 
-CPU = settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow])
-GPU = settings(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+# derandomize: the examples are a fixed function of the test, so a run here and a run on the GPU box see the same cases
+CPU = settings(max_examples=40, deadline=None, derandomize=True, database=None, suppress_health_check=[HealthCheck.too_slow])
+GPU = settings(max_examples=16, deadline=None, derandomize=True, database=None,
+               suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
 
 
 def _bank(seed, n, d_k=16, d_v=24, scale=1.58):
