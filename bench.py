@@ -676,6 +676,11 @@ def main_ours(args, rank, world, local_rank):
                           'the timed region itself carries no per-kernel events',
                 'ms_per_step_profiled': ms_prof / args.steps,
                 'algorithmic_flop_per_launch': wb / nb if nb else None,
+                # executed MMA work per algorithmic unit of this kernel: per 128 queries x 64 slots x 256 channels it issues
+                # 3 S passes (24 x 32 clk) + f16 and two f8 readout products (8 x 128 clk) = 1792 MMA-clk for 512 algorithmic
+                # (O only; S is credited to phase A).  Reported next to `frac`, never instead of it.
+                'executed_mma': {'ratio_to_algorithmic': 1792.0 / 512.0, 'achieved': ach * 1792.0 / 512.0, 'unit': 'TFLOP/s bf16-equivalent',
+                                 'frac': (ach * 1792.0 / 512.0) / tf_peak if tf_peak else None},
                 'read_total': {'achieved': ((wa + wb) / ((msa + msb) * 1e-3) / 1e12) if msa + msb > 0 else 0.0,
                                'phase_a_avg_ms': msa / na if na else None, 'unit': 'TFLOP/s'}}
     extra = {}
