@@ -7,6 +7,8 @@
 // The host brackets each kernel with a cross-GPU barrier (producers done / consumers done).
 #include "vfn_common.cuh"
 
+#include <algorithm>
+
 namespace vfn {
 
 constexpr int PEER_MAX = 16;

@@ -179,11 +179,6 @@ class PeerExchange:
         for name, nbytes in (('ml', obj_n * hw * 8), ('po', obj_n * d_val * hw * 4), ('pair', obj_n * hw * 16)):
             self.off[name] = (total, nbytes)
             total += al(nbytes)
-        if hasattr(symm, 'enable_symm_mem_for_group'):
-            try:
-                symm.enable_symm_mem_for_group(self.group.group_name)
-            except Exception:
-                pass
         self.buf = symm.empty(total, dtype=torch.uint8, device=self.device)
         self.hdl = symm.rendezvous(self.buf, self.group)
         base = [int(p) for p in self.hdl.buffer_ptrs]
