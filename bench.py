@@ -885,6 +885,52 @@ def main_model_clip(args, rank, world, local_rank):
         del gm
     except Exception as e:                                                                # reported, never hidden
         graphed = {'value': None, 'error': f'{type(e).__name__}: {e}'[:300]}
+    # the same weights with vfloodnet_b200.fuse_model on top (segment glue without per-object copies, the
+    # Refine skip branches once per frame, KeyValue head on the tcgen05 implicit GEMM writing bank / query layout),
+    # eager and with the convolution stages as CUDA graphs
+    fused = None
+    try:
+        model_fused = vfn.fuse_model(MC.patched_copy(model_ref, vfn))
+
+        def leg(model, frames, host=False):
+            run = lambda: MC.run_clip(model, vfn.FeatureBank, frames, dev, budget=BUDGET, keep_masks=False,
+                                      frames_on_host=host)
+            for _ in range(2):
+                run()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = None
+            for _ in range(args.steps):
+                r = None
+                r = run()
+            b.record()
+            torch.cuda.synchronize()
+            return args.frames * args.steps / (a.elapsed_time(b) / 1e3), [r['fb'].bank_n(c) for c in range(2)]
+
+        f_eager, f_n = leg(model_fused, dev_clip)
+        tmf = MC.StageTimer(dev)
+        hooks = MC.instrument(model_fused, tmf)
+        try:
+            MC.run_clip(model_fused, vfn.FeatureBank, dev_clip, dev, budget=BUDGET, keep_masks=False, timer=tmf)
+        finally:
+            for h in hooks:
+                h.remove()
+        tot_f = tmf.totals()
+        tot_f['urr'] = tot_ours['urr']
+        gmf = vfn.GraphedAFBURR(model_fused, tuple(dev_clip[0].shape))
+        f_graph, fg_n = leg(gmf, dev_clip)
+        f_graph_e2e, _ = leg(gmf, host_clip, host=True)
+        kv = model_fused.keyval_r4
+        fused = {'value': f_eager, 'unit': 'frames/s', 'graphed': f_graph, 'graphed_e2e': f_graph_e2e,
+                 'final_bank_slots': f_n, 'final_bank_slots_graphed': fg_n,
+                 'stages_ms_per_frame': _stage_table(tot_f, args.frames), 'keyvalue_passes': kv.passes,
+                 'note': 'fuse_model: Refine skip branches evaluated once per frame (not per object), r1 / r2 / r3 never '
+                         'expanded, KeyValue as one fp32-grade tcgen05 implicit GEMM (3 passes of fp16 hi/lo operands) '
+                         'handing keys / values over entry-major'}
+        del gmf, model_fused
+    except Exception as e:                                                                # reported, never hidden
+        fused = {'value': None, 'error': f'{type(e).__name__}: {e}'[:300]}
     # the unmodified reference on the same GPU: same weights, same clip
     torch.backends.cuda.matmul.allow_tf32 = False
     clip_ref(dev_clip[:4], keep_masks=False)
@@ -919,7 +965,7 @@ def main_model_clip(args, rank, world, local_rank):
                     'h2d_bytes_per_step': (args.frames + 1) * frame_bytes,
                     'd2h_bytes_per_step': args.frames * host_clip[1].shape[-1] * host_clip[1].shape[-2]},
             'gpu_launches': int(launches), 'stages_ms_per_frame': st_ours,
-            'stages_pass_wall_ms_per_frame': stage_wall, 'graphed_convolutions': graphed,
+            'stages_pass_wall_ms_per_frame': stage_wall, 'graphed_convolutions': graphed, 'fused_glue': fused,
             'reference_gpu': {'value': args.frames / (ms_ref / 1e3), 'unit': 'frames/s', 'kind': 'reference',
                               'sample': 'unmodified reference AFB_URR + FeatureBank (baseline/_ref), torch CUDA ops on '
                                         'the same GPU, same weights, same clip, free-running',

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VFN_VERSION 101
+#define VFN_VERSION 102
 
 #define VFN_OK 0
 #define VFN_E_ARG (-1)       /* bad argument / unsupported shape */
@@ -98,7 +98,10 @@ int vfn_bank_refresh(const vfn_bank* bank, int64_t first, int64_t count, void* s
  * out: (obj_n, 2*d_val, hw) fp32 = [softmax_i(K_i.q_j/sqrt(d_key)) readout ; q_out] per object
  * (== reference (1,obj_n,1024,HW), bs=1).  If update_bank: info[:,1] += log(cnt+1) with
  * cnt_i = #{j : p_ij > thres_valid} (AFB_URR.py:161-174).  d_lse (obj_n, hw) optional: natural-log LSE.
- * impl: 0 = auto (tcgen05 when shapes allow), 1 = fp32 SIMT kernels, 2 = tcgen05 kernels. */
+ * impl: bits 0-7: 0 = auto (tcgen05 when shapes allow), 1 = fp32 SIMT kernels, 2 = tcgen05 kernels;
+ *       bit 8 (VFN_Q_IN_EM): d_q_in_dm points to an ENTRY-MAJOR (hw, d_key) query tensor - what vfn_keyvalue writes -
+ *       instead of the reference's (d_key, hw); the transpose of the query preparation is skipped (same values). */
+#define VFN_Q_IN_EM 0x100
 size_t vfn_memread_workspace_bytes(int32_t obj_n, int64_t n_max, int64_t hw, int32_t d_key, int32_t d_val);
 int vfn_memread(const vfn_bank* banks, int32_t obj_n, const float* d_q_in_dm, const float* d_q_out_dm, int64_t hw,
                 float thres_valid, int32_t update_bank, float* d_out, float* d_lse, void* d_ws, size_t ws_bytes,
@@ -197,7 +200,7 @@ int vfn_bank_clamp_info(const vfn_bank* bank, int64_t n, void* stream);
  * io[c].d_* are caller-owned device buffers of hw (run_off: hw + 1) elements holding the decisions of this update. */
 typedef struct vfn_update_io {
   const float* d_prev_key_dm;    /* (d_key, hw) candidate keys    (memorize() output, AFB_URR.py:255-272) */
-  const float* d_prev_value_dm;  /* (d_val, hw) candidate values */
+  const float* d_prev_value_dm;  /* (d_val, hw) candidate values; both are (hw, d) when prev_layout == 1 */
   int32_t* d_match_idx;          /* (hw) j*            */
   float* d_match_corr;           /* (hw) c*            */
   int32_t* d_merge_q;            /* (hw) merge pairs sorted by (slot, q) */
@@ -213,7 +216,8 @@ typedef struct vfn_update_io {
   int32_t thresholds[64];        /* T sequence of remove(): the first min(n_iter, 64) thresholds */
   int64_t n_before;              /* bank size before this update */
   int32_t deferred;              /* 1: counts not read back yet - call vfn_bank_update_finish() after the event */
-  int32_t reserved;
+  int32_t prev_layout;           /* input: 0 = d_prev_* are (d, hw) dimension-major (the reference's memorize() output),
+                                  * 1 = (hw, d) entry-major (vfn_keyvalue's *_em outputs: no transpose in the preparation) */
 } vfn_update_io;
 
 size_t vfn_bank_update_workspace_bytes(int32_t obj_n, int64_t n_max, int64_t hw, int32_t d_key, int32_t d_val);
@@ -233,6 +237,25 @@ int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_i
  * (banks with n_live: sets n = n_min = the exact live count the plan kernel staged, so any number of deferred updates
  * may be in flight and only the last one is finished). */
 int vfn_bank_update_finish(vfn_bank* banks, int32_t obj_n, vfn_update_io* io, const int32_t* h_pinned);
+
+/* ---- KeyValue head: KeyValue.forward (AFB_URR.py:94-111), SURVEY 8(f) n3 ---------------------------------------
+ * Key = conv3x3(x, wk (d_key, c_in, 3, 3)) + bk, Value = conv3x3(x, wv (d_val, c_in, 3, 3)) + bv, stride 1, zero
+ * padding 1, on x (B, c_in, h, w) fp32 (r4 of EncoderQ / EncoderM), as one tcgen05 implicit GEMM.
+ * pack_weights (once per model; again after the weights change): fp16 hi/lo operand arrays [tap][n][c] + bias into
+ *   d_packed (vfn_kv_packed_weights_bytes); bk / bv may be NULL.
+ * keyvalue: any of the four outputs may be NULL.  *_em (B, h*w, d) entry-major = the layout of the read's query
+ *   operand (vfn_memread with VFN_Q_IN_EM) and of the update's candidate rows (vfn_update_io.prev_layout = 1);
+ *   *_dm (B, d, h*w) = the reference's `key.view(*key.shape[:2], -1)` (AFB_URR.py:105-109).
+ *   passes: 3 = fp16 hi/lo splits of both operands, hi*hi + lo*hi + hi*lo, fp32 accumulate (the result of a true-fp32
+ *   convolution up to summation order); 1 = hi*hi only (11-bit operands: the class of cuDNN's TF32 default).
+ * Shapes: c_in % 64 == 0, d_key % 32 == 0, d_val % 32 == 0, (d_key + d_val) % 320 == 0 (128 + 512 of AFB_URR.py:250). */
+size_t vfn_kv_packed_weights_bytes(int32_t c_in, int32_t d_key, int32_t d_val);
+int vfn_kv_pack_weights(const float* d_wk, const float* d_bk, const float* d_wv, const float* d_bv, int32_t c_in,
+                        int32_t d_key, int32_t d_val, void* d_packed, void* stream);
+size_t vfn_keyvalue_workspace_bytes(int32_t B, int32_t c_in, int32_t h, int32_t w, int32_t d_key, int32_t d_val);
+int vfn_keyvalue(const float* d_x, int32_t B, int32_t c_in, int32_t h, int32_t w, const void* d_packed, int32_t d_key,
+                 int32_t d_val, int32_t passes, float* d_key_em, float* d_val_em, float* d_key_dm, float* d_val_dm,
+                 void* d_ws, size_t ws_bytes, void* stream);
 
 /* ---- URR: non-convolution parts of Decoder.forward (AFB_URR.py:214-237, myutils/data.py:42-48) -----
  * pre:  p (obj_n,2,h/2,w/2) coarse logits from pred2, r1 (obj_n or 1, c, h, w)  ->

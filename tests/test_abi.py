@@ -27,7 +27,7 @@ def test_header_declares_expected_entry_points():
 def test_library_loads_and_exports_every_declared_symbol():
     from vfloodnet_b200 import _lib
     lib = _lib.load()
-    assert lib.vfn_version() == 101
+    assert lib.vfn_version() == 102
     raw = ctypes.CDLL(_lib.LIB_PATH)
     for name in header_functions():
         assert hasattr(raw, name), f'{name} declared in include/vfn.h but not exported'

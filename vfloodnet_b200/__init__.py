@@ -5,6 +5,8 @@ Public surface mirrors the reference operator API for this path:
     Matcher      (video_module/model/AFB_URR.py:130-178)
     urr_pre / urr_post / decoder_forward / patch_model   (AFB_URR.py:208-239)
     GraphedAFBURR (memorize / segment of AFB_URR.py:255-318 with the convolution stages as CUDA graphs)
+    KeyValueHead  (KeyValue, AFB_URR.py:94-111, as a tcgen05 implicit GEMM writing bank / query layout)
+    fuse_model    (segment glue without per-object copies, AFB_URR.py:287-297, + KeyValueHead)
 Everything computes in libvfn_sm100a.so (include/vfn.h); importing this package without the built library, or
 calling it without a CUDA device, fails loudly - there is no CPU fallback.
 """
@@ -12,5 +14,8 @@ from .feature_bank import FeatureBank
 from .matcher import Matcher
 from .urr import urr_pre, urr_post, decoder_forward, patch_model
 from .graphed import GraphedAFBURR
+from .keyvalue import KeyValueHead
+from .glue import fuse_model, segment_fused
 
-__all__ = ['FeatureBank', 'Matcher', 'urr_pre', 'urr_post', 'decoder_forward', 'patch_model', 'GraphedAFBURR']
+__all__ = ['FeatureBank', 'Matcher', 'urr_pre', 'urr_post', 'decoder_forward', 'patch_model', 'GraphedAFBURR',
+           'KeyValueHead', 'fuse_model', 'segment_fused']

@@ -25,7 +25,7 @@ class VfnUpdateIO(C.Structure):
                 ('d_merge_q', c_vp), ('d_merge_slot', c_vp), ('d_run_off', c_vp), ('d_append_q', c_vp),
                 ('n_merge', c_i32), ('n_runs', c_i32), ('n_append', c_i32), ('evicted', c_i32), ('swapped', c_i32),
                 ('evict_status', c_i32), ('kept', c_i32), ('n_iter', c_i32), ('thresholds', c_i32 * 64),
-                ('n_before', c_i64), ('deferred', c_i32), ('reserved', c_i32)]
+                ('n_before', c_i64), ('deferred', c_i32), ('prev_layout', c_i32)]
 
 
 BANK_P = C.POINTER(VfnBank)
@@ -65,6 +65,11 @@ SIGNATURES = {
     'vfn_bank_update': (c_i32, [BANK_P, BANK_P, c_i32, IO_P, c_i64, c_f32, c_f32, c_f32, c_f64, c_vp, c_sz, c_vp,
                                 c_i32, c_vp, c_vp]),
     'vfn_bank_update_finish': (c_i32, [BANK_P, c_i32, IO_P, c_vp]),
+    'vfn_kv_packed_weights_bytes': (c_sz, [c_i32, c_i32, c_i32]),
+    'vfn_kv_pack_weights': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    'vfn_keyvalue_workspace_bytes': (c_sz, [c_i32, c_i32, c_i32, c_i32, c_i32, c_i32]),
+    'vfn_keyvalue': (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp,
+                             c_vp, c_sz, c_vp]),
     'vfn_urr_pre': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vfn_urr_post': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     'vfn_tail_workspace_bytes': (c_sz, [c_i32, c_i32]),
@@ -86,7 +91,8 @@ SIGNATURES = {
 }
 
 _lib = None
-VFN_VERSION = 101      # include/vfn.h
+VFN_VERSION = 102      # include/vfn.h
+VFN_Q_IN_EM = 0x100    # vfn_memread impl bit 8: q_in is entry-major
 
 
 class VfnError(RuntimeError):
@@ -134,6 +140,15 @@ def check(rc: int, what: str = ''):
 def ptr(t):
     """device/host pointer of a torch tensor (None -> NULL)"""
     return None if t is None else t.data_ptr()
+
+
+def em_backed(t) -> bool:
+    """True for a (d, n) fp32 tensor that is the transposed VIEW of contiguous (n, d) entry-major storage - what
+    vfloodnet_b200.KeyValueHead hands out in place of the reference's (d, n) KeyValue outputs.  The library then reads
+    the rows as they lie (VFN_Q_IN_EM / vfn_update_io.prev_layout) instead of transposing a contiguous copy."""
+    import torch
+    return (t.dim() == 2 and t.dtype == torch.float32 and t.shape[0] > 1 and t.shape[1] > 1 and
+            t.stride(0) == 1 and t.stride(1) == t.shape[0])
 
 
 def stream_ptr(device=None):

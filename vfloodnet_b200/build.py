@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libvfn_sm100a.so')
-SOURCES = ['vfn_bank.cu', 'vfn_simt.cu', 'vfn_tc.cu', 'vfn_urr.cu', 'vfn_update.cu', 'vfn_tail.cu', 'vfn_peer.cu']
+SOURCES = ['vfn_bank.cu', 'vfn_simt.cu', 'vfn_tc.cu', 'vfn_urr.cu', 'vfn_update.cu', 'vfn_tail.cu', 'vfn_peer.cu', 'vfn_kv.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 

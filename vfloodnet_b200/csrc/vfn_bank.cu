@@ -54,7 +54,8 @@ void prof_end(int kind, cudaStream_t st, double work) {
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------------------------------------
-// prep_rows: (d, n) dimension-major  ->  (n, d) entry-major raw / L2-normalised / fp16 hi+lo.
+// prep_rows: (d, n) dimension-major [or (n, d) entry-major when src_em]  ->  (n, d) entry-major raw / L2-normalised /
+// fp16 hi+lo.
 // One launch serves several independent jobs (blockIdx.y): all candidate tensors of a frame in one go.
 // hi/lo receive the split of raw*scale, or of normalised*scale when `split_normed` is set.
 // ------------------------------------------------------------------------------------------------
@@ -81,10 +82,11 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const __grid_constant__ 
   if (q0 >= n || (int)blockIdx.z * chunk >= d) return;
   const int64_t q = q0 + tx;
   if (jb.normed || jb.split_normed) {
+    // same summation order for both source layouts (8 strided partial sums per row, then their sum in order)
     float ss = 0.f;
     if (q < n)
       for (int k = ty; k < d; k += 8) {
-        float v = src[(int64_t)k * n + q];
+        float v = jb.src_em ? src[q * d + k] : src[(int64_t)k * n + q];
         ss = fmaf(v, v, ss);
       }
     part[ty][tx] = ss;
@@ -101,9 +103,18 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const __grid_constant__ 
   // 512-channel job spreads over four times as many CTAs as a 128-channel one
   const int k_end = min(d, (int)(blockIdx.z + 1) * chunk);
   for (int k0 = blockIdx.z * chunk; k0 < k_end; k0 += 32) {
-    for (int r = ty; r < 32; r += 8) {
-      int k = k0 + r;
-      tile[r][tx] = (k < d && q < n) ? src[(int64_t)k * n + q] : 0.f;
+    if (jb.src_em) {
+      // entry-major source (vfn_keyvalue's output): rows are already contiguous in k; the tile is filled transposed
+      for (int r = ty; r < 32; r += 8) {
+        const int64_t qq = q0 + r;
+        const int k = k0 + tx;
+        tile[tx][r] = (k < d && qq < n) ? src[qq * d + k] : 0.f;
+      }
+    } else {
+      for (int r = ty; r < 32; r += 8) {
+        int k = k0 + r;
+        tile[r][tx] = (k < d && q < n) ? src[(int64_t)k * n + q] : 0.f;
+      }
     }
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {

@@ -16,7 +16,7 @@ void set_error(const char* fmt, ...);
 
 // measurement hooks (vfn_profile_* in include/vfn.h): CUDA events on the launching stream around selected kernels
 enum ProfKind { PROF_READ_A = 0, PROF_READ_B = 1, PROF_MATCH = 2, PROF_COMPACT = 3, PROF_MERGE = 4, PROF_APPEND = 5,
-                PROF_URR = 6, PROF_KINDS = 8 };
+                PROF_URR = 6, PROF_KV = 7, PROF_KINDS = 8 };
 void prof_begin(int kind, cudaStream_t st);
 void prof_end(int kind, cudaStream_t st, double work);
 void count_launches(int n);
@@ -25,6 +25,7 @@ void count_launches(int n);
 struct PrepJob {
   const float* src; int d; int64_t n;
   float* raw; float* normed; uint16_t* hi; uint16_t* lo; float scale; int split_normed;
+  int src_em;      // 0: src is (d, n) dimension-major (the reference's layout); 1: src is already (n, d) entry-major
 };
 int launch_prep(const PrepJob* jobs, int n_jobs, cudaStream_t st);
 

@@ -509,14 +509,17 @@ static int check_banks(const vfn_bank* banks, int obj_n, int64_t* n_max, BankSet
   return VFN_OK;
 }
 
-static int run_phase_a(const BankSet& set, ReadPlan& p, const float* q_in_dm, char* ws, cudaStream_t st) {
+static int run_phase_a(const BankSet& set, ReadPlan& p, const float* q_in_dm, char* ws, cudaStream_t st, int q_em = 0) {
   float* Q = reinterpret_cast<float*>(ws + p.off_q);
   float2* part = reinterpret_cast<float2*>(ws + p.off_part);
-  if (p.tc) return tc_phase_a(set.b, p.obj_n, q_in_dm, p.hw, p.split_a, part, ws + p.off_tc, st, &p.split_a, &p.dev_a);
+  if (p.tc) return tc_phase_a(set.b, p.obj_n, q_in_dm, p.hw, p.split_a, part, ws + p.off_tc, st, &p.split_a, &p.dev_a, q_em);
   for (int o = 0; o < p.obj_n; ++o)
     VFN_CHECK_ARG(!set.b[o].n_live || set.b[o].n_min == set.b[o].n,
                   "the fp32 SIMT read needs exact bank sizes (bank %d was passed with bounds)", o);
-  if (int rc = vfn_prep_rows(q_in_dm, p.d_key, p.hw, Q, nullptr, nullptr, nullptr, 1.f, st)) return rc;
+  {
+    PrepJob jb{q_in_dm, p.d_key, p.hw, Q, nullptr, nullptr, nullptr, 1.f, 0, q_em};
+    if (int rc = launch_prep(&jb, 1, st)) return rc;
+  }
   dim3 grid(p.q_tiles, p.split_a, p.obj_n);
   double work = 0;
   for (int o = 0; o < p.obj_n; ++o) work += 2.0 * p.d_key * (double)set.b[o].n * (double)p.hw;
@@ -573,6 +576,8 @@ int vfn_memread_phase_a(const vfn_bank* banks, int32_t obj_n, const float* d_q_i
   int64_t n_max;
   if (int rc = check_banks(banks, obj_n, &n_max, &set)) return rc;
   VFN_CHECK_ARG(d_q_in_dm && d_ml && d_ws && hw > 0, "memread_phase_a: bad args");
+  const int q_em = (impl & VFN_Q_IN_EM) ? 1 : 0;
+  impl &= 0xff;
   if (impl == 2 && !tc_shapes_ok(set.b[0].d_key, set.b[0].d_val)) {
     set_error("tcgen05 read needs d_key=128, d_val=512");
     return VFN_E_UNSUPPORTED;
@@ -581,7 +586,7 @@ int vfn_memread_phase_a(const vfn_bank* banks, int32_t obj_n, const float* d_q_i
   if (ws_bytes < p.total) { set_error("memread: workspace %zu < %zu", ws_bytes, p.total); return VFN_E_CAPACITY; }
   cudaStream_t st = as_stream(stream);
   char* ws = reinterpret_cast<char*>(d_ws);
-  if (int rc = run_phase_a(set, p, d_q_in_dm, ws, st)) return rc;
+  if (int rc = run_phase_a(set, p, d_q_in_dm, ws, st, q_em)) return rc;
   const int64_t rows = hw * obj_n;
   ml_merge_kernel<<<(unsigned)cdiv(rows, 256), 256, 0, st>>>(reinterpret_cast<float2*>(ws + p.off_part), p.split_a,
                                                              p.dev_a, hw, obj_n, reinterpret_cast<float2*>(d_ml));
@@ -604,6 +609,7 @@ int vfn_memread_phase_b(const vfn_bank* banks, int32_t obj_n, const float* d_q_i
   int64_t n_max;
   if (int rc = check_banks(banks, obj_n, &n_max, &set)) return rc;
   VFN_CHECK_ARG(d_q_in_dm && d_lse && d_partial_out && d_ws && hw > 0, "memread_phase_b: bad args");
+  impl &= 0xff;
   ReadPlan p = make_read_plan(obj_n, n_max, hw, set.b[0].d_key, set.b[0].d_val, impl);
   if (ws_bytes < p.total) { set_error("memread: workspace %zu < %zu", ws_bytes, p.total); return VFN_E_CAPACITY; }
   cudaStream_t st = as_stream(stream);
@@ -628,6 +634,8 @@ int vfn_memread(const vfn_bank* banks, int32_t obj_n, const float* d_q_in_dm, co
   int64_t n_max;
   if (int rc = check_banks(banks, obj_n, &n_max, &set)) return rc;
   VFN_CHECK_ARG(d_q_in_dm && d_q_out_dm && d_out && d_ws && hw > 0, "memread: bad args");
+  const int q_em = (impl & VFN_Q_IN_EM) ? 1 : 0;
+  impl &= 0xff;
   if (impl == 2 && !tc_shapes_ok(set.b[0].d_key, set.b[0].d_val)) {
     set_error("tcgen05 read needs d_key=128, d_val=512");
     return VFN_E_UNSUPPORTED;
@@ -636,7 +644,7 @@ int vfn_memread(const vfn_bank* banks, int32_t obj_n, const float* d_q_in_dm, co
   if (ws_bytes < p.total) { set_error("memread: workspace %zu < %zu", ws_bytes, p.total); return VFN_E_CAPACITY; }
   cudaStream_t st = as_stream(stream);
   char* ws = reinterpret_cast<char*>(d_ws);
-  if (int rc = run_phase_a(set, p, d_q_in_dm, ws, st)) return rc;
+  if (int rc = run_phase_a(set, p, d_q_in_dm, ws, st, q_em)) return rc;
   float* lse = reinterpret_cast<float*>(ws + p.off_lse);
   const int64_t rows = hw * obj_n;
   launch_pdl(lse_combine_kernel, dim3((unsigned)cdiv(rows, 256)), dim3(256), 0, st,

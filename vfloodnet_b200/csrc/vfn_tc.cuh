@@ -12,8 +12,9 @@ size_t tc_workspace_bytes(int obj_n, int64_t hw);
 // split_a / split_b are the workspace bounds; the number of pieces actually used comes back in *pieces_out and is the
 // n_split the combine kernels must use - unless the banks carry device-resident live counts (vfn_bank::n_live): then
 // the split is chosen on the device from the live sizes and *pieces_dev_out points to it (NULL otherwise).
+// q_em != 0: q_in is (hw, d_key) entry-major (vfn_keyvalue's output) instead of (d_key, hw)
 int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t hw, int split_a, float2* part,
-               char* ws_tc, cudaStream_t st, int* pieces_out, const int32_t** pieces_dev_out);
+               char* ws_tc, cudaStream_t st, int* pieces_out, const int32_t** pieces_dev_out, int q_em = 0);
 // phase B: partial readouts po[((obj*split_b + s)*d_val + c)*hw + j] and usage counts into bank.cnt
 int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const float* lse, float thres_valid,
                int update_bank, float* po, char* ws_tc, cudaStream_t st, int* pieces_out,

@@ -95,9 +95,10 @@ int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_i
   if (tc) VFN_CUDA_OK(cudaMemsetAsync(tc_match_cand_hi(mws, obj_n, hw, 0), 0,
                                       (size_t)((char*)tc_match_cand_lo(mws, obj_n, hw, obj_n) - (char*)tc_match_cand_hi(mws, obj_n, hw, 0)), st));
   for (int c = 0; c < obj_n; ++c) {
+    const int em = io[c].prev_layout == 1;      // (hw, d) candidates as vfn_keyvalue writes them: no transpose
     jobs[2 * c] = PrepJob{io[c].d_prev_key_dm, d_key, hw, CK(c), NCK(c), tc ? tc_match_cand_hi(mws, obj_n, hw, c) : nullptr,
-                          tc ? tc_match_cand_lo(mws, obj_n, hw, c) : nullptr, NK_SCALE, 1};
-    jobs[2 * c + 1] = PrepJob{io[c].d_prev_value_dm, d_val, hw, CV(c), NCV(c), nullptr, nullptr, 1.f, 0};
+                          tc ? tc_match_cand_lo(mws, obj_n, hw, c) : nullptr, NK_SCALE, 1, em};
+    jobs[2 * c + 1] = PrepJob{io[c].d_prev_value_dm, d_val, hw, CV(c), NCV(c), nullptr, nullptr, 1.f, 0, em};
   }
   if (int rc = launch_prep(jobs, 2 * obj_n, st)) return rc;
 

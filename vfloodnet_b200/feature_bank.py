@@ -19,7 +19,7 @@ import torch
 from . import _lib
 import functools
 
-from ._lib import VfnBank, VfnUpdateIO, check, on_device, ptr, stream_ptr
+from ._lib import VfnBank, VfnUpdateIO, check, em_backed, on_device, ptr, stream_ptr
 
 
 def _on_bank_device(fn):
@@ -333,8 +333,12 @@ class FeatureBank:
             update_rate = self.update_rate
         lib, st = self._lib, stream_ptr()
         obj_n = self.obj_n
-        pk = [prev_key[c].to(self.device, torch.float32).contiguous() for c in range(obj_n)]
-        pv = [prev_value[c].to(self.device, torch.float32).contiguous() for c in range(obj_n)]
+        pk = [prev_key[c].to(self.device, torch.float32) for c in range(obj_n)]
+        pv = [prev_value[c].to(self.device, torch.float32) for c in range(obj_n)]
+        # candidates handed over entry-major (transposed views of (HW, d) storage: KeyValueHead) are read as they lie
+        em = all(em_backed(x) for x in pk) and all(em_backed(x) for x in pv)
+        if not em:
+            pk, pv = [x.contiguous() for x in pk], [x.contiguous() for x in pv]
         d_key, hw = pk[0].shape
         d_val = pv[0].shape[0]
         for c in range(obj_n):
@@ -373,6 +377,7 @@ class FeatureBank:
                      append_q=self._buf(f'append_q{c}', (hw,), torch.int32))
             dec.append(d)
             io[c].d_prev_key_dm, io[c].d_prev_value_dm = ptr(pk[c]), ptr(pv[c])
+            io[c].prev_layout = 1 if em else 0
             io[c].d_match_idx, io[c].d_match_corr = ptr(d['match_idx']), ptr(d['match_corr'])
             io[c].d_merge_q, io[c].d_merge_slot = ptr(d['merge_q']), ptr(d['merge_slot'])
             io[c].d_run_off, io[c].d_append_q = ptr(d['run_off']), ptr(d['append_q'])

@@ -20,6 +20,7 @@ from __future__ import annotations
 import torch
 from torch.nn import functional as NF
 
+from .glue import decoder_trunk_shared, refine_skip
 from .urr import urr_post, urr_pre
 
 
@@ -33,10 +34,13 @@ def _pad16(x):
 
 
 class GraphedAFBURR:
-    def __init__(self, model, frame_shape, obj_n: int = 2, warmup: int = 3):
+    def __init__(self, model, frame_shape, obj_n: int = 2, warmup: int = 3, fused=None):
         """model: a reference AFB_URR (eval mode, on a CUDA device) with vfloodnet_b200.patch_model applied.
-        frame_shape: (1, 3, H, W) of the frames the loop will feed (test_video_seg.py:107 after the resize)."""
+        frame_shape: (1, 3, H, W) of the frames the loop will feed (test_video_seg.py:107 after the resize).
+        fused: capture the copy-free glue of vfloodnet_b200.glue (Refine skip branches once per frame, inside the
+        encoder graph); default: whatever the model runs eagerly (fuse_model applied or not)."""
         self.model, self.obj_n = model, obj_n
+        self.fused = ('_vfn_ref_segment' in model.__dict__) if fused is None else bool(fused)
         dev = next(model.parameters()).device
         if dev.type != 'cuda':
             raise RuntimeError('GraphedAFBURR needs the model on a CUDA device')
@@ -55,10 +59,15 @@ class GraphedAFBURR:
         f, pad = _pad16(self.frame)
         r4, r3, r2, r1 = self.model.encoder_q(f)
         k4, v4 = self.model.keyval_r4(r4)
-        return k4, v4, r3, r2, r1, pad
+        if self.fused:      # the object-independent halves of the two Refine blocks (AFB_URR.py:121) belong to the frame
+            d = self.model.decoder
+            r3, r2 = refine_skip(d.RF3, r3), refine_skip(d.RF2, r2)
+        return k4, v4, r3, r2, r1, pad, tuple(r4.shape[-2:])
 
     def _dec(self):
         d, n = self.model.decoder, self.obj_n
+        if self.fused:
+            return decoder_trunk_shared(d, self.res_global, self.r3, self.r2)
         r3 = self.r3.unsqueeze(1).expand(-1, n, -1, -1, -1).reshape(n, *self.r3.shape[1:])      # AFB_URR.py:291-292
         r2 = self.r2.unsqueeze(1).expand(-1, n, -1, -1, -1).reshape(n, *self.r2.shape[1:])
         p = d.ResMM(d.convFM(self.res_global))
@@ -72,8 +81,9 @@ class GraphedAFBURR:
         return d.local_pred2(NF.relu(q))
 
     def _mem(self):
-        k4, v4 = self.model.memorize(self.frame, self.mask)
-        return torch.stack(k4), torch.stack(v4)
+        # lists of per-object (d, HW) tensors, as the model returns them: views of the graph's own output buffers (with
+        # KeyValueHead: transposed views of entry-major storage, which FeatureBank.update reads as it lies)
+        return self.model.memorize(self.frame, self.mask)
 
     def _graph(self, fn, warmup):
         s = torch.cuda.Stream(self.device)
@@ -89,9 +99,9 @@ class GraphedAFBURR:
 
     def _capture(self, warmup):
         with torch.cuda.device(self.device):
-            self.g_enc, (self.k4, self.v4, self.r3, self.r2, self.r1, self.pad) = self._graph(self._enc, warmup)
+            self.g_enc, (self.k4, self.v4, self.r3, self.r2, self.r1, self.pad, self.grid4) = \
+                self._graph(self._enc, warmup)       # fused: r3 / r2 hold the Refine skip branches; grid4 = r4 grid
             n = self.obj_n
-            self.grid4 = (self.r3.shape[2] // 2, self.r3.shape[3] // 2)               # r4 grid (stride 16)
             self.res_global = torch.zeros((n, 2 * self.v4.shape[1]) + self.grid4, device=self.device)
             self.g_dec, self.p = self._graph(self._dec, warmup)
             c1, h1, w1 = self.r1.shape[1:]
@@ -119,7 +129,7 @@ class GraphedAFBURR:
             self.frame.copy_(frame, non_blocking=True)
         self.mask.copy_(mask, non_blocking=True)
         self.g_mem.replay()
-        return [self.mk4[i] for i in range(self.obj_n)], [self.mv4[i] for i in range(self.obj_n)]
+        return list(self.mk4), list(self.mv4)
 
     @torch.no_grad()
     def segment(self, frame, fb_global):

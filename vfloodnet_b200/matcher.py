@@ -10,7 +10,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from ._lib import check, on_device, ptr, stream_ptr
+from ._lib import VFN_Q_IN_EM, check, em_backed, on_device, ptr, stream_ptr
 from .feature_bank import FeatureBank
 
 
@@ -47,7 +47,10 @@ class Matcher(nn.Module):
         lib = _lib.load()
         if q_in.dim() != 3 or q_in.shape[0] != 1:
             raise ValueError('inference read expects q_in of shape (1, d_key, HW)')   # bs>1 is training only
-        q_in = q_in.to(fb.device, torch.float32).contiguous()
+        q_in = q_in.to(fb.device, torch.float32)
+        q_em = em_backed(q_in[0])          # entry-major storage behind the (1, d_key, HW) shape (KeyValueHead): no copy
+        if not q_em:
+            q_in = q_in.contiguous()
         q_out = q_out.to(fb.device, torch.float32).contiguous()
         _, d_key, hw = q_in.shape
         d_val = q_out.shape[1]
@@ -58,7 +61,8 @@ class Matcher(nn.Module):
         # the tcgen05 read takes the live bank sizes from device memory: updates still in flight need not be finished
         banks = fb.bank_array(bounds_ok=True, impl=int(impl))
         check(lib.vfn_memread(banks, fb.obj_n, ptr(q_in), ptr(q_out), hw, float(self.thres_valid),
-                              int(bool(self.update_bank)), ptr(out), ptr(lse), ptr(ws), ws.numel(), int(impl),
+                              int(bool(self.update_bank)), ptr(out), ptr(lse), ptr(ws), ws.numel(),
+                              int(impl) | (VFN_Q_IN_EM if q_em else 0),
                               stream_ptr()), 'vfn_memread')
         self.last_lse = lse
         self.launches += 6 + (1 if self.update_bank else 0)
