@@ -890,7 +890,7 @@ def main_model_clip(args, rank, world, local_rank):
     # eager and with the convolution stages as CUDA graphs
     fused = None
     try:
-        model_fused = vfn.fuse_model(MC.patched_copy(model_ref, vfn))
+        model_fused = vfn.fuse_model(MC.patched_copy(model_ref, vfn), fold_bn=True)
 
         def leg(model, frames, host=False):
             run = lambda: MC.run_clip(model, vfn.FeatureBank, frames, dev, budget=BUDGET, keep_masks=False,
@@ -927,7 +927,8 @@ def main_model_clip(args, rank, world, local_rank):
                  'stages_ms_per_frame': _stage_table(tot_f, args.frames), 'keyvalue_passes': kv.passes,
                  'note': 'fuse_model: Refine skip branches evaluated once per frame (not per object), r1 / r2 / r3 never '
                          'expanded, KeyValue as one fp32-grade tcgen05 implicit GEMM (3 passes of fp16 hi/lo operands) '
-                         'handing keys / values over entry-major'}
+                         'handing keys / values over entry-major; encoders with BatchNorm folded and conv + bias + ReLU '
+                         '(+ add) as single cuDNN calls (n4)'}
         del gmf, model_fused
     except Exception as e:                                                                # reported, never hidden
         fused = {'value': None, 'error': f'{type(e).__name__}: {e}'[:300]}

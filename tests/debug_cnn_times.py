@@ -78,7 +78,15 @@ def main():
             res['decoder_trunk_shared_b2'] = time_fn(lambda: glue.decoder_trunk_shared(dec, rg, s3, s2), iters=10, warm=3)
             res['decoder_trunk_reference_b2'] = time_fn(
                 lambda: dec.pred2(torch.relu(dec.RF2(r2e, dec.RF3(r3e, dec.ResMM(dec.convFM(rg)))))), iters=10, warm=3)
-        out[tag] = {k: round(v, 4) for k, v in res.items()}
+            import copy
+            from vfloodnet_b200 import folded
+            mf = folded.fold_encoders(copy.deepcopy(model))
+            res['folded_encoder_q_b1'] = time_fn(lambda: mf.encoder_q(fp))
+            res['folded_encoder_m_b2'] = time_fn(lambda: mf.encoder_m(fm2, mk, mk_inv))
+            a4 = mf.encoder_q(fp)[0]
+            res['folded_r4_rel_diff'] = float((a4 - r4).abs().max() / r4.abs().max())
+            del mf
+        out[tag] = {k: round(v, 6) for k, v in res.items()}
     out['r4_absmax'] = float(r4.abs().max())
     out['r4m_absmax'] = float(r4m.abs().max())
     out['key_weight_absmax'] = float(model.keyval_r4.Key.weight.abs().max())

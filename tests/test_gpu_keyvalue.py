@@ -214,7 +214,8 @@ def env():
     ref = model_clip.build_reference_model(ns, dev)
     ours = model_clip.patched_copy(ref, vfn)
     fused = vfn.fuse_model(model_clip.patched_copy(ref, vfn))
-    return dict(ns=ns, vfn=vfn, MC=model_clip, dev=dev, ref=ref, ours=ours, fused=fused)
+    folded = vfn.fuse_model(model_clip.patched_copy(ref, vfn), fold_bn=True)
+    return dict(ns=ns, vfn=vfn, MC=model_clip, dev=dev, ref=ref, ours=ours, fused=fused, folded=folded)
 
 
 def test_fuse_model_surface(env):
@@ -311,3 +312,43 @@ def test_graphed_fused_model_equals_eager_fused(env):
     _report('graphed_fused_vs_eager', dict(max_score_diff=worst, min_iou=min(ious)))
     assert min(ious) >= 0.9999 and worst <= 1e-3, (min(ious), worst)
     assert [e['fb'].bank_n(c) for c in range(2)] == [g['fb'].bank_n(c) for c in range(2)]
+
+
+def test_folded_encoders_vs_reference_modules(env):
+    """BatchNorm folded into the convolutions, conv + bias + ReLU (+ add) as one cuDNN call.  Same
+    function, other rounding: encoder outputs against the reference modules' (true-fp32 convolutions), state_dict
+    untouched, and teacher-forced masks of the fully fused model against the unfused patched model."""
+    vfn, MC, dev = env['vfn'], env['MC'], env['dev']
+    ref, ours, folded = env['ref'], env['ours'], env['folded']
+    sr, sf = ref.state_dict(), folded.state_dict()
+    assert sr.keys() == sf.keys() and all(torch.equal(sr[k], sf[k]) for k in sr)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    stats = dict(enc=[], iou=[], pixels_differ=[])
+    try:
+        with torch.no_grad():
+            clip = MC.make_clip(6)
+            f0, m0 = clip[0].to(dev), MC.first_mask().to(dev)
+            fp = torch.nn.functional.pad(f0, (5, 5, 0, 0))
+            for a, b in zip(ref.encoder_q(fp), folded.encoder_q(fp)):
+                stats['enc'].append(float((a - b).abs().max() / a.abs().max()))
+            assert max(stats['enc']) <= 5e-4, stats
+            k4, v4 = ours.memorize(f0, m0)
+            fb = vfn.FeatureBank(2, MC.BUDGET, dev)
+            fb.init_bank(k4, v4)
+            fbf = vfn.FeatureBank(2, MC.BUDGET, dev)
+            for t in range(1, 7):
+                frame = clip[t].to(dev)
+                fbf.load_state([k.clone() for k in fb.keys], [v.clone() for v in fb.values], [i.clone() for i in fb.info])
+                score, _ = ours.segment(frame, fb)
+                score_f, _ = folded.segment(frame, fbf)
+                pm, pmf = torch.softmax(score, 1), torch.softmax(score_f, 1)
+                am, amf = pm[0].argmax(0), pmf[0].argmax(0)
+                stats['iou'].append(MC.iou(am, amf))
+                stats['pixels_differ'].append(int((am != amf).sum()))
+                k4, v4 = ours.memorize(frame, pm)
+                fb.update(k4, v4, t)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    _report('folded_vs_patched', stats)
+    assert min(stats['iou']) >= 0.999, stats

@@ -7,6 +7,7 @@ Public surface mirrors the reference operator API for this path:
     GraphedAFBURR (memorize / segment of AFB_URR.py:255-318 with the convolution stages as CUDA graphs)
     KeyValueHead  (KeyValue, AFB_URR.py:94-111, as a tcgen05 implicit GEMM writing bank / query layout)
     fuse_model    (segment glue without per-object copies, AFB_URR.py:287-297, + KeyValueHead)
+    fold_encoders (EncoderM / EncoderQ, AFB_URR.py:33-93, BatchNorm folded, conv+bias+ReLU as one cuDNN call)
 Everything computes in libvfn_sm100a.so (include/vfn.h); importing this package without the built library, or
 calling it without a CUDA device, fails loudly - there is no CPU fallback.
 """
@@ -16,6 +17,7 @@ from .urr import urr_pre, urr_post, decoder_forward, patch_model
 from .graphed import GraphedAFBURR
 from .keyvalue import KeyValueHead
 from .glue import fuse_model, segment_fused
+from .folded import fold_encoders
 
 __all__ = ['FeatureBank', 'Matcher', 'urr_pre', 'urr_post', 'decoder_forward', 'patch_model', 'GraphedAFBURR',
-           'KeyValueHead', 'fuse_model', 'segment_fused']
+           'KeyValueHead', 'fuse_model', 'segment_fused', 'fold_encoders']

@@ -102,9 +102,11 @@ def segment_fused(self, frame, fb_global):
     return finish_score(prob, obj_n, pad), None
 
 
-def fuse_model(model, keyvalue: bool = True, keyvalue_passes: int = 3):
-    """On top of `patch_model`: bind the copy-free `segment` glue and (keyvalue=True) replace `model.keyval_r4` by the
-    tcgen05 `KeyValueHead` built from its weights.  Returns the model."""
+def fuse_model(model, keyvalue: bool = True, keyvalue_passes: int = 3, fold_bn: bool = False):
+    """On top of `patch_model`: bind the copy-free `segment` glue, (keyvalue=True) replace `model.keyval_r4` by the
+    tcgen05 `KeyValueHead` built from its weights, and (fold_bn=True) bind the encoders' forward passes
+    with BatchNorm folded into the convolutions and conv + bias + ReLU (+ add) as single cuDNN calls
+    (vfloodnet_b200.folded).  Returns the model."""
     from .urr import patch_model
     from .matcher import Matcher
     if not isinstance(model.global_matcher, Matcher):
@@ -116,4 +118,7 @@ def fuse_model(model, keyvalue: bool = True, keyvalue_passes: int = 3):
         from .keyvalue import KeyValueHead
         if not isinstance(model.keyval_r4, KeyValueHead):
             model.keyval_r4 = KeyValueHead.from_reference(model.keyval_r4, passes=keyvalue_passes)
+    if fold_bn:
+        from .folded import fold_encoders
+        fold_encoders(model)
     return model
