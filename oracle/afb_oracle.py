@@ -302,6 +302,16 @@ def urr_post(p_up: torch.Tensor, uncertainty: torch.Tensor, r1_conf: torch.Tenso
     return NF.softmax(p, dim=1)[:, 1]                                                 # :237
 
 
+def keyvalue_forward(x, wk, bk, wv, bv):
+    """KeyValue.forward (AFB_URR.py:103-111): two 3x3 / padding 1 convolutions of the same feature map, flattened to
+    (B, d, H*W).  Evaluated in the dtype of x (tests pass float64 for the exact value, float32 for the reference's)."""
+    key = NF.conv2d(x, wk.to(x.dtype), None if bk is None else bk.to(x.dtype), padding=1)     # :104 (Key, :100)
+    key = key.view(*key.shape[:2], -1)                                                        # :105
+    val = NF.conv2d(x, wv.to(x.dtype), None if bv is None else bv.to(x.dtype), padding=1)     # :107 (Value, :101)
+    val = val.view(*val.shape[:2], -1)                                                        # :108
+    return key, val
+
+
 def pad_divide_by(in_list, d, in_size):                                               # myutils/data.py:134-151
     h, w = in_size
     new_h = h + d - h % d if h % d > 0 else h

@@ -10,7 +10,7 @@ Two import shims, neither touching arithmetic of the reference's own code:
     provided with the torch-scatter 2.0.8 published semantics (scatter_add_, count, clamp(1), true_divide_).
     This shim is written independently of oracle/ so the oracle's restatement is checked against it.
 
-Outputs (committed): tests/golden/read_*.npz, update_*.npz, urr_*.npz, misc.npz
+Outputs (committed): tests/golden/read_*.npz, update_*.npz, urr_*.npz, keyvalue.npz, misc.npz
 """
 import os
 import sys
@@ -168,6 +168,33 @@ def golden_urr(name, seed, H, W):
     print('urr', name, out.shape)
 
 
+def golden_keyvalue(seed=21):
+    """KeyValue.forward (AFB_URR.py:94-111) of the unmodified reference module on seeded inputs: indim 64 (the kernel
+    serves any multiple of 64), keydim 128, valdim 512, two images of 6 x 7; and the decoder trunk (convFM .. pred2,
+    AFB_URR.py:209-212) with per-object copies of r3 / r2, for the copy-free glue (round 2)."""
+    from video_module.model.AFB_URR import KeyValue, Decoder
+    torch.manual_seed(seed)
+    kv = KeyValue(64, keydim=128, valdim=512).eval()
+    x = torch.randn(2, 64, 6, 7).relu() * 3
+    with torch.no_grad():
+        k, v = kv(x)
+    d = dict(x=t2n(x), wk=t2n(kv.Key.weight), bk=t2n(kv.Key.bias), wv=t2n(kv.Value.weight), bv=t2n(kv.Value.bias),
+             key=t2n(k), val=t2n(v))
+    dec = Decoder('cpu').eval()
+    H, W, obj_n = 32, 48, 2
+    patch = torch.randn(obj_n, 1024, H // 16, W // 16) * 0.5
+    r3 = torch.randn(1, 512, H // 8, W // 8).relu()
+    r2 = torch.randn(1, 256, H // 4, W // 4).relu()
+    with torch.no_grad():
+        p = dec.ResMM(dec.convFM(patch))
+        p = dec.RF3(r3.expand(obj_n, -1, -1, -1).reshape(obj_n, *r3.shape[1:]), p)       # AFB_URR.py:291-292
+        p = dec.RF2(r2.expand(obj_n, -1, -1, -1).reshape(obj_n, *r2.shape[1:]), p)
+        p = dec.pred2(torch.relu(p))
+    d.update(trunk_patch=t2n(patch), trunk_r3=t2n(r3), trunk_r2=t2n(r2), trunk_out=t2n(p), trunk_seed=np.array(seed))
+    np.savez(os.path.join(HERE, 'keyvalue.npz'), **d)
+    print('keyvalue', k.shape, v.shape, p.shape)
+
+
 def golden_misc():
     import myutils
     g = torch.Generator().manual_seed(11)
@@ -184,6 +211,9 @@ def golden_misc():
 if __name__ == '__main__':
     install_shims()
     torch.set_num_threads(1)   # deterministic reduction order for the committed vectors
+    if 'keyvalue' in sys.argv[1:]:             # added in round 2 (n3): generate this file alone
+        golden_keyvalue()
+        sys.exit(0)
     if 'real_dims_evict' in sys.argv[1:]:      # added in round 2: regenerate this file alone
         golden_update('real_dims_evict', 13, 128, 512, 100, 64, 3, budget=350, s_k=3.0)
         sys.exit(0)
@@ -197,4 +227,5 @@ if __name__ == '__main__':
     # d_k=128 / d_v=512 WITH LFU eviction (class_budget 140.0, peaked softmax): the only dims the tcgen05 match/read serve
     golden_update('real_dims_evict', 13, 128, 512, 100, 64, 3, budget=350, s_k=3.0)
     golden_urr('h32w48', 8, 32, 48)
+    golden_keyvalue()
     golden_misc()

@@ -89,6 +89,28 @@ def test_keyvalue_480p_fp32_grade(b):
     assert err <= 0.05 * errtf, (err, errtf)
 
 
+def test_keyvalue_golden_of_the_reference_module():
+    """tests/golden/keyvalue.npz: KeyValue.forward of the unmodified reference (CPU fp32) on seeded inputs; the kernel
+    with the same weights must reproduce it to fp32 convolution rounding, in both layouts"""
+    import numpy as np
+    import vfloodnet_b200 as vfn
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'keyvalue.npz'))
+    key = torch.nn.Conv2d(64, 128, 3, padding=1)
+    val = torch.nn.Conv2d(64, 512, 3, padding=1)
+    with torch.no_grad():
+        key.weight.copy_(torch.from_numpy(g['wk'])); key.bias.copy_(torch.from_numpy(g['bk']))
+        val.weight.copy_(torch.from_numpy(g['wv'])); val.bias.copy_(torch.from_numpy(g['bv']))
+    head = vfn.KeyValueHead(key.cuda(), val.cuda())
+    x = torch.from_numpy(g['x']).cuda()
+    want_k, want_v = torch.from_numpy(g['key']).cuda(), torch.from_numpy(g['val']).cuda()
+    for layout in ('auto', 'em', 'dm'):
+        with torch.no_grad():
+            k, v = head(x, layout=layout)
+        assert k.shape == want_k.shape and v.shape == want_v.shape
+        assert float((k - want_k).abs().max()) <= 5e-6 * float(want_k.abs().max())
+        assert float((v - want_v).abs().max()) <= 5e-6 * float(want_v.abs().max())
+
+
 def test_keyvalue_single_pass_is_tf32_class():
     head = _head(passes=1)
     x = _features(1, 1024, 30, 54)
