@@ -214,11 +214,15 @@ def instrument(model, timer: StageTimer):
 
 def run_clip(model, bank_cls, frames: List[torch.Tensor], device, budget: int = BUDGET, thres_close: float = 0.95,
              update_rate: float = 0.1, timer: Optional[StageTimer] = None, warm_frames: int = 0,
-             on_frame: Optional[Callable] = None, keep_masks: bool = True, frames_on_host: bool = False):
+             on_frame: Optional[Callable] = None, keep_masks: bool = True, frames_on_host: bool = False,
+             pipeline: bool = False):
     """The reference loop: memorize(first frame, first mask) -> init_bank; per frame segment -> softmax -> memorize ->
     update.  frames[0] is the annotated frame.  Returns dict(fb=, masks=[(h,w) uint8 arg-max per frame], probs_last=).
     on_frame(t, frame, score, pred_mask, k4, v4, fb) is called after every update (tests hook comparisons there).
-    frames_on_host: frames are (pinned) host tensors copied in every frame and the arg-max mask is copied back (e2e)."""
+    frames_on_host: frames are (pinned) host tensors copied in every frame and the arg-max mask is copied back (e2e).
+    pipeline: the model offers `prefetch(next_frame)` (vfloodnet_b200.GraphedAFBURR): the frame-only stage of the next
+    segment is issued right after this frame's segment and overlaps memorize + update; frames are handed over as they are
+    (host or device) and the model does the copy."""
     dev = torch.device(device)
     f0 = frames[0].to(dev, non_blocking=True)
     m0 = first_mask(*f0.shape[-2:]).to(dev)
@@ -230,9 +234,11 @@ def run_clip(model, bank_cls, frames: List[torch.Tensor], device, budget: int = 
         fb.init_bank(k4, v4)
         for t in range(1, len(frames)):
             timed = timer is not None and t > warm_frames
-            frame = frames[t].to(dev, non_blocking=True)
+            frame = frames[t] if pipeline else frames[t].to(dev, non_blocking=True)
             a = timer.start('segment') if timed else None
             score, _ = model.segment(frame, fb)
+            if pipeline and t + 1 < len(frames):
+                model.prefetch(frames[t + 1])
             pred_mask = F.softmax(score, dim=1)
             if timed:
                 timer.stop(a)

@@ -892,9 +892,9 @@ def main_model_clip(args, rank, world, local_rank):
     try:
         model_fused = vfn.fuse_model(MC.patched_copy(model_ref, vfn), fold_bn=True)
 
-        def leg(model, frames, host=False):
+        def leg(model, frames, host=False, pipeline=False):
             run = lambda: MC.run_clip(model, vfn.FeatureBank, frames, dev, budget=BUDGET, keep_masks=False,
-                                      frames_on_host=host)
+                                      frames_on_host=host, pipeline=pipeline)
             for _ in range(2):
                 run()
             torch.cuda.synchronize()
@@ -921,8 +921,12 @@ def main_model_clip(args, rank, world, local_rank):
         gmf = vfn.GraphedAFBURR(model_fused, tuple(dev_clip[0].shape))
         f_graph, fg_n = leg(gmf, dev_clip)
         f_graph_e2e, _ = leg(gmf, host_clip, host=True)
+        # frame-level pipelining: the next frame's encoder graph on a side stream, overlapping memorize + update
+        f_pipe, fp_n = leg(gmf, dev_clip, pipeline=True)
+        f_pipe_e2e, _ = leg(gmf, host_clip, host=True, pipeline=True)
         kv = model_fused.keyval_r4
         fused = {'value': f_eager, 'unit': 'frames/s', 'graphed': f_graph, 'graphed_e2e': f_graph_e2e,
+                 'graphed_pipelined': f_pipe, 'graphed_pipelined_e2e': f_pipe_e2e, 'final_bank_slots_pipelined': fp_n,
                  'final_bank_slots': f_n, 'final_bank_slots_graphed': fg_n,
                  'stages_ms_per_frame': _stage_table(tot_f, args.frames), 'keyvalue_passes': kv.passes,
                  'note': 'fuse_model: Refine skip branches evaluated once per frame (not per object), r1 / r2 / r3 never '

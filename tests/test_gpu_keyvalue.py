@@ -374,3 +374,30 @@ def test_folded_encoders_vs_reference_modules(env):
         torch.backends.cudnn.allow_tf32 = old
     _report('folded_vs_patched', stats)
     assert min(stats['iou']) >= 0.999, stats
+
+
+def test_pipelined_graphed_model_equals_unpipelined(env):
+    """GraphedAFBURR.prefetch: the next frame's encoder stage on a side stream while memorize + update of the current
+    frame run.  Same kernels on the same inputs: scores, masks and banks must be IDENTICAL to the un-pipelined graphed
+    loop, with device frames and with pinned host frames."""
+    vfn, MC, dev = env['vfn'], env['MC'], env['dev']
+    host = MC.make_clip(8, pin=True)
+    clip = [f.to(dev) for f in host]
+    gm = vfn.GraphedAFBURR(env['folded'], tuple(clip[0].shape))
+    scores = {}
+
+    def keep(tag):
+        def cb(t, frame, score, pm, k4, v4, fb):
+            scores.setdefault(tag, []).append(score.clone())
+        return cb
+
+    a = MC.run_clip(gm, vfn.FeatureBank, clip, dev, on_frame=keep('plain'))
+    b = MC.run_clip(gm, vfn.FeatureBank, clip, dev, on_frame=keep('pipe'), pipeline=True)
+    c = MC.run_clip(gm, vfn.FeatureBank, host, dev, on_frame=keep('pipe_host'), pipeline=True, frames_on_host=True)
+    torch.cuda.synchronize()
+    for tag in ('pipe', 'pipe_host'):
+        assert all(torch.equal(x, y) for x, y in zip(scores['plain'], scores[tag])), tag
+    for r in (b, c):
+        assert all(torch.equal(x, y) for x, y in zip(a['masks'], r['masks']))
+        assert [a['fb'].bank_n(k) for k in range(2)] == [r['fb'].bank_n(k) for k in range(2)]
+        assert all(torch.equal(a['fb'].keys[k], r['fb'].keys[k]) for k in range(2))

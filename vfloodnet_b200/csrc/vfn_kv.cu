@@ -281,15 +281,25 @@ __global__ void __launch_bounds__(256) kv_combine_kernel(const float* __restrict
   const int n = blockIdx.y * 32 + tx;
   const float bn = bias[n];
   const bool is_key = n < dk;            // dk % 32 == 0: a 32-channel block is all key or all value
-  for (int r = ty; r < 32; r += 8) {
-    const int pos = blockIdx.x * 32 + r;
-    float v = 0.f;
+  // all (row, split) loads of a thread are issued before the first add: 4 x 8 independent loads in flight
+  float pv[4][KV_MAX_SPLIT];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int pos = blockIdx.x * 32 + ty + 8 * i;
+    const int pc = pos < total ? pos : total - 1;
+    const int b = pc / hw, p = pc - b * hw, y = p / w, x = p - y * w;
+    const size_t o = (size_t)b * HpWp + (size_t)y * Wp + x;
+#pragma unroll
+    for (int s = 0; s < KV_MAX_SPLIT; ++s) pv[i][s] = s < split ? part[((size_t)s * m_pad + o) * c_out + n] : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = ty + 8 * i, pos = blockIdx.x * 32 + r;
+    float acc = pv[i][0];                      // splits in ascending order (x + 0 is exact for the unused ones)
+#pragma unroll
+    for (int s = 1; s < KV_MAX_SPLIT; ++s) acc += pv[i][s];
+    const float v = acc * inv + bn;
     if (pos < total) {
-      const int b = pos / hw, p = pos - b * hw, y = p / w, x = p - y * w;
-      const size_t o = (size_t)b * HpWp + (size_t)y * Wp + x;
-      float acc = 0.f;
-      for (int s = 0; s < split; ++s) acc += part[((size_t)s * m_pad + o) * c_out + n];
-      v = acc * inv + bn;
       if (is_key) { if (out.key_em) out.key_em[(size_t)pos * dk + n] = v; }
       else if (out.val_em) out.val_em[(size_t)pos * dv + (n - dk)] = v;
     }
@@ -432,7 +442,7 @@ int vfn_keyvalue(const float* d_x, int32_t B, int32_t c_in, int32_t h, int32_t w
   VFN_CUDA_OK(cudaMemsetAsync(cells, 0, 256, st));
   if (g.rows < KV_MT) VFN_CUDA_OK(cudaMemsetAsync(xh, 0, 2 * kv_x_bytes(g, c_in), st));   // rows the packing never writes
   const int64_t nx = (int64_t)B * c_in * h * w;
-  kv_absmax_kernel<<<n_sm, 256, 0, st>>>(d_x, nx, cells);
+  kv_absmax_kernel<<<4 * n_sm, 256, 0, st>>>(d_x, nx, cells);
   dim3 pg((unsigned)(B * g.Hp), (unsigned)(c_in / 64), (unsigned)cdiv(g.Wp, 32));
   VFN_CUDA_OK(launch_pdl(kv_pack_input_kernel, pg, dim3(32, 8), 0, st, d_x, (int)c_in, (int)h, (int)w,
                          (const uint32_t*)cells, reinterpret_cast<float*>(cells) + 1, xh, xl));

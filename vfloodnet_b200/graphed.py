@@ -48,7 +48,12 @@ class GraphedAFBURR:
         b, c, h, w = frame_shape
         if b != 1:
             raise ValueError('inference path: one frame at a time (bs == 1)')
-        self.frame = torch.zeros(frame_shape, device=dev)
+        self.frame = torch.zeros(frame_shape, device=dev)          # input of the memorize graph
+        self.frame_q = torch.zeros(frame_shape, device=dev)        # input of the encoder graph (the query frame)
+        self._side = torch.cuda.Stream(dev)                        # prefetch(): the next frame's encoder stage
+        self._enc_done = None
+        self._prefetched = None                                    # the object handed to prefetch(), until it is consumed
+        self._seg_src = None                                       # the object handed to the last segment()
         self.mask = torch.zeros((1, obj_n, h, w), device=dev)
         self.mask[:, 0] = 1
         with torch.no_grad():
@@ -56,7 +61,7 @@ class GraphedAFBURR:
 
     # ---- the four stages as plain functions of the static buffers ---------------------------------
     def _enc(self):
-        f, pad = _pad16(self.frame)
+        f, pad = _pad16(self.frame_q)
         r4, r3, r2, r1 = self.model.encoder_q(f)
         k4, v4 = self.model.keyval_r4(r4)
         if self.fused:      # the object-independent halves of the two Refine blocks (AFB_URR.py:121) belong to the frame
@@ -125,11 +130,30 @@ class GraphedAFBURR:
     def memorize(self, frame, mask):
         """AFB_URR.memorize (AFB_URR.py:255-272): lists of (128, HW) / (512, HW) per object (views of static buffers,
         valid until the next memorize)"""
-        if frame.data_ptr() != self.frame.data_ptr():
+        if frame is not self._seg_src:           # segment() left a copy of the frame it was given in self.frame
             self.frame.copy_(frame, non_blocking=True)
         self.mask.copy_(mask, non_blocking=True)
         self.g_mem.replay()
         return list(self.mk4), list(self.mv4)
+
+    @torch.no_grad()
+    def prefetch(self, frame):
+        """Frame-level software pipelining (no reference counterpart; optional).  Call it right after `segment(t)` returned
+        with frame t+1 (a device tensor or a pinned host tensor): the part of `segment` that depends on the frame only -
+        encoder_q, KeyValue, the Refine skip branches: the whole encoder graph - is issued on a side stream, where it
+        overlaps `memorize(t)` and `fb.update(t)` of the current frame (convolutions at batch 1-2 leave SMs idle).  The next
+        `segment` must be given the SAME object; it then only waits for the side stream.  Results are those of the
+        un-pipelined loop (same kernels, same inputs)."""
+        cur = torch.cuda.current_stream(self.device)
+        if self._prefetched is not None:
+            cur.wait_event(self._enc_done)
+        self._side.wait_stream(cur)          # every reader of the encoder buffers issued so far (read, decoder, URR of frame t)
+        with torch.cuda.stream(self._side):
+            self.frame_q.copy_(frame, non_blocking=True)
+            self.g_enc.replay()
+            self._enc_done = torch.cuda.Event()
+            self._enc_done.record(self._side)
+        self._prefetched = frame
 
     @torch.no_grad()
     def segment(self, frame, fb_global):
@@ -137,8 +161,15 @@ class GraphedAFBURR:
         n = fb_global.obj_n
         if n != self.obj_n:
             raise ValueError('object count differs from the captured graphs')
-        self.frame.copy_(frame, non_blocking=True)
-        self.g_enc.replay()
+        cur = torch.cuda.current_stream(self.device)
+        if self._prefetched is not None:
+            cur.wait_event(self._enc_done)       # the side stream is done with the encoder buffers (whatever it ran)
+        if self._prefetched is not frame:
+            self.frame_q.copy_(frame, non_blocking=True)
+            self.g_enc.replay()
+        self._prefetched = None
+        self.frame.copy_(self.frame_q, non_blocking=True)    # memorize(frame, .) of this frame finds it there
+        self._seg_src = frame
         res = self.model.global_matcher(fb_global, self.k4, self.v4)                   # (1, n, 1024, HW): the read
         self.res_global.copy_(res.reshape(n, -1, *self.grid4))
         self.g_dec.replay()
