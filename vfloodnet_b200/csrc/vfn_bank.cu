@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const __grid_constant__ 
   __shared__ float tile[32][33];
   __shared__ float part[8][32];
   __shared__ float denom[32];
+  __shared__ float stage[32][129];      // entry-major sources: 128 columns of the CTA's 32 rows, staged for the norm
   const PrepJob& jb = jobs.j[blockIdx.y];
   const float* __restrict__ src = jb.src;
   const int d = jb.d;
@@ -84,9 +85,29 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const __grid_constant__ 
   if (jb.normed || jb.split_normed) {
     // same summation order for both source layouts (8 strided partial sums per row, then their sum in order)
     float ss = 0.f;
-    if (q < n)
+    if (jb.src_em) {
+      // rows are contiguous: stage 128 columns at a time with coalesced loads, then every thread walks ITS row in the
+      // same k order as below (ty, ty + 8, ...; the chain carries over the stages), so both layouts give the same bits
+      for (int kc = 0; kc < d; kc += 128) {
+        for (int r = ty; r < 32; r += 8) {
+          const int64_t qq = q0 + r;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = kc + tx + 32 * j;
+            stage[r][tx + 32 * j] = (qq < n && k < d) ? src[qq * d + k] : 0.f;
+          }
+        }
+        __syncthreads();
+        const int kend = min(128, d - kc);
+        for (int k = ty; k < kend; k += 8) {
+          const float v = stage[tx][k];
+          ss = fmaf(v, v, ss);
+        }
+        __syncthreads();
+      }
+    } else if (q < n)
       for (int k = ty; k < d; k += 8) {
-        float v = jb.src_em ? src[q * d + k] : src[(int64_t)k * n + q];
+        float v = src[(int64_t)k * n + q];
         ss = fmaf(v, v, ss);
       }
     part[ty][tx] = ss;

@@ -73,9 +73,14 @@ int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_i
   if (ws_bytes < L.total) { set_error("bank_update: workspace %zu < %zu", ws_bytes, L.total); return VFN_E_CAPACITY; }
   cudaStream_t st = as_stream(stream);
   char* ws = reinterpret_cast<char*>(d_ws);
-  auto CK = [&](int c) { return reinterpret_cast<float*>(ws + L.ck + c * L.s_ck); };
+  // entry-major candidates (prev_layout == 1) ARE the raw entry-major rows the merge / append kernels read: no copy
+  auto CK = [&](int c) {
+    return io[c].prev_layout == 1 ? const_cast<float*>(io[c].d_prev_key_dm) : reinterpret_cast<float*>(ws + L.ck + c * L.s_ck);
+  };
   auto NCK = [&](int c) { return reinterpret_cast<float*>(ws + L.nck + c * L.s_ck); };
-  auto CV = [&](int c) { return reinterpret_cast<float*>(ws + L.cv + c * L.s_cv); };
+  auto CV = [&](int c) {
+    return io[c].prev_layout == 1 ? const_cast<float*>(io[c].d_prev_value_dm) : reinterpret_cast<float*>(ws + L.cv + c * L.s_cv);
+  };
   auto NCV = [&](int c) { return reinterpret_cast<float*>(ws + L.ncv + c * L.s_cv); };
   int32_t* counts = reinterpret_cast<int32_t*>(ws + L.counts);
   int32_t* plan = reinterpret_cast<int32_t*>(ws + L.plan);
@@ -96,9 +101,10 @@ int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_i
                                       (size_t)((char*)tc_match_cand_lo(mws, obj_n, hw, obj_n) - (char*)tc_match_cand_hi(mws, obj_n, hw, 0)), st));
   for (int c = 0; c < obj_n; ++c) {
     const int em = io[c].prev_layout == 1;      // (hw, d) candidates as vfn_keyvalue writes them: no transpose
-    jobs[2 * c] = PrepJob{io[c].d_prev_key_dm, d_key, hw, CK(c), NCK(c), tc ? tc_match_cand_hi(mws, obj_n, hw, c) : nullptr,
+    jobs[2 * c] = PrepJob{io[c].d_prev_key_dm, d_key, hw, em ? nullptr : CK(c), NCK(c),
+                          tc ? tc_match_cand_hi(mws, obj_n, hw, c) : nullptr,
                           tc ? tc_match_cand_lo(mws, obj_n, hw, c) : nullptr, NK_SCALE, 1, em};
-    jobs[2 * c + 1] = PrepJob{io[c].d_prev_value_dm, d_val, hw, CV(c), NCV(c), nullptr, nullptr, 1.f, 0, em};
+    jobs[2 * c + 1] = PrepJob{io[c].d_prev_value_dm, d_val, hw, em ? nullptr : CV(c), NCV(c), nullptr, nullptr, 1.f, 0, em};
   }
   if (int rc = launch_prep(jobs, 2 * obj_n, st)) return rc;
 
