@@ -401,3 +401,32 @@ def test_pipelined_graphed_model_equals_unpipelined(env):
         assert all(torch.equal(x, y) for x, y in zip(a['masks'], r['masks']))
         assert [a['fb'].bank_n(k) for k in range(2)] == [r['fb'].bank_n(k) for k in range(2)]
         assert all(torch.equal(a['fb'].keys[k], r['fb'].keys[k]) for k in range(2))
+
+
+def test_fused_model_other_frame_size_with_padding_on_both_axes(env):
+    """360 x 636 frames: pad_divide_by(16) pads both axes (368 x 640); the fused glue must un-pad like the reference
+    (AFB_URR.py:312-316) and agree with the unfused patched model"""
+    vfn, MC, dev = env['vfn'], env['MC'], env['dev']
+    ours, fused = env['ours'], env['folded']
+    h, w = 360, 636
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            f0, f1 = MC.make_frame(0, h=h, w=w).to(dev), MC.make_frame(1, h=h, w=w).to(dev)
+            m0 = MC.first_mask(h, w).to(dev)
+            k4, v4 = ours.memorize(f0, m0)
+            assert k4[0].shape == (128, 23 * 40)
+            fb, fbf = vfn.FeatureBank(2, MC.BUDGET, dev), vfn.FeatureBank(2, MC.BUDGET, dev)
+            fb.init_bank(k4, v4)
+            fbf.init_bank(*fused.memorize(f0, m0))
+            s, _ = ours.segment(f1, fb)
+            sf, _ = fused.segment(f1, fbf)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert s.shape == sf.shape == (1, 2, h, w)
+    assert MC.iou(s[0].argmax(0), sf[0].argmax(0)) >= 0.999
+    gm = vfn.GraphedAFBURR(fused, (1, 3, h, w))
+    with torch.no_grad():
+        sg, _ = gm.segment(f1, fbf)
+    assert sg.shape == (1, 2, h, w)

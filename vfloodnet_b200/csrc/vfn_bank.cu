@@ -80,7 +80,22 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const __grid_constant__ 
   // would otherwise run on 51; normalising jobs keep PREP_CHUNK rows per CTA (every CTA re-reads the whole column for
   // the norm)
   const int chunk = (jb.normed || jb.split_normed) ? PREP_CHUNK : 32;
-  if (q0 >= n || (int)blockIdx.z * chunk >= d) return;
+  if ((int)blockIdx.z * chunk >= d) return;
+  if (q0 >= n) {
+    // zero padding of the operand arrays beyond the last row (rows [n, n_pad)); blocks past n_pad have nothing to do
+    if (jb.hi && q0 < jb.n_pad) {
+      const int k_end = min(d, (int)(blockIdx.z + 1) * chunk);
+      for (int r = ty; r < 32; r += 8) {
+        const int64_t qq = q0 + r;
+        if (qq >= jb.n_pad) break;
+        for (int k = blockIdx.z * chunk + tx; k < k_end; k += 32) {
+          jb.hi[qq * d + k] = 0;
+          if (jb.lo) jb.lo[qq * d + k] = 0;
+        }
+      }
+    }
+    return;
+  }
   const int64_t q = q0 + tx;
   if (jb.normed || jb.split_normed) {
     // same summation order for both source layouts (8 strided partial sums per row, then their sum in order)
@@ -141,6 +156,10 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const __grid_constant__ 
     for (int r = ty; r < 32; r += 8) {
       int64_t qq = q0 + r;
       int k = k0 + tx;
+      if (qq >= n && qq < jb.n_pad && k < d && jb.hi) {      // pad rows inside the last row block
+        jb.hi[qq * d + k] = 0;
+        if (jb.lo) jb.lo[qq * d + k] = 0;
+      }
       if (qq < n && k < d) {
         float v = tile[tx][r];
         int64_t o = qq * d + k;
@@ -168,6 +187,7 @@ int launch_prep(const PrepJob* jobs, int n_jobs, cudaStream_t st) {
   for (int i = 0; i < n_jobs; ++i) {
     pj.j[i] = jobs[i];
     if (jobs[i].n > n_max) n_max = jobs[i].n;
+    if (jobs[i].hi && jobs[i].n_pad > n_max) n_max = jobs[i].n_pad;
     if (jobs[i].d > d_max) d_max = jobs[i].d;
   }
   if (n_max == 0) return VFN_OK;

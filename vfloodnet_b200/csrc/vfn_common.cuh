@@ -26,6 +26,7 @@ struct PrepJob {
   const float* src; int d; int64_t n;
   float* raw; float* normed; uint16_t* hi; uint16_t* lo; float scale; int split_normed;
   int src_em;      // 0: src is (d, n) dimension-major (the reference's layout); 1: src is already (n, d) entry-major
+  int64_t n_pad;   // hi / lo: rows [n, n_pad) are zero-filled by the same launch (operand arrays padded to whole tiles)
 };
 int launch_prep(const PrepJob* jobs, int n_jobs, cudaStream_t st);
 

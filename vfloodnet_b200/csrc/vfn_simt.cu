@@ -368,18 +368,37 @@ __global__ void __launch_bounds__(ST_THREADS) simt_readout_kernel(BankSet banks,
   }
 }
 
+// info[:,1] += log(cnt+1) ; cnt = 0 for slot i of one bank                                  (AFB_URR.py:174)
+__device__ __forceinline__ void finalize_count(const vfn_bank& bk, int64_t i) {
+  const int c = bk.cnt[i];
+  if (c == 0) return;            // log(0 + 1) = 0: info unchanged (most slots of a large bank; skips the fp64 log)
+  bk.cnt[i] = 0;
+  // bank_cnt + 1 is exact in fp32; log evaluated in double and rounded once
+  bk.info[2 * i + 1] += (float)log((double)((float)c + 1.0f));
+}
+
 // out[obj][c][j] = sum_s po[obj][s][c][j] (c < dv) ; out[obj][dv + c][j] = q_out[c][j]     (AFB_URR.py:159,176)
+// counts != 0: the same launch also folds the usage counts of phase B into info (finalize_count) - they are complete
+// when this kernel starts, and a separate 7-block launch cost as much as its gap on the stream
 // V = 4: 128-bit accesses (plane % 4 == 0 and 16-byte aligned bases), same per-element summation order as V = 1
 template <int V>
 __global__ void __launch_bounds__(256) combine_out_kernel(const float* __restrict__ po, int n_split,
                                                           const int32_t* __restrict__ n_split_dev,
                                                           int64_t plane /* dv*hw */, int obj_n,
                                                           const float* __restrict__ q_out, float* __restrict__ out,
-                                                          int with_qout) {
+                                                          int with_qout, BankSet banks, int counts) {
   pdl_wait();
   pdl_trigger();
   const int64_t total = plane * obj_n;
   if (n_split_dev) n_split = *n_split_dev;
+  if (counts) {
+    for (int o = 0; o < obj_n; ++o) {
+      const vfn_bank bk = banks.b[o];
+      const int64_t n = live_n(bk);
+      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        finalize_count(bk, i);
+    }
+  }
   if (V == 4) {
     // grid-stride over float4 positions: a few CTAs per SM, each thread keeps up to four partial planes in flight
     for (int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; idx < total;
@@ -425,31 +444,17 @@ __global__ void __launch_bounds__(256) combine_out_kernel(const float* __restric
 }
 
 static void launch_combine_out(const float* po, int n_split, const int32_t* n_split_dev, int64_t plane, int obj_n,
-                               const float* q_out, float* out, int with_qout, cudaStream_t st) {
+                               const float* q_out, float* out, int with_qout, cudaStream_t st, const BankSet& banks,
+                               int counts) {
   const bool vec = plane % 4 == 0 && ((uintptr_t)po % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
                    (!with_qout || (uintptr_t)q_out % 16 == 0);
   const int64_t need = cdiv(plane * obj_n / 4, 256);
   if (vec)
     launch_pdl(combine_out_kernel<4>, dim3((unsigned)(need < 148 * 4 ? need : 148 * 4)), dim3(256), 0, st, po, n_split,
-               n_split_dev, plane, obj_n, q_out, out, with_qout);
+               n_split_dev, plane, obj_n, q_out, out, with_qout, banks, counts);
   else
     launch_pdl(combine_out_kernel<1>, dim3((unsigned)cdiv(plane * obj_n, 256)), dim3(256), 0, st, po, n_split, n_split_dev,
-               plane, obj_n, q_out, out, with_qout);
-}
-
-// info[:,1] += log(cnt+1) ; cnt = 0                                                       (AFB_URR.py:174)
-__global__ void finalize_counts_kernel(BankSet banks, int obj_n) {
-  pdl_wait();
-  pdl_trigger();
-  const int obj = blockIdx.y;
-  const vfn_bank bk = banks.b[obj];
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= live_n(bk)) return;
-  const int c = bk.cnt[i];
-  if (c == 0) return;            // log(0 + 1) = 0: info unchanged (most slots of a large bank; skips the fp64 log)
-  bk.cnt[i] = 0;
-  // bank_cnt + 1 is exact in fp32; log evaluated in double and rounded once
-  bk.info[2 * i + 1] += (float)log((double)((float)c + 1.0f));
+               plane, obj_n, q_out, out, with_qout, banks, counts);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -531,12 +536,12 @@ static int run_phase_a(const BankSet& set, ReadPlan& p, const float* q_in_dm, ch
   return VFN_OK;
 }
 
-static int run_phase_b(const BankSet& set, ReadPlan& p, const float* lse, float thres_valid, int update_bank,
-                       char* ws, cudaStream_t st) {
+static int run_phase_b(const BankSet& set, ReadPlan& p, const float* q_in_dm, int q_em, const float* lse,
+                       float thres_valid, int update_bank, char* ws, cudaStream_t st) {
   float* Q = reinterpret_cast<float*>(ws + p.off_q);
   float* po = reinterpret_cast<float*>(ws + p.off_po);
-  if (p.tc) return tc_phase_b(set.b, p.obj_n, p.hw, p.split_b, lse, thres_valid, update_bank, po, ws + p.off_tc, st,
-                              &p.split_b, &p.dev_b);
+  if (p.tc) return tc_phase_b(set.b, p.obj_n, q_in_dm, q_em, p.hw, p.split_b, lse, thres_valid, update_bank, po,
+                              ws + p.off_tc, st, &p.split_b, &p.dev_b);
   for (int o = 0; o < p.obj_n; ++o)
     VFN_CHECK_ARG(!set.b[o].n_live || set.b[o].n_min == set.b[o].n,
                   "the fp32 SIMT read needs exact bank sizes (bank %d was passed with bounds)", o);
@@ -609,20 +614,17 @@ int vfn_memread_phase_b(const vfn_bank* banks, int32_t obj_n, const float* d_q_i
   int64_t n_max;
   if (int rc = check_banks(banks, obj_n, &n_max, &set)) return rc;
   VFN_CHECK_ARG(d_q_in_dm && d_lse && d_partial_out && d_ws && hw > 0, "memread_phase_b: bad args");
+  const int q_em = (impl & VFN_Q_IN_EM) ? 1 : 0;
   impl &= 0xff;
   ReadPlan p = make_read_plan(obj_n, n_max, hw, set.b[0].d_key, set.b[0].d_val, impl);
   if (ws_bytes < p.total) { set_error("memread: workspace %zu < %zu", ws_bytes, p.total); return VFN_E_CAPACITY; }
   cudaStream_t st = as_stream(stream);
   char* ws = reinterpret_cast<char*>(d_ws);
-  // phase A of the same call sequence left Q (and the tcgen05 operands) in the workspace
-  if (int rc = run_phase_b(set, p, d_lse, thres_valid, update_bank, ws, st)) return rc;
+  // phase A of the same call sequence left Q in the workspace (fp32 SIMT kernels; the tcgen05 kernels read d_q_in_dm)
+  if (int rc = run_phase_b(set, p, d_q_in_dm, q_em, d_lse, thres_valid, update_bank, ws, st)) return rc;
   const int64_t plane = (int64_t)set.b[0].d_val * hw;
   launch_combine_out(reinterpret_cast<float*>(ws + p.off_po), p.split_b, p.dev_b, plane, obj_n, nullptr, d_partial_out, 0,
-                     st);
-  if (update_bank) {
-    dim3 g((unsigned)cdiv(n_max, 256), obj_n);
-    launch_pdl(finalize_counts_kernel, g, dim3(256), 0, st, set, obj_n);
-  }
+                     st, set, update_bank);
   VFN_LAUNCH_OK();
   return VFN_OK;
 }
@@ -650,15 +652,12 @@ int vfn_memread(const vfn_bank* banks, int32_t obj_n, const float* d_q_in_dm, co
   launch_pdl(lse_combine_kernel, dim3((unsigned)cdiv(rows, 256)), dim3(256), 0, st,
              reinterpret_cast<const float2*>(ws + p.off_part), p.split_a, p.dev_a, hw, obj_n, lse, d_lse);
   VFN_LAUNCH_OK();
-  if (int rc = run_phase_b(set, p, lse, thres_valid, update_bank, ws, st)) return rc;
+  if (int rc = run_phase_b(set, p, d_q_in_dm, q_em, lse, thres_valid, update_bank, ws, st)) return rc;
   const int64_t plane = (int64_t)set.b[0].d_val * hw;
-  launch_combine_out(reinterpret_cast<float*>(ws + p.off_po), p.split_b, p.dev_b, plane, obj_n, d_q_out_dm, d_out, 1, st);
-  if (update_bank) {
-    dim3 g((unsigned)cdiv(n_max, 256), obj_n);
-    launch_pdl(finalize_counts_kernel, g, dim3(256), 0, st, set, obj_n);
-  }
+  launch_combine_out(reinterpret_cast<float*>(ws + p.off_po), p.split_b, p.dev_b, plane, obj_n, d_q_out_dm, d_out, 1, st,
+                     set, update_bank);
   VFN_LAUNCH_OK();
-  count_launches(2 + (update_bank ? 1 : 0));
+  count_launches(2);
   return VFN_OK;
 }
 

@@ -97,14 +97,16 @@ __device__ __forceinline__ void load_a_operand(const TcArgs& args, int obj, int 
                                                uint32_t col_l, int warp, int lane) {
   const int quarter = warp & 3, cg = (warp - 4) >> 2;
   const int row = (quarter << 5) + lane;
-  const uint16_t* base = (cg < 2 ? args.qh : args.ql) + (size_t)obj * args.a_obj_stride;
-  const uint4* src = reinterpret_cast<const uint4*>(base + ((size_t)qt * QT + row) * DK + (cg & 1) * 64);
   const uint32_t taddr = tmem + (((uint32_t)quarter * 32u) << 16) + (cg < 2 ? col_h : col_l) + (uint32_t)(cg & 1) * 32u;
   uint32_t v[32];
+  {
+    const uint16_t* base = (cg < 2 ? args.qh : args.ql) + (size_t)obj * args.a_obj_stride;
+    const uint4* src = reinterpret_cast<const uint4*>(base + ((size_t)qt * QT + row) * DK + (cg & 1) * 64);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const uint4 x = src[i];
-    v[4 * i + 0] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+    for (int i = 0; i < 8; ++i) {
+      const uint4 x = src[i];
+      v[4 * i + 0] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+    }
   }
   tmem_st32(taddr, v);
   tmem_wait_st();
@@ -1330,6 +1332,7 @@ void tc_pick_splits(int obj_n, int64_t n_max, int64_t hw, int* split_a, int* spl
 
 // rows padded to a whole number of query-tile PAIRS (the pair kernels read two adjacent tiles)
 static size_t a_operand_bytes(int64_t hw) { return align_up((size_t)cdiv(hw, 2 * QT) * 2 * QT * DK * sizeof(uint16_t), 256); }
+int64_t tc_operand_rows(int64_t hw) { return cdiv(hw, 2 * QT) * 2 * QT; }
 
 // [Q hi | Q lo | 256 B: device-chosen splits {phase A, phase B}]
 size_t tc_workspace_bytes(int obj_n, int64_t hw) {
@@ -1390,7 +1393,7 @@ int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t h
   bool live;
   if (int rc = live_mode(banks, obj_n, &live)) return rc;
   TcMaps maps;
-  TcArgs a;
+  TcArgs a = {};
   int64_t tmin = INT64_MAX, tmax = 0;
   for (int o = 0; o < obj_n; ++o) {
     const int64_t t = cdiv(banks[o].n, SC_TILE), tl = cdiv(n_low(banks[o]), SC_TILE);
@@ -1409,11 +1412,12 @@ int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t h
     set_split_plan(&a, SC_TILE, obj_n * (int)cdiv(hw, pair ? 2 * QT : QT), 2, pair ? num_sms() / 2 : num_sms(), 0, cell);
     *pieces_dev_out = cell;
   }
-  // Q hi/lo of q * log2(e)/sqrt(d): logits land in the log2 domain; pad rows zeroed
-  VFN_CUDA_OK(cudaMemsetAsync(ws_tc, 0, 2 * a_operand_bytes(hw), st));
-  const float scale = LOG2E / sqrtf((float)DK);
+  // Q hi/lo of q * log2(e)/sqrt(d): logits land in the log2 domain; the pad rows (up to a whole tile pair) are zeroed
+  // by the same launch (a separate memset cost a stream gap per read; forming the operand inside the tensor kernels from
+  // the fp32 tensor was tried and lost: 64 dependent-latency loads per thread at every item start, phase B + 4 %)
   {
-    PrepJob jb{q_in_dm, DK, hw, nullptr, nullptr, const_cast<uint16_t*>(a.qh), const_cast<uint16_t*>(a.ql), scale, 0, q_em};
+    PrepJob jb{q_in_dm, DK, hw, nullptr, nullptr, const_cast<uint16_t*>(a.qh), const_cast<uint16_t*>(a.ql),
+               LOG2E / sqrtf((float)DK), 0, q_em, tc_operand_rows(hw)};
     if (int rc = launch_prep(&jb, 1, st)) return rc;
   }
   double work = 0;
@@ -1425,18 +1429,18 @@ int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t h
     tc_scan_kernel<MODE_LSE><<<num_sms(), TC_THREADS, SC_SMEM, st>>>(maps, a, part);
   prof_end(PROF_READ_A, st, work);
   VFN_LAUNCH_OK();
-  count_launches(2);
+  count_launches(1);      // + 1 counted by launch_prep
   return VFN_OK;
 }
 
-int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const float* lse, float thres_valid,
-               int update_bank, float* po, char* ws_tc, cudaStream_t st, int* pieces_out,
-               const int32_t** pieces_dev_out) {
+int tc_phase_b(const vfn_bank* banks, int obj_n, const float* q_in_dm, int q_em, int64_t hw, int split_b,
+               const float* lse, float thres_valid, int update_bank, float* po, char* ws_tc, cudaStream_t st,
+               int* pieces_out, const int32_t** pieces_dev_out) {
   if (int rc = set_attrs()) return rc;
   bool live;
   if (int rc = live_mode(banks, obj_n, &live)) return rc;
   TcMaps maps;
-  TcArgs a;
+  TcArgs a = {};
   const bool pair = (g_pair & 1) && (num_sms() % 2 == 0);
   const int tile = B_TILE;
   int64_t tmin = INT64_MAX, tmax = 0;
@@ -1455,6 +1459,7 @@ int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const 
   if (pieces > split_b) { set_error("phase B: split %d exceeds workspace bound %d", pieces, split_b); return VFN_E_CAPACITY; }
   *pieces_out = pieces;
   if (int rc = fill_args(banks, obj_n, hw, pieces, tile, ws_tc, &maps, &a, true, pair ? 32 : B_TILE)) return rc;
+  (void)q_in_dm; (void)q_em;      // the operand arrays were left in ws_tc by phase A of the same read
   *pieces_dev_out = nullptr;
   if (live) {
     int32_t* cell = tc_plan_cell(ws_tc, hw) + 1;
@@ -1505,7 +1510,7 @@ int tc_match(const vfn_bank* banks, int obj_n, const float* const* nck_em, int64
   if (int rc = set_attrs()) return rc;
   VFN_CHECK_ARG(obj_n >= 1 && obj_n <= TC_MAX_OBJ, "tcgen05 match supports at most %d objects", TC_MAX_OBJ);
   TcMaps maps;
-  TcArgs a;
+  TcArgs a = {};
   RescoreArgs r;
   int64_t tmin = INT64_MAX, tmax = 0;
   double work = 0;

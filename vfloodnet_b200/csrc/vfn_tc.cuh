@@ -16,15 +16,18 @@ size_t tc_workspace_bytes(int obj_n, int64_t hw);
 int tc_phase_a(const vfn_bank* banks, int obj_n, const float* q_in_dm, int64_t hw, int split_a, float2* part,
                char* ws_tc, cudaStream_t st, int* pieces_out, const int32_t** pieces_dev_out, int q_em = 0);
 // phase B: partial readouts po[((obj*split_b + s)*d_val + c)*hw + j] and usage counts into bank.cnt
-int tc_phase_b(const vfn_bank* banks, int obj_n, int64_t hw, int split_b, const float* lse, float thres_valid,
-               int update_bank, float* po, char* ws_tc, cudaStream_t st, int* pieces_out,
-               const int32_t** pieces_dev_out);
+int tc_phase_b(const vfn_bank* banks, int obj_n, const float* q_in_dm, int q_em, int64_t hw, int split_b,
+               const float* lse, float thres_valid, int update_bank, float* po, char* ws_tc, cudaStream_t st,
+               int* pieces_out, const int32_t** pieces_dev_out);
 
 // cosine match for obj_n banks in one launch: fp16x3 tcgen05 scores -> per-(piece, query, column group) near-tie
 // candidates in the workspace -> exact fp32 re-score (same FMA chain as the SIMT kernel) -> idx_out[o] / corr_out[o].
 // ws: tc_match_workspace_bytes(obj_n, hw).  cand_split != 0: the fp16 hi/lo of 16 * normalised candidates were already
 // written to tc_match_cand_hi/lo(ws, ...) (zero padded to a multiple of 128 rows) by the preparation kernel.
 size_t tc_match_workspace_bytes(int obj_n, int64_t hw);
+// rows of an A-operand array (fp16 hi or lo, 128 columns): hw rounded up to a whole number of query-tile pairs; the rows
+// beyond hw must be zero (PrepJob::n_pad makes the preparation launch write them)
+int64_t tc_operand_rows(int64_t hw);
 uint16_t* tc_match_cand_hi(char* ws, int obj_n, int64_t hw, int obj);
 uint16_t* tc_match_cand_lo(char* ws, int obj_n, int64_t hw, int obj);
 int tc_match(const vfn_bank* banks, int obj_n, const float* const* nck_em, int64_t hw, char* ws, int cand_split,

@@ -97,13 +97,12 @@ int vfn_bank_update(vfn_bank* banks, vfn_bank* alts, int32_t obj_n, vfn_update_i
 
   // (1) candidates: (d, hw) -> entry-major raw + normalised (FeatureBank.py:64,88), + fp16 split of 16 * normalised keys
   PrepJob jobs[8];
-  if (tc) VFN_CUDA_OK(cudaMemsetAsync(tc_match_cand_hi(mws, obj_n, hw, 0), 0,
-                                      (size_t)((char*)tc_match_cand_lo(mws, obj_n, hw, obj_n) - (char*)tc_match_cand_hi(mws, obj_n, hw, 0)), st));
   for (int c = 0; c < obj_n; ++c) {
     const int em = io[c].prev_layout == 1;      // (hw, d) candidates as vfn_keyvalue writes them: no transpose
     jobs[2 * c] = PrepJob{io[c].d_prev_key_dm, d_key, hw, em ? nullptr : CK(c), NCK(c),
                           tc ? tc_match_cand_hi(mws, obj_n, hw, c) : nullptr,
-                          tc ? tc_match_cand_lo(mws, obj_n, hw, c) : nullptr, NK_SCALE, 1, em};
+                          tc ? tc_match_cand_lo(mws, obj_n, hw, c) : nullptr, NK_SCALE, 1, em,
+                          tc ? tc_operand_rows(hw) : 0};       // pad rows of the match operand zeroed by the same launch
     jobs[2 * c + 1] = PrepJob{io[c].d_prev_value_dm, d_val, hw, em ? nullptr : CV(c), NCV(c), nullptr, nullptr, 1.f, 0, em};
   }
   if (int rc = launch_prep(jobs, 2 * obj_n, st)) return rc;

@@ -60,10 +60,11 @@ class Matcher(nn.Module):
         impl = fb.impl if self.impl is None else self.impl
         # the tcgen05 read takes the live bank sizes from device memory: updates still in flight need not be finished
         banks = fb.bank_array(bounds_ok=True, impl=int(impl))
+        l0 = lib.vfn_launch_count()
         check(lib.vfn_memread(banks, fb.obj_n, ptr(q_in), ptr(q_out), hw, float(self.thres_valid),
                               int(bool(self.update_bank)), ptr(out), ptr(lse), ptr(ws), ws.numel(),
                               int(impl) | (VFN_Q_IN_EM if q_em else 0),
                               stream_ptr()), 'vfn_memread')
         self.last_lse = lse
-        self.launches += 6 + (1 if self.update_bank else 0)
+        self.launches += lib.vfn_launch_count() - l0      # 4 on the tcgen05 path: phase A, LSE combine, phase B, combine
         return out
