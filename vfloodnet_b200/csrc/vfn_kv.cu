@@ -403,9 +403,9 @@ int vfn_kv_pack_weights(const float* d_wk, const float* d_bk, const float* d_wv,
 
 size_t vfn_keyvalue_workspace_bytes(int32_t B, int32_t c_in, int32_t h, int32_t w, int32_t d_key, int32_t d_val) {
   if (B < 1 || c_in < KV_KC || h < 1 || w < 1 || d_key < 1 || d_val < 1) return 0;
-  // sized for the largest K split, so that it does not depend on the device the call runs on
-  KvGeom g = kv_geom(B, c_in, h, w, d_key + d_val, 148);
-  return 256 + 2 * kv_x_bytes(g, c_in) + (size_t)KV_MAX_SPLIT * g.m_pad * (d_key + d_val) * sizeof(float);
+  // the K split (number of partial slabs) follows the SM count of the current device, as in vfn_keyvalue itself
+  KvGeom g = kv_geom(B, c_in, h, w, d_key + d_val, kv_num_sms());
+  return 256 + 2 * kv_x_bytes(g, c_in) + (size_t)g.split * g.m_pad * (d_key + d_val) * sizeof(float);
 }
 
 int vfn_keyvalue(const float* d_x, int32_t B, int32_t c_in, int32_t h, int32_t w, const void* d_packed, int32_t d_key,
