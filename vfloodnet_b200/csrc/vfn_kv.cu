@@ -16,8 +16,9 @@
 // (11 significant bits per operand: the TF32 class of the reference's default cuDNN math).
 //
 // Kernel: CTA pairs (cta_group::2, M = 256 = 2 x 128 raster rows, N = 320 = two MMAs of N = 160 per k-step), both
-// operands from shared memory via TMA (128B swizzle), 3 stages of 72 KB per CTA (A hi/lo 2 x 16 KB, this CTA's half of
-// the weight tile 4 x 10 KB), fp32 accumulator 128 lanes x 320 columns in TMEM.  Work items = (row-tile pair, channel
+// operands from shared memory via TMA (128B swizzle): two A slots of 2 x 17 KB (130 raster rows, hi / lo, shared by the
+// three kx taps of a kernel row), three stages of 40 KB with this CTA's half of one tap's weight tile; fp32 accumulator
+// 128 lanes x 320 columns in TMEM.  Work items = (row-tile pair, channel
 // half, K split); one cluster per item; per-item partials are summed in fixed order by the combine kernel, which also
 // applies the scales and the bias and writes the requested layouts.
 #include "vfn_ptx.cuh"
@@ -28,20 +29,27 @@ constexpr int KV_MT = 128;                 // raster rows per CTA (TMEM lanes)
 constexpr int KV_NH = 160;                 // N of one MMA
 constexpr int KV_NT = 2 * KV_NH;           // output channels per work item
 constexpr int KV_KC = 64;                  // input channels per K chunk (128 B of fp16: one swizzle row)
-constexpr int KV_STAGES = 3;
-constexpr int KV_A_BYTES = KV_MT * 128;              // 16 KB: 128 rows x 64 channels, hi or lo
 constexpr int KV_B_BYTES = (KV_NH / 2) * 128;        // 10 KB: this CTA's 80 of the 160 weight rows, hi or lo
-constexpr int KV_STAGE_BYTES = 2 * KV_A_BYTES + 4 * KV_B_BYTES;   // 72 KB
-constexpr int KV_SMEM = KV_STAGES * KV_STAGE_BYTES + 1024 + 256;
 constexpr int KV_THREADS = 384;            // warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4..11 epilogue
 constexpr int KV_MAX_SPLIT = 8;
 constexpr int KV_CHAIN_MAX = 48;           // K chunks accumulated into one TMEM accumulator (see kv_geom)
 constexpr int KV_X_EXP = 13, KV_W_EXP = 12;   // scaled operands: |x| <= 2^13, |w| <= 2^12
 
-struct KvMaps { CUtensorMap xh, xl, wh, wl; };
+// the three kx taps of a kernel row read raster rows r, r+1, r+2: ONE box of 130 rows per (ky, channel chunk) serves all
+// three (two A slots of hi + lo; three stages of weight tiles, one tap each)
+constexpr int KR_A_ROWS = KV_MT + 2;
+constexpr int KR_A_BYTES = 17 * 1024;                // 130 rows x 128 B = 16640 B, padded to whole 1024-byte swizzle atoms
+constexpr int KR_A_SLOT = 2 * KR_A_BYTES;            // hi + lo
+constexpr int KR_A_SLOTS = 2;
+constexpr int KR_B_STAGE = 4 * KV_B_BYTES;           // 40 KB: this CTA's half of the weight tile of one tap, hi + lo
+constexpr int KR_B_STAGES = 3;
+constexpr int KR_SMEM = KR_A_SLOTS * KR_A_SLOT + KR_B_STAGES * KR_B_STAGE + 1024 + 256;
+
+struct KvMaps { CUtensorMap wh, wl, xh_rows, xl_rows; };
 struct KvArgs {
   int Wp, c_chunks, n_chunks, c_out;       // padded raster width; C / 64; 9 * C / 64; 640
   int n_ntiles, split, passes, m_pad;      // c_out / 320; K splits; 1 or 3; rows of one partial slab
+  int n_groups;                            // 3 * C / 64 (ky, channel chunk) groups of three taps
   float* part;                             // [split][m_pad][c_out]
 };
 
@@ -144,22 +152,31 @@ __global__ void __launch_bounds__(256) kv_pack_weights_kernel(const float* __res
 // ------------------------------------------------------------------------------------------------
 // the GEMM: one cluster (CTA pair) per (row-tile pair, channel half, K split)
 // ------------------------------------------------------------------------------------------------
+// The A operand of a (ky, channel chunk) group is loaded ONCE (130 raster rows) and used for kx = 0, 1, 2 through the
+// descriptor's start address (+128 B per raster row): the 128B swizzle of TMA and of the tensor core are both functions
+// of the shared-memory ADDRESS, so a start address inside a 1024-byte atom needs no further treatment (the descriptor's
+// matrix-base-offset field must stay 0: setting it to the row offset gives wrong products - measured, r2z).  A CTA pulls
+// 33 + 3 x 40 KB per three taps from L2 instead of 3 x 72 KB with one box per tap.  K splits are cut at group boundaries.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(KV_THREADS, 1)
     kv_gemm_pair_kernel(const __grid_constant__ KvMaps maps, KvArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stg = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + KV_STAGES * KV_STAGE_BYTES);
-  uint64_t* k_full = bars;                       // [KV_STAGES]  (used on the leader: bytes of both CTAs' loads)
-  uint64_t* k_empty = bars + KV_STAGES;          // [KV_STAGES]  (multicast commit: both CTAs)
-  uint64_t* acc_full = bars + 2 * KV_STAGES;     // [1]
-  uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(bars + 2 * KV_STAGES + 1);
+  uint8_t* abuf = smem;
+  uint8_t* bbuf = smem + KR_A_SLOTS * KR_A_SLOT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bbuf + KR_B_STAGES * KR_B_STAGE);
+  uint64_t* a_full = bars;                          // [2]
+  uint64_t* a_empty = bars + 2;                     // [2]
+  uint64_t* b_full = bars + 4;                      // [3]
+  uint64_t* b_empty = bars + 7;                     // [3]
+  uint64_t* acc_full = bars + 10;
+  uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < KV_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < KR_A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < KR_B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -171,66 +188,77 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(KV_THREADS, 1)
   pdl_wait();
   pdl_trigger();
 
-  // item -> (row-tile pair, channel half, K split); consecutive clusters share the row tiles (A operand) in L2
   const int item = blockIdx.x >> 1;
   const int sp = item % a.split;
   const int nt = (item / a.split) % a.n_ntiles;
   const int mp = item / (a.split * a.n_ntiles);
-  const int c_begin = (int)((long long)a.n_chunks * sp / a.split);
-  const int c_end = (int)((long long)a.n_chunks * (sp + 1) / a.split);
-  const int nch = c_end - c_begin;
+  const int g_begin = (int)((long long)a.n_groups * sp / a.split);
+  const int g_end = (int)((long long)a.n_groups * (sp + 1) / a.split);
+  const int ng = g_end - g_begin;
   const int m0 = (mp * 2 + (int)rank) * KV_MT;
   const int n0 = nt * KV_NT;
   const bool three = a.passes == 3;
 
   if (warp == 0) {
     if (lane == 0) {
-      prefetch_tmap(&maps.xh); prefetch_tmap(&maps.wh);
-      if (three) { prefetch_tmap(&maps.xl); prefetch_tmap(&maps.wl); }
-      const uint32_t bytes_cta = three ? KV_STAGE_BYTES : KV_STAGE_BYTES / 2;
-      for (int i = 0; i < nch; ++i) {
-        const uint32_t st = i % KV_STAGES, ph = (i / KV_STAGES) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1);
-        if (leader) mbar_arrive_expect_tx(&k_full[st], 2 * bytes_cta);
-        const uint32_t kf = mapa_u32(smem_u32(&k_full[st]), 0);
-        const int c = c_begin + i;
-        const int tap = c / a.c_chunks, cc = c - tap * a.c_chunks;
-        const int ky = tap / 3, kx = tap - ky * 3;
-        const int row_a = m0 + ky * a.Wp + kx, col = cc * KV_KC;
-        const int row_b = tap * a.c_out + n0 + (int)rank * (KV_NH / 2);
-        uint8_t* dst = stg + st * KV_STAGE_BYTES;
-        tma_load_2d_pair(dst, &maps.xh, kf, col, row_a);
-        tma_load_2d_pair(dst + 2 * KV_A_BYTES, &maps.wh, kf, col, row_b);
-        tma_load_2d_pair(dst + 2 * KV_A_BYTES + KV_B_BYTES, &maps.wh, kf, col, row_b + KV_NH);
-        if (three) {
-          tma_load_2d_pair(dst + KV_A_BYTES, &maps.xl, kf, col, row_a);
-          tma_load_2d_pair(dst + 2 * KV_A_BYTES + 2 * KV_B_BYTES, &maps.wl, kf, col, row_b);
-          tma_load_2d_pair(dst + 2 * KV_A_BYTES + 3 * KV_B_BYTES, &maps.wl, kf, col, row_b + KV_NH);
+      prefetch_tmap(&maps.xh_rows); prefetch_tmap(&maps.wh);
+      if (three) { prefetch_tmap(&maps.xl_rows); prefetch_tmap(&maps.wl); }
+      const uint32_t a_bytes = (three ? 2u : 1u) * KR_A_ROWS * 128u;
+      const uint32_t b_bytes = three ? KR_B_STAGE : KR_B_STAGE / 2;
+      uint32_t ci = 0;
+      for (int gi = 0; gi < ng; ++gi) {
+        const int g = g_begin + gi, ky = g / a.c_chunks, cc = g - ky * a.c_chunks, col = cc * KV_KC;
+        const uint32_t slot = gi % KR_A_SLOTS, pha = (gi / KR_A_SLOTS) & 1;
+        mbar_wait(&a_empty[slot], pha ^ 1);
+        if (leader) mbar_arrive_expect_tx(&a_full[slot], 2 * a_bytes);
+        const uint32_t af = mapa_u32(smem_u32(&a_full[slot]), 0);
+        uint8_t* ad = abuf + slot * KR_A_SLOT;
+        tma_load_2d_pair(ad, &maps.xh_rows, af, col, m0 + ky * a.Wp);
+        if (three) tma_load_2d_pair(ad + KR_A_BYTES, &maps.xl_rows, af, col, m0 + ky * a.Wp);
+        for (int kx = 0; kx < 3; ++kx, ++ci) {
+          const uint32_t st = ci % KR_B_STAGES, ph = (ci / KR_B_STAGES) & 1;
+          mbar_wait(&b_empty[st], ph ^ 1);
+          if (leader) mbar_arrive_expect_tx(&b_full[st], 2 * b_bytes);
+          const uint32_t bf = mapa_u32(smem_u32(&b_full[st]), 0);
+          const int row_b = (ky * 3 + kx) * a.c_out + n0 + (int)rank * (KV_NH / 2);
+          uint8_t* bd = bbuf + st * KR_B_STAGE;
+          tma_load_2d_pair(bd, &maps.wh, bf, col, row_b);
+          tma_load_2d_pair(bd + KV_B_BYTES, &maps.wh, bf, col, row_b + KV_NH);
+          if (three) {
+            tma_load_2d_pair(bd + 2 * KV_B_BYTES, &maps.wl, bf, col, row_b);
+            tma_load_2d_pair(bd + 3 * KV_B_BYTES, &maps.wl, bf, col, row_b + KV_NH);
+          }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (leader && elect_one()) {     // ONE thread runs the whole issue loop (vfn_tc.cu: tc_phase_b_pair_kernel)
+    if (leader && elect_one()) {
       constexpr uint32_t idesc = make_idesc(2 * KV_MT, KV_NH, FMT_F16, FMT_F16, 0, 0);
-      for (int i = 0; i < nch; ++i) {
-        const uint32_t st = i % KV_STAGES, ph = (i / KV_STAGES) & 1;
-        mbar_wait(&k_full[st], ph);
-        tc_fence_after();
-        const uint32_t base = smem_u32(stg + st * KV_STAGE_BYTES);
-        // passes: (Ah, Bh) (Al, Bh) (Ah, Bl)
-        for (int pass = 0; pass < (three ? 3 : 1); ++pass) {
-          const uint32_t ab = base + (pass == 1 ? (uint32_t)KV_A_BYTES : 0u);
-          const uint32_t bb = base + 2 * KV_A_BYTES + (pass == 2 ? 2u * KV_B_BYTES : 0u);
+      uint32_t ci = 0;
+      for (int gi = 0; gi < ng; ++gi) {
+        const uint32_t slot = gi % KR_A_SLOTS, pha = (gi / KR_A_SLOTS) & 1;
+        mbar_wait(&a_full[slot], pha);
+        const uint32_t abase = smem_u32(abuf + slot * KR_A_SLOT);
+        for (int kx = 0; kx < 3; ++kx, ++ci) {
+          const uint32_t st = ci % KR_B_STAGES, ph = (ci / KR_B_STAGES) & 1;
+          mbar_wait(&b_full[st], ph);
+          tc_fence_after();
+          const uint32_t bbase = smem_u32(bbuf + st * KR_B_STAGE);
+          for (int pass = 0; pass < (three ? 3 : 1); ++pass) {
+            const uint32_t ab = abase + (pass == 1 ? (uint32_t)KR_A_BYTES : 0u) + (uint32_t)kx * 128u;
+            const uint32_t bb = bbase + (pass == 2 ? 2u * KV_B_BYTES : 0u);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = make_sdesc(ab + ks * 32u, 16, 1024);
-            const uint32_t acc = (i | pass | ks) ? 1u : 0u;
-            mma_ss_pair(tmem, ad, make_sdesc(bb + ks * 32u, 16, 1024), idesc, acc);
-            mma_ss_pair(tmem + KV_NH, ad, make_sdesc(bb + KV_B_BYTES + ks * 32u, 16, 1024), idesc, acc);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t ad = make_sdesc(ab + ks * 32u, 16, 1024);
+              const uint32_t acc = (ci | pass | ks) ? 1u : 0u;
+              mma_ss_pair(tmem, ad, make_sdesc(bb + ks * 32u, 16, 1024), idesc, acc);
+              mma_ss_pair(tmem + KV_NH, ad, make_sdesc(bb + KV_B_BYTES + ks * 32u, 16, 1024), idesc, acc);
+            }
           }
+          tc_commit_pair(&b_empty[st]);
         }
-        tc_commit_pair(&k_empty[st]);
+        tc_commit_pair(&a_empty[slot]);
       }
       tc_commit_pair(acc_full);
     }
@@ -239,8 +267,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(KV_THREADS, 1)
     const int quarter = warp & 3, half = (warp - 4) >> 2;
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const int o = m0 + (quarter << 5) + lane;
-    float* dst = a.part + ((size_t)sp * a.m_pad + o) * a.c_out + n0 + half * KV_NH;
+    // TMEM -> registers -> this warp's staging tile in shared memory (the operand buffers are free: acc_full means every
+    // MMA of the pair has completed) -> global rows.  A lane owns one accumulator ROW, so direct stores would put 32
+    // rows x 16 B into every store instruction (10 k clk per item); from the tile a warp writes 512 contiguous bytes.
+    constexpr int PITCH = KV_NH + 4;       // floats; 164 mod 32 = 4: the float4 stores of 8 lanes cover all 32 banks
+    float* tile = reinterpret_cast<float*>(smem) + (size_t)(warp - 4) * 32 * PITCH;
     const uint32_t tl = tmem + (((uint32_t)quarter * 32u) << 16) + (uint32_t)half * KV_NH;
 #pragma unroll 1
     for (int g = 0; g < KV_NH / 32; ++g) {
@@ -249,13 +280,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(KV_THREADS, 1)
       tmem_wait_ld();
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        reinterpret_cast<float4*>(dst + g * 32)[j] =
+        *reinterpret_cast<float4*>(tile + lane * PITCH + g * 32 + 4 * j) =
             make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                         __uint_as_float(v[4 * j + 3]));
     }
+    __syncwarp();
+    float* dst = a.part + ((size_t)sp * a.m_pad + m0 + (quarter << 5)) * a.c_out + n0 + half * KV_NH;
+#pragma unroll 4
+    for (int i = lane; i < 32 * (KV_NH / 4); i += 32) {
+      const int row = i / (KV_NH / 4), c4 = i - row * (KV_NH / 4);
+      *reinterpret_cast<float4*>(dst + (size_t)row * a.c_out + 4 * c4) =
+          *reinterpret_cast<const float4*>(tile + row * PITCH + 4 * c4);
+    }
   }
   tc_fence_before();
-  cluster_sync_all();      // the leader's MMAs read the peer's shared memory: nobody leaves before they are done
+  cluster_sync_all();
   tc_fence_after();
   if (warp == 2) tmem_dealloc_pair(tmem, 512);
 }
@@ -347,9 +386,10 @@ static KvGeom kv_geom(int B, int c_in, int h, int w, int c_out, int n_sm) {
   // 3e-5 at 144); the partial slabs are added in fp32 round-to-nearest by the combine kernel.
   const int s_min = (int)cdiv(g.n_chunks, KV_CHAIN_MAX) < KV_MAX_SPLIT ? (int)cdiv(g.n_chunks, KV_CHAIN_MAX) : KV_MAX_SPLIT;
   best = s_min;
-  for (int s = s_min; s <= KV_MAX_SPLIT && s <= g.n_chunks; ++s) {
+  const int n_groups = g.n_chunks / 3;       // the K range is cut at (ky, channel chunk) groups of three taps
+  for (int s = s_min; s <= KV_MAX_SPLIT && s <= n_groups; ++s) {
     const long long rounds = cdiv((int64_t)base * s, G);
-    const long long cost = rounds * (cdiv(g.n_chunks, s) + 6) + 2 * s;      // + 2 s: the combine reads s partial slabs
+    const long long cost = rounds * (3 * cdiv(n_groups, s) + 6) + 2 * s;    // + 2 s: the combine reads s partial slabs
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
   }
   g.split = best;
@@ -357,7 +397,7 @@ static KvGeom kv_geom(int B, int c_in, int h, int w, int c_out, int n_sm) {
 }
 
 // the tensor map of the raster always spans at least one row tile (maps with fewer rows than their box are avoided)
-static int kv_map_rows(const KvGeom& g) { return g.rows > KV_MT ? g.rows : KV_MT; }
+static int kv_map_rows(const KvGeom& g) { return g.rows > KR_A_ROWS ? g.rows : KR_A_ROWS; }
 static size_t kv_x_bytes(const KvGeom& g, int c_in) { return align_up((size_t)kv_map_rows(g) * c_in * sizeof(uint16_t), 1024); }
 
 static int kv_check_dims(int B, int c_in, int h, int w, int dk, int dv) {
@@ -426,7 +466,7 @@ int vfn_keyvalue(const float* d_x, int32_t B, int32_t c_in, int32_t h, int32_t w
   }
   static bool attr[64] = {false};
   if (first_use_on_device(attr))
-    VFN_CUDA_OK(cudaFuncSetAttribute(kv_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KV_SMEM));
+    VFN_CUDA_OK(cudaFuncSetAttribute(kv_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KR_SMEM));
   cudaStream_t st = as_stream(stream);
   char* ws = reinterpret_cast<char*>(d_ws);
   uint32_t* cells = reinterpret_cast<uint32_t*>(ws);                    // [0] bits of max |x|, [1] 2^-k as float
@@ -440,7 +480,7 @@ int vfn_keyvalue(const float* d_x, int32_t B, int32_t c_in, int32_t h, int32_t w
   const float* inv_sw = reinterpret_cast<const float*>(pk) + 1;
 
   VFN_CUDA_OK(cudaMemsetAsync(cells, 0, 256, st));
-  if (g.rows < KV_MT) VFN_CUDA_OK(cudaMemsetAsync(xh, 0, 2 * kv_x_bytes(g, c_in), st));   // rows the packing never writes
+  if (g.rows < KR_A_ROWS) VFN_CUDA_OK(cudaMemsetAsync(xh, 0, 2 * kv_x_bytes(g, c_in), st));   // rows the packing never writes
   const int64_t nx = (int64_t)B * c_in * h * w;
   kv_absmax_kernel<<<4 * n_sm, 256, 0, st>>>(d_x, nx, cells);
   dim3 pg((unsigned)(B * g.Hp), (unsigned)(c_in / 64), (unsigned)cdiv(g.Wp, 32));
@@ -448,16 +488,17 @@ int vfn_keyvalue(const float* d_x, int32_t B, int32_t c_in, int32_t h, int32_t w
                          (const uint32_t*)cells, reinterpret_cast<float*>(cells) + 1, xh, xl));
 
   KvMaps maps;
-  if (int rc = make_map(&maps.xh, xh, kv_map_rows(g), c_in, KV_MT, 2)) return rc;
-  if (int rc = make_map(&maps.xl, xl, kv_map_rows(g), c_in, KV_MT, 2)) return rc;
   if (int rc = make_map(&maps.wh, wh, (int64_t)9 * c_out, c_in, KV_NH / 2, 2)) return rc;
   if (int rc = make_map(&maps.wl, wl, (int64_t)9 * c_out, c_in, KV_NH / 2, 2)) return rc;
+  if (int rc = make_map(&maps.xh_rows, xh, kv_map_rows(g), c_in, KR_A_ROWS, 2)) return rc;
+  if (int rc = make_map(&maps.xl_rows, xl, kv_map_rows(g), c_in, KR_A_ROWS, 2)) return rc;
   KvArgs a;
   a.Wp = g.Wp; a.c_chunks = c_in / KV_KC; a.n_chunks = g.n_chunks; a.c_out = c_out;
   a.n_ntiles = g.n_ntiles; a.split = g.split; a.passes = passes; a.m_pad = g.m_pad; a.part = part;
+  a.n_groups = g.n_chunks / 3;
   const int items = g.n_mpairs * g.n_ntiles * g.split;
   prof_begin(PROF_KV, st);
-  VFN_CUDA_OK(launch_pdl(kv_gemm_pair_kernel, dim3(2 * items), dim3(KV_THREADS), KV_SMEM, st, maps, a));
+  VFN_CUDA_OK(launch_pdl(kv_gemm_pair_kernel, dim3(2 * items), dim3(KV_THREADS), KR_SMEM, st, maps, a));
   prof_end(PROF_KV, st, 2.0 * 9.0 * c_in * c_out * (double)B * h * w);
   KvOut out{d_key_em, d_val_em, d_key_dm, d_val_dm};
   dim3 cg((unsigned)cdiv((int64_t)B * h * w, 32), (unsigned)(c_out / 32));
