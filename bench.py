@@ -31,10 +31,10 @@ R1_H, R1_W = 240, 432
 D_KEY, D_VAL = 128, 512
 BUDGET = 250000               # test_video_seg.py:24  -> class_budget 100000.0
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE tc_phase_b_pair_kernel launch, from the committed `ncu --set full`
-# capture (profiles/r2f_ncu_summary.md): N = 100000 slots/object, 2 objects, HW = 1620.  The operand arrays that launch
+# capture (profiles/r3d_ncu_summary.md): N = 100000 slots/object, 2 objects, HW = 1620.  The operand arrays that launch
 # has to stream once are 2560 B/slot (kh, kl, vh, v8, vl) = 512 MB; its algorithmic work is 3.32e11 flop.
-NCU_PHASE_B_TRAFFIC = {'bytes': 615.17e6 + 93.33e6,
-                       'note': 'per launch at N=100000 slots/object (ncu capture profiles/r2f_ncu_summary.md); operand '
+NCU_PHASE_B_TRAFFIC = {'bytes': 612.65e6 + 92.52e6,
+                       'note': 'per launch at N=100000 slots/object (ncu capture profiles/r3d_ncu_summary.md); operand '
                                'bytes streamed once = 512 MB; the bench launches average fewer slots'}
 TAIL_SIZE = (1080, 1920)      # original frame size the mask is resized back to (test_video_seg.py:103,114)
 TAIL_KEY_PTS = [(480, 300), (960, 200), (1440, 400), (1800, 100)]
