@@ -118,3 +118,22 @@ def test_folded_encoders_compute_the_reference_encoders(ref, monkeypatch):
         r_train = model.encoder_q(f)
         model.eval()
         assert len(r_train) == 4
+
+
+def test_keyvalue_head_training_mode_is_the_reference_forward_and_eval_has_no_cpu_path():
+    """train mode keeps autograd (the reference's two convolutions, AFB_URR.py:103-111); eval mode on a CPU tensor
+    raises instead of falling back"""
+    import vfloodnet_b200 as vfn
+    torch.manual_seed(0)
+    key, val = torch.nn.Conv2d(64, 128, 3, padding=1), torch.nn.Conv2d(64, 512, 3, padding=1)
+    head = vfn.KeyValueHead(key, val)
+    x = torch.randn(2, 64, 5, 6)
+    head.train()
+    k, v = head(x)
+    assert k.shape == (2, 128, 30) and v.shape == (2, 512, 30) and k.requires_grad
+    k0, v0 = O.keyvalue_forward(x, key.weight, key.bias, val.weight, val.bias)
+    assert torch.equal(k, k0) and torch.equal(v, v0)
+    head.eval()
+    with pytest.raises(RuntimeError):
+        head(x)
+    assert set(head.state_dict().keys()) == {'Key.weight', 'Key.bias', 'Value.weight', 'Value.bias'}

@@ -109,7 +109,7 @@ class _FoldedTrunk:
 
 def _encoder_q_forward(self, in_f):
     """EncoderQ.forward (AFB_URR.py:81-92)"""
-    if self.training:
+    if self.training or in_f.device.type != 'cuda':      # the fused cuDNN calls exist on CUDA only
         return self._vfn_ref_forward(in_f)
     t = self._vfn_folded
     t.refresh()
@@ -119,7 +119,7 @@ def _encoder_q_forward(self, in_f):
 
 def _encoder_m_forward(self, in_f, in_m, in_o):
     """EncoderM.forward (AFB_URR.py:53-64)"""
-    if self.training:
+    if self.training or in_f.device.type != 'cuda':
         return self._vfn_ref_forward(in_f, in_m, in_o)
     t = self._vfn_folded
     t.refresh()

@@ -70,6 +70,11 @@ class KeyValueHead(nn.Module):
     def forward(self, x: torch.Tensor, layout: str = 'auto'):
         """x: (B, C, h, w).  layout: 'auto' (values dimension-major when B == 1, else entry-major), 'em' or 'dm' (both
         outputs in that layout).  Returns key (B, keydim, h*w), val (B, valdim, h*w)."""
+        if self.training:
+            # training (train_video_seg.py) needs autograd through the two convolutions: the reference's own forward
+            # (AFB_URR.py:103-111).  The library path is the inference path.
+            key, val = self.Key(x), self.Value(x)
+            return key.view(*key.shape[:2], -1), val.view(*val.shape[:2], -1)
         if x.device.type != 'cuda':
             raise RuntimeError('KeyValueHead runs on the CUDA library only (no CPU fallback)')
         lib = _lib.load()
