@@ -15,7 +15,7 @@ def main():
     torch.manual_seed(0)
     key = torch.nn.Conv2d(1024, 128, 3, padding=1).cuda()
     val = torch.nn.Conv2d(1024, 512, 3, padding=1).cuda()
-    head = vfn.KeyValueHead(key, val, passes=int(os.environ.get('KV_PASSES', '3')))
+    head = vfn.KeyValueHead(key, val, passes=int(os.environ.get('KV_PASSES', '3'))).eval()
     reps = int(os.environ.get('KV_REPS', '3'))
     for b in (1, 2):
         x = torch.relu(torch.randn(b, 1024, 30, 54, device='cuda')) * 3

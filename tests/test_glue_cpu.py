@@ -126,6 +126,7 @@ def test_keyvalue_head_training_mode_is_the_reference_forward_and_eval_has_no_cp
     import vfloodnet_b200 as vfn
     torch.manual_seed(0)
     key, val = torch.nn.Conv2d(64, 128, 3, padding=1), torch.nn.Conv2d(64, 512, 3, padding=1)
+    assert not vfn.KeyValueHead(key.eval(), val.eval()).training      # the head follows the mode of what it wraps
     head = vfn.KeyValueHead(key, val)
     x = torch.randn(2, 64, 5, 6)
     head.train()

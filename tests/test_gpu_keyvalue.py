@@ -100,12 +100,15 @@ def test_keyvalue_golden_of_the_reference_module():
     with torch.no_grad():
         key.weight.copy_(torch.from_numpy(g['wk'])); key.bias.copy_(torch.from_numpy(g['bk']))
         val.weight.copy_(torch.from_numpy(g['wv'])); val.bias.copy_(torch.from_numpy(g['bv']))
-    head = vfn.KeyValueHead(key.cuda(), val.cuda())
+    head = vfn.KeyValueHead(key.cuda(), val.cuda()).eval()
     x = torch.from_numpy(g['x']).cuda()
     want_k, want_v = torch.from_numpy(g['key']).cuda(), torch.from_numpy(g['val']).cuda()
+    assert not head.training
     for layout in ('auto', 'em', 'dm'):
         with torch.no_grad():
+            n0 = head.launches
             k, v = head(x, layout=layout)
+            assert head.launches > n0            # the library path ran (train mode would run the two cuDNN convolutions)
         assert k.shape == want_k.shape and v.shape == want_v.shape
         assert float((k - want_k).abs().max()) <= 5e-6 * float(want_k.abs().max())
         assert float((v - want_v).abs().max()) <= 5e-6 * float(want_v.abs().max())
@@ -178,7 +181,7 @@ def test_keyvalue_rejects_what_it_cannot_do():
         head(torch.zeros(1, 64, 4, 4))                                   # CPU tensor: no fallback
     with pytest.raises(ValueError):
         vfn.KeyValueHead(torch.nn.Conv2d(64, 128, 1), torch.nn.Conv2d(64, 512, 1))
-    bad = vfn.KeyValueHead(torch.nn.Conv2d(48, 128, 3, padding=1).cuda(), torch.nn.Conv2d(48, 512, 3, padding=1).cuda())
+    bad = vfn.KeyValueHead(torch.nn.Conv2d(48, 128, 3, padding=1).cuda(), torch.nn.Conv2d(48, 512, 3, padding=1).cuda()).eval()
     with pytest.raises((ValueError, RuntimeError)):
         bad(torch.zeros(1, 48, 4, 4, device='cuda'))                     # c_in not a multiple of 64
 

@@ -378,13 +378,17 @@ def test_urr_local_streaming_equals_tiled(vfn, obj_n, c, h, w, shared):
     r1 = torch.randn((1 if shared else obj_n, c, h, w), generator=g).cuda()
     r1 = r1.expand(obj_n, -1, -1, -1) if shared else r1
     try:
-        lib.vfn_debug_set_urr_stream(0)
-        ref = vfn.urr_pre(p, r1, (1, obj_n, h, w))[3].clone()
-        for mode in (1, 2):                  # two objects per warp / one object per warp
+        lib.vfn_debug_set_urr_stream(0)      # separate stage-1 / stage-2 launches + the tiled stage-3 kernel
+        ref_all = [x.clone() for x in vfn.urr_pre(p, r1, (1, obj_n, h, w))]
+        ref = ref_all[3]
+        for mode in (1, 2):                  # fused stage 1 + 2; streaming stage 3 with two objects / one object per warp
             lib.vfn_debug_set_urr_stream(mode)
-            got = vfn.urr_pre(p, r1, (1, obj_n, h, w))[3]
+            got_all = vfn.urr_pre(p, r1, (1, obj_n, h, w))
+            got = got_all[3]
             torch.cuda.synchronize()
             assert torch.equal(ref, got), (mode, (ref - got).abs().max().item())
+            for name, a, b in zip(('p_up', 'uncertainty', 'r1_conf'), ref_all[:3], got_all[:3]):
+                assert torch.equal(a, b), (mode, name)
     finally:
         lib.vfn_debug_set_urr_stream(1)
 

@@ -92,6 +92,79 @@ __global__ void urr_window_kernel(const float* __restrict__ seg, int obj_n, int 
   avg[(int64_t)o * h * w + (int64_t)y * w + x] = sum / 49.f;
 }
 
+// stages 1 + 2 in one launch (w, h any size; obj_n <= URR_MAX_OBJ): a CTA owns a 32 x 16 pixel tile, evaluates stage 1
+// on the tile plus its 3-pixel halo into shared memory (the halo's stage-1 values are recomputed, 1.6x of a cheap
+// stage), writes p_up / seg / unc for its own pixels and takes the 7x7 windows from shared memory in the order of
+// urr_window_kernel (dy outer, dx inner): the same bits as the two separate launches, one stream gap fewer per frame.
+constexpr int SW_W = 32, SW_H = 16, SW_HW = SW_W + 6, SW_HH = SW_H + 6;
+__global__ void __launch_bounds__(256) urr_segwin_kernel(const float* __restrict__ p, int obj_n, int h, int w,
+                                                        float* __restrict__ p_up, float* __restrict__ seg,
+                                                        float* __restrict__ unc, float* __restrict__ conf,
+                                                        float* __restrict__ avg) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float sseg[URR_MAX_OBJ][SW_HH][SW_HW + 1];
+  const int x0t = blockIdx.x * SW_W, y0t = blockIdx.y * SW_H;
+  const int hin = h >> 1, win = w >> 1;
+  const int64_t plane = (int64_t)h * w;
+  for (int i = threadIdx.x; i < SW_HH * SW_HW; i += blockDim.x) {
+    const int ly = i / SW_HW, lx = i - ly * SW_HW;
+    const int y = y0t + ly - 3, x = x0t + lx - 3;
+    if (y < 0 || y >= h || x < 0 || x >= w) continue;          // never read: the windows skip pixels outside the image
+    const bool own = ly >= 3 && ly < 3 + SW_H && lx >= 3 && lx < 3 + SW_W;
+    int y0, y1, x0, x1;
+    float ly0, ly1, lx0, lx1;
+    src_index(y, hin, y0, y1, ly0, ly1);
+    src_index(x, win, x0, x1, lx0, lx1);
+    float fg[URR_MAX_OBJ];
+    float mx = -INFINITY;
+    for (int o = 0; o < obj_n; ++o) {
+      const float* pl = p + (int64_t)o * 2 * hin * win;
+      const float a = bilerp(pl, win, y0, y1, x0, x1, ly0, ly1, lx0, lx1);
+      const float b = bilerp(pl + hin * win, win, y0, y1, x0, x1, ly0, ly1, lx0, lx1);
+      if (own) {
+        p_up[((int64_t)o * 2 + 0) * plane + (int64_t)y * w + x] = a;
+        p_up[((int64_t)o * 2 + 1) * plane + (int64_t)y * w + x] = b;
+      }
+      const float m = fmaxf(a, b);
+      const float e0 = expf(a - m), e1 = expf(b - m);
+      fg[o] = e1 / (e0 + e1);                       // softmax(p, dim=1)[:, 1]           AFB_URR.py:217
+      mx = fmaxf(mx, fg[o]);
+    }
+    float sum = 0.f;
+    for (int o = 0; o < obj_n; ++o) { fg[o] = expf(fg[o] - mx); sum += fg[o]; }
+    float t1 = -INFINITY, t2 = -INFINITY;
+    for (int o = 0; o < obj_n; ++o) {
+      const float s = fg[o] / sum;                  // object-level softmax                AFB_URR.py:219
+      sseg[o][ly][lx] = s;
+      if (own) seg[(int64_t)o * plane + (int64_t)y * w + x] = s;
+      if (s > t1) { t2 = t1; t1 = s; } else if (s > t2) { t2 = s; }
+    }
+    if (own) unc[(int64_t)y * w + x] = expf(1.f - t1 / (t2 + 1e-8f));   // myutils/data.py:45-47
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < SW_H * SW_W * obj_n; i += blockDim.x) {
+    const int o = i / (SW_H * SW_W), r = i - o * (SW_H * SW_W);
+    const int ty = r / SW_W, tx = r - ty * SW_W;
+    const int y = y0t + ty, x = x0t + tx;
+    if (y >= h || x >= w) continue;
+    float mx = -INFINITY, sum = 0.f;
+    for (int dy = -3; dy <= 3; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= h) continue;
+      for (int dx = -3; dx <= 3; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= w) continue;
+        const float v = sseg[o][ty + 3 + dy][tx + 3 + dx];
+        mx = fmaxf(mx, v);
+        sum += v;
+      }
+    }
+    conf[(int64_t)o * plane + (int64_t)y * w + x] = mx;
+    avg[(int64_t)o * plane + (int64_t)y * w + x] = sum / 49.f;
+  }
+}
+
 // stage 3: local_match[o][ch] = r1[ch] ; local_match[o][C+ch] = box7(r1[ch]*seg[o])/49 / (avg[o] + 1e-8)
 // CTA = one channel x one 16-row x 128-column tile, ALL objects (r1 is read once and shared by the objects, the
 // reference's `expand`).  Stage 1 puts r1 and r1*seg[o] (with a 3-pixel halo) in shared memory; stage 2 gives each
@@ -347,10 +420,16 @@ int vfn_urr_pre(const float* d_p, const float* d_r1, int64_t r1_obj_stride, int3
   VFN_CHECK_ARG(h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "urr_pre: h,w must be even");
   VFN_CHECK_ARG(c > 0, "urr_pre: channels must be positive");
   cudaStream_t st = as_stream(stream);
-  dim3 g1((unsigned)cdiv(w, 128), h);
-  launch_pdl(urr_seg_kernel, g1, dim3(128), 0, st, d_p, obj_n, h, w, d_p_up, d_seg, d_unc);
-  dim3 g2((unsigned)cdiv(w, 128), h, obj_n);
-  launch_pdl(urr_window_kernel, g2, dim3(128), 0, st, d_seg, obj_n, h, w, d_conf, d_avg);
+  if (g_urr_stream == 0) {       // the two separate launches: cross-check of the fused stage 1 + 2 kernel in tests/
+    dim3 g1((unsigned)cdiv(w, 128), h);
+    launch_pdl(urr_seg_kernel, g1, dim3(128), 0, st, d_p, obj_n, h, w, d_p_up, d_seg, d_unc);
+    dim3 g2((unsigned)cdiv(w, 128), h, obj_n);
+    launch_pdl(urr_window_kernel, g2, dim3(128), 0, st, d_seg, obj_n, h, w, d_conf, d_avg);
+    count_launches(1);
+  } else {
+    dim3 g12((unsigned)cdiv(w, SW_W), (unsigned)cdiv(h, SW_H));
+    launch_pdl(urr_segwin_kernel, g12, dim3(256), 0, st, d_p, obj_n, h, w, d_p_up, d_seg, d_unc, d_conf, d_avg);
+  }
   dim3 g3((unsigned)cdiv(w, UT_W), (unsigned)cdiv(h, UT_H), c);
   prof_begin(PROF_URR, st);
   if (w % 4 == 0 && g_urr_stream) {
@@ -379,7 +458,7 @@ int vfn_urr_pre(const float* d_p, const float* d_r1, int64_t r1_obj_stride, int3
   // algorithmic bytes: read r1 once, write [r1 ; r1_local] per object, + small planes
   prof_end(PROF_URR, st, 4.0 * (double)h * w * ((r1_obj_stride ? obj_n : 1) * (double)c + obj_n * (2.0 * c + 8.0)));
   VFN_LAUNCH_OK();
-  count_launches(3);
+  count_launches(2);
   return VFN_OK;
 }
 

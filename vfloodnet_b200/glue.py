@@ -117,7 +117,7 @@ def fuse_model(model, keyvalue: bool = True, keyvalue_passes: int = 3, fold_bn: 
     if keyvalue:
         from .keyvalue import KeyValueHead
         if not isinstance(model.keyval_r4, KeyValueHead):
-            model.keyval_r4 = KeyValueHead.from_reference(model.keyval_r4, passes=keyvalue_passes)
+            model.keyval_r4 = KeyValueHead.from_reference(model.keyval_r4, passes=keyvalue_passes).train(model.training)
     if fold_bn:
         from .folded import fold_encoders
         fold_encoders(model)

@@ -37,6 +37,7 @@ class KeyValueHead(nn.Module):
         if passes not in (1, 3):
             raise ValueError('passes: 3 (fp32 grade) or 1 (TF32 class)')
         self.Key, self.Value = key_conv, value_conv
+        self.train(key_conv.training)        # a head built around the convolutions of an eval() model is in eval mode
         self.keydim, self.valdim = key_conv.out_channels, value_conv.out_channels
         self.passes = passes
         self._packed = None
