@@ -288,32 +288,45 @@ __global__ void __launch_bounds__(UL_WARPS * 32) urr_local_stream_kernel(
 #pragma unroll
     for (int r = 0; r < 8; ++r) ring[o][r] = z4;
 
-  auto load_row = [&](int y, float4& rv, float4 (&sv)[NO]) {
-    const bool ok = col_ok && y >= 0 && y < h;
-    rv = ok ? __ldg(rp + (int64_t)y * w4) : z4;
-#pragma unroll
-    for (int o = 0; o < NO; ++o) sv[o] = (ok && o < no) ? __ldg(sp + (int64_t)o * plane4 + (int64_t)y * w4) : z4;
-  };
-  float4 rbuf[2], sbuf[2][NO];
+  // running row pointers (advanced by one row per iteration): the 64-bit index products of every load and store of a
+  // row were a quarter of the kernel's instructions
   const int y_end = y1 + UHALO;
   int yin = y0 - UHALO;
-  load_row(yin, rbuf[0], sbuf[0]);
+  const float4* rrow = rp + (int64_t)yin * w4;            // row `yin` of r1 (may point outside the plane: never read then)
+  const float4* srow[NO];
+  const float4* arow[NO];
+  float4* orow[NO];                                       // raw copy of row `yin`; the local row is 3 rows up, + loc4
+#pragma unroll
+  for (int o = 0; o < NO; ++o) {
+    srow[o] = sp + (int64_t)o * plane4 + (int64_t)yin * w4;
+    arow[o] = ap + (int64_t)o * plane4 + (int64_t)(yin - UHALO) * w4;
+    orow[o] = out + (int64_t)o * obj_out4 + (int64_t)yin * w4;
+  }
+  const int64_t loc_off = loc4 - (int64_t)UHALO * w4;
+  auto load_row = [&](int y, int ahead, float4& rv, float4 (&sv)[NO]) {      // row y = yin + ahead
+    const bool ok = col_ok && y >= 0 && y < h;
+    rv = ok ? __ldg(rrow + (int64_t)ahead * w4) : z4;
+#pragma unroll
+    for (int o = 0; o < NO; ++o) sv[o] = (ok && o < no) ? __ldg(srow[o] + (int64_t)ahead * w4) : z4;
+  };
+  float4 rbuf[2], sbuf[2][NO];
+  load_row(yin, 0, rbuf[0], sbuf[0]);
   while (yin < y_end) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       if (yin < y_end) {                                               // warp-uniform; only the last group stops early
-        load_row(yin + 1 < y_end ? yin + 1 : -1, rbuf[(u + 1) & 1], sbuf[(u + 1) & 1]);   // prefetch the next row
+        load_row(yin + 1 < y_end ? yin + 1 : -1, 1, rbuf[(u + 1) & 1], sbuf[(u + 1) & 1]);   // prefetch the next row
         const float4 rv = rbuf[u & 1];
         const int yout = yin - UHALO;
         const bool emit = out_lane && yout >= y0;
         float4 av[NO];
 #pragma unroll
         for (int o = 0; o < NO; ++o)
-          av[o] = (emit && o < no) ? __ldg(ap + (int64_t)o * plane4 + (int64_t)yout * w4) : z4;
+          av[o] = (emit && o < no) ? __ldg(arow[o]) : z4;
         if (out_lane && yin >= y0 && yin < y1) {     // the raw copy [r1 ; .] of the row just loaded (AFB_URR.py:231)
 #pragma unroll
           for (int o = 0; o < NO; ++o)
-            if (o < no) __stcs(out + (int64_t)o * obj_out4 + (int64_t)yin * w4, rv);
+            if (o < no) __stcs(orow[o], rv);
         }
 #pragma unroll
         for (int o = 0; o < NO; ++o) {
@@ -344,11 +357,14 @@ __global__ void __launch_bounds__(UL_WARPS * 32) urr_local_stream_kernel(
               }
               const float4 res = make_float4(urr_ratio(tot.x, av[o].x), urr_ratio(tot.y, av[o].y),
                                              urr_ratio(tot.z, av[o].z), urr_ratio(tot.w, av[o].w));
-              __stcs(out + (int64_t)o * obj_out4 + (int64_t)yout * w4 + loc4, res);
+              __stcs(orow[o] + loc_off, res);
             }
           }
         }
         ++yin;
+        rrow += w4;
+#pragma unroll
+        for (int o = 0; o < NO; ++o) { srow[o] += w4; arow[o] += w4; orow[o] += w4; }
       }
     }
   }
