@@ -433,3 +433,27 @@ def test_fused_model_other_frame_size_with_padding_on_both_axes(env):
     with torch.no_grad():
         sg, _ = gm.segment(f1, fbf)
     assert sg.shape == (1, 2, h, w)
+
+
+def test_prefetch_of_another_frame_is_discarded(env):
+    """GraphedAFBURR.prefetch(A) followed by segment(B): the side stream's work is waited for and the encoder stage is
+    run again for B - the result is that of a plain segment(B)"""
+    vfn, MC, dev = env['vfn'], env['MC'], env['dev']
+    clip = [f.to(dev) for f in MC.make_clip(3)]
+    gm = vfn.GraphedAFBURR(env['fused'], tuple(clip[0].shape))
+    with torch.no_grad():
+        fb = vfn.FeatureBank(2, MC.BUDGET, dev)
+        fb.init_bank(*gm.memorize(clip[0], MC.first_mask().to(dev)))
+        fb.update_bank = False
+        gm.global_matcher.update_bank = False            # two reads of the same bank state must not differ by usage counts
+        try:
+            want, _ = gm.segment(clip[2], fb)
+            want = want.clone()
+            gm.prefetch(clip[1])
+            got, _ = gm.segment(clip[2], fb)
+            assert torch.equal(want, got)
+            gm.prefetch(clip[2])
+            got2, _ = gm.segment(clip[2], fb)
+            assert torch.equal(want, got2)
+        finally:
+            gm.global_matcher.update_bank = True
